@@ -1,0 +1,123 @@
+"""ctypes binding of the C ABI declared in ``include/bpreveal_b200.h``.
+
+The shared library is built in-tree by ``bpreveal_b200/csrc/Makefile`` (``__graft_entry__.build``).
+There is deliberately no fallback: if the library is missing, or a call fails, an exception is
+raised.  PyTorch is used by the callers only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbpreveal_b200.so")
+
+c_void_p = C.c_void_p
+c_int = C.c_int
+c_ll = C.c_longlong
+c_float = C.c_float
+
+
+class Conv3Args(C.Structure):
+    _fields_ = [
+        ("B", c_int), ("L_in", c_int), ("L_out", c_int), ("F", c_int),
+        ("tap_off", c_int * 3),
+        ("mode", c_int),
+        ("in_hi", c_void_p), ("in_lo", c_void_p),
+        ("w_hi", c_void_p), ("w_lo", c_void_p),
+        ("bias", c_void_p),
+        ("resid_hi", c_void_p), ("resid_lo", c_void_p),
+        ("L_res", c_int), ("resid_off", c_int),
+        ("out_hi", c_void_p), ("out_lo", c_void_p),
+        ("out2_hi", c_void_p), ("out2_lo", c_void_p),
+        ("mask_out", c_void_p),
+        ("mask_in", c_void_p),
+        ("mult_hi", c_void_p), ("mult_lo", c_void_p),
+        ("zx_in", c_void_p),
+        ("zx_div", c_int),
+        ("z_out", c_void_p),
+    ]
+
+
+class Wgrad3Args(C.Structure):
+    _fields_ = [
+        ("B", c_int), ("L_in", c_int), ("L_out", c_int), ("F", c_int), ("dil", c_int),
+        ("act_hi", c_void_p), ("act_lo", c_void_p),
+        ("gz_hi", c_void_p), ("gz_lo", c_void_p),
+        ("dw", c_void_p), ("db", c_void_p),
+        ("ws", c_void_p), ("ws_bytes", c_ll),
+    ]
+
+
+class InputConvArgs(C.Structure):
+    _fields_ = [
+        ("B", c_int), ("L_in", c_int), ("L_out", c_int), ("W", c_int), ("Fw", c_int), ("F", c_int),
+        ("x", c_void_p), ("w", c_void_p), ("bias", c_void_p),
+        ("out_hi", c_void_p), ("out_lo", c_void_p),
+        ("mask_out", c_void_p), ("z_out", c_void_p),
+        ("zx_in", c_void_p), ("zx_div", c_int),
+        ("mult_hi", c_void_p), ("mult_lo", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/bpreveal_b200.h one to one.
+SIGNATURES = {
+    "bpb_version": (c_int, []),
+    "bpb_last_error": (C.c_char_p, []),
+    "bpb_device_info": (c_int, [C.POINTER(c_int)] * 3),
+    "bpb_conv3_tc": (c_int, [C.POINTER(Conv3Args), c_void_p]),
+    "bpb_wgrad3_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
+    "bpb_wgrad3_tc": (c_int, [C.POINTER(Wgrad3Args), c_void_p]),
+    "bpb_input_conv_fwd": (c_int, [C.POINTER(InputConvArgs), c_void_p]),
+    "bpb_input_conv_wgrad_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
+    "bpb_input_conv_wgrad": (c_int, [c_int] * 6 + [c_void_p] * 6 + [c_ll, c_void_p]),
+    "bpb_input_conv_dgrad": (c_int, [c_int] * 6 + [c_void_p] * 5),
+    "bpb_heads_fwd": (c_int, [c_int] * 8 + [c_void_p] * 10),
+    "bpb_heads_bwd_ws_bytes": (c_ll, [c_int] * 5),
+    "bpb_heads_bwd": (c_int, [c_int] * 8 + [c_void_p] * 19 + [c_ll, c_void_p]),
+    "bpb_loss_fwd_bwd": (c_int, [c_int] * 4 + [c_void_p] * 11),
+    "bpb_adam_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 + [c_void_p]),
+    "bpb_prep_conv3_weights": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "bpb_slide_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                             c_void_p]),
+    "bpb_slide_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                              c_void_p]),
+    "bpb_log_row_sums": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "bpb_transform_fwd": (c_int, [c_ll, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "bpb_transform_bwd": (c_int, [c_ll, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "bpb_add_f32": (c_int, [c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bpb_mul_f32": (c_int, [c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bpb_counts_lse": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
+}
+
+_lib = None
+
+
+class BprevealB200Error(RuntimeError):
+    """Raised when the native library is missing or a native call fails."""
+
+
+def load():
+    """Load (once) and return the native library; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BprevealB200Error(
+            f"{LIB_PATH} is missing: build it with `make -C bpreveal_b200/csrc` "
+            "(or __graft_entry__.build()).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().bpb_last_error().decode("utf-8", "replace")
+        raise BprevealB200Error(f"{what} failed (status {rc}): {msg}")

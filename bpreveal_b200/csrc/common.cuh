@@ -1,0 +1,44 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, TMA tensor-map
+// encoding through the driver entry point (no link-time dependency on libcuda, so the library
+// loads on a box without a GPU), device properties.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/bpreveal_b200.h"
+
+namespace bp {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+int max_smem_optin();
+
+// 3-D bf16 tensor [d2][d1][d0] (d0 innermost, contiguous), box [1][box1][64], 128B swizzle.
+bool make_tmap_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                  uint32_t box0, uint32_t box1);
+// 2-D bf16 tensor [d1][d0], box [box1][64], 128B swizzle.
+bool make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint32_t box0,
+                  uint32_t box1);
+
+#define BP_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      bp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                    __LINE__);                                                           \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define BP_REQUIRE(cond, ...)      \
+  do {                             \
+    if (!(cond)) {                 \
+      bp::set_error(__VA_ARGS__);  \
+      return 2;                    \
+    }                              \
+  } while (0)
+
+}  // namespace bp

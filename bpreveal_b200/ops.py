@@ -1,0 +1,257 @@
+"""Python-side launchers for the C-ABI kernels (device pointers come from torch tensors).
+
+A "plane set" is a tuple ``(hi, lo)`` of bf16 tensors ``[B, L, F]``; ``lo`` is ``None`` on the bf16
+path.  Nothing here computes on the host: every function validates shapes and calls into
+``libbpreveal_b200.so`` on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Conv3Args, InputConvArgs, Wgrad3Args, check
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "native ops need contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _planes(ps):
+    if ps is None:
+        return None, None
+    if isinstance(ps, torch.Tensor):
+        return ps, None
+    return ps[0], ps[1]
+
+
+def new_planes(B, L, F, precise, device):
+    hi = torch.empty((B, L, F), dtype=torch.bfloat16, device=device)
+    lo = torch.empty((B, L, F), dtype=torch.bfloat16, device=device) if precise else None
+    return (hi, lo)
+
+
+def planes_to_float(ps):
+    hi, lo = _planes(ps)
+    v = hi.float()
+    if lo is not None:
+        v = v + lo.float()
+    return v
+
+
+def device_info():
+    lib = _lib.load()
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    check(lib.bpb_device_info(C.byref(a), C.byref(b), C.byref(c)), "bpb_device_info")
+    return a.value, b.value, c.value
+
+
+def conv3(inp, w, tap_off, mode, L_out, bias=None, resid=None, resid_off=0, out=None, out2=None,
+          mask_out=None, mask_in=None, mult=None, zx_in=None, zx_div=1, z_out=None):
+    """bpb_conv3_tc.  ``w`` is the prepared operand tensor [planes, 3, F, F] (bf16)."""
+    lib = _lib.load()
+    in_hi, in_lo = _planes(inp)
+    B, L_in, F = in_hi.shape
+    a = Conv3Args()
+    a.B, a.L_in, a.L_out, a.F = B, L_in, L_out, F
+    a.tap_off[0], a.tap_off[1], a.tap_off[2] = tap_off
+    a.mode = mode
+    a.in_hi, a.in_lo = _p(in_hi), _p(in_lo)
+    assert w.dtype == torch.bfloat16 and w.shape[-3:] == (3, F, F)
+    a.w_hi = _p(w)
+    a.w_lo = (w.data_ptr() + 3 * F * F * 2) if in_lo is not None else None
+    if in_lo is not None:
+        assert w.shape[0] == 2, "precise path needs hi and lo weight planes"
+    a.bias = _p(bias)
+    r_hi, r_lo = _planes(resid)
+    a.resid_hi, a.resid_lo = _p(r_hi), _p(r_lo)
+    a.L_res = r_hi.shape[1] if r_hi is not None else 0
+    a.resid_off = resid_off
+    o_hi, o_lo = _planes(out)
+    a.out_hi, a.out_lo = _p(o_hi), _p(o_lo)
+    p_hi, p_lo = _planes(out2)
+    a.out2_hi, a.out2_lo = _p(p_hi), _p(p_lo)
+    for t in (o_hi, o_lo, p_hi, p_lo):
+        assert t is None or tuple(t.shape) == (B, L_out, F)
+    a.mask_out, a.mask_in = _p(mask_out), _p(mask_in)
+    m_hi, m_lo = _planes(mult)
+    a.mult_hi, a.mult_lo = _p(m_hi), _p(m_lo)
+    a.zx_in, a.zx_div, a.z_out = _p(zx_in), zx_div, _p(z_out)
+    check(lib.bpb_conv3_tc(C.byref(a), _stream()), "bpb_conv3_tc")
+
+
+def wgrad3_ws_bytes(B, L_out, F, precise):
+    n = _lib.load().bpb_wgrad3_ws_bytes(B, L_out, F, 1 if precise else 0)
+    if n < 0:
+        check(1, "bpb_wgrad3_ws_bytes")
+    return n
+
+
+def wgrad3(act, gz, dil, dw, db, ws):
+    lib = _lib.load()
+    a_hi, a_lo = _planes(act)
+    g_hi, g_lo = _planes(gz)
+    B, L_in, F = a_hi.shape
+    a = Wgrad3Args()
+    a.B, a.L_in, a.L_out, a.F, a.dil = B, L_in, g_hi.shape[1], F, dil
+    a.act_hi, a.act_lo, a.gz_hi, a.gz_lo = _p(a_hi), _p(a_lo), _p(g_hi), _p(g_lo)
+    assert dw.dtype == torch.float32 and dw.numel() == 3 * F * F
+    a.dw, a.db = _p(dw), _p(db)
+    a.ws, a.ws_bytes = _p(ws), ws.numel() * ws.element_size()
+    check(lib.bpb_wgrad3_tc(C.byref(a), _stream()), "bpb_wgrad3_tc")
+
+
+def input_conv_fwd(x, w, bias, F, out, mask_out=None, z_out=None, zx_in=None, zx_div=1,
+                   mult=None):
+    lib = _lib.load()
+    B, L_in, nb = x.shape
+    assert nb == 4 and x.dtype == torch.uint8
+    W, _, Fw = w.shape
+    a = InputConvArgs()
+    a.B, a.L_in, a.L_out, a.W, a.Fw, a.F = B, L_in, L_in - W + 1, W, Fw, F
+    a.x, a.w, a.bias = _p(x), _p(w), _p(bias)
+    o_hi, o_lo = _planes(out)
+    a.out_hi, a.out_lo = _p(o_hi), _p(o_lo)
+    a.mask_out, a.z_out, a.zx_in, a.zx_div = _p(mask_out), _p(z_out), _p(zx_in), zx_div
+    m_hi, m_lo = _planes(mult)
+    a.mult_hi, a.mult_lo = _p(m_hi), _p(m_lo)
+    check(lib.bpb_input_conv_fwd(C.byref(a), _stream()), "bpb_input_conv_fwd")
+
+
+def input_conv_wgrad_ws_bytes(B, L_out, W, Fw):
+    n = _lib.load().bpb_input_conv_wgrad_ws_bytes(B, L_out, W, Fw)
+    if n < 0:
+        check(1, "bpb_input_conv_wgrad_ws_bytes")
+    return n
+
+
+def input_conv_wgrad(x, gz, W, Fw, dw, db, ws):
+    lib = _lib.load()
+    g_hi, g_lo = _planes(gz)
+    B, L_out, F = g_hi.shape
+    check(lib.bpb_input_conv_wgrad(B, x.shape[1], L_out, W, Fw, F, _p(x), _p(g_hi), _p(g_lo),
+                                   _p(dw), _p(db), _p(ws), ws.numel() * ws.element_size(),
+                                   _stream()), "bpb_input_conv_wgrad")
+
+
+def input_conv_dgrad(gz, w, L_in, dx):
+    lib = _lib.load()
+    g_hi, g_lo = _planes(gz)
+    B, L_out, F = g_hi.shape
+    W, _, Fw = w.shape
+    check(lib.bpb_input_conv_dgrad(B, L_in, L_out, W, Fw, F, _p(g_hi), _p(g_lo), _p(w), _p(dx),
+                                   _stream()), "bpb_input_conv_dgrad")
+
+
+def heads_fwd(act, pw, pb, cw, cb, logits, gap, logcounts):
+    lib = _lib.load()
+    a_hi, a_lo = _planes(act)
+    B, L_in, F = a_hi.shape
+    W, Fw, T = pw.shape
+    H = cw.shape[1]
+    check(lib.bpb_heads_fwd(B, L_in, L_in - W + 1, W, Fw, F, T, H, _p(a_hi), _p(a_lo), _p(pw),
+                            _p(pb), _p(cw), _p(cb), _p(logits), _p(gap), _p(logcounts),
+                            _stream()), "bpb_heads_fwd")
+
+
+def heads_bwd_ws_bytes(B, L_in, W, Fw, T):
+    n = _lib.load().bpb_heads_bwd_ws_bytes(B, L_in, W, Fw, T)
+    if n < 0:
+        check(1, "bpb_heads_bwd_ws_bytes")
+    return n
+
+
+def heads_bwd(act, gap, pw, cw, dlogits, dlogcounts, g=None, gz=None, mask_in=None, mult=None,
+              dpw=None, dpb=None, dcw=None, dcb=None, ws=None):
+    lib = _lib.load()
+    a_hi, a_lo = _planes(act)
+    B, L_in, F = a_hi.shape
+    W, Fw, T = pw.shape
+    H = cw.shape[1]
+    g_hi, g_lo = _planes(g)
+    z_hi, z_lo = _planes(gz)
+    m_hi, m_lo = _planes(mult)
+    check(lib.bpb_heads_bwd(B, L_in, L_in - W + 1, W, Fw, F, T, H, _p(a_hi), _p(a_lo), _p(gap),
+                            _p(pw), _p(cw), _p(dlogits), _p(dlogcounts), _p(dpw), _p(dpb),
+                            _p(dcw), _p(dcb), _p(g_hi), _p(g_lo), _p(z_hi), _p(z_lo),
+                            _p(mask_in), _p(m_hi), _p(m_lo), _p(ws),
+                            ws.numel() * ws.element_size() if ws is not None else 0, _stream()),
+          "bpb_heads_bwd")
+
+
+def loss_fwd_bwd(task_off, logits, logcounts, counts, profile_weight, lam, losses, dlogits=None,
+                 dlogcounts=None, logcounts_true=None):
+    lib = _lib.load()
+    B, L, T = logits.shape
+    H = logcounts.shape[1]
+    check(lib.bpb_loss_fwd_bwd(B, L, T, H, _p(task_off), _p(logits), _p(logcounts), _p(counts),
+                               _p(logcounts_true), _p(profile_weight), _p(lam), _p(losses),
+                               _p(dlogits), _p(dlogcounts), _stream()), "bpb_loss_fwd_bwd")
+
+
+def adam_step(param, grad, m, v, step_and_lr, beta1=0.9, beta2=0.999, eps=1e-7, grad_scale=1.0):
+    lib = _lib.load()
+    check(lib.bpb_adam_step(param.numel(), _p(param), _p(grad), _p(m), _p(v), _p(step_and_lr),
+                            beta1, beta2, eps, grad_scale, _stream()), "bpb_adam_step")
+
+
+def prep_conv3_weights(w, F, fwd, bwd, precise):
+    lib = _lib.load()
+    Fw = w.shape[1]
+    check(lib.bpb_prep_conv3_weights(Fw, F, _p(w), _p(fwd), _p(bwd), 1 if precise else 0,
+                                     _stream()), "bpb_prep_conv3_weights")
+
+
+def slide_u8(src, dst, row_idx, col_idx):
+    lib = _lib.load()
+    rows, src_cols, depth = src.shape
+    check(lib.bpb_slide_u8(_p(src), _p(dst), rows, src_cols, dst.shape[1], depth, _p(row_idx),
+                           _p(col_idx), _stream()), "bpb_slide_u8")
+
+
+def slide_f32(src, dst, row_idx, col_idx):
+    lib = _lib.load()
+    rows, src_cols, depth = src.shape
+    check(lib.bpb_slide_f32(_p(src), _p(dst), rows, src_cols, dst.shape[1], depth, _p(row_idx),
+                            _p(col_idx), _stream()), "bpb_slide_f32")
+
+
+def log_row_sums(vals, out):
+    lib = _lib.load()
+    rows = vals.shape[0]
+    check(lib.bpb_log_row_sums(_p(vals), _p(out), rows, vals.numel() // rows, _stream()),
+          "bpb_log_row_sums")
+
+
+def transform_fwd(u, y, act, coeffs):
+    lib = _lib.load()
+    check(lib.bpb_transform_fwd(u.numel(), _p(u), _p(y), act.numel(), _p(act), _p(coeffs),
+                                _stream()), "bpb_transform_fwd")
+
+
+def transform_bwd(u, dy, act, coeffs, dcoeffs):
+    lib = _lib.load()
+    check(lib.bpb_transform_bwd(u.numel(), _p(u), _p(dy), act.numel(), _p(act), _p(coeffs),
+                                _p(dcoeffs), _stream()), "bpb_transform_bwd")
+
+
+def add_f32(a, b, out):
+    check(_lib.load().bpb_add_f32(a.numel(), _p(a), _p(b), _p(out), _stream()), "bpb_add_f32")
+
+
+def mul_f32(a, b, out):
+    check(_lib.load().bpb_mul_f32(a.numel(), _p(a), _p(b), _p(out), _stream()), "bpb_mul_f32")
+
+
+def counts_lse(use_bias, bias_lc, resid_lc, out, dscale=None):
+    B, H = resid_lc.shape
+    check(_lib.load().bpb_counts_lse(B, H, _p(use_bias), _p(bias_lc), _p(resid_lc), _p(out),
+                                     _p(dscale), _stream()), "bpb_counts_lse")

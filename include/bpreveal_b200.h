@@ -1,0 +1,208 @@
+/*
+ * bpreveal_b200 -- C ABI of the B200-native BPNet hot path.
+ *
+ * The reference (mmtrebuchet/bpreveal) has NO native/FFI boundary on this path: the model is a
+ * Keras graph (src/models.py:53-115, 226-387), the losses are TF ops (src/losses.py:15-63) and
+ * attribution is a patched TF gradient registry (src/internal/shap.py:612-678).  The entry points
+ * below are therefore the seam a maintainer would bind from Python (ctypes);
+ * each one names the reference code whose arithmetic it replaces.  The only pre-existing native
+ * signatures near the path are slide/slideChar (src/internal/libslide.c:44-91), mirrored by
+ * bpb_slide_*.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless named host_*; `stream` is a cudaStream_t
+ * passed as void*; all functions return 0 on success, non-zero on failure with the message
+ * available from bpb_last_error() (thread-local).  No function allocates device memory or
+ * synchronises the device.  Activations are channels-last [B][L][F] bf16 ("planes"); the precise
+ * path carries every activation as a (hi, lo) pair of bf16 planes whose sum is the value (fp32
+ * accumulate everywhere); lo pointers are NULL on the bf16 path.  F must be a multiple of 64
+ * (callers zero-pad narrower models).
+ */
+#ifndef BPREVEAL_B200_H
+#define BPREVEAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t bpb_bf16; /* raw bfloat16 bits */
+
+int bpb_version(void);
+const char* bpb_last_error(void);
+/* Fills SM count and compute capability of the current device. */
+int bpb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * K2/K6/K8: width-3 dilated convolution as a tcgen05 implicit GEMM (M = positions, N = F,
+ * K = 3F), used for the forward of models.py:92-104 (conv + bias + ReLU + crop + residual add),
+ * for its data gradient, and for the DeepSHAP-rescale backward (shap.py:612-639).
+ *
+ *   acc[b,t,n] = sum_{j<3} sum_c in[b, t + tap_off[j], c] * w[(j*F + n)*F + c]      (rows outside
+ *                [0, L_in) read as zero)
+ *   mode 0 (forward):  v = acc + bias[n];
+ *                      if zx_in:   mult = rescale(zx_in[b / zx_div, t, n], v)  -> out2
+ *                      if z_out:   z_out[b,t,n] = v (fp32)
+ *                      if mask_out: bit n%64 of mask_out[(b*L_out + t)*(F/64) + n/64] = (v > 0)
+ *                      out[b,t,n] = relu(v) + resid[b, t + resid_off, n]
+ *   mode 1 (backward): v = acc + (0 <= t + resid_off < L_res ? resid[b, t + resid_off, n] : 0)
+ *                      out[b,t,n] = v
+ *                      out2[b,t,n] = v * (mask_in bit | mult_in[b,t,n] | 1)
+ * w is [n_wplanes][3][F][F] bf16 with the contraction index innermost.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int B, L_in, L_out, F;
+  int tap_off[3];
+  int mode;
+  const bpb_bf16 *in_hi, *in_lo;     /* [B][L_in][F] */
+  const bpb_bf16 *w_hi, *w_lo;       /* [3][F][F], k innermost */
+  const float* bias;                 /* [F] or NULL */
+  const bpb_bf16 *resid_hi, *resid_lo; /* [B][L_res][F] or NULL */
+  int L_res, resid_off;
+  bpb_bf16 *out_hi, *out_lo;         /* [B][L_out][F] or NULL */
+  bpb_bf16 *out2_hi, *out2_lo;       /* [B][L_out][F] or NULL */
+  uint64_t* mask_out;                /* [B][L_out][F/64] or NULL */
+  const uint64_t* mask_in;           /* [B][L_out][F/64] or NULL */
+  const bpb_bf16 *mult_hi, *mult_lo; /* [B][L_out][F] or NULL */
+  const float* zx_in;                /* [B/zx_div][L_out][F] fp32 or NULL */
+  int zx_div;
+  float* z_out;                      /* [B][L_out][F] fp32 or NULL */
+} bpb_conv3_args;
+int bpb_conv3_tc(const bpb_conv3_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7: weight / bias gradient of the dilated convolution (tcgen05, MN-major operands, split-K
+ * over positions; partial sums go to a caller-provided workspace and are added in a fixed order,
+ * so the result is deterministic):
+ *   dw[j][c][n] = sum_{b,t} act[b, t + j*dil, c] * gz[b,t,n]      (padded Keras layout (3, F, F))
+ *   db[n]       = sum_{b,t} gz[b,t,n]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int B, L_in, L_out, F, dil;
+  const bpb_bf16 *act_hi, *act_lo; /* [B][L_in][F] */
+  const bpb_bf16 *gz_hi, *gz_lo;   /* [B][L_out][F] */
+  float* dw;                       /* [3][F][F] fp32, overwritten */
+  float* db;                       /* [F] fp32, overwritten, or NULL */
+  float* ws;                       /* workspace of bpb_wgrad3_ws_bytes() bytes */
+  long long ws_bytes;
+} bpb_wgrad3_args;
+long long bpb_wgrad3_ws_bytes(int B, int L_out, int F, int precise);
+int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1: input convolution on one-hot DNA (models.py:85-90).  x is u8 [B][L_in][4]; w is the fp32
+ * Keras kernel [W][4][Fw]; bias [Fw]; output activations are written with row stride F >= Fw
+ * (padding channels are written as zero).
+ *   z[b,t,f] = bias[f] + sum_{j<W} sum_c x[b,t+j,c] w[j][c][f];  out = relu(z)
+ * Optional outputs: relu mask bits, fp32 z (attribution of the query), rescale multiplier
+ * against zx_in (attribution of a shuffled reference).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int B, L_in, L_out, W, Fw, F;
+  const uint8_t* x;
+  const float *w, *bias;
+  bpb_bf16 *out_hi, *out_lo;
+  uint64_t* mask_out;
+  float* z_out;
+  const float* zx_in;
+  int zx_div;
+  bpb_bf16 *mult_hi, *mult_lo;
+} bpb_input_conv_args;
+int bpb_input_conv_fwd(const bpb_input_conv_args* a, void* stream);
+/* dw[j][c][f] = sum_{b,t} x[b,t+j,c] gz[b,t,f]; db[f] = sum gz  (dw is [W][4][Fw], overwritten) */
+long long bpb_input_conv_wgrad_ws_bytes(int B, int L_out, int W, int Fw);
+int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, int F, const uint8_t* x,
+                         const bpb_bf16* gz_hi, const bpb_bf16* gz_lo, float* dw, float* db,
+                         float* ws, long long ws_bytes, void* stream);
+/* dx[b,s,c] = sum_j sum_f gz[b,s-j,f] w[j][c][f]  (fp32 out [B][L_in][4]); attribution only */
+int bpb_input_conv_dgrad(int B, int L_in, int L_out, int W, int Fw, int F, const bpb_bf16* gz_hi,
+                         const bpb_bf16* gz_lo, const float* w, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3/K4: output heads (models.py:20-50).  All heads are evaluated together: T = sum of num-tasks.
+ *   logits[b,t,k] = pb[k] + sum_{j<W} sum_c act[b,t+j,c] pw[j][c][k]        (fp32 [B][L_out][T])
+ *   gap[b,c]      = mean_t act[b,t,c]                                       (fp32 [B][F])
+ *   logcounts[b,h] = cb[h] + sum_c gap[b,c] cw[c][h]                        (fp32 [B][H])
+ * pw is the concatenation of the heads' Keras kernels along the task axis; cw likewise [Fw][H].
+ * ------------------------------------------------------------------------------------------ */
+int bpb_heads_fwd(int B, int L_in, int L_out, int W, int Fw, int F, int T, int H,
+                  const bpb_bf16* act_hi, const bpb_bf16* act_lo, const float* pw,
+                  const float* pb, const float* cw, const float* cb, float* logits, float* gap,
+                  float* logcounts, void* stream);
+/* Backward of the heads: given dlogits [B][L_out][T] and dlogcounts [B][H] (fp32):
+ *   dpw/dpb/dcw/dcb overwritten (skipped when dpw == NULL);
+ *   g[b,s,c] = sum_j sum_k dlogits[b,s-j,k] pw[j][c][k] + sum_h dlogcounts[b,h] cw[c][h] / L_in
+ *   written as g (planes) and gz = g * mask_in / mult_in (planes), like bpb_conv3_tc mode 1. */
+long long bpb_heads_bwd_ws_bytes(int B, int L_in, int W, int Fw, int T);
+int bpb_heads_bwd(int B, int L_in, int L_out, int W, int Fw, int F, int T, int H,
+                  const bpb_bf16* act_hi, const bpb_bf16* act_lo, const float* gap,
+                  const float* pw, const float* cw, const float* dlogits,
+                  const float* dlogcounts, float* dpw, float* dpb, float* dcw, float* dcb,
+                  bpb_bf16* g_hi, bpb_bf16* g_lo, bpb_bf16* gz_hi, bpb_bf16* gz_lo,
+                  const uint64_t* mask_in, const bpb_bf16* mult_hi, const bpb_bf16* mult_lo,
+                  float* ws, long long ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5: losses (losses.py:15-63, training.py:64-65).  Heads are described by task offsets
+ * task_off[H+1] into the T axis.  Per head h:
+ *   mnll_h = -(1/B) sum_b [lgamma(N_b+1) - sum_j lgamma(k_bj+1) + sum_j k_bj log_softmax(l_b)_j]
+ *   mse_h  = (1/B) sum_b (logcounts[b,h] - log(sum_j k_bj))^2  (times lambda_h in the total)
+ * Writes losses[0..H) = mnll, losses[H..2H) = lambda*mse (what Keras logs as the loss value of
+ * reweightableMse) and, if dlogits != NULL, the gradient of
+ *   sum_h profile_weight[h] * mnll_h + sum_h lambda[h] * mse_h
+ * wrt logits and logcounts.  counts are fp32 [B][L][T]; logits may carry an additive frozen
+ * bias term (combined model) which the caller adds beforehand.  task_off, profile_weight and
+ * lambda are device arrays; logcounts_true [B][H] may be NULL (then log(sum_j k_bj) is used, which
+ * is what generators.py:139-140 feeds).
+ * ------------------------------------------------------------------------------------------ */
+int bpb_loss_fwd_bwd(int B, int L, int T, int H, const int* task_off, const float* logits,
+                     const float* logcounts, const float* counts, const float* logcounts_true,
+                     const float* profile_weight, const float* lambda, float* losses,
+                     float* dlogits, float* dlogcounts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K9: Keras-semantics Adam over one flat fp32 bucket:
+ *   m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)
+ * `step_and_lr` is a device buffer {float step, float lr} so that the update can live inside a
+ * CUDA graph; grad_scale multiplies g first (1/world_size after an all-reduce sum).
+ * ------------------------------------------------------------------------------------------ */
+int bpb_adam_step(long long n, float* param, const float* grad, float* m, float* v,
+                  const float* step_and_lr, float beta1, float beta2, float eps, float grad_scale,
+                  void* stream);
+
+/* fp32 Keras conv kernel [3][Fw][Fw] -> padded bf16 operand layouts of bpb_conv3_tc:
+ *   fwd[j][n][c] = w[j][c][n]   and   bwd[j][n][c] = w[j][n][c]   (each [planes][3][F][F], zero
+ *   padded; planes = 2 (hi then lo) when precise, else 1) */
+int bpb_prep_conv3_weights(int Fw, int F, const float* w, bpb_bf16* fwd, bpb_bf16* bwd,
+                           int precise, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Epoch jitter / shuffle gather (generators.py:129-138, libslide.c:44-91):
+ *   dst[row_idx[r]] = src[r, col_idx[r] : col_idx[r] + dst_cols]
+ * ------------------------------------------------------------------------------------------ */
+int bpb_slide_u8(const uint8_t* src, uint8_t* dst, int rows, int src_cols, int dst_cols,
+                 int depth, const int* row_idx, const int* col_idx, void* stream);
+int bpb_slide_f32(const float* src, float* dst, int rows, int src_cols, int dst_cols, int depth,
+                  const int* row_idx, const int* col_idx, void* stream);
+/* logcounts targets: out[r] = log(sum over (cols, depth) of vals[r]) (generators.py:139-140) */
+int bpb_log_row_sums(const float* vals, float* out, int rows, int n_per_row, void* stream);
+
+/* Elementwise helpers used by the transformation / combined models and attribution. */
+/* y = sum over terms of  m1 * act(m2*u + b2) + b1  (models.py:118-175); act: 0 linear (m2,b2
+ * unused), 1 sigmoid, 2 relu; coeffs is [n_terms][4] = {m1, b1, m2, b2} on the device. */
+int bpb_transform_fwd(long long n, const float* u, float* y, int n_terms, const int* act,
+                      const float* coeffs, void* stream);
+/* dcoeffs[t][4] += sum_i dy[i] * d y_i / d{m1,b1,m2,b2} (trainTransformationModel) */
+int bpb_transform_bwd(long long n, const float* u, const float* dy, int n_terms, const int* act,
+                      const float* coeffs, float* dcoeffs, void* stream);
+int bpb_add_f32(long long n, const float* a, const float* b, float* out, void* stream);
+int bpb_mul_f32(long long n, const float* a, const float* b, float* out, void* stream);
+/* layers.py:52-75 CountsLogSumExp in fp64 where use_bias[h] != 0, identity on the residual
+ * otherwise (models.py:366-380); dresid_scale (optional) = d out / d resid_lc. */
+int bpb_counts_lse(int B, int H, const int* use_bias, const float* bias_lc, const float* resid_lc,
+                   float* out, float* dresid_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPREVEAL_B200_H */
