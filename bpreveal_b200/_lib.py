@@ -77,7 +77,8 @@ SIGNATURES = {
     "bpb_heads_bwd": (c_int, [c_int] * 8 + [c_void_p] * 19 + [c_ll, c_void_p]),
     "bpb_loss_fwd_bwd": (c_int, [c_int] * 4 + [c_void_p] * 11),
     "bpb_adam_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 + [c_void_p]),
-    "bpb_prep_conv3_weights": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "bpb_prep_conv3_weights": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                       c_void_p]),
     "bpb_slide_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p]),
     "bpb_slide_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -88,6 +89,9 @@ SIGNATURES = {
                                   c_void_p]),
     "bpb_add_f32": (c_int, [c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bpb_mul_f32": (c_int, [c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bpb_shuffle_rows": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bpb_shap_combine": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_void_p]),
     "bpb_counts_lse": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
 }

@@ -135,7 +135,7 @@ input_conv_wgrad_kernel(int B, int L_in, int L_out, int W, int Fw, int F,
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const int pair = threadIdx.x + s * blockDim.x;
+      const int pair = blockIdx.y * 2048 + threadIdx.x + s * blockDim.x;
       if (pair < n_pairs) {
         const int j = pair / Fw, f = pair % Fw;
         for (int r = 0; r < kIwStrip; ++r) {
@@ -148,21 +148,21 @@ input_conv_wgrad_kernel(int B, int L_in, int L_out, int W, int Fw, int F,
         }
       }
     }
-    if (threadIdx.x < Fw) {
+    if (blockIdx.y == 0 && threadIdx.x < Fw) {
       for (int r = 0; r < kIwStrip; ++r) accb += sg[r * Fw + threadIdx.x];
     }
   }
   float* wsp = ws + static_cast<size_t>(blockIdx.x) * n_out;
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    const int pair = threadIdx.x + s * blockDim.x;
+    const int pair = blockIdx.y * 2048 + threadIdx.x + s * blockDim.x;
     if (pair < n_pairs) {
       const int j = pair / Fw, f = pair % Fw;
 #pragma unroll
       for (int c = 0; c < 4; ++c) wsp[(j * 4 + c) * Fw + f] = acc[s][c];
     }
   }
-  if (threadIdx.x < Fw) wsp[W * 4 * Fw + threadIdx.x] = accb;
+  if (blockIdx.y == 0 && threadIdx.x < Fw) wsp[W * 4 * Fw + threadIdx.x] = accb;
 }
 
 __global__ void partial_reduce_kernel(const float* __restrict__ ws, int nparts, long long n,
@@ -490,7 +490,7 @@ extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, i
                                     void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BP_REQUIRE(x && gz_hi && dw && db && ws, "bpb_input_conv_wgrad: NULL argument");
-  BP_REQUIRE(W * Fw <= 2048, "bpb_input_conv_wgrad: W*Fw=%d exceeds 2048", W * Fw);
+  BP_REQUIRE(Fw <= 1024, "bpb_input_conv_wgrad: Fw=%d exceeds 1024", Fw);
   const int blocks = iw_blocks(B, L_out);
   const long long n_out = static_cast<long long>(W) * 4 * Fw + Fw;
   BP_REQUIRE(ws_bytes >= blocks * n_out * 4, "bpb_input_conv_wgrad: workspace too small");
@@ -503,7 +503,8 @@ extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, i
   }
   BP_REQUIRE(smem <= 200 * 1024, "bpb_input_conv_wgrad: too many filters for shared memory");
   const int strips_per_seq = (L_out + kIwStrip - 1) / kIwStrip;
-  input_conv_wgrad_kernel<<<blocks, 1024, smem, stream>>>(
+  dim3 wgrid(blocks, (W * Fw + 2047) / 2048);
+  input_conv_wgrad_kernel<<<wgrid, 1024, smem, stream>>>(
       B, L_in, L_out, W, Fw, F, x, reinterpret_cast<const __nv_bfloat16*>(gz_hi),
       reinterpret_cast<const __nv_bfloat16*>(gz_lo), ws, strips_per_seq);
   BP_CHECK_CUDA(cudaGetLastError());

@@ -106,22 +106,30 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
   }
 }
 
-// fp32 Keras kernel [3][Fw][Fw] (tap, cin, cout) -> bf16 operand layouts [planes][3][F][F]
-__global__ void prep_conv3_kernel(int Fw, int F, const float* __restrict__ w,
+// fp32 Keras kernels [layers][3][Fw][Fw] (tap, cin, cout) -> bf16 operand layouts
+// [layers][planes][3][F][F]
+__global__ void prep_conv3_kernel(int n_layers, int Fw, int F, const float* __restrict__ w,
                                   __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ bwd,
                                   int precise) {
-  const int total = 3 * F * F;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int j = i / (F * F), n = (i / F) % F, c = i % F;
+  const long long per = 3LL * F * F;
+  const long long total = per * n_layers;
+  const int planes = precise ? 2 : 1;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int l = static_cast<int>(i / per);
+    const int r = static_cast<int>(i % per);
+    const int j = r / (F * F), n = (r / F) % F, c = r % F;
+    const float* wl = w + static_cast<size_t>(l) * 3 * Fw * Fw;
     // fwd[j][n][c] = w[j][c][n] ; bwd[j][n][c] = w[j][n][c]
-    const float vf = (n < Fw && c < Fw) ? w[(j * Fw + c) * Fw + n] : 0.f;
-    const float vb = (n < Fw && c < Fw) ? w[(j * Fw + n) * Fw + c] : 0.f;
+    const float vf = (n < Fw && c < Fw) ? wl[(j * Fw + c) * Fw + n] : 0.f;
+    const float vb = (n < Fw && c < Fw) ? wl[(j * Fw + n) * Fw + c] : 0.f;
     const __nv_bfloat16 hf = __float2bfloat16_rn(vf), hb = __float2bfloat16_rn(vb);
-    fwd[i] = hf;
-    bwd[i] = hb;
+    const size_t o = static_cast<size_t>(l) * planes * per + r;
+    fwd[o] = hf;
+    bwd[o] = hb;
     if (precise) {
-      fwd[total + i] = __float2bfloat16_rn(vf - __bfloat162float(hf));
-      bwd[total + i] = __float2bfloat16_rn(vb - __bfloat162float(hb));
+      fwd[o + per] = __float2bfloat16_rn(vf - __bfloat162float(hf));
+      bwd[o + per] = __float2bfloat16_rn(vb - __bfloat162float(hb));
     }
   }
 }
@@ -288,14 +296,15 @@ extern "C" int bpb_adam_step(long long n, float* param, const float* grad, float
   return 0;
 }
 
-extern "C" int bpb_prep_conv3_weights(int Fw, int F, const float* w, bpb_bf16* fwd, bpb_bf16* bwd,
-                                      int precise, void* stream_) {
+extern "C" int bpb_prep_conv3_weights(int n_layers, int Fw, int F, const float* w, bpb_bf16* fwd,
+                                      bpb_bf16* bwd, int precise, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BP_REQUIRE(w && fwd && bwd, "bpb_prep_conv3_weights: NULL argument");
-  BP_REQUIRE(F % 64 == 0 && Fw > 0 && Fw <= F, "bpb_prep_conv3_weights: bad F=%d Fw=%d", F, Fw);
-  prep_conv3_kernel<<<ew_blocks(3LL * F * F), 256, 0, stream>>>(
-      Fw, F, w, reinterpret_cast<__nv_bfloat16*>(fwd), reinterpret_cast<__nv_bfloat16*>(bwd),
-      precise);
+  BP_REQUIRE(F % 64 == 0 && Fw > 0 && Fw <= F && n_layers > 0,
+             "bpb_prep_conv3_weights: bad F=%d Fw=%d layers=%d", F, Fw, n_layers);
+  prep_conv3_kernel<<<ew_blocks(3LL * F * F * n_layers), 256, 0, stream>>>(
+      n_layers, Fw, F, w, reinterpret_cast<__nv_bfloat16*>(fwd),
+      reinterpret_cast<__nv_bfloat16*>(bwd), precise);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -380,6 +389,85 @@ extern "C" int bpb_counts_lse(int B, int H, const int* use_bias, const float* bi
   BP_REQUIRE(use_bias && bias_lc && resid_lc && out, "bpb_counts_lse: NULL argument");
   counts_lse_kernel<<<(B * H + 127) / 128, 128, 0, stream>>>(B, H, use_bias, bias_lc, resid_lc,
                                                              out, dresid_scale);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// DeepSHAP combiners.  standard (shap.py:26-30):  phi[q,t,c] = mean_r mult[q,r,t,c] (x - ref)
+// hypothetical (interpretUtils.py:1295-1312):     phi[q,t,i] = mean_r sum_c (1[c==i] - ref_c) mult_c
+// ------------------------------------------------------------------------------------------
+namespace bp {
+__global__ void shap_combine_kernel(int Q, int n, int L, const uint8_t* __restrict__ x,
+                                    const uint8_t* __restrict__ refs,
+                                    const float* __restrict__ mult, int hypothetical,
+                                    float* __restrict__ phi) {
+  const long long total = static_cast<long long>(Q) * L;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i / L), t = static_cast<int>(i % L);
+    const uchar4 xv = *reinterpret_cast<const uchar4*>(x + i * 4);
+    const float xf[4] = {float(xv.x), float(xv.y), float(xv.z), float(xv.w)};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < n; ++r) {
+      const size_t row = (static_cast<size_t>(q) * n + r) * L + t;
+      const uchar4 rv = *reinterpret_cast<const uchar4*>(refs + row * 4);
+      const float4 m = *reinterpret_cast<const float4*>(mult + row * 4);
+      const float rf[4] = {float(rv.x), float(rv.y), float(rv.z), float(rv.w)};
+      const float mf[4] = {m.x, m.y, m.z, m.w};
+      if (!hypothetical) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] += mf[c] * (xf[c] - rf[c]);
+      } else {
+        float base = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) base -= rf[c] * mf[c];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] += base + mf[c];
+      }
+    }
+    const float inv = 1.f / static_cast<float>(n);
+    *reinterpret_cast<float4*>(phi + i * 4) =
+        make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+  }
+}
+}  // namespace bp
+
+extern "C" int bpb_shap_combine(int Q, int n, int L, const uint8_t* x, const uint8_t* refs,
+                                const float* mult, int hypothetical, float* phi, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(x && refs && mult && phi && n > 0, "bpb_shap_combine: bad argument");
+  if (Q <= 0) return 0;
+  bp::shap_combine_kernel<<<bp::ew_blocks(static_cast<long long>(Q) * L), 256, 0, stream>>>(
+      Q, n, L, x, refs, mult, hypothetical, phi);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// refs[q*n + r, t, :] = x[q, perm[r, t], :]   (interpretUtils.py:1216-1222, kmer size 1)
+namespace bp {
+__global__ void shuffle_rows_kernel(int Q, int n, int L, const uint8_t* __restrict__ x,
+                                    const int* __restrict__ perm, uint8_t* __restrict__ refs) {
+  const long long total = static_cast<long long>(Q) * n * L;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i % L);
+    const int r = static_cast<int>((i / L) % n);
+    const int q = static_cast<int>(i / (static_cast<long long>(L) * n));
+    const int src = perm[r * L + t];
+    reinterpret_cast<uint32_t*>(refs)[i] =
+        reinterpret_cast<const uint32_t*>(x)[static_cast<size_t>(q) * L + src];
+  }
+}
+}  // namespace bp
+
+extern "C" int bpb_shuffle_rows(int Q, int n, int L, const uint8_t* x, const int* perm,
+                                uint8_t* refs, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(x && perm && refs && n > 0, "bpb_shuffle_rows: bad argument");
+  if (Q <= 0) return 0;
+  bp::shuffle_rows_kernel<<<bp::ew_blocks(static_cast<long long>(Q) * n * L), 256, 0, stream>>>(
+      Q, n, L, x, perm, refs);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,455 @@
+"""Device-side execution of a BPNet ("solo") network: forward, training step, DeepSHAP backward.
+
+This is the B200 replacement for what TensorFlow executes for the Keras graph built by the
+reference's ``models.soloModel`` (src/models.py:53-115): parameters live in one flat fp32 bucket
+(one Adam launch, one NCCL all-reduce), activations are channels-last bf16 planes that stay
+resident in HBM, every layer is one native launch (see ``include/bpreveal_b200.h``) and a whole
+step is captured in a CUDA graph.  All arithmetic is done by the CUDA kernels in ``csrc/``.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+@dataclasses.dataclass
+class NetConfig:
+    inputLength: int
+    outputLength: int
+    numFilters: int
+    numLayers: int
+    inputFilterWidth: int
+    outputFilterWidth: int
+    headTasks: list  # num-tasks per head
+    precise: bool = False  # hi/lo bf16 planes, ~fp32 accuracy
+
+    @property
+    def Fp(self):
+        return ((self.numFilters + 63) // 64) * 64
+
+    @property
+    def T(self):
+        return int(sum(self.headTasks))
+
+    @property
+    def H(self):
+        return len(self.headTasks)
+
+    def lengths(self):
+        """Activation lengths: [after conv1, after dil0, ...] (models.py:87-104)."""
+        L = [self.inputLength - self.inputFilterWidth + 1]
+        for i in range(self.numLayers):
+            L.append(L[-1] - 2 * 2 ** (i + 1))
+        return L
+
+    def validate(self):
+        L = self.lengths()
+        lout = L[-1] - self.outputFilterWidth + 1
+        if lout != self.outputLength:
+            raise ValueError(
+                f"Inconsistent network: input {self.inputLength} gives output {lout}, "
+                f"not {self.outputLength}")
+
+
+class ParamBucket:
+    """Flat fp32 parameter bucket with named views in (padded) Keras layouts."""
+
+    def __init__(self, cfg: NetConfig, device):
+        self.cfg = cfg
+        Fw, Fp, L = cfg.numFilters, cfg.Fp, cfg.numLayers
+        W, Wo, T, H = cfg.inputFilterWidth, cfg.outputFilterWidth, cfg.T, cfg.H
+        self.spec = [
+            ("dil_w", (L, 3, Fp, Fp)), ("dil_b", (L, Fp)),
+            ("conv1_w", (W, 4, Fw)), ("conv1_b", (Fw,)),
+            ("prof_w", (Wo, Fw, T)), ("prof_b", (T,)),
+            ("cnt_w", (Fw, H)), ("cnt_b", (H,)),
+        ]
+        self.offsets = {}
+        off = 0
+        for name, shape in self.spec:
+            n = int(np.prod(shape))
+            self.offsets[name] = (off, n, shape)
+            off += (n + 3) // 4 * 4  # keep every view 16-byte aligned
+        self.numel = off
+        self.flat = torch.zeros((off,), dtype=torch.float32, device=device)
+
+    def view(self, flat, name):
+        off, n, shape = self.offsets[name]
+        return flat[off:off + n].view(shape)
+
+    def views(self, flat=None):
+        flat = self.flat if flat is None else flat
+        return {name: self.view(flat, name) for name, _ in self.spec}
+
+
+class SoloNet:
+    """One BPNet tower + heads on one GPU."""
+
+    def __init__(self, cfg: NetConfig, device=None):
+        cfg.validate()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else "cuda")
+        self.params = ParamBucket(cfg, self.device)
+        self.p = self.params.views()
+        self.grads_flat = None
+        self.adam_m = None
+        self.adam_v = None
+        self.step_and_lr = torch.zeros((2,), dtype=torch.float32, device=self.device)
+        self.step = 0
+        planes = 2 if cfg.precise else 1
+        Fp, L = cfg.Fp, cfg.numLayers
+        self.w_fwd = torch.zeros((max(L, 1), planes, 3, Fp, Fp), dtype=torch.bfloat16,
+                                 device=self.device)
+        self.w_bwd = torch.zeros_like(self.w_fwd)
+        self.task_off = torch.tensor(np.concatenate([[0], np.cumsum(cfg.headTasks)]),
+                                     dtype=torch.int32, device=self.device)
+        self._ws = {}
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ parameters
+    def init_random(self, seed=1234, scale=1.0, biasScale=0.0):
+        """Glorot-uniform kernels, zero biases (Keras defaults)."""
+        cfg = self.cfg
+        rng = np.random.default_rng(seed)
+
+        def glorot(shape, fi, fo):
+            lim = math.sqrt(6.0 / (fi + fo))
+            return rng.uniform(-lim, lim, size=shape).astype(np.float32) * scale
+
+        Fn = cfg.numFilters
+        sd = {"conv1_w": glorot((cfg.inputFilterWidth, 4, Fn), cfg.inputFilterWidth * 4,
+                                cfg.inputFilterWidth * Fn),
+              "conv1_b": (rng.standard_normal(Fn) * biasScale).astype(np.float32)}
+        for i in range(cfg.numLayers):
+            sd[f"dil{i}_w"] = glorot((3, Fn, Fn), 3 * Fn, 3 * Fn)
+            sd[f"dil{i}_b"] = (rng.standard_normal(Fn) * biasScale).astype(np.float32)
+        for h, T in enumerate(cfg.headTasks):
+            sd[f"prof{h}_w"] = glorot((cfg.outputFilterWidth, Fn, T), cfg.outputFilterWidth * Fn,
+                                      cfg.outputFilterWidth * T)
+            sd[f"prof{h}_b"] = (rng.standard_normal(T) * biasScale).astype(np.float32)
+            sd[f"cnt{h}_w"] = glorot((Fn, 1), Fn, 1)
+            sd[f"cnt{h}_b"] = (rng.standard_normal(1) * biasScale).astype(np.float32)
+        self.load_state(sd)
+        return sd
+
+    def load_state(self, sd):
+        """Load a dict of numpy arrays keyed like ``oracle.init_solo_params`` (Keras layouts)."""
+        cfg = self.cfg
+        Fn = cfg.numFilters
+        p = self.p
+        dev = self.device
+
+        def t(a):
+            return torch.as_tensor(np.asarray(a, dtype=np.float32), device=dev)
+
+        self.params.flat.zero_()
+        p["conv1_w"].copy_(t(sd["conv1_w"]))
+        p["conv1_b"].copy_(t(sd["conv1_b"]))
+        for i in range(cfg.numLayers):
+            p["dil_w"][i, :, :Fn, :Fn].copy_(t(sd[f"dil{i}_w"]))
+            p["dil_b"][i, :Fn].copy_(t(sd[f"dil{i}_b"]))
+        k = 0
+        for h, T in enumerate(cfg.headTasks):
+            p["prof_w"][:, :, k:k + T].copy_(t(sd[f"prof{h}_w"]))
+            p["prof_b"][k:k + T].copy_(t(sd[f"prof{h}_b"]))
+            p["cnt_w"][:, h:h + 1].copy_(t(sd[f"cnt{h}_w"]))
+            p["cnt_b"][h:h + 1].copy_(t(sd[f"cnt{h}_b"]))
+            k += T
+        self.refresh_weights()
+
+    def state(self, flat=None):
+        """Inverse of ``load_state`` (numpy, unpadded Keras layouts)."""
+        cfg = self.cfg
+        Fn = cfg.numFilters
+        p = self.params.views(flat)
+        sd = {"conv1_w": p["conv1_w"].cpu().numpy().copy(),
+              "conv1_b": p["conv1_b"].cpu().numpy().copy()}
+        for i in range(cfg.numLayers):
+            sd[f"dil{i}_w"] = p["dil_w"][i, :, :Fn, :Fn].cpu().numpy().copy()
+            sd[f"dil{i}_b"] = p["dil_b"][i, :Fn].cpu().numpy().copy()
+        k = 0
+        for h, T in enumerate(cfg.headTasks):
+            sd[f"prof{h}_w"] = p["prof_w"][:, :, k:k + T].cpu().numpy().copy()
+            sd[f"prof{h}_b"] = p["prof_b"][k:k + T].cpu().numpy().copy()
+            sd[f"cnt{h}_w"] = p["cnt_w"][:, h:h + 1].cpu().numpy().copy()
+            sd[f"cnt{h}_b"] = p["cnt_b"][h:h + 1].cpu().numpy().copy()
+            k += T
+        return sd
+
+    def refresh_weights(self):
+        """fp32 master weights -> bf16 tcgen05 operand layouts (after load / after Adam)."""
+        if self.cfg.numLayers > 0:
+            ops.prep_conv3_weights(self.p["dil_w"], self.cfg.Fp, self.w_fwd, self.w_bwd,
+                                   self.cfg.precise)
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, B, kind):
+        key = (B, kind)
+        if key in self._ws:
+            return self._ws[key]
+        cfg, dev = self.cfg, self.device
+        Fp, prec = cfg.Fp, cfg.precise
+        Ls = cfg.lengths()
+        ws = {"B": B}
+        ws["x"] = torch.zeros((B, cfg.inputLength, 4), dtype=torch.uint8, device=dev)
+        ws["logits"] = torch.empty((B, cfg.outputLength, cfg.T), dtype=torch.float32, device=dev)
+        ws["gap"] = torch.empty((B, Fp), dtype=torch.float32, device=dev)
+        ws["logcounts"] = torch.empty((B, cfg.H), dtype=torch.float32, device=dev)
+        if kind == "predict":
+            # two ping-pong activation buffers sized for the longest layer
+            ws["ping"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
+        else:
+            ws["acts"] = [ops.new_planes(B, L, Fp, prec, dev) for L in Ls]
+        if kind == "train":
+            ws["masks"] = [torch.empty((B, L, Fp // 64), dtype=torch.int64, device=dev)
+                           for L in Ls]
+            ws["counts"] = torch.zeros((B, cfg.outputLength, cfg.T), dtype=torch.float32,
+                                       device=dev)
+            ws["losses"] = torch.zeros((2 * cfg.H,), dtype=torch.float32, device=dev)
+            ws["dlogits"] = torch.empty_like(ws["logits"])
+            ws["dlogcounts"] = torch.empty_like(ws["logcounts"])
+            ws["g"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
+            ws["gz"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
+            nb = max([ops.wgrad3_ws_bytes(B, L, Fp, prec) for L in Ls[1:]] +
+                     [ops.input_conv_wgrad_ws_bytes(B, Ls[0], cfg.inputFilterWidth,
+                                                    cfg.numFilters),
+                      ops.heads_bwd_ws_bytes(B, Ls[-1], cfg.outputFilterWidth, cfg.numFilters,
+                                             cfg.T)])
+            ws["scratch"] = torch.empty((nb // 4 + 4,), dtype=torch.float32, device=dev)
+        if kind == "shap_x":
+            ws["z"] = [torch.empty((B, L, Fp), dtype=torch.float32, device=dev) for L in Ls]
+        if kind == "shap_r":
+            ws["mult"] = [ops.new_planes(B, L, Fp, prec, dev) for L in Ls]
+            ws["ping"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
+            del ws["acts"]
+            ws["dlogits"] = torch.zeros_like(ws["logits"])
+            ws["dlogcounts"] = torch.zeros_like(ws["logcounts"])
+            ws["g"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
+            ws["gz"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
+            ws["dx"] = torch.empty((B, cfg.inputLength, 4), dtype=torch.float32, device=dev)
+        self._ws[key] = ws
+        return ws
+
+    @staticmethod
+    def _sub(planes, L):
+        """View of the first L rows per sequence of an over-allocated plane set as a new
+        contiguous [B, L, F] tensor sharing the same storage start (buffers are reused across
+        layers of different lengths, so the view is re-shaped over the flat storage)."""
+        hi, lo = planes
+        B, _, Fp = hi.shape
+        h = hi.view(-1)[:B * L * Fp].view(B, L, Fp)
+        l_ = lo.view(-1)[:B * L * Fp].view(B, L, Fp) if lo is not None else None
+        return (h, l_)
+
+    # ------------------------------------------------------------------ forward
+    def _forward(self, ws, x, save_masks=False, z_list=None, zx_list=None, zx_div=1,
+                 mult_list=None):
+        cfg = self.cfg
+        p = self.p
+        Ls = cfg.lengths()
+        keep = "acts" in ws
+
+        def buf(i):
+            return ws["acts"][i] if keep else self._sub(ws["ping"][i % 2], Ls[i])
+
+        a = buf(0)
+        ops.input_conv_fwd(x, p["conv1_w"], p["conv1_b"], cfg.Fp, a,
+                           mask_out=ws["masks"][0] if save_masks else None,
+                           z_out=z_list[0] if z_list else None,
+                           zx_in=zx_list[0] if zx_list else None, zx_div=zx_div,
+                           mult=mult_list[0] if mult_list else None)
+        for i in range(cfg.numLayers):
+            d = 2 ** (i + 1)
+            nxt = buf(i + 1)
+            ops.conv3(a, self.w_fwd[i], (0, d, 2 * d), 0, Ls[i + 1], bias=p["dil_b"][i], resid=a,
+                      resid_off=d, out=nxt,
+                      mask_out=ws["masks"][i + 1] if save_masks else None,
+                      z_out=z_list[i + 1] if z_list else None,
+                      zx_in=zx_list[i + 1] if zx_list else None, zx_div=zx_div,
+                      out2=mult_list[i + 1] if mult_list else None)
+            a = nxt
+        ops.heads_fwd(a, p["prof_w"], p["prof_b"], p["cnt_w"], p["cnt_b"], ws["logits"],
+                      ws["gap"], ws["logcounts"])
+        return a
+
+    def predict_into(self, ws):
+        """Forward on ws['x'] -> ws['logits'], ws['logcounts'] (graph-capturable)."""
+        self._forward(ws, ws["x"])
+
+    def predict(self, x_u8, batchSize=64):
+        """x_u8: (N, Lin, 4) uint8 CUDA tensor -> (logits (N, Lout, T), logcounts (N, H))."""
+        cfg = self.cfg
+        N = x_u8.shape[0]
+        out_l = torch.empty((N, cfg.outputLength, cfg.T), dtype=torch.float32, device=self.device)
+        out_c = torch.empty((N, cfg.H), dtype=torch.float32, device=self.device)
+        for s in range(0, N, batchSize):
+            e = min(N, s + batchSize)
+            ws = self._workspace(e - s, "predict")
+            ws["x"].copy_(x_u8[s:e])
+            self._run_graph(("predict", e - s), lambda ws=ws: self.predict_into(ws))
+            out_l[s:e].copy_(ws["logits"])
+            out_c[s:e].copy_(ws["logcounts"])
+        return out_l, out_c
+
+    # ------------------------------------------------------------------ training
+    def enable_training(self):
+        if self.grads_flat is None:
+            self.grads_flat = torch.zeros_like(self.params.flat)
+            self.adam_m = torch.zeros_like(self.params.flat)
+            self.adam_v = torch.zeros_like(self.params.flat)
+            self.g = self.params.views(self.grads_flat)
+            self.profile_weight = torch.ones((self.cfg.H,), dtype=torch.float32,
+                                             device=self.device)
+            self.lam = torch.ones((self.cfg.H,), dtype=torch.float32, device=self.device)
+
+    def forward_backward_into(self, ws, bias_logits=None, bias_logcounts=None, use_bias=None):
+        """Forward + losses + backward on ws['x'], ws['counts'] -> self.grads_flat, ws['losses'].
+
+        For the combined model (models.py:363-380) the frozen bias outputs are added before the
+        loss: logits by addition, logcounts by CountsLogSumExp where ``use_bias[h]``."""
+        cfg, p, g = self.cfg, self.p, self.g
+        Ls = cfg.lengths()
+        aL = self._forward(ws, ws["x"], save_masks=True)
+        logits, lc = ws["logits"], ws["logcounts"]
+        if bias_logits is not None:
+            if "logits_c" not in ws:
+                ws["logits_c"] = torch.empty_like(logits)
+                ws["lc_c"] = torch.empty_like(lc)
+                ws["dscale"] = torch.empty_like(lc)
+            ops.add_f32(logits, bias_logits, ws["logits_c"])
+            ops.counts_lse(use_bias, bias_logcounts, lc, ws["lc_c"], ws["dscale"])
+            logits, lc = ws["logits_c"], ws["lc_c"]
+        ops.loss_fwd_bwd(self.task_off, logits, lc, ws["counts"], self.profile_weight, self.lam,
+                         ws["losses"], ws["dlogits"], ws["dlogcounts"])
+        if bias_logits is not None:
+            ops.mul_f32(ws["dlogcounts"], ws["dscale"], ws["dlogcounts"])
+        nL = cfg.numLayers
+        gcur = self._sub(ws["g"][nL % 2], Ls[nL])
+        gzcur = self._sub(ws["gz"][nL % 2], Ls[nL])
+        ops.heads_bwd(aL, ws["gap"], p["prof_w"], p["cnt_w"], ws["dlogits"], ws["dlogcounts"],
+                      g=gcur, gz=gzcur, mask_in=ws["masks"][nL], dpw=g["prof_w"],
+                      dpb=g["prof_b"], dcw=g["cnt_w"], dcb=g["cnt_b"], ws=ws["scratch"])
+        for i in range(nL - 1, -1, -1):
+            d = 2 ** (i + 1)
+            ops.wgrad3(ws["acts"][i], gzcur, d, g["dil_w"][i], g["dil_b"][i], ws["scratch"])
+            gnext = self._sub(ws["g"][i % 2], Ls[i])
+            gznext = self._sub(ws["gz"][i % 2], Ls[i])
+            ops.conv3(gzcur, self.w_bwd[i], (0, -d, -2 * d), 1, Ls[i], resid=gcur, resid_off=-d,
+                      out=gnext if i > 0 else None, out2=gznext, mask_in=ws["masks"][i])
+            gcur, gzcur = gnext, gznext
+        ops.input_conv_wgrad(ws["x"], gzcur, cfg.inputFilterWidth, cfg.numFilters, g["conv1_w"],
+                             g["conv1_b"], ws["scratch"])
+
+    def apply_adam(self, grad_scale=1.0):
+        # the optimiser step counter lives on the device so that the update replays inside a graph
+        self.step_and_lr[0:1].add_(1.0)
+        ops.adam_step(self.params.flat, self.grads_flat, self.adam_m, self.adam_v,
+                      self.step_and_lr, grad_scale=grad_scale)
+        self.refresh_weights()
+
+    def set_step(self, step, lr):
+        self.step = step
+        self.step_and_lr.copy_(torch.tensor([float(step), float(lr)], dtype=torch.float32),
+                               non_blocking=False)
+
+    def train_step(self, x_u8, counts, lr, use_graph=True, allreduce=None, world=1):
+        """One optimisation step.  ``x_u8`` / ``counts`` may live on the device or in (pinned)
+        host memory.  With ``allreduce`` (a callable taking the flat gradient bucket, e.g. an NCCL
+        all-reduce) the step is data parallel: local forward/backward, one all-reduce of the
+        bucket, identical Adam on every rank with the gradient scaled by 1/world."""
+        self.enable_training()
+        B = x_u8.shape[0]
+        ws = self._workspace(B, "train")
+        ws["x"].copy_(x_u8, non_blocking=True)
+        ws["counts"].copy_(counts, non_blocking=True)
+        self.step += 1
+        if lr != getattr(self, "_lr_on_device", None):
+            self.step_and_lr[1:2].fill_(float(lr))  # stream-ordered scalar fill, only on change
+            self._lr_on_device = lr
+
+        if allreduce is None:
+            def body():
+                self.forward_backward_into(ws)
+                self.apply_adam()
+            if use_graph:
+                self._run_graph(("train", B), body)
+            else:
+                body()
+        else:
+            def body_a():
+                self.forward_backward_into(ws)
+
+            def body_b():
+                self.apply_adam(grad_scale=1.0 / world)
+            if use_graph:
+                self._run_graph(("train_fb", B), body_a)
+                allreduce(self.grads_flat)
+                self._run_graph(("train_opt", B, world), body_b)
+            else:
+                body_a()
+                allreduce(self.grads_flat)
+                body_b()
+        return ws["losses"]
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def _run_graph(self, key, body):
+        g = self._graphs.get(key)
+        if g is None:
+            # warm up once eagerly (configures kernel attributes outside of capture)
+            body()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[key] = g
+            # The eager warm-up already produced this call's result and, for training, already
+            # applied the update, so the first call does not replay.
+            return
+        g.replay()
+
+    # ------------------------------------------------------------------ DeepSHAP (PISA / flat)
+    def shap_batch(self, x_u8, refs_u8, dlogits_fn):
+        """DeepSHAP-rescale multipliers for Q queries against n references each.
+
+        x_u8: (Q, Lin, 4); refs_u8: (Q*n, Lin, 4), the n references of query q at rows
+        q*n .. q*n+n-1.  ``dlogits_fn(ws_x, ws_r)`` must fill ws_r['dlogits'] / ws_r['dlogcounts']
+        with the gradient of the metric wrt the outputs of every (query, reference) pair.
+        Returns (dx (Q*n, Lin, 4) fp32 multipliers, ws_x, ws_r).  shap.py:347-394, 612-639.
+        """
+        cfg, p = self.cfg, self.p
+        Ls = cfg.lengths()
+        Q = x_u8.shape[0]
+        R = refs_u8.shape[0]
+        n = R // Q
+        wx = self._workspace(Q, "shap_x")
+        wr = self._workspace(R, "shap_r")
+        wx["x"].copy_(x_u8)
+        wr["x"].copy_(refs_u8)
+        self._forward(wx, wx["x"], z_list=wx["z"])
+        self._forward(wr, wr["x"], zx_list=wx["z"], zx_div=n, mult_list=wr["mult"])
+        dlogits_fn(wx, wr)
+        nL = cfg.numLayers
+        gcur = self._sub(wr["g"][nL % 2], Ls[nL])
+        gzcur = self._sub(wr["gz"][nL % 2], Ls[nL])
+        ops.heads_bwd(None_planes(wr, Ls[nL], cfg), wr["gap"], p["prof_w"], p["cnt_w"],
+                      wr["dlogits"], wr["dlogcounts"], g=gcur, gz=gzcur, mult=wr["mult"][nL])
+        for i in range(nL - 1, -1, -1):
+            d = 2 ** (i + 1)
+            gnext = self._sub(wr["g"][i % 2], Ls[i])
+            gznext = self._sub(wr["gz"][i % 2], Ls[i])
+            ops.conv3(gzcur, self.w_bwd[i], (0, -d, -2 * d), 1, Ls[i], resid=gcur, resid_off=-d,
+                      out=gnext if i > 0 else None, out2=gznext, mult=wr["mult"][i])
+            gcur, gzcur = gnext, gznext
+        ops.input_conv_dgrad(gzcur, p["conv1_w"], cfg.inputLength, wr["dx"])
+        return wr["dx"], wx, wr
+
+
+def None_planes(ws, L, cfg):
+    """The heads' data gradient does not read activations; pass a correctly shaped plane view so
+    that the launcher can read the geometry."""
+    return SoloNet._sub(ws["ping"][0], L)

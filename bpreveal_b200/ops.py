@@ -204,10 +204,12 @@ def adam_step(param, grad, m, v, step_and_lr, beta1=0.9, beta2=0.999, eps=1e-7, 
 
 
 def prep_conv3_weights(w, F, fwd, bwd, precise):
+    """w: [3, Fw, Fw] or [layers, 3, Fw, Fw] fp32 -> fwd/bwd [layers, planes, 3, F, F] bf16."""
     lib = _lib.load()
-    Fw = w.shape[1]
-    check(lib.bpb_prep_conv3_weights(Fw, F, _p(w), _p(fwd), _p(bwd), 1 if precise else 0,
-                                     _stream()), "bpb_prep_conv3_weights")
+    Fw = w.shape[-1]
+    n_layers = w.shape[0] if w.dim() == 4 else 1
+    check(lib.bpb_prep_conv3_weights(n_layers, Fw, F, _p(w), _p(fwd), _p(bwd),
+                                     1 if precise else 0, _stream()), "bpb_prep_conv3_weights")
 
 
 def slide_u8(src, dst, row_idx, col_idx):
@@ -255,3 +257,18 @@ def counts_lse(use_bias, bias_lc, resid_lc, out, dscale=None):
     B, H = resid_lc.shape
     check(_lib.load().bpb_counts_lse(B, H, _p(use_bias), _p(bias_lc), _p(resid_lc), _p(out),
                                      _p(dscale), _stream()), "bpb_counts_lse")
+
+
+def shuffle_rows(x, perm, refs):
+    Q, L, _ = x.shape
+    n = perm.shape[0]
+    check(_lib.load().bpb_shuffle_rows(Q, n, L, _p(x), _p(perm), _p(refs), _stream()),
+          "bpb_shuffle_rows")
+
+
+def shap_combine(x, refs, mult, phi, hypothetical=False):
+    Q, L, _ = x.shape
+    n = refs.shape[0] // Q
+    check(_lib.load().bpb_shap_combine(Q, n, L, _p(x), _p(refs), _p(mult),
+                                       1 if hypothetical else 0, _p(phi), _stream()),
+          "bpb_shap_combine")

