@@ -6,38 +6,59 @@
 // gradient (shap.py:612-639).
 //
 // GEMM view: M = 128 consecutive positions of one sequence, N = NT output channels, K = 3 taps x
-// F input channels.  The A operand of tap j is the activation tile at row offset tap_off[j]: one
-// TMA box [128 rows x 64 ch] (128-byte swizzle, K-major) per (tap, 64-channel chunk, plane); rows
-// outside the sequence are zero-filled by TMA, which gives the 'valid' forward conv and the 'full'
-// backward conv from the same code.  Accumulators live in TMEM (4 or 2 stages), one elected thread
-// issues tcgen05.mma, four epilogue warps read TMEM, fuse bias / ReLU / crop+residual (forward) or
-// residual-gradient + ReLU-mask / rescale-multiplier (backward) and TMA-store bf16 planes.
+// F input channels.  Rows outside the sequence are zero-filled by TMA, which gives the 'valid'
+// forward conv and the 'full' backward conv from the same code.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5
-// epilogue (TMEM quadrant = warp % 4).
+// Two operand-staging schemes:
+//   HALO   (small dilations, weights resident): ONE TMA box of 128 + span rows per tile and
+//          channel chunk; the three taps are UMMA descriptors that start at row offsets
+//          0 / d / 2d of that box (SWIZZLE_128B is a function of the absolute smem address, so a
+//          descriptor may start at any row).  Activations are read from L2 once instead of three
+//          times, and the forward residual a[t+d] is read back from the same box.
+//   SLAB   (any dilation / width): one [128 x 64] box per (tap, chunk, pass), as a classic
+//          multi-stage K pipeline; weights resident in smem when they fit, else streamed.
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9
+// epilogue.  Epilogue warp w reads TMEM lane quadrant w % 4 (rows) and the column half
+// (w - 2) / 4 of each 64-channel chunk, so two warps per scheduler hide each other's latency.
+// The epilogue fuses bias / ReLU / ReLU-mask bits / crop + residual (forward) or residual
+// gradient + mask / rescale multiplier (backward) and writes bf16 planes through double-buffered
+// swizzled staging tiles and TMA stores.  Residual tiles that are not already in the HALO box
+// arrive through their own small TMA ring, so the epilogue never waits on a global load.
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace bp {
 
 constexpr int kTileM = 128;
-constexpr int kATileBytes = kTileM * 128;  // [128 x 64] bf16
+constexpr int kTileBytes = kTileM * 128;  // [128 x 64] bf16
 constexpr int kMaxStages = 12;
+constexpr int kMaxRStages = 4;
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+
+enum { EPI_FWD = 0, EPI_FWD_Z = 1, EPI_FWD_R = 2, EPI_BWD_MASK = 3, EPI_BWD_MULT = 4 };
 
 struct ConvKParams {
-  int B, L_out, tiles_per_seq, n_ntiles, NC, n_planes, n_passes, F;
-  int tap_off[3];
-  int mode, stages;
-  int L_res, resid_off;
+  int B, L_out, tiles_per_seq, n_ntiles, NC, F;
+  int tap_row[3];  // SLAB: row offset of tap j relative to t0; HALO: row of tap j inside the box
+  int box_off;     // HALO: first box row = t0 + box_off
+  int sub_bytes;   // HALO: bytes of one (chunk, plane) box, padded to 1024
+  int box_bytes;   // HALO: bytes TMA writes per box (rows * 128)
+  int stages, rstages, nstg;
+  int resid_off, resid_row;  // residual tile = rows t0 + resid_off (resid_row: inside the box)
   int zx_div;
-  int has_out, has_out2;
+  int has_out, has_out2, has_resid;
   const float* bias;
-  const __nv_bfloat16 *resid_hi, *resid_lo;
   const __nv_bfloat16 *mult_hi, *mult_lo;
-  const unsigned long long* mask_in;
-  unsigned long long* mask_out;
+  const uint32_t* mask_in;
+  uint32_t* mask_out;
   const float* zx_in;
   float* z_out;
+};
+
+struct ConvMaps {
+  CUtensorMap A[2], W, O[2], P[2], R[2];
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -59,55 +80,82 @@ __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
   for (int i = 0; i < 8; ++i) r[i] = f[i] - h[i];
   lo = pack8(r);
 }
+__device__ __forceinline__ uint4 lds128(const uint8_t* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint8_t* p, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
 
-template <int NT, bool RESIDENT>
-__global__ void __launch_bounds__(192, 1)
-conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
-                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmP0,
-                const __grid_constant__ CUtensorMap tmP1, const ConvKParams p) {
+template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   constexpr int ACC = (NT <= 128) ? 4 : 2;
+  constexpr int NCH = NT / 64;
+  constexpr int NPASS = (PLANES == 2) ? 3 : 1;
   constexpr uint32_t TMEM_COLS = ACC * NT;
   constexpr int B_TILE_BYTES = NT * 128;
-  constexpr int STAGE_BYTES = kATileBytes + (RESIDENT ? 0 : B_TILE_BYTES);
+  constexpr int SLAB_BYTES = kTileBytes + (RESIDENT ? 0 : B_TILE_BYTES);
   constexpr uint32_t IDESC = umma_idesc_bf16(128, NT, 0, 0);
+  constexpr bool IS_FWD = (EPI <= EPI_FWD_R);
+  // the forward residual a[t + d] already sits in the HALO box
+  constexpr bool RING_RESID = !(HALO && IS_FWD);
+  static_assert(!HALO || RESIDENT, "HALO staging needs resident weights");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
-  const int w_tiles = RESIDENT ? p.n_planes * 3 * p.NC : 0;
+  const int w_tiles = RESIDENT ? PLANES * 3 * p.NC : 0;
+  const int stage_bytes = HALO ? p.NC * PLANES * p.sub_bytes : SLAB_BYTES;
+  const int n_out = p.has_out + p.has_out2;
+  const int stg_bytes = n_out * PLANES * kTileBytes;
+  const int rstage_bytes = PLANES * kTileBytes;
   uint8_t* w_smem = smem;
   uint8_t* ring = w_smem + static_cast<size_t>(w_tiles) * B_TILE_BYTES;
-  uint8_t* stg = ring + static_cast<size_t>(p.stages) * STAGE_BYTES;
-  const int n_stg = (p.has_out + p.has_out2) * p.n_planes;
-  float* s_bias = reinterpret_cast<float*>(stg + static_cast<size_t>(n_stg) * kATileBytes);
+  uint8_t* stg = ring + static_cast<size_t>(p.stages) * stage_bytes;
+  uint8_t* rring = stg + static_cast<size_t>(p.nstg) * stg_bytes;
+  float* s_bias = reinterpret_cast<float*>(
+      rring + ((RING_RESID && p.has_resid) ? static_cast<size_t>(p.rstages) * rstage_bytes : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + p.F);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kMaxStages;
-  uint64_t* acc_full = bars + 2 * kMaxStages;
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* acc_full = empty + kMaxStages;
   uint64_t* acc_empty = acc_full + 4;
-  uint64_t* w_full = acc_empty + 4;
+  uint64_t* rfull = acc_empty + 4;
+  uint64_t* rempty = rfull + kMaxRStages;
+  uint64_t* w_full = rempty + kMaxRStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.B * p.tiles_per_seq * p.n_ntiles;
-  const int nsteps = 3 * p.NC * p.n_passes;
 
   if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmW);
-    if (p.n_planes == 2) tma_prefetch_desc(&tmA1);
-    if (p.has_out) tma_prefetch_desc(&tmO0);
-    if (p.has_out2) tma_prefetch_desc(&tmP0);
+    tma_prefetch_desc(&tm.A[0]);
+    tma_prefetch_desc(&tm.W);
+    if (PLANES == 2) tma_prefetch_desc(&tm.A[1]);
+    if (p.has_out) tma_prefetch_desc(&tm.O[0]);
+    if (p.has_out2) tma_prefetch_desc(&tm.P[0]);
+    if (RING_RESID && p.has_resid) tma_prefetch_desc(&tm.R[0]);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      // HALO forward: the box is released by the MMA commit AND by the 8 epilogue warps
+      mbar_init(&empty[i], (HALO && IS_FWD && p.has_resid) ? 9 : 1);
     }
     for (int i = 0; i < ACC; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], 8);
+    }
+    for (int i = 0; i < kMaxRStages; ++i) {
+      mbar_init(&rfull[i], 1);
+      mbar_init(&rempty[i], 8);
     }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -124,32 +172,55 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     if (elect_one()) {
       if (RESIDENT) {
         mbar_expect_tx(w_full, static_cast<uint32_t>(w_tiles) * B_TILE_BYTES);
-        for (int wp = 0; wp < p.n_planes; ++wp)
+        for (int wp = 0; wp < PLANES; ++wp)
           for (int j = 0; j < 3; ++j)
             for (int c = 0; c < p.NC; ++c)
-              tma_load_2d(&tmW, w_smem + static_cast<size_t>((wp * 3 + j) * p.NC + c) * B_TILE_BYTES,
+              tma_load_2d(&tm.W, w_smem + static_cast<size_t>((wp * 3 + j) * p.NC + c) * B_TILE_BYTES,
                           w_full, c * 64, (wp * 3 + j) * p.F);
       }
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, rs = 0, rphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_ntiles;
         const int mt = (tile / p.n_ntiles) % p.tiles_per_seq;
         const int b = tile / (p.n_ntiles * p.tiles_per_seq);
         const int t0 = mt * kTileM;
-        for (int step = 0; step < nsteps; ++step) {
-          const int pass = step % p.n_passes;
-          const int c = (step / p.n_passes) % p.NC;
-          const int j = step / (p.n_passes * p.NC);
+        if (HALO) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
-          uint8_t* dst = ring + static_cast<size_t>(stage) * STAGE_BYTES;
-          tma_load_3d(pass == 1 ? &tmA1 : &tmA0, dst, &full[stage], c * 64, t0 + p.tap_off[j], b);
-          if (!RESIDENT) {
-            const int wp = (pass == 2) ? 1 : 0;
-            tma_load_2d(&tmW, dst + kATileBytes, &full[stage], c * 64,
-                        (wp * 3 + j) * p.F + nt * NT);
-          }
+          mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.NC * PLANES * p.box_bytes));
+          uint8_t* dst = ring + static_cast<size_t>(stage) * stage_bytes;
+          for (int c = 0; c < p.NC; ++c)
+            for (int pl = 0; pl < PLANES; ++pl)
+              tma_load_3d(&tm.A[pl], dst + static_cast<size_t>(c * PLANES + pl) * p.sub_bytes,
+                          &full[stage], c * 64, t0 + p.box_off, b);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+        } else {
+          const int nsteps = 3 * p.NC * NPASS;
+          for (int step = 0; step < nsteps; ++step) {
+            const int pass = step % NPASS;
+            const int c = (step / NPASS) % p.NC;
+            const int j = step / (NPASS * p.NC);
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], SLAB_BYTES);
+            uint8_t* dst = ring + static_cast<size_t>(stage) * SLAB_BYTES;
+            tma_load_3d(&tm.A[pass == 1 ? 1 : 0], dst, &full[stage], c * 64, t0 + p.tap_row[j], b);
+            if (!RESIDENT) {
+              const int wp = (pass == 2) ? 1 : 0;
+              tma_load_2d(&tm.W, dst + kTileBytes, &full[stage], c * 64,
+                          (wp * 3 + j) * p.F + nt * NT);
+            }
+            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (RING_RESID && p.has_resid) {
+          for (int ch = 0; ch < NCH; ++ch) {
+            mbar_wait(&rempty[rs], rphase ^ 1);
+            mbar_expect_tx(&rfull[rs], static_cast<uint32_t>(rstage_bytes));
+            uint8_t* dst = rring + static_cast<size_t>(rs) * rstage_bytes;
+            for (int pl = 0; pl < PLANES; ++pl)
+              tma_load_3d(&tm.R[pl], dst + pl * kTileBytes, &rfull[rs], nt * NT + ch * 64,
+                          t0 + p.resid_off, b);
+            if (++rs == static_cast<uint32_t>(p.rstages)) { rs = 0; rphase ^= 1; }
+          }
         }
       }
     }
@@ -162,41 +233,63 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * NT;
-        for (int step = 0; step < nsteps; ++step) {
-          const int pass = step % p.n_passes;
-          const int c = (step / p.n_passes) % p.NC;
-          const int j = step / (p.n_passes * p.NC);
+        if (HALO) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * STAGE_BYTES);
-          uint32_t b_addr;
-          if (RESIDENT) {
-            const int wp = (pass == 2) ? 1 : 0;
-            b_addr = smem_u32(w_smem + static_cast<size_t>((wp * 3 + j) * p.NC + c) * B_TILE_BYTES);
-          } else {
-            b_addr = a_addr + kATileBytes;
-          }
+          const uint32_t base = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
+          uint32_t accum = 0;
+          for (int pass = 0; pass < NPASS; ++pass)
+            for (int c = 0; c < p.NC; ++c)
+              for (int j = 0; j < 3; ++j) {
+                const uint32_t a_addr = base + (c * PLANES + (pass == 1 ? 1 : 0)) * p.sub_bytes +
+                                        p.tap_row[j] * 128;
+                const uint32_t b_addr =
+                    smem_u32(w_smem) + (((pass == 2 ? 1 : 0) * 3 + j) * p.NC + c) * B_TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
-                      umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, (step | k) != 0 ? 1u : 0u);
-          }
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
+                            umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, accum);
+                  accum = 1;
+                }
+              }
           umma_commit(&empty[stage]);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+        } else {
+          const int nsteps = 3 * p.NC * NPASS;
+          for (int step = 0; step < nsteps; ++step) {
+            const int pass = step % NPASS;
+            const int c = (step / NPASS) % p.NC;
+            const int j = step / (NPASS * p.NC);
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * SLAB_BYTES);
+            uint32_t b_addr;
+            if (RESIDENT) {
+              const int wp = (pass == 2) ? 1 : 0;
+              b_addr = smem_u32(w_smem) + ((wp * 3 + j) * p.NC + c) * B_TILE_BYTES;
+            } else {
+              b_addr = a_addr + kTileBytes;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
+                        umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, (step | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+          }
         }
         umma_commit(&acc_full[as]);
         if (++as == ACC) { as = 0; aphase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------- epilogue warps
+    // ------------------------------------------------------------- epilogue warps (2..9)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;
     const int chunks_per_row = p.F >> 6;
-    uint32_t as = 0, aphase = 0;
-    uint8_t* stg_out = stg;
-    uint8_t* stg_out2 = stg + static_cast<size_t>(p.has_out * p.n_planes) * kATileBytes;
+    uint32_t as = 0, aphase = 0, rs = 0, rphase = 0, hs = 0, hphase = 0, kc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_ntiles;
       const int mt = (tile / p.n_ntiles) % p.tiles_per_seq;
@@ -204,58 +297,81 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const int t0 = mt * kTileM;
       const int t = t0 + row;
       const bool valid = t < p.L_out;
-      const int tr = t + p.resid_off;
-      const bool rvalid = valid && p.resid_hi != nullptr && tr >= 0 && tr < p.L_res;
       const size_t orow = static_cast<size_t>(b) * p.L_out + t;
 
-      for (int ch = 0; ch < NT / 64; ++ch) {
+#pragma unroll 1
+      for (int ch = 0; ch < NCH; ++ch, ++kc) {
         const int n0 = nt * NT + ch * 64;
-        // Issue the row-wise global reads first so that they overlap the accumulator wait.
-        uint4 rr[8], rl[8];
-        if (rvalid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(
-              p.resid_hi + (static_cast<size_t>(b) * p.L_res + tr) * p.F + n0);
+        const int cq = half * 4;  // first 16-byte chunk of this thread's 32 columns
+        uint32_t mbits = ~0u;
+        if (EPI == EPI_BWD_MASK && p.mask_in != nullptr && valid)
+          mbits = __ldg(p.mask_in + (orow * chunks_per_row + (n0 >> 6)) * 2 + half);
+
+        // ---- residual (already in shared memory: HALO box or residual ring)
+        uint4 rr[4], rl[4];
+        if (p.has_resid) {
+          if (RING_RESID) {
+            mbar_wait(&rfull[rs], rphase);
+            const uint8_t* src = rring + static_cast<size_t>(rs) * rstage_bytes;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) rr[g] = __ldg(rp + g);
-          if (p.resid_lo) {
-            const uint4* rq = reinterpret_cast<const uint4*>(
-                p.resid_lo + (static_cast<size_t>(b) * p.L_res + tr) * p.F + n0);
+            for (int g = 0; g < 4; ++g) {
+              rr[g] = lds128(src + sw128(row, cq + g));
+              if (PLANES == 2) rl[g] = lds128(src + kTileBytes + sw128(row, cq + g));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rempty[rs]);
+            if (++rs == static_cast<uint32_t>(p.rstages)) { rs = 0; rphase ^= 1; }
+          } else {
+            if (ch == 0) mbar_wait(&full[hs], hphase);
+            // n_ntiles == 1 in HALO mode, so the chunk index is the channel-chunk index
+            const uint8_t* src = ring + static_cast<size_t>(hs) * stage_bytes +
+                                 static_cast<size_t>(ch * PLANES) * p.sub_bytes;
+            const uint32_t brow = row + p.resid_row;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) rl[g] = __ldg(rq + g);
+            for (int g = 0; g < 4; ++g) {
+              rr[g] = lds128(src + sw128(brow, cq + g));
+              if (PLANES == 2) rl[g] = lds128(src + p.sub_bytes + sw128(brow, cq + g));
+            }
+            if (ch == NCH - 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty[hs]);
+              if (++hs == static_cast<uint32_t>(p.stages)) { hs = 0; hphase ^= 1; }
+            }
           }
         }
-        unsigned long long mbits = ~0ull;
-        if (p.mode == 1 && p.mask_in != nullptr && valid)
-          mbits = __ldg(p.mask_in + orow * chunks_per_row + (n0 >> 6));
 
+        // ---- accumulator
         if (ch == 0) {
           mbar_wait(&acc_full[as], aphase);
           tc_fence_after();
         }
-        uint32_t acc[64];
-        const uint32_t taddr = tmem_base + as * NT + ch * 64 + (static_cast<uint32_t>(q * 32) << 16);
-        tmem_ld32(taddr, acc);
-        tmem_ld32(taddr + 32, acc + 32);
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + as * NT + ch * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16),
+                  acc);
         tmem_ld_wait();
-        if (ch == NT / 64 - 1) {
+        if (ch == NCH - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
 
-        // staging buffers must be free (previous TMA stores have read them)
-        if (et == 0) tma_store_wait_read<0>();
-        named_bar_sync(1, 128);
+        uint8_t* sb = stg + static_cast<size_t>(p.nstg == 2 ? (kc & 1) : 0) * stg_bytes;
+        uint8_t* sb2 = sb + static_cast<size_t>(p.has_out * PLANES) * kTileBytes;
+        if (p.nstg == 1) {
+          // single staging buffer: the previous chunk's stores must have read it
+          if (et == 0) tma_store_wait_read<0>();
+          named_bar_sync(1, kEpiThreads);
+        }
 
-        unsigned long long obits = 0ull;
+        uint32_t obits = 0u;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           float v[8], r[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]);
-          if (rvalid) {
+          if (p.has_resid) {
             unpack8(rr[g], r);
-            if (p.resid_lo) {
+            if (PLANES == 2) {
               float r2[8];
               unpack8(rl[g], r2);
 #pragma unroll
@@ -266,16 +382,19 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             for (int i = 0; i < 8; ++i) r[i] = 0.f;
           }
           float o[8], o2[8];
-          if (p.mode == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += s_bias[n0 + g * 8 + i];
-            if (p.zx_in != nullptr) {
+          if (IS_FWD) {
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + half * 32 + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + half * 32 + g * 8 + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            if (EPI == EPI_FWD_R) {
               // DeepSHAP rescale multiplier of this reference against the query's pre-activation
               // (shap.py:623-638); only the query-half gradient is used downstream (shap.py:374).
               float zx[8];
               if (valid) {
                 const float4* zp = reinterpret_cast<const float4*>(
-                    p.zx_in + (static_cast<size_t>(b / p.zx_div) * p.L_out + t) * p.F + n0 + g * 8);
+                    p.zx_in + (static_cast<size_t>(b / p.zx_div) * p.L_out + t) * p.F + n0 +
+                    half * 32 + g * 8);
                 const float4 z0 = __ldg(zp), z1 = __ldg(zp + 1);
                 zx[0] = z0.x; zx[1] = z0.y; zx[2] = z0.z; zx[3] = z0.w;
                 zx[4] = z1.x; zx[5] = z1.y; zx[6] = z1.z; zx[7] = z1.w;
@@ -290,28 +409,29 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 o2[i] = (fabsf(din) < 1e-6f) ? (zx[i] > 0.f ? 1.f : 0.f) : dout / din;
               }
             }
-            if (p.z_out != nullptr && valid) {
-              float4* zo = reinterpret_cast<float4*>(p.z_out + orow * p.F + n0 + g * 8);
-              zo[0] = make_float4(v[0], v[1], v[2], v[3]);
-              zo[1] = make_float4(v[4], v[5], v[6], v[7]);
+            if (EPI == EPI_FWD_Z) {
+              if (valid) {
+                float4* zo = reinterpret_cast<float4*>(p.z_out + orow * p.F + n0 + half * 32 + g * 8);
+                zo[0] = make_float4(v[0], v[1], v[2], v[3]);
+                zo[1] = make_float4(v[4], v[5], v[6], v[7]);
+              }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (v[i] > 0.f) obits |= 1ull << (g * 8 + i);
+              if (v[i] > 0.f) obits |= 1u << (g * 8 + i);
               o[i] = fmaxf(v[i], 0.f) + r[i];
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = v[i] + r[i];
-            if (p.mult_hi != nullptr) {
+            if (EPI == EPI_BWD_MULT) {
               float m[8];
               if (valid) {
-                const uint4 mu = __ldg(reinterpret_cast<const uint4*>(p.mult_hi + orow * p.F + n0) + g);
-                unpack8(mu, m);
-                if (p.mult_lo) {
+                const size_t moff = orow * p.F + n0 + half * 32 + g * 8;
+                unpack8(__ldg(reinterpret_cast<const uint4*>(p.mult_hi + moff)), m);
+                if (PLANES == 2) {
                   float m2[8];
-                  const uint4 ml = __ldg(reinterpret_cast<const uint4*>(p.mult_lo + orow * p.F + n0) + g);
-                  unpack8(ml, m2);
+                  unpack8(__ldg(reinterpret_cast<const uint4*>(p.mult_lo + moff)), m2);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) m[i] += m2[i];
                 }
@@ -323,44 +443,46 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               for (int i = 0; i < 8; ++i) o2[i] = o[i] * m[i];
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o2[i] = ((mbits >> (g * 8 + i)) & 1ull) ? o[i] : 0.f;
+              for (int i = 0; i < 8; ++i) o2[i] = ((mbits >> (g * 8 + i)) & 1u) ? o[i] : 0.f;
             }
           }
-          const uint32_t off = sw128(row, g);
+          const uint32_t off = sw128(row, cq + g);
           if (p.has_out) {
-            if (p.n_planes == 2) {
+            if (PLANES == 2) {
               uint4 h, l;
               split8(o, h, l);
-              *reinterpret_cast<uint4*>(stg_out + off) = h;
-              *reinterpret_cast<uint4*>(stg_out + kATileBytes + off) = l;
+              sts128(sb + off, h);
+              sts128(sb + kTileBytes + off, l);
             } else {
-              *reinterpret_cast<uint4*>(stg_out + off) = pack8(o);
+              sts128(sb + off, pack8(o));
             }
           }
-          if (p.has_out2) {
-            if (p.n_planes == 2) {
+          if ((EPI == EPI_FWD_R || !IS_FWD) && p.has_out2) {
+            if (PLANES == 2) {
               uint4 h, l;
               split8(o2, h, l);
-              *reinterpret_cast<uint4*>(stg_out2 + off) = h;
-              *reinterpret_cast<uint4*>(stg_out2 + kATileBytes + off) = l;
+              sts128(sb2 + off, h);
+              sts128(sb2 + kTileBytes + off, l);
             } else {
-              *reinterpret_cast<uint4*>(stg_out2 + off) = pack8(o2);
+              sts128(sb2 + off, pack8(o2));
             }
           }
         }
-        if (p.mode == 0 && p.mask_out != nullptr && valid)
-          p.mask_out[orow * chunks_per_row + (n0 >> 6)] = obits;
+        if (IS_FWD && p.mask_out != nullptr && valid)
+          p.mask_out[(orow * chunks_per_row + (n0 >> 6)) * 2 + half] = obits;
 
+        // ---- publish: generic-proxy writes -> async proxy, one barrier, one thread stores
         fence_proxy_async();
-        named_bar_sync(1, 128);
+        if (p.nstg == 2 && et == 0) tma_store_wait_read<0>();  // buffer of chunk kc-1 is free again
+        named_bar_sync(1, kEpiThreads);
         if (et == 0) {
           if (p.has_out) {
-            tma_store_3d(&tmO0, stg_out, n0, t0, b);
-            if (p.n_planes == 2) tma_store_3d(&tmO1, stg_out + kATileBytes, n0, t0, b);
+            tma_store_3d(&tm.O[0], sb, n0, t0, b);
+            if (PLANES == 2) tma_store_3d(&tm.O[1], sb + kTileBytes, n0, t0, b);
           }
           if (p.has_out2) {
-            tma_store_3d(&tmP0, stg_out2, n0, t0, b);
-            if (p.n_planes == 2) tma_store_3d(&tmP1, stg_out2 + kATileBytes, n0, t0, b);
+            tma_store_3d(&tm.P[0], sb2, n0, t0, b);
+            if (PLANES == 2) tma_store_3d(&tm.P[1], sb2 + kTileBytes, n0, t0, b);
           }
           tma_store_commit();
         }
@@ -376,20 +498,42 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int NT, bool RESIDENT>
-static int launch_conv3(const CUtensorMap* maps, const ConvKParams& kp, size_t smem_bytes, int grid,
+template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO>
+static int launch_conv3(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
                         cudaStream_t stream) {
-  auto kern = conv3_tc_kernel<NT, RESIDENT>;
+  auto kern = conv3_tc_kernel<EPI, NT, RESIDENT, PLANES, HALO>;
   static bool configured = false;
   if (!configured) {
     BP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        max_smem_optin()));
     configured = true;
   }
-  kern<<<grid, 192, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                          maps[6], kp);
+  kern<<<grid, kThreads, smem_bytes, stream>>>(maps, kp);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int EPI, int PLANES>
+static int dispatch_shape(int NT, bool resident, bool halo, const ConvMaps& maps,
+                          const ConvKParams& kp, size_t smem, int grid, cudaStream_t s) {
+  if (NT == 64) {
+    if (halo) return launch_conv3<EPI, 64, true, PLANES, true>(maps, kp, smem, grid, s);
+    if (resident) return launch_conv3<EPI, 64, true, PLANES, false>(maps, kp, smem, grid, s);
+    return launch_conv3<EPI, 64, false, PLANES, false>(maps, kp, smem, grid, s);
+  }
+  if (NT == 128) {
+    if (halo) return launch_conv3<EPI, 128, true, PLANES, true>(maps, kp, smem, grid, s);
+    if (resident) return launch_conv3<EPI, 128, true, PLANES, false>(maps, kp, smem, grid, s);
+    return launch_conv3<EPI, 128, false, PLANES, false>(maps, kp, smem, grid, s);
+  }
+  return launch_conv3<EPI, 256, false, PLANES, false>(maps, kp, smem, grid, s);
+}
+
+template <int EPI>
+static int dispatch_planes(int planes, int NT, bool resident, bool halo, const ConvMaps& maps,
+                           const ConvKParams& kp, size_t smem, int grid, cudaStream_t s) {
+  if (planes == 2) return dispatch_shape<EPI, 2>(NT, resident, halo, maps, kp, smem, grid, s);
+  return dispatch_shape<EPI, 1>(NT, resident, halo, maps, kp, smem, grid, s);
 }
 
 }  // namespace bp
@@ -412,9 +556,27 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   if (n_planes == 2) {
     BP_REQUIRE(!has_out || a->out_lo, "bpb_conv3_tc: precise path needs out_lo");
     BP_REQUIRE(!has_out2 || a->out2_lo, "bpb_conv3_tc: precise path needs out2_lo");
+    BP_REQUIRE(!a->resid_hi || a->resid_lo, "bpb_conv3_tc: precise path needs resid_lo");
+    BP_REQUIRE(!a->mult_hi || a->mult_lo, "bpb_conv3_tc: precise path needs mult_lo");
   }
-  if (a->mode == 0 && has_out2)
-    BP_REQUIRE(a->zx_in != nullptr && a->zx_div > 0, "bpb_conv3_tc: forward out2 needs zx_in");
+  int epi;
+  if (a->mode == 0) {
+    if (has_out2) {
+      BP_REQUIRE(a->zx_in != nullptr && a->zx_div > 0, "bpb_conv3_tc: forward out2 needs zx_in");
+      BP_REQUIRE(a->z_out == nullptr && a->mask_out == nullptr,
+                 "bpb_conv3_tc: forward out2 cannot be combined with z_out / mask_out");
+      epi = EPI_FWD_R;
+    } else {
+      epi = a->z_out ? EPI_FWD_Z : EPI_FWD;
+    }
+    BP_REQUIRE(a->mask_in == nullptr && a->mult_hi == nullptr,
+               "bpb_conv3_tc: mask_in / mult are backward inputs");
+  } else {
+    BP_REQUIRE(a->z_out == nullptr && a->mask_out == nullptr && a->zx_in == nullptr,
+               "bpb_conv3_tc: z_out / mask_out / zx_in are forward arguments");
+    BP_REQUIRE(!(a->mask_in && a->mult_hi), "bpb_conv3_tc: give mask_in or mult, not both");
+    epi = a->mult_hi ? EPI_BWD_MULT : EPI_BWD_MASK;
+  }
 
   const int F = a->F;
   const int NT = (F % 256 == 0) ? 256 : (F % 128 == 0 ? 128 : 64);
@@ -424,72 +586,131 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   kp.tiles_per_seq = (a->L_out + kTileM - 1) / kTileM;
   kp.n_ntiles = F / NT;
   kp.NC = F / 64;
-  kp.n_planes = n_planes;
-  kp.n_passes = n_planes == 2 ? 3 : 1;
   kp.F = F;
-  for (int j = 0; j < 3; ++j) kp.tap_off[j] = a->tap_off[j];
-  kp.mode = a->mode;
-  kp.L_res = a->L_res;
   kp.resid_off = a->resid_off;
   kp.zx_div = a->zx_div > 0 ? a->zx_div : 1;
   kp.has_out = has_out;
   kp.has_out2 = has_out2;
+  kp.has_resid = a->resid_hi ? 1 : 0;
   kp.bias = a->bias;
-  kp.resid_hi = reinterpret_cast<const __nv_bfloat16*>(a->resid_hi);
-  kp.resid_lo = reinterpret_cast<const __nv_bfloat16*>(a->resid_lo);
   kp.mult_hi = reinterpret_cast<const __nv_bfloat16*>(a->mult_hi);
   kp.mult_lo = reinterpret_cast<const __nv_bfloat16*>(a->mult_lo);
-  kp.mask_in = reinterpret_cast<const unsigned long long*>(a->mask_in);
-  kp.mask_out = reinterpret_cast<unsigned long long*>(a->mask_out);
+  kp.mask_in = reinterpret_cast<const uint32_t*>(a->mask_in);
+  kp.mask_out = reinterpret_cast<uint32_t*>(a->mask_out);
   kp.zx_in = a->zx_in;
   kp.z_out = a->z_out;
 
+  // ---- shared-memory plan
   const int max_smem = max_smem_optin();
   BP_REQUIRE(max_smem > 0, "bpb_conv3_tc: no CUDA device");
-  const size_t fixed = 1024 /*align slack*/ + static_cast<size_t>(has_out + has_out2) * n_planes * kATileBytes +
-                       static_cast<size_t>(F) * 4 + (2 * kMaxStages + 9) * 8 + 16;
+  int min_off = a->tap_off[0], max_off = a->tap_off[0];
+  for (int j = 1; j < 3; ++j) {
+    if (a->tap_off[j] < min_off) min_off = a->tap_off[j];
+    if (a->tap_off[j] > max_off) max_off = a->tap_off[j];
+  }
+  const int span = max_off - min_off;
+  const bool is_fwd = a->mode == 0;
+  const int n_out = has_out + has_out2;
   const size_t b_tile = static_cast<size_t>(NT) * 128;
   const size_t w_res = static_cast<size_t>(n_planes) * 3 * kp.NC * b_tile;
-  bool resident = (kp.n_ntiles == 1) && (NT <= 128) &&
-                  (fixed + w_res + 4 * static_cast<size_t>(kATileBytes) <= static_cast<size_t>(max_smem));
-  const size_t stage_bytes = kATileBytes + (resident ? 0 : b_tile);
-  const size_t avail = static_cast<size_t>(max_smem) - fixed - (resident ? w_res : 0);
-  int stages = static_cast<int>(avail / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  BP_REQUIRE(stages >= 2, "bpb_conv3_tc: not enough shared memory for F=%d planes=%d", F, n_planes);
-  kp.stages = stages;
-  const size_t smem_bytes = fixed + (resident ? w_res : 0) + stages * stage_bytes;
+  const size_t fixed = 1024 /*align slack*/ + static_cast<size_t>(F) * 4 +
+                       (2 * kMaxStages + 8 + 2 * kMaxRStages + 1) * 8 + 16;
+  const bool can_reside = (kp.n_ntiles == 1) && (NT <= 128);
 
-  CUtensorMap maps[7];
-  memset(maps, 0, sizeof(maps));
+  bool halo = false, resident = false;
+  int stages = 0, rstages = 0, nstg = 0;
+  size_t stage_bytes = 0;
+  int box_rows = 0;
+  auto try_plan = [&](bool want_halo, bool want_res, int want_nstg, int want_rst, int min_stages) {
+    const bool ring_resid = kp.has_resid && !(want_halo && is_fwd);
+    size_t used = fixed + (want_res ? w_res : 0) +
+                  static_cast<size_t>(want_nstg) * n_out * n_planes * kTileBytes +
+                  (ring_resid ? static_cast<size_t>(want_rst) * n_planes * kTileBytes : 0);
+    if (used >= static_cast<size_t>(max_smem)) return false;
+    size_t sb;
+    int rows = 0;
+    if (want_halo) {
+      rows = kTileM + span;
+      sb = static_cast<size_t>(kp.NC) * n_planes * ((static_cast<size_t>(rows) * 128 + 1023) / 1024 * 1024);
+    } else {
+      sb = kTileBytes + (want_res ? 0 : b_tile);
+    }
+    int st = static_cast<int>((static_cast<size_t>(max_smem) - used) / sb);
+    if (st > kMaxStages) st = kMaxStages;
+    if (want_halo && st > 6) st = 6;
+    if (st < min_stages) return false;
+    halo = want_halo; resident = want_res; nstg = want_nstg; rstages = ring_resid ? want_rst : 0;
+    stages = st; stage_bytes = sb; box_rows = rows;
+    return true;
+  };
+  const bool halo_ok = can_reside && span <= 128 && span > 0 && kTileM + span <= 256;
+  bool planned = false;
+  if (halo_ok) planned = try_plan(true, true, 2, 3, 3) || try_plan(true, true, 2, 2, 2);
+  if (!planned && can_reside)
+    planned = try_plan(false, true, 2, 3, 4) || try_plan(false, true, 1, 2, 3);
+  if (!planned) planned = try_plan(false, false, 2, 3, 3) || try_plan(false, false, 1, 2, 2);
+  BP_REQUIRE(planned, "bpb_conv3_tc: not enough shared memory for F=%d planes=%d", F, n_planes);
+  kp.stages = stages;
+  kp.rstages = rstages > 0 ? rstages : 1;
+  kp.nstg = nstg;
+  if (halo) {
+    kp.box_off = min_off;
+    kp.box_bytes = box_rows * 128;
+    kp.sub_bytes = (kp.box_bytes + 1023) / 1024 * 1024;
+    for (int j = 0; j < 3; ++j) kp.tap_row[j] = a->tap_off[j] - min_off;
+    kp.resid_row = a->resid_off - min_off;
+    if (is_fwd && kp.has_resid) {
+      BP_REQUIRE(a->resid_hi == a->in_hi && a->resid_lo == a->in_lo && kp.resid_row >= 0 &&
+                     kp.resid_row <= span,
+                 "bpb_conv3_tc: forward residual must be the input tensor at an offset inside the taps");
+    }
+  } else {
+    for (int j = 0; j < 3; ++j) kp.tap_row[j] = a->tap_off[j];
+  }
+  const size_t smem_bytes = fixed + (resident ? w_res : 0) + stages * stage_bytes +
+                            static_cast<size_t>(nstg) * n_out * n_planes * kTileBytes +
+                            static_cast<size_t>(rstages) * n_planes * kTileBytes;
+
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
   const uint64_t wrows = static_cast<uint64_t>(3) * F;
-  if (!make_tmap_3d(&maps[0], a->in_hi, F, a->L_in, a->B, 64, kTileM)) return 3;
-  if (n_planes == 2 && !make_tmap_3d(&maps[1], a->in_lo, F, a->L_in, a->B, 64, kTileM)) return 3;
-  // Weights: planes are separate allocations; the kernel addresses plane wp at row offset
-  // wp*3*F, so the hi/lo planes must be contiguous when both are used.
+  const uint32_t a_box = halo ? static_cast<uint32_t>(box_rows) : kTileM;
+  if (!make_tmap_3d(&maps.A[0], a->in_hi, F, a->L_in, a->B, 64, a_box)) return 3;
+  if (n_planes == 2 && !make_tmap_3d(&maps.A[1], a->in_lo, F, a->L_in, a->B, 64, a_box)) return 3;
+  // Weights: the kernel addresses plane wp at row offset wp*3*F, so the hi/lo planes must be
+  // contiguous when both are used.
   if (n_planes == 2)
     BP_REQUIRE(a->w_lo == a->w_hi + static_cast<size_t>(3) * F * F,
                "bpb_conv3_tc: w_lo must directly follow w_hi in memory");
-  if (!make_tmap_2d(&maps[2], a->w_hi, F, wrows * n_planes, 64, NT)) return 3;
+  if (!make_tmap_2d(&maps.W, a->w_hi, F, wrows * n_planes, 64, NT)) return 3;
   if (has_out) {
-    if (!make_tmap_3d(&maps[3], a->out_hi, F, a->L_out, a->B, 64, kTileM)) return 3;
-    if (n_planes == 2 && !make_tmap_3d(&maps[4], a->out_lo, F, a->L_out, a->B, 64, kTileM)) return 3;
+    if (!make_tmap_3d(&maps.O[0], a->out_hi, F, a->L_out, a->B, 64, kTileM)) return 3;
+    if (n_planes == 2 && !make_tmap_3d(&maps.O[1], a->out_lo, F, a->L_out, a->B, 64, kTileM)) return 3;
   }
   if (has_out2) {
-    if (!make_tmap_3d(&maps[5], a->out2_hi, F, a->L_out, a->B, 64, kTileM)) return 3;
-    if (n_planes == 2 && !make_tmap_3d(&maps[6], a->out2_lo, F, a->L_out, a->B, 64, kTileM)) return 3;
+    if (!make_tmap_3d(&maps.P[0], a->out2_hi, F, a->L_out, a->B, 64, kTileM)) return 3;
+    if (n_planes == 2 && !make_tmap_3d(&maps.P[1], a->out2_lo, F, a->L_out, a->B, 64, kTileM)) return 3;
+  }
+  if (kp.has_resid && rstages > 0) {
+    BP_REQUIRE(a->L_res > 0, "bpb_conv3_tc: L_res must be given with resid");
+    if (!make_tmap_3d(&maps.R[0], a->resid_hi, F, a->L_res, a->B, 64, kTileM)) return 3;
+    if (n_planes == 2 && !make_tmap_3d(&maps.R[1], a->resid_lo, F, a->L_res, a->B, 64, kTileM)) return 3;
   }
 
   const int total_tiles = kp.B * kp.tiles_per_seq * kp.n_ntiles;
   int grid = sm_count();
   if (grid > total_tiles) grid = total_tiles;
 
-  if (NT == 64) {
-    return resident ? launch_conv3<64, true>(maps, kp, smem_bytes, grid, stream)
-                    : launch_conv3<64, false>(maps, kp, smem_bytes, grid, stream);
-  } else if (NT == 128) {
-    return resident ? launch_conv3<128, true>(maps, kp, smem_bytes, grid, stream)
-                    : launch_conv3<128, false>(maps, kp, smem_bytes, grid, stream);
+  switch (epi) {
+    case EPI_FWD:
+      return dispatch_planes<EPI_FWD>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
+    case EPI_FWD_Z:
+      return dispatch_planes<EPI_FWD_Z>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
+    case EPI_FWD_R:
+      return dispatch_planes<EPI_FWD_R>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
+    case EPI_BWD_MASK:
+      return dispatch_planes<EPI_BWD_MASK>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
+    default:
+      return dispatch_planes<EPI_BWD_MULT>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
   }
-  return launch_conv3<256, false>(maps, kp, smem_bytes, grid, stream);
 }

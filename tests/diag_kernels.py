@@ -60,7 +60,8 @@ def group_conv_fwd(cases=None):
     ok = True
     cases = cases or [(3, 300, 64, 2, False), (2, 1100, 64, 64, False), (2, 700, 128, 8, False),
                       (1, 600, 256, 4, False), (2, 300, 64, 4, True), (1, 700, 128, 16, True),
-                      (2, 52, 64, 2, False), (1, 500, 192, 2, False)]
+                      (2, 52, 64, 2, False), (1, 500, 192, 2, False), (2, 1200, 64, 256, False),
+                      (2, 900, 64, 128, True), (3, 3066, 64, 2, False), (2, 700, 128, 128, False)]
     for (B, L, Fn, d, precise) in cases:
         print(f"conv fwd B={B} L={L} F={Fn} d={d} precise={precise}", flush=True)
         g = torch.Generator(device="cpu").manual_seed(1)
@@ -94,7 +95,12 @@ def group_conv_bwd():
     for (B, L_out_f, Fn, d, precise, use_mult) in [(3, 300, 64, 2, False, False),
                                                    (2, 900, 64, 128, False, True),
                                                    (2, 400, 128, 8, True, False),
-                                                   (1, 300, 256, 4, False, False)]:
+                                                   (1, 300, 256, 4, False, False),
+                                                   (2, 300, 64, 4, True, True),
+                                                   (3, 1000, 64, 32, False, False),
+                                                   (2, 500, 64, 64, False, False),
+                                                   (2, 1022, 64, 512, False, False),
+                                                   (2, 300, 128, 16, False, True)]:
         # gz has length L_out_f (forward output), result has length L_out_f + 2d
         print(f"conv bwd B={B} Lg={L_out_f} F={Fn} d={d} precise={precise} mult={use_mult}",
               flush=True)
