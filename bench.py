@@ -343,4 +343,14 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception:
+        # a pipeline watchdog trap leaves its culprit in the host-mapped debug buffer
+        try:
+            from bpreveal_b200 import _lib
+            for rec in _lib.debug_dump():
+                print("watchdog: tag=0x%x block=%d thread=%d parity=%d tile=%d" % rec, file=sys.stderr)
+        except Exception:  # noqa: BLE001
+            pass
+        raise

@@ -65,6 +65,7 @@ SIGNATURES = {
     "bpb_version": (c_int, []),
     "bpb_last_error": (C.c_char_p, []),
     "bpb_device_info": (c_int, [C.POINTER(c_int)] * 3),
+    "bpb_debug_dump": (c_int, [C.POINTER(C.c_uint), c_int]),
     "bpb_conv3_tc": (c_int, [C.POINTER(Conv3Args), c_void_p]),
     "bpb_wgrad3_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "bpb_wgrad3_tc": (c_int, [C.POINTER(Wgrad3Args), c_void_p]),
@@ -119,6 +120,15 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def debug_dump():
+    """Watchdog records of timed-out pipeline waits: (tag, block, thread, parity, payload)."""
+    buf = (C.c_uint * 2048)()
+    n = load().bpb_debug_dump(buf, 2048)
+    if n == 0 or buf[0] == 0:
+        return []
+    return [tuple(buf[8 + 5 * i:13 + 5 * i]) for i in range(min(int(buf[0]), 400))]
 
 
 def check(rc, what):

@@ -37,6 +37,28 @@ static DevInfo& devinfo() {
 int sm_count() { return devinfo().sms; }
 int max_smem_optin() { return devinfo().smem; }
 
+static unsigned* g_dbg_host = nullptr;
+static unsigned* g_dbg_dev = nullptr;
+unsigned* debug_buffer() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 2048 * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    memset(h, 0, 2048 * sizeof(unsigned));
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    g_dbg_host = static_cast<unsigned*>(h);
+    g_dbg_dev = static_cast<unsigned*>(d);
+  });
+  return g_dbg_dev;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -107,6 +129,13 @@ extern "C" {
 int bpb_version(void) { return 1; }
 
 const char* bpb_last_error(void) { return bp::g_err; }
+
+int bpb_debug_dump(unsigned* out, int n) {
+  if (bp::g_dbg_host == nullptr) return 0;
+  if (n > 2048) n = 2048;
+  for (int i = 0; i < n; ++i) out[i] = bp::g_dbg_host[i];
+  return n;
+}
 
 int bpb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   bp::DevInfo& d = bp::devinfo();

@@ -15,6 +15,8 @@ namespace bp {
 void set_error(const char* fmt, ...);
 int sm_count();
 int max_smem_optin();
+// Device pointer of the 2048-word host-mapped watchdog buffer (nullptr if it cannot be allocated).
+unsigned* debug_buffer();
 
 // 3-D bf16 tensor [d2][d1][d0] (d0 innermost, contiguous), box [1][box1][64], 128B swizzle.
 bool make_tmap_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,

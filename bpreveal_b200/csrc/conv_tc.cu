@@ -28,19 +28,21 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace bp {
 
 constexpr int kTileM = 128;
 constexpr int kTileBytes = kTileM * 128;  // [128 x 64] bf16
 constexpr int kMaxStages = 12;
 constexpr int kMaxRStages = 4;
-constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
 
 enum { EPI_FWD = 0, EPI_FWD_Z = 1, EPI_FWD_R = 2, EPI_BWD_MASK = 3, EPI_BWD_MULT = 4 };
 
 struct ConvKParams {
   int B, L_out, tiles_per_seq, n_ntiles, NC, F;
+  int step_b, step_mt, step_nt;  // gridDim.x tiles expressed as (sequences, M tiles, N tiles)
   int tap_row[3];  // SLAB: row offset of tap j relative to t0; HALO: row of tap j inside the box
   int box_off;     // HALO: first box row = t0 + box_off
   int sub_bytes;   // HALO: bytes of one (chunk, plane) box, padded to 1024
@@ -48,13 +50,15 @@ struct ConvKParams {
   int stages, rstages, nstg;
   int resid_off, resid_row;  // residual tile = rows t0 + resid_off (resid_row: inside the box)
   int zx_div;
-  int has_out, has_out2, has_resid;
+  int has_out, has_out2;
+  int epi_groups, ring_resid;
   const float* bias;
   const __nv_bfloat16 *mult_hi, *mult_lo;
   const uint32_t* mask_in;
   uint32_t* mask_out;
   const float* zx_in;
   float* z_out;
+  unsigned* dbg;
 };
 
 struct ConvMaps {
@@ -93,8 +97,50 @@ __device__ __forceinline__ void sts128(uint8_t* p, const uint4& v) {
                : "memory");
 }
 
-template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO>
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(smem_u32(p)));
+  return v;
+}
+// 1.0f where v > 0 else 0.0f (one FSET.BF on the ALU pipe).  The ReLU, the residual add and the
+// mask-bit accumulation then run on the FMA pipes: relu(v) + r == fma(v, flag, r) for finite v, and
+// the 32 mask bits are summed as flag * 2^k in two fp32 accumulators (16 bits each, exact).
+__device__ __forceinline__ float gt0_flag(float v) {
+  float f;
+  asm("set.gt.f32.f32 %0, %1, 0f00000000;" : "=f"(f) : "f"(v));
+  return f;
+}
+
+// Persistent tile walk without per-tile integer divisions: tile = (b, mt, nt), nt fastest,
+// advanced by gridDim.x tiles per iteration.
+struct TileWalk {
+  int b, mt, nt;
+  __device__ __forceinline__ void init(const ConvKParams& p) {
+    const int tile = blockIdx.x;
+    nt = tile % p.n_ntiles;
+    mt = (tile / p.n_ntiles) % p.tiles_per_seq;
+    b = tile / (p.n_ntiles * p.tiles_per_seq);
+  }
+  __device__ __forceinline__ void next(const ConvKParams& p) {
+    nt += p.step_nt;
+    if (nt >= p.n_ntiles) { nt -= p.n_ntiles; ++mt; }
+    mt += p.step_mt;
+    if (mt >= p.tiles_per_seq) { mt -= p.tiles_per_seq; ++b; }
+    b += p.step_b;
+  }
+};
+
+// ring index += n (mod size), flipping the phase bit at every wrap
+__device__ __forceinline__ void ring_advance(uint32_t& idx, uint32_t& phase, uint32_t n,
+                                             uint32_t size) {
+  idx += n;
+  while (idx >= size) { idx -= size; phase ^= 1; }
+}
+
+template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG>
+__global__ void __launch_bounds__(64 + kEpiThreads * EG, 1)
 conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   constexpr int ACC = (NT <= 128) ? 4 : 2;
   constexpr int NCH = NT / 64;
@@ -122,7 +168,7 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   uint8_t* stg = ring + static_cast<size_t>(p.stages) * stage_bytes;
   uint8_t* rring = stg + static_cast<size_t>(p.nstg) * stg_bytes;
   float* s_bias = reinterpret_cast<float*>(
-      rring + ((RING_RESID && p.has_resid) ? static_cast<size_t>(p.rstages) * rstage_bytes : 0));
+      rring + (RING_RESID ? static_cast<size_t>(p.rstages) * rstage_bytes : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + p.F);
   uint64_t* full = bars;
   uint64_t* empty = full + kMaxStages;
@@ -135,7 +181,6 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.B * p.tiles_per_seq * p.n_ntiles;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm.A[0]);
@@ -143,11 +188,11 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     if (PLANES == 2) tma_prefetch_desc(&tm.A[1]);
     if (p.has_out) tma_prefetch_desc(&tm.O[0]);
     if (p.has_out2) tma_prefetch_desc(&tm.P[0]);
-    if (RING_RESID && p.has_resid) tma_prefetch_desc(&tm.R[0]);
+    if (RING_RESID) tma_prefetch_desc(&tm.R[0]);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full[i], 1);
       // HALO forward: the box is released by the MMA commit AND by the 8 epilogue warps
-      mbar_init(&empty[i], (HALO && IS_FWD && p.has_resid) ? 9 : 1);
+      mbar_init(&empty[i], (HALO && IS_FWD) ? 9 : 1);
     }
     for (int i = 0; i < ACC; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -178,14 +223,13 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               tma_load_2d(&tm.W, w_smem + static_cast<size_t>((wp * 3 + j) * p.NC + c) * B_TILE_BYTES,
                           w_full, c * 64, (wp * 3 + j) * p.F);
       }
-      uint32_t stage = 0, phase = 0, rs = 0, rphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_ntiles;
-        const int mt = (tile / p.n_ntiles) % p.tiles_per_seq;
-        const int b = tile / (p.n_ntiles * p.tiles_per_seq);
-        const int t0 = mt * kTileM;
+      uint32_t stage = 0, phase = 0, rs = 0, rphase = 0, ntile = 0;
+      TileWalk tw;
+      for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
+        const int nt = tw.nt, b = tw.b;
+        const int t0 = tw.mt * kTileM;
         if (HALO) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
           mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.NC * PLANES * p.box_bytes));
           uint8_t* dst = ring + static_cast<size_t>(stage) * stage_bytes;
           for (int c = 0; c < p.NC; ++c)
@@ -199,7 +243,7 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             const int pass = step % NPASS;
             const int c = (step / NPASS) % p.NC;
             const int j = step / (NPASS * p.NC);
-            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
             mbar_expect_tx(&full[stage], SLAB_BYTES);
             uint8_t* dst = ring + static_cast<size_t>(stage) * SLAB_BYTES;
             tma_load_3d(&tm.A[pass == 1 ? 1 : 0], dst, &full[stage], c * 64, t0 + p.tap_row[j], b);
@@ -211,9 +255,9 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
           }
         }
-        if (RING_RESID && p.has_resid) {
+        if (RING_RESID) {
           for (int ch = 0; ch < NCH; ++ch) {
-            mbar_wait(&rempty[rs], rphase ^ 1);
+            mbar_wait_wd(&rempty[rs], rphase ^ 1, p.dbg, 0x200 + rs, ntile);
             mbar_expect_tx(&rfull[rs], static_cast<uint32_t>(rstage_bytes));
             uint8_t* dst = rring + static_cast<size_t>(rs) * rstage_bytes;
             for (int pl = 0; pl < PLANES; ++pl)
@@ -227,14 +271,15 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
     if (elect_one()) {
-      if (RESIDENT) mbar_wait(w_full, 0);
-      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[as], aphase ^ 1);
+      if (RESIDENT) mbar_wait_wd(w_full, 0, p.dbg, 0x300);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0, ntile = 0;
+      TileWalk tw;
+      for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
+        mbar_wait_wd(&acc_empty[as], aphase ^ 1, p.dbg, 0x400 + as, ntile);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * NT;
         if (HALO) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
           tc_fence_after();
           const uint32_t base = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
           uint32_t accum = 0;
@@ -260,7 +305,7 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             const int pass = step % NPASS;
             const int c = (step / NPASS) % p.NC;
             const int j = step / (NPASS * p.NC);
-            mbar_wait(&full[stage], phase);
+            mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * SLAB_BYTES);
             uint32_t b_addr;
@@ -283,18 +328,30 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       }
     }
   } else {
-    // ------------------------------------------------------------- epilogue warps (2..9)
+    // ------------------------------------------------------------- epilogue warps (2..)
+    // EG groups of 8 warps; group g owns this CTA's tiles g, g + EG, ... (its own staging buffer
+    // and named barrier), so one group's stores / barrier waits overlap the other's math.
+    const int grp = (warp - 2) >> 3;
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = ((warp - 2) >> 2) & 1;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;
+    const int et = threadIdx.x - 64 - grp * kEpiThreads;
+    const int bar_id = 1 + grp;
     const int chunks_per_row = p.F >> 6;
     uint32_t as = 0, aphase = 0, rs = 0, rphase = 0, hs = 0, hphase = 0, kc = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_ntiles;
-      const int mt = (tile / p.n_ntiles) % p.tiles_per_seq;
-      const int b = tile / (p.n_ntiles * p.tiles_per_seq);
-      const int t0 = mt * kTileM;
+    TileWalk tw;
+    tw.init(p);
+    if (EG == 2 && grp == 1 && tw.b < p.B) {
+      tw.next(p);
+      ring_advance(as, aphase, 1, ACC);
+      ring_advance(rs, rphase, NCH, p.rstages);
+      ring_advance(hs, hphase, 1, p.stages);
+    }
+    uint32_t ntile = grp;
+    for (; tw.b < p.B; tw.next(p), ntile += EG) {
+      const int nt = tw.nt, b = tw.b;
+      const int t0 = tw.mt * kTileM;
+      const int bz = (EPI == EPI_FWD_R) ? b / p.zx_div : 0;
       const int t = t0 + row;
       const bool valid = t < p.L_out;
       const size_t orow = static_cast<size_t>(b) * p.L_out + t;
@@ -309,9 +366,9 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
 
         // ---- residual (already in shared memory: HALO box or residual ring)
         uint4 rr[4], rl[4];
-        if (p.has_resid) {
+        {
           if (RING_RESID) {
-            mbar_wait(&rfull[rs], rphase);
+            mbar_wait_wd(&rfull[rs], rphase, p.dbg, 0x600 + rs, ntile);
             const uint8_t* src = rring + static_cast<size_t>(rs) * rstage_bytes;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -320,9 +377,9 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&rempty[rs]);
-            if (++rs == static_cast<uint32_t>(p.rstages)) { rs = 0; rphase ^= 1; }
+            ring_advance(rs, rphase, 1, p.rstages);
           } else {
-            if (ch == 0) mbar_wait(&full[hs], hphase);
+            if (ch == 0) mbar_wait_wd(&full[hs], hphase, p.dbg, 0x700 + hs, ntile);
             // n_ntiles == 1 in HALO mode, so the chunk index is the channel-chunk index
             const uint8_t* src = ring + static_cast<size_t>(hs) * stage_bytes +
                                  static_cast<size_t>(ch * PLANES) * p.sub_bytes;
@@ -335,14 +392,14 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             if (ch == NCH - 1) {
               __syncwarp();
               if (lane == 0) mbar_arrive(&empty[hs]);
-              if (++hs == static_cast<uint32_t>(p.stages)) { hs = 0; hphase ^= 1; }
+              ring_advance(hs, hphase, EG, p.stages);
             }
           }
         }
 
         // ---- accumulator
         if (ch == 0) {
-          mbar_wait(&acc_full[as], aphase);
+          mbar_wait_wd(&acc_full[as], aphase, p.dbg, 0x800 + as, ntile);
           tc_fence_after();
         }
         uint32_t acc[32];
@@ -355,36 +412,32 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
 
-        uint8_t* sb = stg + static_cast<size_t>(p.nstg == 2 ? (kc & 1) : 0) * stg_bytes;
+        const bool one_buf = (EG == 2) || p.nstg == 1;  // one staging buffer per writer group
+        uint8_t* sb = stg + static_cast<size_t>(EG == 2 ? grp : (p.nstg == 2 ? (kc & 1) : 0)) * stg_bytes;
         uint8_t* sb2 = sb + static_cast<size_t>(p.has_out * PLANES) * kTileBytes;
-        if (p.nstg == 1) {
+        if (one_buf) {
           // single staging buffer: the previous chunk's stores must have read it
           if (et == 0) tma_store_wait_read<0>();
-          named_bar_sync(1, kEpiThreads);
+          named_bar_sync(bar_id, kEpiThreads);
         }
 
-        uint32_t obits = 0u;
+        float obits_lo = 0.f, obits_hi = 0.f;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float v[8], r[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]);
-          if (p.has_resid) {
-            unpack8(rr[g], r);
-            if (PLANES == 2) {
-              float r2[8];
-              unpack8(rl[g], r2);
+          unpack8(rr[g], r);
+          if (PLANES == 2) {
+            float r2[8];
+            unpack8(rl[g], r2);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) r[i] += r2[i];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = 0.f;
+            for (int i = 0; i < 8; ++i) r[i] += r2[i];
           }
           float o[8], o2[8];
           if (IS_FWD) {
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + half * 32 + g * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + half * 32 + g * 8 + 4);
+            const float4 b0 = lds_f4(s_bias + n0 + half * 32 + g * 8);
+            const float4 b1 = lds_f4(s_bias + n0 + half * 32 + g * 8 + 4);
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             if (EPI == EPI_FWD_R) {
@@ -393,7 +446,7 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               float zx[8];
               if (valid) {
                 const float4* zp = reinterpret_cast<const float4*>(
-                    p.zx_in + (static_cast<size_t>(b / p.zx_div) * p.L_out + t) * p.F + n0 +
+                    p.zx_in + (static_cast<size_t>(bz) * p.L_out + t) * p.F + n0 +
                     half * 32 + g * 8);
                 const float4 z0 = __ldg(zp), z1 = __ldg(zp + 1);
                 zx[0] = z0.x; zx[1] = z0.y; zx[2] = z0.z; zx[3] = z0.w;
@@ -418,8 +471,10 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (v[i] > 0.f) obits |= 1u << (g * 8 + i);
-              o[i] = fmaxf(v[i], 0.f) + r[i];
+              const float flag = gt0_flag(v[i]);
+              if (g < 2) obits_lo = fmaf(flag, static_cast<float>(1u << (g * 8 + i)), obits_lo);
+              else obits_hi = fmaf(flag, static_cast<float>(1u << (g * 8 + i - 16)), obits_hi);
+              o[i] = fmaf(v[i], flag, r[i]);
             }
           } else {
 #pragma unroll
@@ -469,12 +524,13 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           }
         }
         if (IS_FWD && p.mask_out != nullptr && valid)
-          p.mask_out[(orow * chunks_per_row + (n0 >> 6)) * 2 + half] = obits;
+          p.mask_out[(orow * chunks_per_row + (n0 >> 6)) * 2 + half] =
+              static_cast<uint32_t>(obits_lo) | (static_cast<uint32_t>(obits_hi) << 16);
 
         // ---- publish: generic-proxy writes -> async proxy, one barrier, one thread stores
         fence_proxy_async();
-        if (p.nstg == 2 && et == 0) tma_store_wait_read<0>();  // buffer of chunk kc-1 is free again
-        named_bar_sync(1, kEpiThreads);
+        if (!one_buf && et == 0) tma_store_wait_read<0>();  // buffer of chunk kc-1 is free again
+        named_bar_sync(bar_id, kEpiThreads);
         if (et == 0) {
           if (p.has_out) {
             tma_store_3d(&tm.O[0], sb, n0, t0, b);
@@ -487,7 +543,12 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           tma_store_commit();
         }
       }
-      if (++as == ACC) { as = 0; aphase ^= 1; }
+      ring_advance(as, aphase, EG, ACC);
+      if (EG == 2) {
+        // skip the other group's tile
+        tw.next(p);
+        if (RING_RESID) ring_advance(rs, rphase, NCH, p.rstages);
+      }
     }
     if (et == 0) tma_store_wait_all<0>();
   }
@@ -500,17 +561,30 @@ conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
 
 template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO>
 static int launch_conv3(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
-                        cudaStream_t stream) {
-  auto kern = conv3_tc_kernel<EPI, NT, RESIDENT, PLANES, HALO>;
+                        cudaStream_t stream);
+
+template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG>
+static int launch_conv3_eg(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
+                           cudaStream_t stream) {
+  auto kern = conv3_tc_kernel<EPI, NT, RESIDENT, PLANES, HALO, EG>;
   static bool configured = false;
   if (!configured) {
     BP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        max_smem_optin()));
     configured = true;
   }
-  kern<<<grid, kThreads, smem_bytes, stream>>>(maps, kp);
+  kern<<<grid, 64 + kEpiThreads * EG, smem_bytes, stream>>>(maps, kp);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// Two epilogue groups whenever the plan has two staging buffers (bf16 path).
+template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO>
+static int launch_conv3(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
+                        cudaStream_t stream) {
+  if (PLANES == 1 && kp.nstg == 2 && kp.epi_groups == 2 && (kp.rstages % 2 == 0 || !kp.ring_resid))
+    return launch_conv3_eg<EPI, NT, RESIDENT, 1, HALO, 2>(maps, kp, smem_bytes, grid, stream);
+  return launch_conv3_eg<EPI, NT, RESIDENT, PLANES, HALO, 1>(maps, kp, smem_bytes, grid, stream);
 }
 
 template <int EPI, int PLANES>
@@ -538,6 +612,12 @@ static int dispatch_planes(int planes, int NT, bool resident, bool halo, const C
 
 }  // namespace bp
 
+// Tuning knob (BPB_EPI_GROUPS=1|2, default 2): number of 8-warp epilogue groups on the bf16 path.
+static int g_epi_groups = [] {
+  const char* e = getenv("BPB_EPI_GROUPS");
+  return (e && e[0] == '1') ? 1 : 2;
+}();
+
 extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   using namespace bp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -547,6 +627,8 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   BP_REQUIRE(a->B > 0 && a->L_in > 0 && a->L_out > 0, "bpb_conv3_tc: bad geometry B=%d L_in=%d L_out=%d",
              a->B, a->L_in, a->L_out);
   BP_REQUIRE(a->in_hi && a->w_hi, "bpb_conv3_tc: in_hi / w_hi must not be NULL");
+  BP_REQUIRE(a->resid_hi != nullptr && a->L_res > 0,
+             "bpb_conv3_tc: the residual tensor is mandatory (models.py:97-102 always adds it)");
   BP_REQUIRE(a->mode == 0 || a->mode == 1, "bpb_conv3_tc: mode must be 0 or 1");
   const int n_planes = a->in_lo ? 2 : 1;
   if (n_planes == 2)
@@ -590,8 +672,8 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   kp.resid_off = a->resid_off;
   kp.zx_div = a->zx_div > 0 ? a->zx_div : 1;
   kp.has_out = has_out;
+  kp.epi_groups = g_epi_groups;
   kp.has_out2 = has_out2;
-  kp.has_resid = a->resid_hi ? 1 : 0;
   kp.bias = a->bias;
   kp.mult_hi = reinterpret_cast<const __nv_bfloat16*>(a->mult_hi);
   kp.mult_lo = reinterpret_cast<const __nv_bfloat16*>(a->mult_lo);
@@ -599,6 +681,7 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   kp.mask_out = reinterpret_cast<uint32_t*>(a->mask_out);
   kp.zx_in = a->zx_in;
   kp.z_out = a->z_out;
+  kp.dbg = debug_buffer();
 
   // ---- shared-memory plan
   const int max_smem = max_smem_optin();
@@ -617,12 +700,13 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
                        (2 * kMaxStages + 8 + 2 * kMaxRStages + 1) * 8 + 16;
   const bool can_reside = (kp.n_ntiles == 1) && (NT <= 128);
 
+  const bool two_groups = (n_planes == 1) && g_epi_groups == 2;
   bool halo = false, resident = false;
   int stages = 0, rstages = 0, nstg = 0;
   size_t stage_bytes = 0;
   int box_rows = 0;
   auto try_plan = [&](bool want_halo, bool want_res, int want_nstg, int want_rst, int min_stages) {
-    const bool ring_resid = kp.has_resid && !(want_halo && is_fwd);
+    const bool ring_resid = !(want_halo && is_fwd);
     size_t used = fixed + (want_res ? w_res : 0) +
                   static_cast<size_t>(want_nstg) * n_out * n_planes * kTileBytes +
                   (ring_resid ? static_cast<size_t>(want_rst) * n_planes * kTileBytes : 0);
@@ -638,20 +722,31 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
     int st = static_cast<int>((static_cast<size_t>(max_smem) - used) / sb);
     if (st > kMaxStages) st = kMaxStages;
     if (want_halo && st > 6) st = 6;
+    // same-group ownership of every HALO box slot as well (see the residual ring note below)
+    if (want_halo && two_groups && is_fwd && want_nstg == 2 && st > 2 && (st & 1)) st -= 1;
     if (st < min_stages) return false;
     halo = want_halo; resident = want_res; nstg = want_nstg; rstages = ring_resid ? want_rst : 0;
     stages = st; stage_bytes = sb; box_rows = rows;
     return true;
   };
   const bool halo_ok = can_reside && span <= 128 && span > 0 && kTileM + span <= 256;
+  // With two epilogue groups (bf16 path, two staging buffers) the residual ring must have an EVEN
+  // number of slots: a slot is then always consumed by the same group.  With an odd ring a group
+  // would skip every other phase of a slot's mbarrier, and a parity wait cannot tell "the phase I
+  // skipped is still in flight" from "my phase is complete" (observed as a rare deadlock).
+  const int r_hi = two_groups ? 4 : 3;
   bool planned = false;
-  if (halo_ok) planned = try_plan(true, true, 2, 3, 3) || try_plan(true, true, 2, 2, 2);
+  if (halo_ok) planned = try_plan(true, true, 2, r_hi, 3) || try_plan(true, true, 2, 2, 2);
   if (!planned && can_reside)
-    planned = try_plan(false, true, 2, 3, 4) || try_plan(false, true, 1, 2, 3);
-  if (!planned) planned = try_plan(false, false, 2, 3, 3) || try_plan(false, false, 1, 2, 2);
+    planned = try_plan(false, true, 2, r_hi, 4) || try_plan(false, true, 2, 2, 3) ||
+              try_plan(false, true, 1, 2, 3);
+  if (!planned)
+    planned = try_plan(false, false, 2, r_hi, 3) || try_plan(false, false, 2, 2, 2) ||
+              try_plan(false, false, 1, 2, 2);
   BP_REQUIRE(planned, "bpb_conv3_tc: not enough shared memory for F=%d planes=%d", F, n_planes);
   kp.stages = stages;
   kp.rstages = rstages > 0 ? rstages : 1;
+  kp.ring_resid = rstages > 0 ? 1 : 0;
   kp.nstg = nstg;
   if (halo) {
     kp.box_off = min_off;
@@ -659,7 +754,7 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
     kp.sub_bytes = (kp.box_bytes + 1023) / 1024 * 1024;
     for (int j = 0; j < 3; ++j) kp.tap_row[j] = a->tap_off[j] - min_off;
     kp.resid_row = a->resid_off - min_off;
-    if (is_fwd && kp.has_resid) {
+    if (is_fwd) {
       BP_REQUIRE(a->resid_hi == a->in_hi && a->resid_lo == a->in_lo && kp.resid_row >= 0 &&
                      kp.resid_row <= span,
                  "bpb_conv3_tc: forward residual must be the input tensor at an offset inside the taps");
@@ -691,8 +786,7 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
     if (!make_tmap_3d(&maps.P[0], a->out2_hi, F, a->L_out, a->B, 64, kTileM)) return 3;
     if (n_planes == 2 && !make_tmap_3d(&maps.P[1], a->out2_lo, F, a->L_out, a->B, 64, kTileM)) return 3;
   }
-  if (kp.has_resid && rstages > 0) {
-    BP_REQUIRE(a->L_res > 0, "bpb_conv3_tc: L_res must be given with resid");
+  if (rstages > 0) {
     if (!make_tmap_3d(&maps.R[0], a->resid_hi, F, a->L_res, a->B, 64, kTileM)) return 3;
     if (n_planes == 2 && !make_tmap_3d(&maps.R[1], a->resid_lo, F, a->L_res, a->B, 64, kTileM)) return 3;
   }
@@ -700,6 +794,9 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   const int total_tiles = kp.B * kp.tiles_per_seq * kp.n_ntiles;
   int grid = sm_count();
   if (grid > total_tiles) grid = total_tiles;
+  kp.step_nt = grid % kp.n_ntiles;
+  kp.step_mt = (grid / kp.n_ntiles) % kp.tiles_per_seq;
+  kp.step_b = grid / (kp.n_ntiles * kp.tiles_per_seq);
 
   switch (epi) {
     case EPI_FWD:

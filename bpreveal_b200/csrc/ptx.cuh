@@ -58,6 +58,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Watchdog variant: a wait that does not complete within ~2^24 polls (about a second) records
+// {tag, block, thread, parity, payload} in the host-mapped debug buffer, keeps polling for a while
+// so that the other stuck waiters of the grid can record too, then traps: a pipeline deadlock
+// surfaces as a launch failure with its culprits instead of a hung GPU.
+constexpr unsigned kDbgWords = 2048, kDbgRecWords = 5, kDbgMaxRecs = 400;
+static __device__ __noinline__ void mbar_timeout(unsigned* dbg, uint32_t tag, uint32_t parity,
+                                          uint32_t payload) {
+  if (dbg != nullptr) {
+    const unsigned n = atomicAdd(dbg, 1u);
+    if (n < kDbgMaxRecs) {
+      unsigned* r = dbg + 8 + n * kDbgRecWords;
+      r[0] = tag; r[1] = blockIdx.x; r[2] = threadIdx.x; r[3] = parity; r[4] = payload;
+      __threadfence_system();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, unsigned* dbg,
+                                             uint32_t tag, uint32_t payload = 0) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    ++spins;
+    if (spins == (1u << 24)) mbar_timeout(dbg, tag, parity, payload);
+    if (spins == (1u << 24) + (1u << 22)) __trap();
+  }
+}
 
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -183,23 +183,33 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-// out[i] = sum_s ws[s][i]   (fixed order)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, long long n_dw,
-                                    long long n_db, float* __restrict__ dw,
-                                    float* __restrict__ db) {
+// out[i] = sum_s ws[s][i] in a fixed order (deterministic).  One block owns 32 consecutive outputs;
+// warp w adds the splits s = w, w + 8, ... (each a coalesced 128-byte read, four independent
+// chains), then the eight warp partials are added in warp order.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, long long n_dw, long long n_db,
+                    float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float part[8][32];
   const long long n = n_dw + n_db;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int s = 0;
-    for (; s + 4 <= ksplit; s += 4) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long i = static_cast<long long>(blockIdx.x) * 32 + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < n) {
+    int s = warp;
+    for (; s + 24 < ksplit; s += 32) {
       s0 += ws[(s + 0) * n + i];
-      s1 += ws[(s + 1) * n + i];
-      s2 += ws[(s + 2) * n + i];
-      s3 += ws[(s + 3) * n + i];
+      s1 += ws[(s + 8) * n + i];
+      s2 += ws[(s + 16) * n + i];
+      s3 += ws[(s + 24) * n + i];
     }
-    for (; s < ksplit; ++s) s0 += ws[s * n + i];
-    const float tot = (s0 + s1) + (s2 + s3);
+    for (; s < ksplit; s += 8) s0 += ws[s * n + i];
+  }
+  part[warp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (warp == 0 && i < n) {
+    float tot = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) tot += part[w][lane];
     if (i < n_dw) dw[i] = tot;
     else if (db) db[i - n_dw] = tot;
   }
@@ -320,9 +330,8 @@ extern "C" int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream_) {
 
   const long long n_dw = static_cast<long long>(3) * a->F * a->F;
   const long long n_db = a->F;
-  const int threads = 256;
-  const int blocks = static_cast<int>((n_dw + n_db + threads - 1) / threads);
-  wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(a->ws, pl.ksplit, n_dw, n_db, a->dw, a->db);
+  const int blocks = static_cast<int>((n_dw + n_db + 31) / 32);
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(a->ws, pl.ksplit, n_dw, n_db, a->dw, a->db);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

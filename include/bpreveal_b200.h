@@ -32,6 +32,11 @@ int bpb_version(void);
 const char* bpb_last_error(void);
 /* Fills SM count and compute capability of the current device. */
 int bpb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Pipeline watchdog: kernels whose mbarrier waits time out record
+ * records in a host-mapped buffer and trap.  Copies up to n (<= 2048) words: word 0 = number of
+ * timed-out waits, words 8.. = records of 5 words {tag, block, thread, parity, payload}.
+ * Returns the number of words copied (host_out is a HOST pointer). */
+int bpb_debug_dump(unsigned* host_out, int n);
 
 /* ------------------------------------------------------------------------------------------
  * K2/K6/K8: width-3 dilated convolution as a tcgen05 implicit GEMM (M = positions, N = F,

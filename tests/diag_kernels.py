@@ -338,10 +338,16 @@ def group_bench():
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
+            # device time: replay a CUDA graph of 20 launches (host-side launch cost excluded)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(20):
+                    fn()
+            gr.replay()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(20):
-                fn()
+            gr.replay()
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / 20 * 1e3
@@ -352,9 +358,53 @@ def group_bench():
     return True
 
 
+def group_stress():
+    """Every C1 tower layer shape, forward and backward, many launches (races show up here)."""
+    B, Fn = 64, 64
+    L = 3066
+    for i in range(9):
+        d = 2 ** (i + 1)
+        L_out = L - 2 * d
+        x = torch.randn((B, L, Fn), device=dev)
+        w = torch.randn((3, Fn, Fn), device=dev) / 14
+        xin = split(x, False)
+        fwd, bwd = prep_w(w, Fn, False)
+        out = ops.new_planes(B, L_out, Fn, False, dev)
+        mask = torch.zeros((B, L_out, 1), dtype=torch.int64, device=dev)
+        bias = torch.zeros((Fn,), device=dev)
+        gin = ops.new_planes(B, L, Fn, False, dev)
+        gz2 = ops.new_planes(B, L, Fn, False, dev)
+        mask_in = torch.zeros((B, L, 1), dtype=torch.int64, device=dev)
+        def f_fwd():
+            ops.conv3(xin, fwd, (0, d, 2 * d), 0, L_out, bias=bias, resid=xin, resid_off=d,
+                      out=out, mask_out=mask)
+
+        def f_bwd():
+            ops.conv3(out, bwd, (0, -d, -2 * d), 1, L, resid=out, resid_off=-d,
+                      out=gin, out2=gz2, mask_in=mask_in)
+
+        def f_bwd0():
+            ops.conv3(out, bwd, (0, -d, -2 * d), 1, L, resid=out, resid_off=-d,
+                      out=None, out2=gz2, mask_in=mask_in)
+
+        for name, fn in (("fwd", f_fwd), ("bwd", f_bwd), ("bwd-noout", f_bwd0)):
+            fn()
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(20):
+                    fn()
+            for _ in range(10):
+                gr.replay()
+            torch.cuda.synchronize()
+            print(f"layer {i} d={d} {name} ok", flush=True)
+        L = L_out
+    return True
+
+
 if __name__ == "__main__":
     groups = {"conv_fwd": group_conv_fwd, "conv_bwd": group_conv_bwd, "wgrad": group_wgrad,
-              "edges": group_edges, "bench": group_bench}
+              "edges": group_edges, "bench": group_bench, "stress": group_stress}
     allok = True
     for name in sys.argv[1:]:
         print(f"=== {name}", flush=True)
