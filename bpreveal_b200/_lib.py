@@ -52,11 +52,20 @@ class Wgrad3Args(C.Structure):
 class InputConvArgs(C.Structure):
     _fields_ = [
         ("B", c_int), ("L_in", c_int), ("L_out", c_int), ("W", c_int), ("Fw", c_int), ("F", c_int),
-        ("x", c_void_p), ("w", c_void_p), ("bias", c_void_p),
+        ("x8", c_void_p), ("w_op", c_void_p), ("w_planes", c_int), ("bias", c_void_p),
         ("out_hi", c_void_p), ("out_lo", c_void_p),
         ("mask_out", c_void_p), ("z_out", c_void_p),
         ("zx_in", c_void_p), ("zx_div", c_int),
         ("mult_hi", c_void_p), ("mult_lo", c_void_p),
+    ]
+
+
+class HeadsDgradArgs(C.Structure):
+    _fields_ = [
+        ("B", c_int), ("L_in", c_int), ("L_out", c_int), ("W", c_int), ("F", c_int), ("Cp", c_int),
+        ("d8_hi", c_void_p), ("d8_lo", c_void_p), ("w_op", c_void_p),
+        ("g_hi", c_void_p), ("g_lo", c_void_p), ("gz_hi", c_void_p), ("gz_lo", c_void_p),
+        ("mask_in", c_void_p), ("mult_hi", c_void_p), ("mult_lo", c_void_p),
     ]
 
 
@@ -69,7 +78,16 @@ SIGNATURES = {
     "bpb_conv3_tc": (c_int, [C.POINTER(Conv3Args), c_void_p]),
     "bpb_wgrad3_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "bpb_wgrad3_tc": (c_int, [C.POINTER(Wgrad3Args), c_void_p]),
+    "bpb_onehot_expand": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "bpb_input_conv_wop_elems": (c_ll, [c_int, c_int, c_int]),
+    "bpb_prep_input_conv_weights": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                            c_void_p]),
     "bpb_input_conv_fwd": (c_int, [C.POINTER(InputConvArgs), c_void_p]),
+    "bpb_heads_d8_elems": (c_ll, [c_int] * 5),
+    "bpb_heads_dgrad_wop_elems": (c_ll, [c_int] * 4),
+    "bpb_heads_pack_grad": (c_int, [c_int] * 8 + [c_void_p] * 4),
+    "bpb_prep_heads_dgrad_weights": (c_int, [c_int] * 6 + [c_void_p] * 3 + [c_int, c_void_p]),
+    "bpb_heads_dgrad_tc": (c_int, [C.POINTER(HeadsDgradArgs), c_void_p]),
     "bpb_input_conv_wgrad_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "bpb_input_conv_wgrad": (c_int, [c_int] * 6 + [c_void_p] * 6 + [c_ll, c_void_p]),
     "bpb_input_conv_dgrad": (c_int, [c_int] * 6 + [c_void_p] * 5),

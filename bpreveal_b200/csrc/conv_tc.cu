@@ -1,622 +1,7 @@
-// K2 / K6 / K8: width-3 dilated convolution of the BPNet tower as a tcgen05 implicit GEMM.
-//
-// Replaces, for models.py:92-104 of the reference, the chain SpaceToBatchND -> Conv2D ->
-// BatchToSpaceND -> BiasAdd -> Relu -> StridedSlice (Cropping1D) -> AddV2 that TensorFlow runs per
-// dilated layer, its data gradient, and the DeepSHAP-rescale variant of that
-// gradient (shap.py:612-639).
-//
-// GEMM view: M = 128 consecutive positions of one sequence, N = NT output channels, K = 3 taps x
-// F input channels.  Rows outside the sequence are zero-filled by TMA, which gives the 'valid'
-// forward conv and the 'full' backward conv from the same code.
-//
-// Two operand-staging schemes:
-//   HALO   (small dilations, weights resident): ONE TMA box of 128 + span rows per tile and
-//          channel chunk; the three taps are UMMA descriptors that start at row offsets
-//          0 / d / 2d of that box (SWIZZLE_128B is a function of the absolute smem address, so a
-//          descriptor may start at any row).  Activations are read from L2 once instead of three
-//          times, and the forward residual a[t+d] is read back from the same box.
-//   SLAB   (any dilation / width): one [128 x 64] box per (tap, chunk, pass), as a classic
-//          multi-stage K pipeline; weights resident in smem when they fit, else streamed.
-//
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9
-// epilogue.  Epilogue warp w reads TMEM lane quadrant w % 4 (rows) and the column half
-// (w - 2) / 4 of each 64-channel chunk, so two warps per scheduler hide each other's latency.
-// The epilogue fuses bias / ReLU / ReLU-mask bits / crop + residual (forward) or residual
-// gradient + mask / rescale multiplier (backward) and writes bf16 planes through double-buffered
-// swizzled staging tiles and TMA stores.  Residual tiles that are not already in the HALO box
-// arrive through their own small TMA ring, so the epilogue never waits on a global load.
-#include "common.cuh"
-#include "ptx.cuh"
-
-#include <cstdlib>
-
-namespace bp {
-
-constexpr int kTileM = 128;
-constexpr int kTileBytes = kTileM * 128;  // [128 x 64] bf16
-constexpr int kMaxStages = 12;
-constexpr int kMaxRStages = 4;
-constexpr int kEpiThreads = 256;
-
-enum { EPI_FWD = 0, EPI_FWD_Z = 1, EPI_FWD_R = 2, EPI_BWD_MASK = 3, EPI_BWD_MULT = 4 };
-
-struct ConvKParams {
-  int B, L_out, tiles_per_seq, n_ntiles, NC, F;
-  int step_b, step_mt, step_nt;  // gridDim.x tiles expressed as (sequences, M tiles, N tiles)
-  int tap_row[3];  // SLAB: row offset of tap j relative to t0; HALO: row of tap j inside the box
-  int box_off;     // HALO: first box row = t0 + box_off
-  int sub_bytes;   // HALO: bytes of one (chunk, plane) box, padded to 1024
-  int box_bytes;   // HALO: bytes TMA writes per box (rows * 128)
-  int stages, rstages, nstg;
-  int resid_off, resid_row;  // residual tile = rows t0 + resid_off (resid_row: inside the box)
-  int zx_div;
-  int has_out, has_out2;
-  int epi_groups, ring_resid;
-  const float* bias;
-  const __nv_bfloat16 *mult_hi, *mult_lo;
-  const uint32_t* mask_in;
-  uint32_t* mask_out;
-  const float* zx_in;
-  float* z_out;
-  unsigned* dbg;
-};
-
-struct ConvMaps {
-  CUtensorMap A[2], W, O[2], P[2], R[2];
-};
-
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
-  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 u;
-  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
-  u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
-  return u;
-}
-// lo plane = bf16(value - float(bf16(value)))
-__device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
-  hi = pack8(f);
-  float h[8], r[8];
-  unpack8(hi, h);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = f[i] - h[i];
-  lo = pack8(r);
-}
-__device__ __forceinline__ uint4 lds128(const uint8_t* p) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "r"(smem_u32(p)));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint8_t* p, const uint4& v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y),
-               "r"(v.z), "r"(v.w)
-               : "memory");
-}
-
-__device__ __forceinline__ float4 lds_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(smem_u32(p)));
-  return v;
-}
-// 1.0f where v > 0 else 0.0f (one FSET.BF on the ALU pipe).  The ReLU, the residual add and the
-// mask-bit accumulation then run on the FMA pipes: relu(v) + r == fma(v, flag, r) for finite v, and
-// the 32 mask bits are summed as flag * 2^k in two fp32 accumulators (16 bits each, exact).
-__device__ __forceinline__ float gt0_flag(float v) {
-  float f;
-  asm("set.gt.f32.f32 %0, %1, 0f00000000;" : "=f"(f) : "f"(v));
-  return f;
-}
-
-// Persistent tile walk without per-tile integer divisions: tile = (b, mt, nt), nt fastest,
-// advanced by gridDim.x tiles per iteration.
-struct TileWalk {
-  int b, mt, nt;
-  __device__ __forceinline__ void init(const ConvKParams& p) {
-    const int tile = blockIdx.x;
-    nt = tile % p.n_ntiles;
-    mt = (tile / p.n_ntiles) % p.tiles_per_seq;
-    b = tile / (p.n_ntiles * p.tiles_per_seq);
-  }
-  __device__ __forceinline__ void next(const ConvKParams& p) {
-    nt += p.step_nt;
-    if (nt >= p.n_ntiles) { nt -= p.n_ntiles; ++mt; }
-    mt += p.step_mt;
-    if (mt >= p.tiles_per_seq) { mt -= p.tiles_per_seq; ++b; }
-    b += p.step_b;
-  }
-};
-
-// ring index += n (mod size), flipping the phase bit at every wrap
-__device__ __forceinline__ void ring_advance(uint32_t& idx, uint32_t& phase, uint32_t n,
-                                             uint32_t size) {
-  idx += n;
-  while (idx >= size) { idx -= size; phase ^= 1; }
-}
-
-template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG>
-__global__ void __launch_bounds__(64 + kEpiThreads * EG, 1)
-conv3_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
-  constexpr int ACC = (NT <= 128) ? 4 : 2;
-  constexpr int NCH = NT / 64;
-  constexpr int NPASS = (PLANES == 2) ? 3 : 1;
-  constexpr uint32_t TMEM_COLS = ACC * NT;
-  constexpr int B_TILE_BYTES = NT * 128;
-  constexpr int SLAB_BYTES = kTileBytes + (RESIDENT ? 0 : B_TILE_BYTES);
-  constexpr uint32_t IDESC = umma_idesc_bf16(128, NT, 0, 0);
-  constexpr bool IS_FWD = (EPI <= EPI_FWD_R);
-  // the forward residual a[t + d] already sits in the HALO box
-  constexpr bool RING_RESID = !(HALO && IS_FWD);
-  static_assert(!HALO || RESIDENT, "HALO staging needs resident weights");
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-
-  const int w_tiles = RESIDENT ? PLANES * 3 * p.NC : 0;
-  const int stage_bytes = HALO ? p.NC * PLANES * p.sub_bytes : SLAB_BYTES;
-  const int n_out = p.has_out + p.has_out2;
-  const int stg_bytes = n_out * PLANES * kTileBytes;
-  const int rstage_bytes = PLANES * kTileBytes;
-  uint8_t* w_smem = smem;
-  uint8_t* ring = w_smem + static_cast<size_t>(w_tiles) * B_TILE_BYTES;
-  uint8_t* stg = ring + static_cast<size_t>(p.stages) * stage_bytes;
-  uint8_t* rring = stg + static_cast<size_t>(p.nstg) * stg_bytes;
-  float* s_bias = reinterpret_cast<float*>(
-      rring + (RING_RESID ? static_cast<size_t>(p.rstages) * rstage_bytes : 0));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + p.F);
-  uint64_t* full = bars;
-  uint64_t* empty = full + kMaxStages;
-  uint64_t* acc_full = empty + kMaxStages;
-  uint64_t* acc_empty = acc_full + 4;
-  uint64_t* rfull = acc_empty + 4;
-  uint64_t* rempty = rfull + kMaxRStages;
-  uint64_t* w_full = rempty + kMaxRStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tm.A[0]);
-    tma_prefetch_desc(&tm.W);
-    if (PLANES == 2) tma_prefetch_desc(&tm.A[1]);
-    if (p.has_out) tma_prefetch_desc(&tm.O[0]);
-    if (p.has_out2) tma_prefetch_desc(&tm.P[0]);
-    if (RING_RESID) tma_prefetch_desc(&tm.R[0]);
-    for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full[i], 1);
-      // HALO forward: the box is released by the MMA commit AND by the 8 epilogue warps
-      mbar_init(&empty[i], (HALO && IS_FWD) ? 9 : 1);
-    }
-    for (int i = 0; i < ACC; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 8);
-    }
-    for (int i = 0; i < kMaxRStages; ++i) {
-      mbar_init(&rfull[i], 1);
-      mbar_init(&rempty[i], 8);
-    }
-    mbar_init(w_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < p.F; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------- TMA producer
-    if (elect_one()) {
-      if (RESIDENT) {
-        mbar_expect_tx(w_full, static_cast<uint32_t>(w_tiles) * B_TILE_BYTES);
-        for (int wp = 0; wp < PLANES; ++wp)
-          for (int j = 0; j < 3; ++j)
-            for (int c = 0; c < p.NC; ++c)
-              tma_load_2d(&tm.W, w_smem + static_cast<size_t>((wp * 3 + j) * p.NC + c) * B_TILE_BYTES,
-                          w_full, c * 64, (wp * 3 + j) * p.F);
-      }
-      uint32_t stage = 0, phase = 0, rs = 0, rphase = 0, ntile = 0;
-      TileWalk tw;
-      for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
-        const int nt = tw.nt, b = tw.b;
-        const int t0 = tw.mt * kTileM;
-        if (HALO) {
-          mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
-          mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.NC * PLANES * p.box_bytes));
-          uint8_t* dst = ring + static_cast<size_t>(stage) * stage_bytes;
-          for (int c = 0; c < p.NC; ++c)
-            for (int pl = 0; pl < PLANES; ++pl)
-              tma_load_3d(&tm.A[pl], dst + static_cast<size_t>(c * PLANES + pl) * p.sub_bytes,
-                          &full[stage], c * 64, t0 + p.box_off, b);
-          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
-        } else {
-          const int nsteps = 3 * p.NC * NPASS;
-          for (int step = 0; step < nsteps; ++step) {
-            const int pass = step % NPASS;
-            const int c = (step / NPASS) % p.NC;
-            const int j = step / (NPASS * p.NC);
-            mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
-            mbar_expect_tx(&full[stage], SLAB_BYTES);
-            uint8_t* dst = ring + static_cast<size_t>(stage) * SLAB_BYTES;
-            tma_load_3d(&tm.A[pass == 1 ? 1 : 0], dst, &full[stage], c * 64, t0 + p.tap_row[j], b);
-            if (!RESIDENT) {
-              const int wp = (pass == 2) ? 1 : 0;
-              tma_load_2d(&tm.W, dst + kTileBytes, &full[stage], c * 64,
-                          (wp * 3 + j) * p.F + nt * NT);
-            }
-            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
-          }
-        }
-        if (RING_RESID) {
-          for (int ch = 0; ch < NCH; ++ch) {
-            mbar_wait_wd(&rempty[rs], rphase ^ 1, p.dbg, 0x200 + rs, ntile);
-            mbar_expect_tx(&rfull[rs], static_cast<uint32_t>(rstage_bytes));
-            uint8_t* dst = rring + static_cast<size_t>(rs) * rstage_bytes;
-            for (int pl = 0; pl < PLANES; ++pl)
-              tma_load_3d(&tm.R[pl], dst + pl * kTileBytes, &rfull[rs], nt * NT + ch * 64,
-                          t0 + p.resid_off, b);
-            if (++rs == static_cast<uint32_t>(p.rstages)) { rs = 0; rphase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------- MMA issuer
-    if (elect_one()) {
-      if (RESIDENT) mbar_wait_wd(w_full, 0, p.dbg, 0x300);
-      uint32_t stage = 0, phase = 0, as = 0, aphase = 0, ntile = 0;
-      TileWalk tw;
-      for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
-        mbar_wait_wd(&acc_empty[as], aphase ^ 1, p.dbg, 0x400 + as, ntile);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * NT;
-        if (HALO) {
-          mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
-          tc_fence_after();
-          const uint32_t base = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
-          uint32_t accum = 0;
-          for (int pass = 0; pass < NPASS; ++pass)
-            for (int c = 0; c < p.NC; ++c)
-              for (int j = 0; j < 3; ++j) {
-                const uint32_t a_addr = base + (c * PLANES + (pass == 1 ? 1 : 0)) * p.sub_bytes +
-                                        p.tap_row[j] * 128;
-                const uint32_t b_addr =
-                    smem_u32(w_smem) + (((pass == 2 ? 1 : 0) * 3 + j) * p.NC + c) * B_TILE_BYTES;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
-                            umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, accum);
-                  accum = 1;
-                }
-              }
-          umma_commit(&empty[stage]);
-          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
-        } else {
-          const int nsteps = 3 * p.NC * NPASS;
-          for (int step = 0; step < nsteps; ++step) {
-            const int pass = step % NPASS;
-            const int c = (step / NPASS) % p.NC;
-            const int j = step / (NPASS * p.NC);
-            mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * SLAB_BYTES);
-            uint32_t b_addr;
-            if (RESIDENT) {
-              const int wp = (pass == 2) ? 1 : 0;
-              b_addr = smem_u32(w_smem) + ((wp * 3 + j) * p.NC + c) * B_TILE_BYTES;
-            } else {
-              b_addr = a_addr + kTileBytes;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
-                        umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, (step | k) != 0 ? 1u : 0u);
-            umma_commit(&empty[stage]);
-            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
-          }
-        }
-        umma_commit(&acc_full[as]);
-        if (++as == ACC) { as = 0; aphase ^= 1; }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------- epilogue warps (2..)
-    // EG groups of 8 warps; group g owns this CTA's tiles g, g + EG, ... (its own staging buffer
-    // and named barrier), so one group's stores / barrier waits overlap the other's math.
-    const int grp = (warp - 2) >> 3;
-    const int q = warp & 3;
-    const int half = ((warp - 2) >> 2) & 1;
-    const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64 - grp * kEpiThreads;
-    const int bar_id = 1 + grp;
-    const int chunks_per_row = p.F >> 6;
-    uint32_t as = 0, aphase = 0, rs = 0, rphase = 0, hs = 0, hphase = 0, kc = 0;
-    TileWalk tw;
-    tw.init(p);
-    if (EG == 2 && grp == 1 && tw.b < p.B) {
-      tw.next(p);
-      ring_advance(as, aphase, 1, ACC);
-      ring_advance(rs, rphase, NCH, p.rstages);
-      ring_advance(hs, hphase, 1, p.stages);
-    }
-    uint32_t ntile = grp;
-    for (; tw.b < p.B; tw.next(p), ntile += EG) {
-      const int nt = tw.nt, b = tw.b;
-      const int t0 = tw.mt * kTileM;
-      const int bz = (EPI == EPI_FWD_R) ? b / p.zx_div : 0;
-      const int t = t0 + row;
-      const bool valid = t < p.L_out;
-      const size_t orow = static_cast<size_t>(b) * p.L_out + t;
-
-#pragma unroll 1
-      for (int ch = 0; ch < NCH; ++ch, ++kc) {
-        const int n0 = nt * NT + ch * 64;
-        const int cq = half * 4;  // first 16-byte chunk of this thread's 32 columns
-        uint32_t mbits = ~0u;
-        if (EPI == EPI_BWD_MASK && p.mask_in != nullptr && valid)
-          mbits = __ldg(p.mask_in + (orow * chunks_per_row + (n0 >> 6)) * 2 + half);
-
-        // ---- residual (already in shared memory: HALO box or residual ring)
-        uint4 rr[4], rl[4];
-        {
-          if (RING_RESID) {
-            mbar_wait_wd(&rfull[rs], rphase, p.dbg, 0x600 + rs, ntile);
-            const uint8_t* src = rring + static_cast<size_t>(rs) * rstage_bytes;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              rr[g] = lds128(src + sw128(row, cq + g));
-              if (PLANES == 2) rl[g] = lds128(src + kTileBytes + sw128(row, cq + g));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&rempty[rs]);
-            ring_advance(rs, rphase, 1, p.rstages);
-          } else {
-            if (ch == 0) mbar_wait_wd(&full[hs], hphase, p.dbg, 0x700 + hs, ntile);
-            // n_ntiles == 1 in HALO mode, so the chunk index is the channel-chunk index
-            const uint8_t* src = ring + static_cast<size_t>(hs) * stage_bytes +
-                                 static_cast<size_t>(ch * PLANES) * p.sub_bytes;
-            const uint32_t brow = row + p.resid_row;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              rr[g] = lds128(src + sw128(brow, cq + g));
-              if (PLANES == 2) rl[g] = lds128(src + p.sub_bytes + sw128(brow, cq + g));
-            }
-            if (ch == NCH - 1) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&empty[hs]);
-              ring_advance(hs, hphase, EG, p.stages);
-            }
-          }
-        }
-
-        // ---- accumulator
-        if (ch == 0) {
-          mbar_wait_wd(&acc_full[as], aphase, p.dbg, 0x800 + as, ntile);
-          tc_fence_after();
-        }
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + as * NT + ch * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16),
-                  acc);
-        tmem_ld_wait();
-        if (ch == NCH - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
-        }
-
-        const bool one_buf = (EG == 2) || p.nstg == 1;  // one staging buffer per writer group
-        uint8_t* sb = stg + static_cast<size_t>(EG == 2 ? grp : (p.nstg == 2 ? (kc & 1) : 0)) * stg_bytes;
-        uint8_t* sb2 = sb + static_cast<size_t>(p.has_out * PLANES) * kTileBytes;
-        if (one_buf) {
-          // single staging buffer: the previous chunk's stores must have read it
-          if (et == 0) tma_store_wait_read<0>();
-          named_bar_sync(bar_id, kEpiThreads);
-        }
-
-        float obits_lo = 0.f, obits_hi = 0.f;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float v[8], r[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]);
-          unpack8(rr[g], r);
-          if (PLANES == 2) {
-            float r2[8];
-            unpack8(rl[g], r2);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] += r2[i];
-          }
-          float o[8], o2[8];
-          if (IS_FWD) {
-            const float4 b0 = lds_f4(s_bias + n0 + half * 32 + g * 8);
-            const float4 b1 = lds_f4(s_bias + n0 + half * 32 + g * 8 + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            if (EPI == EPI_FWD_R) {
-              // DeepSHAP rescale multiplier of this reference against the query's pre-activation
-              // (shap.py:623-638); only the query-half gradient is used downstream (shap.py:374).
-              float zx[8];
-              if (valid) {
-                const float4* zp = reinterpret_cast<const float4*>(
-                    p.zx_in + (static_cast<size_t>(bz) * p.L_out + t) * p.F + n0 +
-                    half * 32 + g * 8);
-                const float4 z0 = __ldg(zp), z1 = __ldg(zp + 1);
-                zx[0] = z0.x; zx[1] = z0.y; zx[2] = z0.z; zx[3] = z0.w;
-                zx[4] = z1.x; zx[5] = z1.y; zx[6] = z1.z; zx[7] = z1.w;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) zx[i] = 0.f;
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float din = zx[i] - v[i];
-                const float dout = fmaxf(zx[i], 0.f) - fmaxf(v[i], 0.f);
-                o2[i] = (fabsf(din) < 1e-6f) ? (zx[i] > 0.f ? 1.f : 0.f) : dout / din;
-              }
-            }
-            if (EPI == EPI_FWD_Z) {
-              if (valid) {
-                float4* zo = reinterpret_cast<float4*>(p.z_out + orow * p.F + n0 + half * 32 + g * 8);
-                zo[0] = make_float4(v[0], v[1], v[2], v[3]);
-                zo[1] = make_float4(v[4], v[5], v[6], v[7]);
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float flag = gt0_flag(v[i]);
-              if (g < 2) obits_lo = fmaf(flag, static_cast<float>(1u << (g * 8 + i)), obits_lo);
-              else obits_hi = fmaf(flag, static_cast<float>(1u << (g * 8 + i - 16)), obits_hi);
-              o[i] = fmaf(v[i], flag, r[i]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = v[i] + r[i];
-            if (EPI == EPI_BWD_MULT) {
-              float m[8];
-              if (valid) {
-                const size_t moff = orow * p.F + n0 + half * 32 + g * 8;
-                unpack8(__ldg(reinterpret_cast<const uint4*>(p.mult_hi + moff)), m);
-                if (PLANES == 2) {
-                  float m2[8];
-                  unpack8(__ldg(reinterpret_cast<const uint4*>(p.mult_lo + moff)), m2);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) m[i] += m2[i];
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) m[i] = 0.f;
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o2[i] = o[i] * m[i];
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o2[i] = ((mbits >> (g * 8 + i)) & 1u) ? o[i] : 0.f;
-            }
-          }
-          const uint32_t off = sw128(row, cq + g);
-          if (p.has_out) {
-            if (PLANES == 2) {
-              uint4 h, l;
-              split8(o, h, l);
-              sts128(sb + off, h);
-              sts128(sb + kTileBytes + off, l);
-            } else {
-              sts128(sb + off, pack8(o));
-            }
-          }
-          if ((EPI == EPI_FWD_R || !IS_FWD) && p.has_out2) {
-            if (PLANES == 2) {
-              uint4 h, l;
-              split8(o2, h, l);
-              sts128(sb2 + off, h);
-              sts128(sb2 + kTileBytes + off, l);
-            } else {
-              sts128(sb2 + off, pack8(o2));
-            }
-          }
-        }
-        if (IS_FWD && p.mask_out != nullptr && valid)
-          p.mask_out[(orow * chunks_per_row + (n0 >> 6)) * 2 + half] =
-              static_cast<uint32_t>(obits_lo) | (static_cast<uint32_t>(obits_hi) << 16);
-
-        // ---- publish: generic-proxy writes -> async proxy, one barrier, one thread stores
-        fence_proxy_async();
-        if (!one_buf && et == 0) tma_store_wait_read<0>();  // buffer of chunk kc-1 is free again
-        named_bar_sync(bar_id, kEpiThreads);
-        if (et == 0) {
-          if (p.has_out) {
-            tma_store_3d(&tm.O[0], sb, n0, t0, b);
-            if (PLANES == 2) tma_store_3d(&tm.O[1], sb + kTileBytes, n0, t0, b);
-          }
-          if (p.has_out2) {
-            tma_store_3d(&tm.P[0], sb2, n0, t0, b);
-            if (PLANES == 2) tma_store_3d(&tm.P[1], sb2 + kTileBytes, n0, t0, b);
-          }
-          tma_store_commit();
-        }
-      }
-      ring_advance(as, aphase, EG, ACC);
-      if (EG == 2) {
-        // skip the other group's tile
-        tw.next(p);
-        if (RING_RESID) ring_advance(rs, rphase, NCH, p.rstages);
-      }
-    }
-    if (et == 0) tma_store_wait_all<0>();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
-}
-
-template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO>
-static int launch_conv3(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
-                        cudaStream_t stream);
-
-template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG>
-static int launch_conv3_eg(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
-                           cudaStream_t stream) {
-  auto kern = conv3_tc_kernel<EPI, NT, RESIDENT, PLANES, HALO, EG>;
-  static bool configured = false;
-  if (!configured) {
-    BP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       max_smem_optin()));
-    configured = true;
-  }
-  kern<<<grid, 64 + kEpiThreads * EG, smem_bytes, stream>>>(maps, kp);
-  BP_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// Two epilogue groups whenever the plan has two staging buffers (bf16 path).
-template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO>
-static int launch_conv3(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
-                        cudaStream_t stream) {
-  if (PLANES == 1 && kp.nstg == 2 && kp.epi_groups == 2 && (kp.rstages % 2 == 0 || !kp.ring_resid))
-    return launch_conv3_eg<EPI, NT, RESIDENT, 1, HALO, 2>(maps, kp, smem_bytes, grid, stream);
-  return launch_conv3_eg<EPI, NT, RESIDENT, PLANES, HALO, 1>(maps, kp, smem_bytes, grid, stream);
-}
-
-template <int EPI, int PLANES>
-static int dispatch_shape(int NT, bool resident, bool halo, const ConvMaps& maps,
-                          const ConvKParams& kp, size_t smem, int grid, cudaStream_t s) {
-  if (NT == 64) {
-    if (halo) return launch_conv3<EPI, 64, true, PLANES, true>(maps, kp, smem, grid, s);
-    if (resident) return launch_conv3<EPI, 64, true, PLANES, false>(maps, kp, smem, grid, s);
-    return launch_conv3<EPI, 64, false, PLANES, false>(maps, kp, smem, grid, s);
-  }
-  if (NT == 128) {
-    if (halo) return launch_conv3<EPI, 128, true, PLANES, true>(maps, kp, smem, grid, s);
-    if (resident) return launch_conv3<EPI, 128, true, PLANES, false>(maps, kp, smem, grid, s);
-    return launch_conv3<EPI, 128, false, PLANES, false>(maps, kp, smem, grid, s);
-  }
-  return launch_conv3<EPI, 256, false, PLANES, false>(maps, kp, smem, grid, s);
-}
-
-template <int EPI>
-static int dispatch_planes(int planes, int NT, bool resident, bool halo, const ConvMaps& maps,
-                           const ConvKParams& kp, size_t smem, int grid, cudaStream_t s) {
-  if (planes == 2) return dispatch_shape<EPI, 2>(NT, resident, halo, maps, kp, smem, grid, s);
-  return dispatch_shape<EPI, 1>(NT, resident, halo, maps, kp, smem, grid, s);
-}
-
-}  // namespace bp
-
-// Tuning knob (BPB_EPI_GROUPS=1|2, default 2): number of 8-warp epilogue groups on the bf16 path.
-static int g_epi_groups = [] {
-  const char* e = getenv("BPB_EPI_GROUPS");
-  return (e && e[0] == '1') ? 1 : 2;
-}();
+// K2 / K6 / K8 entry point: width-3 dilated residual convolution of the BPNet tower, its data
+// gradient and the DeepSHAP-rescale variant of that gradient (models.py:92-104,
+// shap.py:612-639 of the reference), on the shared tcgen05 engine of conv_core.cuh.
+#include "conv_core.cuh"
 
 extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   using namespace bp;
@@ -638,8 +23,11 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   if (n_planes == 2) {
     BP_REQUIRE(!has_out || a->out_lo, "bpb_conv3_tc: precise path needs out_lo");
     BP_REQUIRE(!has_out2 || a->out2_lo, "bpb_conv3_tc: precise path needs out2_lo");
-    BP_REQUIRE(!a->resid_hi || a->resid_lo, "bpb_conv3_tc: precise path needs resid_lo");
+    BP_REQUIRE(a->resid_lo, "bpb_conv3_tc: precise path needs resid_lo");
     BP_REQUIRE(!a->mult_hi || a->mult_lo, "bpb_conv3_tc: precise path needs mult_lo");
+    // the kernel addresses weight plane wp at row offset wp*3*F
+    BP_REQUIRE(a->w_lo == a->w_hi + static_cast<size_t>(3) * a->F * a->F,
+               "bpb_conv3_tc: w_lo must directly follow w_hi in memory");
   }
   int epi;
   if (a->mode == 0) {
@@ -660,154 +48,47 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
     epi = a->mult_hi ? EPI_BWD_MULT : EPI_BWD_MASK;
   }
 
-  const int F = a->F;
-  const int NT = (F % 256 == 0) ? 256 : (F % 128 == 0 ? 128 : 64);
-  ConvKParams kp{};
-  kp.B = a->B;
-  kp.L_out = a->L_out;
-  kp.tiles_per_seq = (a->L_out + kTileM - 1) / kTileM;
-  kp.n_ntiles = F / NT;
-  kp.NC = F / 64;
-  kp.F = F;
-  kp.resid_off = a->resid_off;
-  kp.zx_div = a->zx_div > 0 ? a->zx_div : 1;
-  kp.has_out = has_out;
-  kp.epi_groups = g_epi_groups;
-  kp.has_out2 = has_out2;
-  kp.bias = a->bias;
-  kp.mult_hi = reinterpret_cast<const __nv_bfloat16*>(a->mult_hi);
-  kp.mult_lo = reinterpret_cast<const __nv_bfloat16*>(a->mult_lo);
-  kp.mask_in = reinterpret_cast<const uint32_t*>(a->mask_in);
-  kp.mask_out = reinterpret_cast<uint32_t*>(a->mask_out);
-  kp.zx_in = a->zx_in;
-  kp.z_out = a->z_out;
-  kp.dbg = debug_buffer();
-
-  // ---- shared-memory plan
-  const int max_smem = max_smem_optin();
-  BP_REQUIRE(max_smem > 0, "bpb_conv3_tc: no CUDA device");
-  int min_off = a->tap_off[0], max_off = a->tap_off[0];
-  for (int j = 1; j < 3; ++j) {
-    if (a->tap_off[j] < min_off) min_off = a->tap_off[j];
-    if (a->tap_off[j] > max_off) max_off = a->tap_off[j];
-  }
-  const int span = max_off - min_off;
-  const bool is_fwd = a->mode == 0;
-  const int n_out = has_out + has_out2;
-  const size_t b_tile = static_cast<size_t>(NT) * 128;
-  const size_t w_res = static_cast<size_t>(n_planes) * 3 * kp.NC * b_tile;
-  const size_t fixed = 1024 /*align slack*/ + static_cast<size_t>(F) * 4 +
-                       (2 * kMaxStages + 8 + 2 * kMaxRStages + 1) * 8 + 16;
-  const bool can_reside = (kp.n_ntiles == 1) && (NT <= 128);
-
-  const bool two_groups = (n_planes == 1) && g_epi_groups == 2;
-  bool halo = false, resident = false;
-  int stages = 0, rstages = 0, nstg = 0;
-  size_t stage_bytes = 0;
-  int box_rows = 0;
-  auto try_plan = [&](bool want_halo, bool want_res, int want_nstg, int want_rst, int min_stages) {
-    const bool ring_resid = !(want_halo && is_fwd);
-    size_t used = fixed + (want_res ? w_res : 0) +
-                  static_cast<size_t>(want_nstg) * n_out * n_planes * kTileBytes +
-                  (ring_resid ? static_cast<size_t>(want_rst) * n_planes * kTileBytes : 0);
-    if (used >= static_cast<size_t>(max_smem)) return false;
-    size_t sb;
-    int rows = 0;
-    if (want_halo) {
-      rows = kTileM + span;
-      sb = static_cast<size_t>(kp.NC) * n_planes * ((static_cast<size_t>(rows) * 128 + 1023) / 1024 * 1024);
-    } else {
-      sb = kTileBytes + (want_res ? 0 : b_tile);
-    }
-    int st = static_cast<int>((static_cast<size_t>(max_smem) - used) / sb);
-    if (st > kMaxStages) st = kMaxStages;
-    if (want_halo && st > 6) st = 6;
-    // same-group ownership of every HALO box slot as well (see the residual ring note below)
-    if (want_halo && two_groups && is_fwd && want_nstg == 2 && st > 2 && (st & 1)) st -= 1;
-    if (st < min_stages) return false;
-    halo = want_halo; resident = want_res; nstg = want_nstg; rstages = ring_resid ? want_rst : 0;
-    stages = st; stage_bytes = sb; box_rows = rows;
-    return true;
-  };
-  const bool halo_ok = can_reside && span <= 128 && span > 0 && kTileM + span <= 256;
-  // With two epilogue groups (bf16 path, two staging buffers) the residual ring must have an EVEN
-  // number of slots: a slot is then always consumed by the same group.  With an odd ring a group
-  // would skip every other phase of a slot's mbarrier, and a parity wait cannot tell "the phase I
-  // skipped is still in flight" from "my phase is complete" (observed as a rare deadlock).
-  const int r_hi = two_groups ? 4 : 3;
-  bool planned = false;
-  if (halo_ok) planned = try_plan(true, true, 2, r_hi, 3) || try_plan(true, true, 2, 2, 2);
-  if (!planned && can_reside)
-    planned = try_plan(false, true, 2, r_hi, 4) || try_plan(false, true, 2, 2, 3) ||
-              try_plan(false, true, 1, 2, 3);
-  if (!planned)
-    planned = try_plan(false, false, 2, r_hi, 3) || try_plan(false, false, 2, 2, 2) ||
-              try_plan(false, false, 1, 2, 2);
-  BP_REQUIRE(planned, "bpb_conv3_tc: not enough shared memory for F=%d planes=%d", F, n_planes);
-  kp.stages = stages;
-  kp.rstages = rstages > 0 ? rstages : 1;
-  kp.ring_resid = rstages > 0 ? 1 : 0;
-  kp.nstg = nstg;
-  if (halo) {
-    kp.box_off = min_off;
-    kp.box_bytes = box_rows * 128;
-    kp.sub_bytes = (kp.box_bytes + 1023) / 1024 * 1024;
-    for (int j = 0; j < 3; ++j) kp.tap_row[j] = a->tap_off[j] - min_off;
-    kp.resid_row = a->resid_off - min_off;
-    if (is_fwd) {
-      BP_REQUIRE(a->resid_hi == a->in_hi && a->resid_lo == a->in_lo && kp.resid_row >= 0 &&
-                     kp.resid_row <= span,
-                 "bpb_conv3_tc: forward residual must be the input tensor at an offset inside the taps");
-    }
-  } else {
-    for (int j = 0; j < 3; ++j) kp.tap_row[j] = a->tap_off[j];
-  }
-  const size_t smem_bytes = fixed + (resident ? w_res : 0) + stages * stage_bytes +
-                            static_cast<size_t>(nstg) * n_out * n_planes * kTileBytes +
-                            static_cast<size_t>(rstages) * n_planes * kTileBytes;
-
-  ConvMaps maps;
-  memset(&maps, 0, sizeof(maps));
-  const uint64_t wrows = static_cast<uint64_t>(3) * F;
-  const uint32_t a_box = halo ? static_cast<uint32_t>(box_rows) : kTileM;
-  if (!make_tmap_3d(&maps.A[0], a->in_hi, F, a->L_in, a->B, 64, a_box)) return 3;
-  if (n_planes == 2 && !make_tmap_3d(&maps.A[1], a->in_lo, F, a->L_in, a->B, 64, a_box)) return 3;
-  // Weights: the kernel addresses plane wp at row offset wp*3*F, so the hi/lo planes must be
-  // contiguous when both are used.
-  if (n_planes == 2)
-    BP_REQUIRE(a->w_lo == a->w_hi + static_cast<size_t>(3) * F * F,
-               "bpb_conv3_tc: w_lo must directly follow w_hi in memory");
-  if (!make_tmap_2d(&maps.W, a->w_hi, F, wrows * n_planes, 64, NT)) return 3;
-  if (has_out) {
-    if (!make_tmap_3d(&maps.O[0], a->out_hi, F, a->L_out, a->B, 64, kTileM)) return 3;
-    if (n_planes == 2 && !make_tmap_3d(&maps.O[1], a->out_lo, F, a->L_out, a->B, 64, kTileM)) return 3;
-  }
-  if (has_out2) {
-    if (!make_tmap_3d(&maps.P[0], a->out2_hi, F, a->L_out, a->B, 64, kTileM)) return 3;
-    if (n_planes == 2 && !make_tmap_3d(&maps.P[1], a->out2_lo, F, a->L_out, a->B, 64, kTileM)) return 3;
-  }
-  if (rstages > 0) {
-    if (!make_tmap_3d(&maps.R[0], a->resid_hi, F, a->L_res, a->B, 64, kTileM)) return 3;
-    if (n_planes == 2 && !make_tmap_3d(&maps.R[1], a->resid_lo, F, a->L_res, a->B, 64, kTileM)) return 3;
-  }
-
-  const int total_tiles = kp.B * kp.tiles_per_seq * kp.n_ntiles;
-  int grid = sm_count();
-  if (grid > total_tiles) grid = total_tiles;
-  kp.step_nt = grid % kp.n_ntiles;
-  kp.step_mt = (grid / kp.n_ntiles) % kp.tiles_per_seq;
-  kp.step_b = grid / (kp.n_ntiles * kp.tiles_per_seq);
-
-  switch (epi) {
-    case EPI_FWD:
-      return dispatch_planes<EPI_FWD>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
-    case EPI_FWD_Z:
-      return dispatch_planes<EPI_FWD_Z>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
-    case EPI_FWD_R:
-      return dispatch_planes<EPI_FWD_R>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
-    case EPI_BWD_MASK:
-      return dispatch_planes<EPI_BWD_MASK>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
-    default:
-      return dispatch_planes<EPI_BWD_MULT>(n_planes, NT, resident, halo, maps, kp, smem_bytes, grid, stream);
-  }
+  ConvDesc d{};
+  d.who = "bpb_conv3_tc";
+  d.B = a->B;
+  d.L_out = a->L_out;
+  d.F = a->F;
+  d.epi = epi;
+  d.planes = n_planes;
+  d.a_ptr[0] = a->in_hi;
+  d.a_ptr[1] = a->in_lo;
+  d.n_aplanes = n_planes;
+  d.a_inner = a->F;
+  d.a_rows = a->L_in;
+  d.a_row_stride_bytes = static_cast<unsigned long long>(a->F) * 2;
+  d.a_batch_stride_bytes = static_cast<unsigned long long>(a->F) * 2 * a->L_in;
+  d.n_taps = 3;
+  d.KC = a->F / 64;
+  d.last_nk = 4;
+  for (int j = 0; j < 3; ++j) d.tap_off[j] = a->tap_off[j];
+  d.w_ptr = a->w_hi;
+  d.n_wplanes = n_planes;
+  // hi*hi, lo*hi, hi*lo (the lo*lo term is below fp32 resolution)
+  d.npass = n_planes == 2 ? 3 : 1;
+  d.pa_bits = 0b010;
+  d.pw_bits = 0b010000;
+  d.bias = a->bias;
+  d.bias_n = a->F;
+  d.resid[0] = a->resid_hi;
+  d.resid[1] = a->resid_lo;
+  d.L_res = a->L_res;
+  d.resid_off = a->resid_off;
+  d.out[0] = a->out_hi;
+  d.out[1] = a->out_lo;
+  d.out2[0] = a->out2_hi;
+  d.out2[1] = a->out2_lo;
+  d.mask_in = a->mask_in;
+  d.mask_out = a->mask_out;
+  d.mult[0] = a->mult_hi;
+  d.mult[1] = a->mult_lo;
+  d.zx_in = a->zx_in;
+  d.zx_div = a->zx_div;
+  d.z_out = a->z_out;
+  d.allow_halo = true;
+  return conv_run<true>(d, stream);
 }

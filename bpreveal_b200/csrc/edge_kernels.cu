@@ -17,76 +17,6 @@ __device__ __forceinline__ void store_planes(__nv_bfloat16* hi, __nv_bfloat16* l
 }
 
 // ------------------------------------------------------------------------------------------
-// K1 forward.  One block = 128 positions of one sequence; thread = (position, 8 filters).
-// ------------------------------------------------------------------------------------------
-constexpr int kIcTile = 128;
-
-__global__ void __launch_bounds__(256)
-input_conv_fwd_kernel(int L_in, int L_out, int W, int Fw, int F, const uint8_t* __restrict__ x,
-                      const float* __restrict__ w, const float* __restrict__ bias,
-                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                      unsigned long long* __restrict__ mask_out, float* __restrict__ z_out,
-                      const float* __restrict__ zx_in, int zx_div,
-                      __nv_bfloat16* __restrict__ mult_hi, __nv_bfloat16* __restrict__ mult_lo) {
-  extern __shared__ float sm[];
-  float* sw = sm;                                   // [W][4][Fw]
-  uint8_t* sx = reinterpret_cast<uint8_t*>(sw + W * 4 * Fw);  // [(128 + W - 1)][4]
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kIcTile;
-  for (int i = threadIdx.x; i < W * 4 * Fw; i += blockDim.x) sw[i] = w[i];
-  const int nrows = kIcTile + W - 1;
-  for (int i = threadIdx.x; i < nrows * 4; i += blockDim.x) {
-    const int r = t0 + i / 4;
-    sx[i] = (r < L_in) ? x[(static_cast<size_t>(b) * L_in + r) * 4 + (i & 3)] : 0;
-  }
-  __syncthreads();
-  const int ngroups = F / 8;
-  for (int item = threadIdx.x; item < kIcTile * ngroups; item += blockDim.x) {
-    const int r = item / ngroups, g = item % ngroups;
-    const int t = t0 + r;
-    if (t >= L_out) continue;
-    const int f0 = g * 8;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (f0 + i < Fw) ? bias[f0 + i] : 0.f;
-    if (f0 < Fw) {
-      for (int j = 0; j < W; ++j) {
-        const uint8_t* xr = sx + (r + j) * 4;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float xv = static_cast<float>(xr[c]);
-          if (xv != 0.f) {
-            const float* wr = sw + (j * 4 + c) * Fw + f0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (f0 + i < Fw) v[i] = fmaf(xv, wr[i], v[i]);
-          }
-        }
-      }
-    }
-    const size_t orow = static_cast<size_t>(b) * L_out + t;
-    unsigned int bits = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const size_t idx = orow * F + f0 + i;
-      if (v[i] > 0.f) bits |= 1u << i;
-      if (z_out) z_out[idx] = v[i];
-      if (zx_in) {
-        const float zx = zx_in[(static_cast<size_t>(b / zx_div) * L_out + t) * F + f0 + i];
-        const float din = zx - v[i];
-        const float m = (fabsf(din) < 1e-6f) ? (zx > 0.f ? 1.f : 0.f)
-                                             : (fmaxf(zx, 0.f) - fmaxf(v[i], 0.f)) / din;
-        store_planes(mult_hi, mult_lo, idx, m);
-      }
-      store_planes(out_hi, out_lo, idx, fmaxf(v[i], 0.f));
-    }
-    if (mask_out)
-      reinterpret_cast<unsigned char*>(mask_out)[orow * (F / 8) + g] =
-          static_cast<unsigned char>(bits);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // K1 weight gradient.  dw[j][c][f] = sum x[b,t+j,c] gz[b,t,f].  A block walks a strip of
 // positions; thread (j, f) keeps one accumulator per base and adds gz[t'-j][f] into the
 // accumulator of the base found at t' (uniform branch).  Partials go to a workspace.
@@ -443,32 +373,6 @@ static int pad_tasks(int T) { return T <= 2 ? 2 : (T <= 4 ? 4 : (T <= 8 ? 8 : 16
 
 using namespace bp;
 
-extern "C" int bpb_input_conv_fwd(const bpb_input_conv_args* a, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BP_REQUIRE(a && a->x && a->w && a->bias && a->out_hi, "bpb_input_conv_fwd: NULL argument");
-  BP_REQUIRE(a->F % 64 == 0 && a->Fw <= a->F && a->Fw > 0, "bpb_input_conv_fwd: bad F=%d Fw=%d",
-             a->F, a->Fw);
-  BP_REQUIRE(a->L_out == a->L_in - a->W + 1, "bpb_input_conv_fwd: L_out must be L_in - W + 1");
-  if (a->zx_in) BP_REQUIRE(a->mult_hi && a->zx_div > 0, "bpb_input_conv_fwd: zx_in needs mult_hi");
-  const size_t smem = static_cast<size_t>(a->W) * 4 * a->Fw * 4 + (kIcTile + a->W - 1) * 4 + 16;
-  static bool configured = false;
-  if (!configured) {
-    BP_CHECK_CUDA(cudaFuncSetAttribute(input_conv_fwd_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
-  BP_REQUIRE(smem <= 200 * 1024, "bpb_input_conv_fwd: filter too large for shared memory");
-  dim3 grid((a->L_out + kIcTile - 1) / kIcTile, a->B);
-  input_conv_fwd_kernel<<<grid, 256, smem, stream>>>(
-      a->L_in, a->L_out, a->W, a->Fw, a->F, a->x, a->w, a->bias,
-      reinterpret_cast<__nv_bfloat16*>(a->out_hi), reinterpret_cast<__nv_bfloat16*>(a->out_lo),
-      reinterpret_cast<unsigned long long*>(a->mask_out), a->z_out, a->zx_in,
-      a->zx_div > 0 ? a->zx_div : 1, reinterpret_cast<__nv_bfloat16*>(a->mult_hi),
-      reinterpret_cast<__nv_bfloat16*>(a->mult_lo));
-  BP_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 static int iw_blocks(int B, int L_out) {
   int strips = B * ((L_out + kIwStrip - 1) / kIwStrip);
   int g = sm_count();
@@ -603,8 +507,8 @@ extern "C" int bpb_heads_bwd(int B, int L_in, int L_out, int W, int Fw, int F, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BP_REQUIRE(pw && cw && dlogits && dlogcounts, "bpb_heads_bwd: NULL argument");
   BP_REQUIRE(T >= 1 && T <= 16, "bpb_heads_bwd: total tasks T=%d must be in 1..16", T);
-  BP_REQUIRE(g_hi || gz_hi, "bpb_heads_bwd: neither g nor gz requested");
-  {
+  BP_REQUIRE(g_hi || gz_hi || dpw, "bpb_heads_bwd: nothing requested");
+  if (g_hi || gz_hi) {
     const size_t smem = static_cast<size_t>(64 + W - 1) * T * 4;
     dim3 grid((L_in + 63) / 64, B);
     heads_dgrad_kernel<<<grid, 256, smem, stream>>>(

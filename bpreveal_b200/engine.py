@@ -106,6 +106,13 @@ class SoloNet:
         self.w_fwd = torch.zeros((max(L, 1), planes, 3, Fp, Fp), dtype=torch.bfloat16,
                                  device=self.device)
         self.w_bwd = torch.zeros_like(self.w_fwd)
+        # tcgen05 operands of the input convolution and of the heads' data gradient
+        self.cp = ops.heads_cp(cfg.T, cfg.H)
+        # K1 weights as 2 (bf16 path) / 3 (precise path) bf16 remainder planes: the first layer's
+        # pre-activations (and so its ReLU mask) stay fp32-accurate at the cost of K = 8 W extra MMAs
+        self.w_in_planes = planes + 1
+        self.w_in_op = ops.input_conv_wop(cfg.inputFilterWidth, Fp, self.w_in_planes, self.device)
+        self.w_hd_op = ops.heads_dgrad_wop(cfg.outputFilterWidth, Fp, self.cp, planes, self.device)
         self.task_off = torch.tensor(np.concatenate([[0], np.cumsum(cfg.headTasks)]),
                                      dtype=torch.int32, device=self.device)
         self._ws = {}
@@ -183,9 +190,13 @@ class SoloNet:
 
     def refresh_weights(self):
         """fp32 master weights -> bf16 tcgen05 operand layouts (after load / after Adam)."""
-        if self.cfg.numLayers > 0:
-            ops.prep_conv3_weights(self.p["dil_w"], self.cfg.Fp, self.w_fwd, self.w_bwd,
-                                   self.cfg.precise)
+        cfg = self.cfg
+        planes = 2 if cfg.precise else 1
+        if cfg.numLayers > 0:
+            ops.prep_conv3_weights(self.p["dil_w"], cfg.Fp, self.w_fwd, self.w_bwd, cfg.precise)
+        ops.prep_input_conv_weights(self.p["conv1_w"], cfg.Fp, self.w_in_op, self.w_in_planes)
+        ops.prep_heads_dgrad_weights(self.p["prof_w"], self.p["cnt_w"], cfg.Fp, self.cp,
+                                     self.w_hd_op, planes)
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, B, kind):
@@ -197,6 +208,7 @@ class SoloNet:
         Ls = cfg.lengths()
         ws = {"B": B}
         ws["x"] = torch.zeros((B, cfg.inputLength, 4), dtype=torch.uint8, device=dev)
+        ws["x8"] = torch.zeros((B, cfg.inputLength, 8), dtype=torch.bfloat16, device=dev)
         ws["logits"] = torch.empty((B, cfg.outputLength, cfg.T), dtype=torch.float32, device=dev)
         ws["gap"] = torch.empty((B, Fp), dtype=torch.float32, device=dev)
         ws["logcounts"] = torch.empty((B, cfg.H), dtype=torch.float32, device=dev)
@@ -221,6 +233,8 @@ class SoloNet:
                       ops.heads_bwd_ws_bytes(B, Ls[-1], cfg.outputFilterWidth, cfg.numFilters,
                                              cfg.T)])
             ws["scratch"] = torch.empty((nb // 4 + 4,), dtype=torch.float32, device=dev)
+            ws["d8"] = ops.heads_d8(B, Ls[-1], cfg.outputFilterWidth, self.cp,
+                                    2 if prec else 1, dev)
         if kind == "shap_x":
             ws["z"] = [torch.empty((B, L, Fp), dtype=torch.float32, device=dev) for L in Ls]
         if kind == "shap_r":
@@ -232,6 +246,8 @@ class SoloNet:
             ws["g"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
             ws["gz"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
             ws["dx"] = torch.empty((B, cfg.inputLength, 4), dtype=torch.float32, device=dev)
+            ws["d8"] = ops.heads_d8(B, Ls[-1], cfg.outputFilterWidth, self.cp,
+                                    2 if prec else 1, dev)
         self._ws[key] = ws
         return ws
 
@@ -258,7 +274,9 @@ class SoloNet:
             return ws["acts"][i] if keep else self._sub(ws["ping"][i % 2], Ls[i])
 
         a = buf(0)
-        ops.input_conv_fwd(x, p["conv1_w"], p["conv1_b"], cfg.Fp, a,
+        ops.onehot_expand(x, ws["x8"])
+        ops.input_conv_fwd(ws["x8"], self.w_in_op, self.w_in_planes, cfg.inputFilterWidth,
+                           cfg.numFilters, p["conv1_b"], cfg.Fp, a,
                            mask_out=ws["masks"][0] if save_masks else None,
                            z_out=z_list[0] if z_list else None,
                            zx_in=zx_list[0] if zx_list else None, zx_div=zx_div,
@@ -331,9 +349,14 @@ class SoloNet:
         nL = cfg.numLayers
         gcur = self._sub(ws["g"][nL % 2], Ls[nL])
         gzcur = self._sub(ws["gz"][nL % 2], Ls[nL])
+        planes = 2 if cfg.precise else 1
         ops.heads_bwd(aL, ws["gap"], p["prof_w"], p["cnt_w"], ws["dlogits"], ws["dlogcounts"],
-                      g=gcur, gz=gzcur, mask_in=ws["masks"][nL], dpw=g["prof_w"],
-                      dpb=g["prof_b"], dcw=g["cnt_w"], dcb=g["cnt_b"], ws=ws["scratch"])
+                      dpw=g["prof_w"], dpb=g["prof_b"], dcw=g["cnt_w"], dcb=g["cnt_b"],
+                      ws=ws["scratch"])
+        ops.heads_pack_grad(ws["dlogits"], ws["dlogcounts"], Ls[nL], cfg.outputFilterWidth,
+                            self.cp, planes, ws["d8"])
+        ops.heads_dgrad(ws["d8"], self.w_hd_op, ws["B"], Ls[nL], cfg.outputFilterWidth, cfg.Fp,
+                        self.cp, planes, g=gcur, gz=gzcur, mask_in=ws["masks"][nL])
         for i in range(nL - 1, -1, -1):
             d = 2 ** (i + 1)
             ops.wgrad3(ws["acts"][i], gzcur, d, g["dil_w"][i], g["dil_b"][i], ws["scratch"])
@@ -436,8 +459,11 @@ class SoloNet:
         nL = cfg.numLayers
         gcur = self._sub(wr["g"][nL % 2], Ls[nL])
         gzcur = self._sub(wr["gz"][nL % 2], Ls[nL])
-        ops.heads_bwd(None_planes(wr, Ls[nL], cfg), wr["gap"], p["prof_w"], p["cnt_w"],
-                      wr["dlogits"], wr["dlogcounts"], g=gcur, gz=gzcur, mult=wr["mult"][nL])
+        planes = 2 if cfg.precise else 1
+        ops.heads_pack_grad(wr["dlogits"], wr["dlogcounts"], Ls[nL], cfg.outputFilterWidth,
+                            self.cp, planes, wr["d8"])
+        ops.heads_dgrad(wr["d8"], self.w_hd_op, R, Ls[nL], cfg.outputFilterWidth, cfg.Fp, self.cp,
+                        planes, g=gcur, gz=gzcur, mult=wr["mult"][nL])
         for i in range(nL - 1, -1, -1):
             d = 2 ** (i + 1)
             gnext = self._sub(wr["g"][i % 2], Ls[i])
@@ -447,9 +473,3 @@ class SoloNet:
             gcur, gzcur = gnext, gznext
         ops.input_conv_dgrad(gzcur, p["conv1_w"], cfg.inputLength, wr["dx"])
         return wr["dx"], wx, wr
-
-
-def None_planes(ws, L, cfg):
-    """The heads' data gradient does not read activations; pass a correctly shaped plane view so
-    that the launcher can read the geometry."""
-    return SoloNet._sub(ws["ping"][0], L)

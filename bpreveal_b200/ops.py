@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import Conv3Args, InputConvArgs, Wgrad3Args, check
+from ._lib import Conv3Args, HeadsDgradArgs, InputConvArgs, Wgrad3Args, check
 
 
 def _p(t):
@@ -109,15 +109,32 @@ def wgrad3(act, gz, dil, dw, db, ws):
     check(lib.bpb_wgrad3_tc(C.byref(a), _stream()), "bpb_wgrad3_tc")
 
 
-def input_conv_fwd(x, w, bias, F, out, mask_out=None, z_out=None, zx_in=None, zx_div=1,
-                   mult=None):
-    lib = _lib.load()
-    B, L_in, nb = x.shape
-    assert nb == 4 and x.dtype == torch.uint8
+def onehot_expand(x, x8):
+    """u8 one-hot [B, L, 4] -> bf16 [B, L, 8] (the tcgen05 operand of the input convolution)."""
+    B, L, nb = x.shape
+    assert nb == 4 and x.dtype == torch.uint8 and tuple(x8.shape) == (B, L, 8)
+    check(_lib.load().bpb_onehot_expand(B, L, _p(x), _p(x8), _stream()), "bpb_onehot_expand")
+
+
+def input_conv_wop(W, F, planes, device):
+    n = _lib.load().bpb_input_conv_wop_elems(W, F, planes)
+    return torch.zeros((n,), dtype=torch.bfloat16, device=device)
+
+
+def prep_input_conv_weights(w, F, w_op, planes):
     W, _, Fw = w.shape
+    check(_lib.load().bpb_prep_input_conv_weights(W, Fw, F, _p(w), _p(w_op), planes, _stream()),
+          "bpb_prep_input_conv_weights")
+
+
+def input_conv_fwd(x8, w_op, w_planes, W, Fw, bias, F, out, mask_out=None, z_out=None, zx_in=None,
+                   zx_div=1, mult=None):
+    lib = _lib.load()
+    B, L_in, c8 = x8.shape
+    assert c8 == 8 and x8.dtype == torch.bfloat16
     a = InputConvArgs()
     a.B, a.L_in, a.L_out, a.W, a.Fw, a.F = B, L_in, L_in - W + 1, W, Fw, F
-    a.x, a.w, a.bias = _p(x), _p(w), _p(bias)
+    a.x8, a.w_op, a.w_planes, a.bias = _p(x8), _p(w_op), w_planes, _p(bias)
     o_hi, o_lo = _planes(out)
     a.out_hi, a.out_lo = _p(o_hi), _p(o_lo)
     a.mask_out, a.z_out, a.zx_in, a.zx_div = _p(mask_out), _p(z_out), _p(zx_in), zx_div
@@ -185,6 +202,51 @@ def heads_bwd(act, gap, pw, cw, dlogits, dlogcounts, g=None, gz=None, mask_in=No
                             _p(mask_in), _p(m_hi), _p(m_lo), _p(ws),
                             ws.numel() * ws.element_size() if ws is not None else 0, _stream()),
           "bpb_heads_bwd")
+
+
+def heads_cp(T, H):
+    """Channel padding of the packed head gradient d8 (multiple of 8 holding T + H values)."""
+    return (T + H + 7) // 8 * 8
+
+
+def heads_d8(B, L_in, W, Cp, planes, device):
+    n = _lib.load().bpb_heads_d8_elems(B, L_in, W, Cp, planes)
+    return torch.zeros((n,), dtype=torch.bfloat16, device=device)
+
+
+def heads_dgrad_wop(W, F, Cp, planes, device):
+    n = _lib.load().bpb_heads_dgrad_wop_elems(W, F, Cp, planes)
+    return torch.zeros((n,), dtype=torch.bfloat16, device=device)
+
+
+def prep_heads_dgrad_weights(pw, cw, F, Cp, w_op, planes):
+    W, Fw, T = pw.shape
+    H = cw.shape[1]
+    check(_lib.load().bpb_prep_heads_dgrad_weights(W, Fw, F, T, H, Cp, _p(pw), _p(cw), _p(w_op),
+                                                   planes, _stream()),
+          "bpb_prep_heads_dgrad_weights")
+
+
+def heads_pack_grad(dlogits, dlogcounts, L_in, W, Cp, planes, d8):
+    B, L_out, T = dlogits.shape
+    H = dlogcounts.shape[1]
+    check(_lib.load().bpb_heads_pack_grad(B, L_in, L_out, W, T, H, Cp, planes, _p(dlogits),
+                                          _p(dlogcounts), _p(d8), _stream()),
+          "bpb_heads_pack_grad")
+
+
+def heads_dgrad(d8, w_op, B, L_in, W, F, Cp, planes, g=None, gz=None, mask_in=None, mult=None):
+    a = HeadsDgradArgs()
+    a.B, a.L_in, a.L_out, a.W, a.F, a.Cp = B, L_in, L_in - W + 1, W, F, Cp
+    a.d8_hi = _p(d8)
+    a.d8_lo = (d8.data_ptr() + (d8.numel() // 2) * 2) if planes == 2 else None  # second half
+    a.w_op = _p(w_op)
+    g_hi, g_lo = _planes(g)
+    z_hi, z_lo = _planes(gz)
+    m_hi, m_lo = _planes(mult)
+    a.g_hi, a.g_lo, a.gz_hi, a.gz_lo = _p(g_hi), _p(g_lo), _p(z_hi), _p(z_lo)
+    a.mask_in, a.mult_hi, a.mult_lo = _p(mask_in), _p(m_hi), _p(m_lo)
+    check(_lib.load().bpb_heads_dgrad_tc(C.byref(a), _stream()), "bpb_heads_dgrad_tc")
 
 
 def loss_fwd_bwd(task_off, logits, logcounts, counts, profile_weight, lam, losses, dlogits=None,

@@ -95,17 +95,28 @@ long long bpb_wgrad3_ws_bytes(int B, int L_out, int F, int precise);
 int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * K1: input convolution on one-hot DNA (models.py:85-90).  x is u8 [B][L_in][4]; w is the fp32
- * Keras kernel [W][4][Fw]; bias [Fw]; output activations are written with row stride F >= Fw
- * (padding channels are written as zero).
+ * K1: input convolution on one-hot DNA (models.py:85-90) as a tcgen05 GEMM.
  *   z[b,t,f] = bias[f] + sum_{j<W} sum_c x[b,t+j,c] w[j][c][f];  out = relu(z)
+ * The sequence is first expanded to x8 = bf16 [B][L_in][8] (channels 4..7 zero); row t of the
+ * implicit im2col matrix is then the contiguous run x8[b, t, 0] .. x8[b, t+W-1, 7], which a TMA
+ * tensor map with overlapping rows (row stride 16 bytes) loads directly.  The Keras kernel is
+ * prepared once per weight update as w_op = bf16 [w_planes][F][KC*64] with k = j*8 + c
+ * (KC = ceil(8 W / 64)); the planes are successive bf16 remainders of the fp32 weight, so with
+ * w_planes = 3 the product is exact to fp32 (the one-hot operand is exact in bf16).  Output activations are written with row stride F >= Fw
+ * (padding channels are written as zero).
  * Optional outputs: relu mask bits, fp32 z (attribution of the query), rescale multiplier
  * against zx_in (attribution of a shuffled reference).
  * ------------------------------------------------------------------------------------------ */
+int bpb_onehot_expand(int B, int L, const uint8_t* x, bpb_bf16* x8, void* stream);
+long long bpb_input_conv_wop_elems(int W, int F, int planes);
+int bpb_prep_input_conv_weights(int W, int Fw, int F, const float* w, bpb_bf16* w_op, int planes,
+                                void* stream);
 typedef struct {
   int B, L_in, L_out, W, Fw, F;
-  const uint8_t* x;
-  const float *w, *bias;
+  const bpb_bf16* x8;   /* [B][L_in][8] */
+  const bpb_bf16* w_op; /* [w_planes][F][KC*64] */
+  int w_planes;
+  const float* bias;    /* [Fw] */
   bpb_bf16 *out_hi, *out_lo;
   uint64_t* mask_out;
   float* z_out;
@@ -146,6 +157,31 @@ int bpb_heads_bwd(int B, int L_in, int L_out, int W, int Fw, int F, int T, int H
                   bpb_bf16* g_hi, bpb_bf16* g_lo, bpb_bf16* gz_hi, bpb_bf16* gz_lo,
                   const uint64_t* mask_in, const bpb_bf16* mult_hi, const bpb_bf16* mult_lo,
                   float* ws, long long ws_bytes, void* stream);
+
+/* Data gradient of the heads on tensor cores.  bpb_heads_pack_grad writes
+ *   d8[b, r, ch] = dlogits[b, r-(W-1), ch]  (ch < T, zero outside the profile)
+ *                = dlogcounts[b, ch-T] / L_in  (T <= ch < T+H, every row)        bf16 planes
+ * as [planes][B][L_in+W-1][Cp] (Cp a multiple of 8 >= T+H); bpb_prep_heads_dgrad_weights lays the
+ * profile / counts kernels out as the matching GEMM operand; bpb_heads_dgrad_tc then computes
+ *   g[b,s,c]  = sum_j sum_k dlogits[b,s-j,k] pw[j][c][k] + sum_h dlogcounts[b,h] cw[c][h] / L_in
+ *   gz = g * mask_in / mult   (as bpb_conv3_tc mode 1)
+ * bpb_heads_bwd with g == gz == NULL computes only the parameter gradients. */
+long long bpb_heads_d8_elems(int B, int L_in, int W, int Cp, int planes);
+long long bpb_heads_dgrad_wop_elems(int W, int F, int Cp, int planes);
+int bpb_heads_pack_grad(int B, int L_in, int L_out, int W, int T, int H, int Cp, int planes,
+                        const float* dlogits, const float* dlogcounts, bpb_bf16* d8, void* stream);
+int bpb_prep_heads_dgrad_weights(int W, int Fw, int F, int T, int H, int Cp, const float* pw,
+                                 const float* cw, bpb_bf16* w_op, int planes, void* stream);
+typedef struct {
+  int B, L_in, L_out, W, F, Cp;
+  const bpb_bf16 *d8_hi, *d8_lo; /* [B][L_in+W-1][Cp] */
+  const bpb_bf16* w_op;          /* [planes][F][KC*64], KC = ceil(W*Cp/64) */
+  bpb_bf16 *g_hi, *g_lo;         /* [B][L_in][F] or NULL */
+  bpb_bf16 *gz_hi, *gz_lo;       /* [B][L_in][F] or NULL */
+  const uint64_t* mask_in;
+  const bpb_bf16 *mult_hi, *mult_lo;
+} bpb_heads_dgrad_args;
+int bpb_heads_dgrad_tc(const bpb_heads_dgrad_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K5: losses (losses.py:15-63, training.py:64-65).  Heads are described by task offsets
