@@ -212,7 +212,7 @@ def main():
     orig_check = ops.check
 
     kernels_per_call = {"bpb_wgrad3_tc": 2, "bpb_input_conv_wgrad": 2, "bpb_heads_fwd": 2,
-                        "bpb_heads_bwd": 4}
+                        "bpb_heads_wgrad_tc": 2}
 
     def counting_check(rc, what):
         counter["n"] += kernels_per_call.get(what, 1)
@@ -267,7 +267,7 @@ def main():
                 return r
             setattr(ops, name, inner)
 
-        names = ["conv3", "wgrad3", "input_conv_fwd", "input_conv_wgrad", "heads_fwd", "heads_bwd",
+        names = ["conv3", "wgrad3", "input_conv_fwd", "input_conv_wgrad", "heads_fwd", "heads_wgrad", "heads_dgrad", "heads_pack_grad", "onehot_expand",
                  "loss_fwd_bwd", "adam_step", "prep_conv3_weights"]
         for nm in names:
             wrap(nm)

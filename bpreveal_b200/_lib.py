@@ -85,15 +85,15 @@ SIGNATURES = {
     "bpb_input_conv_fwd": (c_int, [C.POINTER(InputConvArgs), c_void_p]),
     "bpb_heads_d8_elems": (c_ll, [c_int] * 5),
     "bpb_heads_dgrad_wop_elems": (c_ll, [c_int] * 4),
-    "bpb_heads_pack_grad": (c_int, [c_int] * 8 + [c_void_p] * 4),
+    "bpb_heads_pack_grad": (c_int, [c_int] * 8 + [c_void_p] * 6),
     "bpb_prep_heads_dgrad_weights": (c_int, [c_int] * 6 + [c_void_p] * 3 + [c_int, c_void_p]),
     "bpb_heads_dgrad_tc": (c_int, [C.POINTER(HeadsDgradArgs), c_void_p]),
     "bpb_input_conv_wgrad_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "bpb_input_conv_wgrad": (c_int, [c_int] * 6 + [c_void_p] * 6 + [c_ll, c_void_p]),
+    "bpb_heads_wgrad_ws_bytes": (c_ll, [c_int] * 5),
+    "bpb_heads_wgrad_tc": (c_int, [c_int] * 8 + [c_void_p] * 7 + [c_ll, c_void_p]),
     "bpb_input_conv_dgrad": (c_int, [c_int] * 6 + [c_void_p] * 5),
     "bpb_heads_fwd": (c_int, [c_int] * 8 + [c_void_p] * 10),
-    "bpb_heads_bwd_ws_bytes": (c_ll, [c_int] * 5),
-    "bpb_heads_bwd": (c_int, [c_int] * 8 + [c_void_p] * 19 + [c_ll, c_void_p]),
     "bpb_loss_fwd_bwd": (c_int, [c_int] * 4 + [c_void_p] * 11),
     "bpb_adam_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 + [c_void_p]),
     "bpb_prep_conv3_weights": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,

@@ -72,6 +72,34 @@ heads_pack_grad_kernel(int B, int L_in, int L_out, int W, int T, int H, int Cp, 
   store_split(d8, n_el, planes, i, v);
 }
 
+// Bias gradients of the heads in fp32 (they are sums of terms that cancel almost exactly -- the
+// multinomial gradient of a head sums to zero -- so they are not taken from the bf16 d8 tensor):
+//   dpb[k] = sum_{b,t} dlogits[b,t,k]    dcb[h] = sum_b dlogcounts[b,h]
+// One block per output, fixed summation order (deterministic).
+__global__ void __launch_bounds__(1024)
+heads_bias_grad_kernel(long long n_rows, int T, int B, int H, const float* __restrict__ dlogits,
+                       const float* __restrict__ dlc, float* __restrict__ dpb,
+                       float* __restrict__ dcb) {
+  __shared__ float red[1024];
+  const int o = blockIdx.x;
+  float s = 0.f;
+  if (o < T) {
+    for (long long r = threadIdx.x; r < n_rows; r += blockDim.x) s += dlogits[r * T + o];
+  } else {
+    for (int b = threadIdx.x; b < B; b += blockDim.x) s += dlc[b * H + (o - T)];
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (o < T) dpb[o] = red[0];
+    else dcb[o - T] = red[0];
+  }
+}
+
 // pw [W][Fw][T], cw [Fw][H] fp32 -> op [planes][F][KC*64] bf16, k = j'*Cp + ch with j' = W-1-j;
 // the counts columns ride on tap j' = 0 only.
 __global__ void __launch_bounds__(256)
@@ -192,7 +220,7 @@ extern "C" long long bpb_heads_dgrad_wop_elems(int W, int F, int Cp, int planes)
 
 extern "C" int bpb_heads_pack_grad(int B, int L_in, int L_out, int W, int T, int H, int Cp,
                                    int planes, const float* dlogits, const float* dlogcounts,
-                                   bpb_bf16* d8, void* stream_) {
+                                   bpb_bf16* d8, float* dpb, float* dcb, void* stream_) {
   using namespace bp;
   BP_REQUIRE(dlogits && dlogcounts && d8, "bpb_heads_pack_grad: NULL argument");
   BP_REQUIRE(Cp % 8 == 0 && Cp >= T + H && L_out == L_in - W + 1 && (planes == 1 || planes == 2),
@@ -203,6 +231,12 @@ extern "C" int bpb_heads_pack_grad(int B, int L_in, int L_out, int W, int T, int
       B, L_in, L_out, W, T, H, Cp, planes, dlogits, dlogcounts,
       reinterpret_cast<__nv_bfloat16*>(d8));
   BP_CHECK_CUDA(cudaGetLastError());
+  if (dpb != nullptr) {
+    BP_REQUIRE(dcb != nullptr, "bpb_heads_pack_grad: dpb and dcb go together");
+    heads_bias_grad_kernel<<<T + H, 1024, 0, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<long long>(B) * L_out, T, B, H, dlogits, dlogcounts, dpb, dcb);
+    BP_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

@@ -1,7 +1,13 @@
-// K7: weight and bias gradient of the width-3 dilated convolution (models.py:92-96 of the
-// reference; TensorFlow computes it as Conv2DBackpropFilter + BiasAddGrad).
+// K7: every parameter gradient of the network as one split-K tcgen05 kernel: the width-3 dilated
+// convolutions (models.py:92-96 of the reference; TensorFlow computes them as
+// Conv2DBackpropFilter + BiasAddGrad), the one-hot input convolution (models.py:85-90) and the
+// profile / counts heads (models.py:39-49).
 //
 //   dw[j][c][n] = sum_{b,t} act[b, t + j*dil, c] * gz[b,t,n]     db[n] = sum_{b,t} gz[b,t,n]
+//
+// For the input convolution `act` is the implicit im2col view of the 8-channel one-hot tensor,
+// for the heads `gz` is the implicit im2col view of the packed loss gradient d8 (overlapping-row
+// TMA maps, see rowconv_tc.cu); the reduction kernel scatters the sums into the Keras layouts.
 //
 // GEMM view: M = 64 input channels of one (tap, channel-chunk) "unit", N = NT output channels,
 // K = positions.  Both operands are the same [128 positions x 64 channels] TMA tiles the forward
@@ -20,10 +26,12 @@ constexpr int kWgMaxStages = 8;
 
 struct WgradKParams {
   int B, L_out, tiles_per_seq, F, NC, dil;
-  int n_planes, n_passes;
+  int n_passes, pa_bits, pg_bits, db_mask;  // pass i: A plane (pa_bits >> i) & 1, G plane likewise
   int n_units, UG, n_groups, n_ntiles, n_items, ksplit;
   int stages;
-  float* ws;  // [ksplit][3*F*F + F]
+  int Ncols;   // columns of the result (NT * n_ntiles)
+  float* ws;   // [ksplit][(n_units * 64 + 1) * Ncols]
+  unsigned* dbg;
 };
 
 template <int NT>
@@ -93,11 +101,11 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int pass = v % p.n_passes;
         const int b = kb / p.tiles_per_seq;
         const int t0 = (kb % p.tiles_per_seq) * 128;
-        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x1100 + stage, v);
         mbar_expect_tx(&full[stage], static_cast<uint32_t>((NSUB + nu) * kWgTile));
         uint8_t* dst = ring + stage * stage_bytes;
-        const CUtensorMap* mg = (pass == 2) ? &tmG1 : &tmG0;
-        const CUtensorMap* ma = (pass == 1) ? &tmA1 : &tmA0;
+        const CUtensorMap* mg = ((p.pg_bits >> pass) & 1) ? &tmG1 : &tmG0;
+        const CUtensorMap* ma = ((p.pa_bits >> pass) & 1) ? &tmA1 : &tmA0;
         for (int s = 0; s < NSUB; ++s)
           tma_load_3d(mg, dst + s * kWgTile, &full[stage], nt * NT + s * 64, t0, b);
         for (int i = 0; i < nu; ++i) {
@@ -114,7 +122,7 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t db_started = 0;
       for (int v = 0; v < visits; ++v) {
         const int pass = v % p.n_passes;
-        mbar_wait(&full[stage], phase);
+        mbar_wait_wd(&full[stage], phase, p.dbg, 0x1500 + stage, v);
         tc_fence_after();
         const uint32_t g_addr = smem_u32(ring + stage * stage_bytes);
         for (int i = 0; i < nu; ++i) {
@@ -125,7 +133,7 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                       umma_smem_desc(g_addr + k * 2048, kWgTile, 1024), IDESC,
                       (v | k) != 0 ? 1u : 0u);
         }
-        if (do_db && pass != 1) {
+        if (do_db && ((p.db_mask >> pass) & 1)) {
           const uint32_t o_addr = smem_u32(ones);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -142,12 +150,12 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else {
     // epilogue: TMEM partial sums -> workspace slice of this split
     const int q = warp & 3;
-    mbar_wait(acc_full, 0);
+    mbar_wait_wd(acc_full, 0, p.dbg, 0x1800, 0);
     tc_fence_after();
-    float* wsp = p.ws + static_cast<size_t>(split) * (static_cast<size_t>(3) * p.F * p.F + p.F);
+    const size_t rows = static_cast<size_t>(p.n_units) * 64;
+    float* wsp = p.ws + static_cast<size_t>(split) * (rows + 1) * p.Ncols;
     for (int i = 0; i < nu; ++i) {
       const int u = u0 + i;
-      const int j = u / p.NC, c = u % p.NC;
       // M=64 accumulators occupy lanes 0-15 of each TMEM quadrant: row = 16*q + lane.
       const int m = 16 * q + lane;
       for (int col = 0; col < NT; col += 32) {
@@ -156,7 +164,7 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tmem_ld_wait();
         if (lane < 16) {
           float4* dst = reinterpret_cast<float4*>(
-              wsp + (static_cast<size_t>(j) * p.F + c * 64 + m) * p.F + nt * NT + col);
+              wsp + (static_cast<size_t>(u) * 64 + m) * p.Ncols + nt * NT + col);
 #pragma unroll
           for (int x = 0; x < 8; ++x)
             dst[x] = make_float4(__uint_as_float(r[4 * x]), __uint_as_float(r[4 * x + 1]),
@@ -170,7 +178,7 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tmem_ld32(tmem_base + p.UG * NT + col, r);
         tmem_ld_wait();
         if (lane == 0) {
-          float* dst = wsp + static_cast<size_t>(3) * p.F * p.F + nt * NT + col;
+          float* dst = wsp + rows * p.Ncols + nt * NT + col;
 #pragma unroll
           for (int x = 0; x < 32; ++x) dst[x] = __uint_as_float(r[x]);
         }
@@ -183,14 +191,50 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+// Scatter of one reduced element into the caller's Keras-layout gradient tensors.
+struct WgradScatter {
+  int mode;  // 0 tower conv, 1 input conv, 2 heads
+  int rows, cols;
+  int W, Fw, T, H, Cp;
+  float *o0, *o1, *o2;  // mode 0: dw, db | mode 1: dw1, db1 | mode 2: dpw, -, dcw
+};
+
+__device__ __forceinline__ void wgrad_scatter(const WgradScatter& sc, long long i, float tot) {
+  const long long n_main = static_cast<long long>(sc.rows) * sc.cols;
+  const bool is_b = i >= n_main;
+  const int r = is_b ? 0 : static_cast<int>(i / sc.cols);
+  const int n = static_cast<int>(is_b ? i - n_main : i % sc.cols);
+  if (sc.mode == 0) {
+    if (!is_b) sc.o0[i] = tot;
+    else if (sc.o1) sc.o1[n] = tot;
+  } else if (sc.mode == 1) {
+    // rows = im2col index k = j*8 + c of the one-hot window, cols = filters
+    if (n >= sc.Fw) return;
+    if (is_b) {
+      if (sc.o1) sc.o1[n] = tot;
+    } else {
+      const int j = r >> 3, c = r & 7;
+      if (j < sc.W && c < 4) sc.o0[(j * 4 + c) * sc.Fw + n] = tot;
+    }
+  } else {
+    // rows = tower channel c, cols = im2col index kk = j'*Cp + ch of the packed loss gradient
+    const int jp = n / sc.Cp, ch = n % sc.Cp;
+    if (jp >= sc.W) return;
+    if (is_b) return;  // the heads' bias gradients are computed in fp32 by bpb_heads_pack_grad
+    if (r < sc.Fw) {
+      if (ch < sc.T) sc.o0[(static_cast<long long>(sc.W - 1 - jp) * sc.Fw + r) * sc.T + ch] = tot;
+      else if (ch < sc.T + sc.H && jp == 0) sc.o2[r * sc.H + (ch - sc.T)] = tot;
+    }
+  }
+}
+
 // out[i] = sum_s ws[s][i] in a fixed order (deterministic).  One block owns 32 consecutive outputs;
 // warp w adds the splits s = w, w + 8, ... (each a coalesced 128-byte read, four independent
 // chains), then the eight warp partials are added in warp order.
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, long long n_dw, long long n_db,
-                    float* __restrict__ dw, float* __restrict__ db) {
+wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, const WgradScatter sc) {
   __shared__ float part[8][32];
-  const long long n = n_dw + n_db;
+  const long long n = (static_cast<long long>(sc.rows) + 1) * sc.cols;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = static_cast<long long>(blockIdx.x) * 32 + lane;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -210,28 +254,45 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, long long n_dw, lo
     float tot = part[0][lane];
 #pragma unroll
     for (int w = 1; w < 8; ++w) tot += part[w][lane];
-    if (i < n_dw) dw[i] = tot;
-    else if (db) db[i - n_dw] = tot;
+    wgrad_scatter(sc, i, tot);
   }
 }
+
+// One launch: out[u*64 + m][n] = sum over positions of A_u[pos][m] * G[pos][n], u = (tap, chunk).
+struct WgradDesc {
+  const char* who;
+  int B, rows;      // sequences, positions per sequence (the K extent)
+  int n_taps, NC;   // units: tap j (A rows shifted by j*dil) x 64-channel chunk c of the A operand
+  int dil;
+  int Ncols;        // result columns = channels of the G operand (multiple of 64)
+  // operands as strided bf16 tensors [B][rows][inner]
+  const void* a_ptr[2];
+  unsigned long long a_inner, a_rows, a_row_stride_bytes, a_batch_stride_bytes;
+  const void* g_ptr[2];
+  unsigned long long g_inner, g_rows, g_row_stride_bytes, g_batch_stride_bytes;
+  int n_passes, pa_bits, pg_bits, db_mask;
+  float* ws;
+  long long ws_bytes;
+  WgradScatter sc;
+};
 
 struct WgradPlan {
   int NT, UG, n_units, n_groups, n_ntiles, n_items, ksplit, stages;
   size_t smem_bytes, ws_bytes;
 };
 
-static bool plan_wgrad(int B, int L_out, int F, int n_planes, WgradPlan* pl) {
-  const int NT = (F % 256 == 0) ? 256 : (F % 128 == 0 ? 128 : 64);
+static bool plan_wgrad(int B, int rows, int n_units, int Ncols, WgradPlan* pl) {
+  const int NT = (Ncols % 256 == 0) ? 256 : (Ncols % 128 == 0 ? 128 : 64);
   pl->NT = NT;
-  pl->n_units = 3 * (F / 64);
+  pl->n_units = n_units;
   int ug = 512 / NT - 1;  // one accumulator slot is reserved for the bias-gradient unit
-  if (ug > pl->n_units) ug = pl->n_units;
-  if (ug > 3) ug = 3;
+  if (ug > n_units) ug = n_units;
+  if (ug > 4) ug = 4;
   pl->UG = ug;
-  pl->n_groups = (pl->n_units + ug - 1) / ug;
-  pl->n_ntiles = F / NT;
+  pl->n_groups = (n_units + ug - 1) / ug;
+  pl->n_ntiles = Ncols / NT;
   pl->n_items = pl->n_groups * pl->n_ntiles;
-  const int kblocks = B * ((L_out + 127) / 128);
+  const int kblocks = B * ((rows + 127) / 128);
   int ks = sm_count() / pl->n_items;
   if (ks < 1) ks = 1;
   if (ks > kblocks) ks = kblocks;
@@ -239,13 +300,14 @@ static bool plan_wgrad(int B, int L_out, int F, int n_planes, WgradPlan* pl) {
   const size_t stage_bytes = static_cast<size_t>(NT / 64 + ug) * kWgTile;
   const size_t fixed = 1024 + kWgTile + (2 * kWgMaxStages + 2) * 8 + 16;
   const int max_smem = max_smem_optin();
+  if (max_smem <= 0) return false;
   int stages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   if (stages < 1) return false;
   pl->stages = stages;
   pl->smem_bytes = fixed + stages * stage_bytes;
-  pl->ws_bytes = static_cast<size_t>(ks) * (static_cast<size_t>(3) * F * F + F) * sizeof(float);
-  (void)n_planes;
+  pl->ws_bytes = static_cast<size_t>(ks) * (static_cast<size_t>(n_units) * 64 + 1) * Ncols *
+                 sizeof(float);
   return true;
 }
 
@@ -264,47 +326,23 @@ static int launch_wgrad(const CUtensorMap* maps, const WgradKParams& kp, size_t 
   return 0;
 }
 
-}  // namespace bp
-
-extern "C" long long bpb_wgrad3_ws_bytes(int B, int L_out, int F, int precise) {
-  bp::WgradPlan pl;
-  if (bp::max_smem_optin() <= 0) {
-    bp::set_error("bpb_wgrad3_ws_bytes: no CUDA device");
-    return -1;
-  }
-  if (F <= 0 || F % 64 != 0 || !bp::plan_wgrad(B, L_out, F, precise ? 2 : 1, &pl)) {
-    bp::set_error("bpb_wgrad3_ws_bytes: unsupported F=%d", F);
-    return -1;
-  }
-  return static_cast<long long>(pl.ws_bytes);
-}
-
-extern "C" int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream_) {
-  using namespace bp;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BP_REQUIRE(a != nullptr, "bpb_wgrad3_tc: null args");
-  BP_REQUIRE(a->F > 0 && a->F % 64 == 0, "bpb_wgrad3_tc: F=%d must be a positive multiple of 64",
-             a->F);
-  BP_REQUIRE(a->act_hi && a->gz_hi && a->dw && a->ws, "bpb_wgrad3_tc: NULL tensor");
-  BP_REQUIRE((a->act_lo != nullptr) == (a->gz_lo != nullptr),
-             "bpb_wgrad3_tc: act_lo and gz_lo must both be given or both be NULL");
-  BP_REQUIRE(max_smem_optin() > 0, "bpb_wgrad3_tc: no CUDA device");
-  const int n_planes = a->act_lo ? 2 : 1;
+static int wgrad_run(const WgradDesc& d, cudaStream_t stream) {
   WgradPlan pl;
-  BP_REQUIRE(plan_wgrad(a->B, a->L_out, a->F, n_planes, &pl), "bpb_wgrad3_tc: cannot plan F=%d",
-             a->F);
-  BP_REQUIRE(static_cast<size_t>(a->ws_bytes) >= pl.ws_bytes,
-             "bpb_wgrad3_tc: workspace too small (%lld < %zu)", a->ws_bytes, pl.ws_bytes);
-
+  BP_REQUIRE(plan_wgrad(d.B, d.rows, d.n_taps * d.NC, d.Ncols, &pl), "%s: cannot plan (no device?)",
+             d.who);
+  BP_REQUIRE(static_cast<size_t>(d.ws_bytes) >= pl.ws_bytes, "%s: workspace too small (%lld < %zu)",
+             d.who, d.ws_bytes, pl.ws_bytes);
   WgradKParams kp{};
-  kp.B = a->B;
-  kp.L_out = a->L_out;
-  kp.tiles_per_seq = (a->L_out + 127) / 128;
-  kp.F = a->F;
-  kp.NC = a->F / 64;
-  kp.dil = a->dil;
-  kp.n_planes = n_planes;
-  kp.n_passes = n_planes == 2 ? 3 : 1;
+  kp.B = d.B;
+  kp.L_out = d.rows;
+  kp.tiles_per_seq = (d.rows + 127) / 128;
+  kp.F = d.Ncols;
+  kp.NC = d.NC;
+  kp.dil = d.dil;
+  kp.n_passes = d.n_passes;
+  kp.pa_bits = d.pa_bits;
+  kp.pg_bits = d.pg_bits;
+  kp.db_mask = d.db_mask;
   kp.n_units = pl.n_units;
   kp.UG = pl.UG;
   kp.n_groups = pl.n_groups;
@@ -312,15 +350,22 @@ extern "C" int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream_) {
   kp.n_items = pl.n_items;
   kp.ksplit = pl.ksplit;
   kp.stages = pl.stages;
-  kp.ws = a->ws;
+  kp.Ncols = d.Ncols;
+  kp.ws = d.ws;
+  kp.dbg = debug_buffer();
 
   CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));
-  if (!make_tmap_3d(&maps[0], a->act_hi, a->F, a->L_in, a->B, 64, 128)) return 3;
-  if (n_planes == 2 && !make_tmap_3d(&maps[1], a->act_lo, a->F, a->L_in, a->B, 64, 128)) return 3;
-  if (!make_tmap_3d(&maps[2], a->gz_hi, a->F, a->L_out, a->B, 64, 128)) return 3;
-  if (n_planes == 2 && !make_tmap_3d(&maps[3], a->gz_lo, a->F, a->L_out, a->B, 64, 128)) return 3;
-
+  for (int pl_i = 0; pl_i < 2; ++pl_i) {
+    if (d.a_ptr[pl_i] &&
+        !make_tmap_3d_strided(&maps[pl_i], d.a_ptr[pl_i], d.a_inner, d.a_rows, d.B,
+                              d.a_row_stride_bytes, d.a_batch_stride_bytes, 64, 128))
+      return 3;
+    if (d.g_ptr[pl_i] &&
+        !make_tmap_3d_strided(&maps[2 + pl_i], d.g_ptr[pl_i], d.g_inner, d.g_rows, d.B,
+                              d.g_row_stride_bytes, d.g_batch_stride_bytes, 64, 128))
+      return 3;
+  }
   const int grid = pl.n_items * pl.ksplit;
   int rc;
   if (pl.NT == 64) rc = launch_wgrad<64>(maps, kp, pl.smem_bytes, grid, stream);
@@ -328,10 +373,171 @@ extern "C" int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream_) {
   else rc = launch_wgrad<256>(maps, kp, pl.smem_bytes, grid, stream);
   if (rc) return rc;
 
-  const long long n_dw = static_cast<long long>(3) * a->F * a->F;
-  const long long n_db = a->F;
-  const int blocks = static_cast<int>((n_dw + n_db + 31) / 32);
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(a->ws, pl.ksplit, n_dw, n_db, a->dw, a->db);
+  WgradScatter sc = d.sc;
+  sc.rows = pl.n_units * 64;
+  sc.cols = d.Ncols;
+  const long long n = (static_cast<long long>(sc.rows) + 1) * sc.cols;
+  wgrad_reduce_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, stream>>>(d.ws, pl.ksplit, sc);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+static long long wgrad_ws_bytes(const char* who, int B, int rows, int n_units, int Ncols) {
+  WgradPlan pl;
+  if (Ncols <= 0 || Ncols % 64 != 0 || !plan_wgrad(B, rows, n_units, Ncols, &pl)) {
+    set_error("%s: unsupported geometry or no CUDA device", who);
+    return -1;
+  }
+  return static_cast<long long>(pl.ws_bytes);
+}
+
+static int window_kc(int W, int C) { return (W * C + 63) / 64; }
+
+}  // namespace bp
+
+extern "C" long long bpb_wgrad3_ws_bytes(int B, int L_out, int F, int precise) {
+  (void)precise;
+  return bp::wgrad_ws_bytes("bpb_wgrad3_ws_bytes", B, L_out, F > 0 ? 3 * (F / 64) : 0, F);
+}
+
+extern "C" int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream_) {
+  using namespace bp;
+  BP_REQUIRE(a != nullptr, "bpb_wgrad3_tc: null args");
+  BP_REQUIRE(a->F > 0 && a->F % 64 == 0, "bpb_wgrad3_tc: F=%d must be a positive multiple of 64",
+             a->F);
+  BP_REQUIRE(a->act_hi && a->gz_hi && a->dw && a->ws, "bpb_wgrad3_tc: NULL tensor");
+  BP_REQUIRE((a->act_lo != nullptr) == (a->gz_lo != nullptr),
+             "bpb_wgrad3_tc: act_lo and gz_lo must both be given or both be NULL");
+  const bool precise = a->act_lo != nullptr;
+  WgradDesc d{};
+  d.who = "bpb_wgrad3_tc";
+  d.B = a->B;
+  d.rows = a->L_out;
+  d.n_taps = 3;
+  d.NC = a->F / 64;
+  d.dil = a->dil;
+  d.Ncols = a->F;
+  d.a_ptr[0] = a->act_hi;
+  d.a_ptr[1] = a->act_lo;
+  d.a_inner = a->F;
+  d.a_rows = a->L_in;
+  d.a_row_stride_bytes = static_cast<unsigned long long>(a->F) * 2;
+  d.a_batch_stride_bytes = d.a_row_stride_bytes * a->L_in;
+  d.g_ptr[0] = a->gz_hi;
+  d.g_ptr[1] = a->gz_lo;
+  d.g_inner = a->F;
+  d.g_rows = a->L_out;
+  d.g_row_stride_bytes = static_cast<unsigned long long>(a->F) * 2;
+  d.g_batch_stride_bytes = d.g_row_stride_bytes * a->L_out;
+  // hi*hi, lo*hi, hi*lo; the bias gradient adds the hi and lo planes of gz (passes 0 and 2)
+  d.n_passes = precise ? 3 : 1;
+  d.pa_bits = 0b010;
+  d.pg_bits = 0b100;
+  d.db_mask = 0b101;
+  d.ws = a->ws;
+  d.ws_bytes = a->ws_bytes;
+  d.sc.mode = 0;
+  d.sc.o0 = a->dw;
+  d.sc.o1 = a->db;
+  return wgrad_run(d, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" long long bpb_input_conv_wgrad_ws_bytes(int B, int L_out, int W, int F) {
+  return bp::wgrad_ws_bytes("bpb_input_conv_wgrad_ws_bytes", B, L_out, bp::window_kc(W, 8), F);
+}
+
+extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, int F,
+                                    const bpb_bf16* x8, const bpb_bf16* gz_hi,
+                                    const bpb_bf16* gz_lo, float* dw, float* db, float* ws,
+                                    long long ws_bytes, void* stream_) {
+  using namespace bp;
+  BP_REQUIRE(x8 && gz_hi && dw && ws, "bpb_input_conv_wgrad: NULL argument");
+  BP_REQUIRE(F > 0 && F % 64 == 0 && Fw <= F && L_out == L_in - W + 1,
+             "bpb_input_conv_wgrad: bad geometry");
+  WgradDesc d{};
+  d.who = "bpb_input_conv_wgrad";
+  d.B = B;
+  d.rows = L_out;
+  d.n_taps = 1;
+  d.NC = window_kc(W, 8);
+  d.dil = 0;
+  d.Ncols = F;
+  d.a_ptr[0] = x8;
+  d.a_inner = static_cast<unsigned long long>(W) * 8;
+  d.a_rows = L_out;
+  d.a_row_stride_bytes = 16;
+  d.a_batch_stride_bytes = static_cast<unsigned long long>(L_in) * 16;
+  d.g_ptr[0] = gz_hi;
+  d.g_ptr[1] = gz_lo;
+  d.g_inner = F;
+  d.g_rows = L_out;
+  d.g_row_stride_bytes = static_cast<unsigned long long>(F) * 2;
+  d.g_batch_stride_bytes = d.g_row_stride_bytes * L_out;
+  // the one-hot operand is exact: x*gz_hi (+ x*gz_lo)
+  d.n_passes = gz_lo ? 2 : 1;
+  d.pa_bits = 0;
+  d.pg_bits = 0b10;
+  d.db_mask = 0b11;
+  d.ws = ws;
+  d.ws_bytes = ws_bytes;
+  d.sc.mode = 1;
+  d.sc.W = W;
+  d.sc.Fw = Fw;
+  d.sc.o0 = dw;
+  d.sc.o1 = db;
+  return wgrad_run(d, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" long long bpb_heads_wgrad_ws_bytes(int B, int L_in, int W, int F, int Cp) {
+  return bp::wgrad_ws_bytes("bpb_heads_wgrad_ws_bytes", B, L_in, F > 0 ? F / 64 : 0,
+                            bp::window_kc(W, Cp) * 64);
+}
+
+extern "C" int bpb_heads_wgrad_tc(int B, int L_in, int W, int Fw, int F, int T, int H, int Cp,
+                                  const bpb_bf16* act_hi, const bpb_bf16* act_lo,
+                                  const bpb_bf16* d8_hi, const bpb_bf16* d8_lo, float* dpw,
+                                  float* dcw, float* ws, long long ws_bytes, void* stream_) {
+  using namespace bp;
+  BP_REQUIRE(act_hi && d8_hi && dpw && dcw && ws, "bpb_heads_wgrad_tc: NULL argument");
+  BP_REQUIRE((act_lo != nullptr) == (d8_lo != nullptr),
+             "bpb_heads_wgrad_tc: act_lo and d8_lo must both be given or both be NULL");
+  BP_REQUIRE(F > 0 && F % 64 == 0 && Fw <= F && Cp % 8 == 0 && Cp >= T + H,
+             "bpb_heads_wgrad_tc: bad geometry");
+  const bool precise = act_lo != nullptr;
+  const int Lp = L_in + W - 1;
+  WgradDesc d{};
+  d.who = "bpb_heads_wgrad_tc";
+  d.B = B;
+  d.rows = L_in;
+  d.n_taps = 1;
+  d.NC = F / 64;
+  d.dil = 0;
+  d.Ncols = window_kc(W, Cp) * 64;
+  d.a_ptr[0] = act_hi;
+  d.a_ptr[1] = act_lo;
+  d.a_inner = F;
+  d.a_rows = L_in;
+  d.a_row_stride_bytes = static_cast<unsigned long long>(F) * 2;
+  d.a_batch_stride_bytes = d.a_row_stride_bytes * L_in;
+  d.g_ptr[0] = d8_hi;
+  d.g_ptr[1] = d8_lo;
+  d.g_inner = static_cast<unsigned long long>(W) * Cp;
+  d.g_rows = L_in;
+  d.g_row_stride_bytes = static_cast<unsigned long long>(Cp) * 2;
+  d.g_batch_stride_bytes = static_cast<unsigned long long>(Lp) * Cp * 2;
+  d.n_passes = precise ? 3 : 1;
+  d.pa_bits = 0b010;
+  d.pg_bits = 0b100;
+  d.db_mask = 0b101;
+  d.ws = ws;
+  d.ws_bytes = ws_bytes;
+  d.sc.mode = 2;
+  d.sc.W = W;
+  d.sc.Fw = Fw;
+  d.sc.T = T;
+  d.sc.H = H;
+  d.sc.Cp = Cp;
+  d.sc.o0 = dpw;
+  d.sc.o2 = dcw;
+  return wgrad_run(d, static_cast<cudaStream_t>(stream_));
 }

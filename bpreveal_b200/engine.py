@@ -228,10 +228,8 @@ class SoloNet:
             ws["g"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
             ws["gz"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
             nb = max([ops.wgrad3_ws_bytes(B, L, Fp, prec) for L in Ls[1:]] +
-                     [ops.input_conv_wgrad_ws_bytes(B, Ls[0], cfg.inputFilterWidth,
-                                                    cfg.numFilters),
-                      ops.heads_bwd_ws_bytes(B, Ls[-1], cfg.outputFilterWidth, cfg.numFilters,
-                                             cfg.T)])
+                     [ops.input_conv_wgrad_ws_bytes(B, Ls[0], cfg.inputFilterWidth, Fp),
+                      ops.heads_wgrad_ws_bytes(B, Ls[-1], cfg.outputFilterWidth, Fp, self.cp)])
             ws["scratch"] = torch.empty((nb // 4 + 4,), dtype=torch.float32, device=dev)
             ws["d8"] = ops.heads_d8(B, Ls[-1], cfg.outputFilterWidth, self.cp,
                                     2 if prec else 1, dev)
@@ -350,11 +348,10 @@ class SoloNet:
         gcur = self._sub(ws["g"][nL % 2], Ls[nL])
         gzcur = self._sub(ws["gz"][nL % 2], Ls[nL])
         planes = 2 if cfg.precise else 1
-        ops.heads_bwd(aL, ws["gap"], p["prof_w"], p["cnt_w"], ws["dlogits"], ws["dlogcounts"],
-                      dpw=g["prof_w"], dpb=g["prof_b"], dcw=g["cnt_w"], dcb=g["cnt_b"],
-                      ws=ws["scratch"])
         ops.heads_pack_grad(ws["dlogits"], ws["dlogcounts"], Ls[nL], cfg.outputFilterWidth,
-                            self.cp, planes, ws["d8"])
+                            self.cp, planes, ws["d8"], dpb=g["prof_b"], dcb=g["cnt_b"])
+        ops.heads_wgrad(aL, ws["d8"], cfg.outputFilterWidth, cfg.numFilters, cfg.T, cfg.H,
+                        self.cp, planes, g["prof_w"], g["cnt_w"], ws["scratch"])
         ops.heads_dgrad(ws["d8"], self.w_hd_op, ws["B"], Ls[nL], cfg.outputFilterWidth, cfg.Fp,
                         self.cp, planes, g=gcur, gz=gzcur, mask_in=ws["masks"][nL])
         for i in range(nL - 1, -1, -1):
@@ -365,7 +362,7 @@ class SoloNet:
             ops.conv3(gzcur, self.w_bwd[i], (0, -d, -2 * d), 1, Ls[i], resid=gcur, resid_off=-d,
                       out=gnext if i > 0 else None, out2=gznext, mask_in=ws["masks"][i])
             gcur, gzcur = gnext, gznext
-        ops.input_conv_wgrad(ws["x"], gzcur, cfg.inputFilterWidth, cfg.numFilters, g["conv1_w"],
+        ops.input_conv_wgrad(ws["x8"], gzcur, cfg.inputFilterWidth, cfg.numFilters, g["conv1_w"],
                              g["conv1_b"], ws["scratch"])
 
     def apply_adam(self, grad_scale=1.0):

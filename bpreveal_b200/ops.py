@@ -143,18 +143,18 @@ def input_conv_fwd(x8, w_op, w_planes, W, Fw, bias, F, out, mask_out=None, z_out
     check(lib.bpb_input_conv_fwd(C.byref(a), _stream()), "bpb_input_conv_fwd")
 
 
-def input_conv_wgrad_ws_bytes(B, L_out, W, Fw):
-    n = _lib.load().bpb_input_conv_wgrad_ws_bytes(B, L_out, W, Fw)
+def input_conv_wgrad_ws_bytes(B, L_out, W, F):
+    n = _lib.load().bpb_input_conv_wgrad_ws_bytes(B, L_out, W, F)
     if n < 0:
         check(1, "bpb_input_conv_wgrad_ws_bytes")
     return n
 
 
-def input_conv_wgrad(x, gz, W, Fw, dw, db, ws):
+def input_conv_wgrad(x8, gz, W, Fw, dw, db, ws):
     lib = _lib.load()
     g_hi, g_lo = _planes(gz)
     B, L_out, F = g_hi.shape
-    check(lib.bpb_input_conv_wgrad(B, x.shape[1], L_out, W, Fw, F, _p(x), _p(g_hi), _p(g_lo),
+    check(lib.bpb_input_conv_wgrad(B, x8.shape[1], L_out, W, Fw, F, _p(x8), _p(g_hi), _p(g_lo),
                                    _p(dw), _p(db), _p(ws), ws.numel() * ws.element_size(),
                                    _stream()), "bpb_input_conv_wgrad")
 
@@ -179,29 +179,21 @@ def heads_fwd(act, pw, pb, cw, cb, logits, gap, logcounts):
                             _stream()), "bpb_heads_fwd")
 
 
-def heads_bwd_ws_bytes(B, L_in, W, Fw, T):
-    n = _lib.load().bpb_heads_bwd_ws_bytes(B, L_in, W, Fw, T)
+def heads_wgrad_ws_bytes(B, L_in, W, F, Cp):
+    n = _lib.load().bpb_heads_wgrad_ws_bytes(B, L_in, W, F, Cp)
     if n < 0:
-        check(1, "bpb_heads_bwd_ws_bytes")
+        check(1, "bpb_heads_wgrad_ws_bytes")
     return n
 
 
-def heads_bwd(act, gap, pw, cw, dlogits, dlogcounts, g=None, gz=None, mask_in=None, mult=None,
-              dpw=None, dpb=None, dcw=None, dcb=None, ws=None):
-    lib = _lib.load()
+def heads_wgrad(act, d8, W, Fw, T, H, Cp, planes, dpw, dcw, ws):
     a_hi, a_lo = _planes(act)
     B, L_in, F = a_hi.shape
-    W, Fw, T = pw.shape
-    H = cw.shape[1]
-    g_hi, g_lo = _planes(g)
-    z_hi, z_lo = _planes(gz)
-    m_hi, m_lo = _planes(mult)
-    check(lib.bpb_heads_bwd(B, L_in, L_in - W + 1, W, Fw, F, T, H, _p(a_hi), _p(a_lo), _p(gap),
-                            _p(pw), _p(cw), _p(dlogits), _p(dlogcounts), _p(dpw), _p(dpb),
-                            _p(dcw), _p(dcb), _p(g_hi), _p(g_lo), _p(z_hi), _p(z_lo),
-                            _p(mask_in), _p(m_hi), _p(m_lo), _p(ws),
-                            ws.numel() * ws.element_size() if ws is not None else 0, _stream()),
-          "bpb_heads_bwd")
+    d8_lo = (d8.data_ptr() + (d8.numel() // 2) * 2) if planes == 2 else None
+    check(_lib.load().bpb_heads_wgrad_tc(B, L_in, W, Fw, F, T, H, Cp, _p(a_hi), _p(a_lo), _p(d8),
+                                         d8_lo, _p(dpw), _p(dcw), _p(ws),
+                                         ws.numel() * ws.element_size(), _stream()),
+          "bpb_heads_wgrad_tc")
 
 
 def heads_cp(T, H):
@@ -227,11 +219,11 @@ def prep_heads_dgrad_weights(pw, cw, F, Cp, w_op, planes):
           "bpb_prep_heads_dgrad_weights")
 
 
-def heads_pack_grad(dlogits, dlogcounts, L_in, W, Cp, planes, d8):
+def heads_pack_grad(dlogits, dlogcounts, L_in, W, Cp, planes, d8, dpb=None, dcb=None):
     B, L_out, T = dlogits.shape
     H = dlogcounts.shape[1]
     check(_lib.load().bpb_heads_pack_grad(B, L_in, L_out, W, T, H, Cp, planes, _p(dlogits),
-                                          _p(dlogcounts), _p(d8), _stream()),
+                                          _p(dlogcounts), _p(d8), _p(dpb), _p(dcb), _stream()),
           "bpb_heads_pack_grad")
 
 

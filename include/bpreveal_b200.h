@@ -125,9 +125,10 @@ typedef struct {
   bpb_bf16 *mult_hi, *mult_lo;
 } bpb_input_conv_args;
 int bpb_input_conv_fwd(const bpb_input_conv_args* a, void* stream);
-/* dw[j][c][f] = sum_{b,t} x[b,t+j,c] gz[b,t,f]; db[f] = sum gz  (dw is [W][4][Fw], overwritten) */
-long long bpb_input_conv_wgrad_ws_bytes(int B, int L_out, int W, int Fw);
-int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, int F, const uint8_t* x,
+/* dw[j][c][f] = sum_{b,t} x[b,t+j,c] gz[b,t,f]; db[f] = sum gz  (dw is [W][4][Fw], overwritten).
+ * Runs on the K7 tensor-core kernel: the A operand is the implicit im2col view of x8. */
+long long bpb_input_conv_wgrad_ws_bytes(int B, int L_out, int W, int F);
+int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, int F, const bpb_bf16* x8,
                          const bpb_bf16* gz_hi, const bpb_bf16* gz_lo, float* dw, float* db,
                          float* ws, long long ws_bytes, void* stream);
 /* dx[b,s,c] = sum_j sum_f gz[b,s-j,f] w[j][c][f]  (fp32 out [B][L_in][4]); attribution only */
@@ -145,31 +146,34 @@ int bpb_heads_fwd(int B, int L_in, int L_out, int W, int Fw, int F, int T, int H
                   const bpb_bf16* act_hi, const bpb_bf16* act_lo, const float* pw,
                   const float* pb, const float* cw, const float* cb, float* logits, float* gap,
                   float* logcounts, void* stream);
-/* Backward of the heads: given dlogits [B][L_out][T] and dlogcounts [B][H] (fp32):
- *   dpw/dpb/dcw/dcb overwritten (skipped when dpw == NULL);
- *   g[b,s,c] = sum_j sum_k dlogits[b,s-j,k] pw[j][c][k] + sum_h dlogcounts[b,h] cw[c][h] / L_in
- *   written as g (planes) and gz = g * mask_in / mult_in (planes), like bpb_conv3_tc mode 1. */
-long long bpb_heads_bwd_ws_bytes(int B, int L_in, int W, int Fw, int T);
-int bpb_heads_bwd(int B, int L_in, int L_out, int W, int Fw, int F, int T, int H,
-                  const bpb_bf16* act_hi, const bpb_bf16* act_lo, const float* gap,
-                  const float* pw, const float* cw, const float* dlogits,
-                  const float* dlogcounts, float* dpw, float* dpb, float* dcw, float* dcb,
-                  bpb_bf16* g_hi, bpb_bf16* g_lo, bpb_bf16* gz_hi, bpb_bf16* gz_lo,
-                  const uint64_t* mask_in, const bpb_bf16* mult_hi, const bpb_bf16* mult_lo,
-                  float* ws, long long ws_bytes, void* stream);
+/* Parameter gradients of the heads on the K7 tensor-core kernel, from the packed loss gradient
+ * d8 (see below) and the last tower activations act [B][L_in][F]:
+ *   dpw[j][c][k] = sum_{b,t} act[b,t+j,c] dlogits[b,t,k]
+ *   dcw[c][h]    = sum_b mean_t(act[b,t,c]) dlogcounts[b,h]
+ * (overwritten; Keras layouts [W][Fw][T], [Fw][H]).  The bias gradients come from
+ * bpb_heads_pack_grad. */
+long long bpb_heads_wgrad_ws_bytes(int B, int L_in, int W, int F, int Cp);
+int bpb_heads_wgrad_tc(int B, int L_in, int W, int Fw, int F, int T, int H, int Cp,
+                       const bpb_bf16* act_hi, const bpb_bf16* act_lo, const bpb_bf16* d8_hi,
+                       const bpb_bf16* d8_lo, float* dpw, float* dcw, float* ws,
+                       long long ws_bytes, void* stream);
 
 /* Data gradient of the heads on tensor cores.  bpb_heads_pack_grad writes
  *   d8[b, r, ch] = dlogits[b, r-(W-1), ch]  (ch < T, zero outside the profile)
  *                = dlogcounts[b, ch-T] / L_in  (T <= ch < T+H, every row)        bf16 planes
  * as [planes][B][L_in+W-1][Cp] (Cp a multiple of 8 >= T+H); bpb_prep_heads_dgrad_weights lays the
- * profile / counts kernels out as the matching GEMM operand; bpb_heads_dgrad_tc then computes
+ * profile / counts kernels out as the matching GEMM operand
+ * (with dpb != NULL it also writes the heads' bias gradients dpb[k] = sum dlogits[b,t,k] and
+ * dcb[h] = sum_b dlogcounts[b,h] in fp32: their terms cancel almost exactly, so they are not
+ * derived from the rounded d8); bpb_heads_dgrad_tc then computes
  *   g[b,s,c]  = sum_j sum_k dlogits[b,s-j,k] pw[j][c][k] + sum_h dlogcounts[b,h] cw[c][h] / L_in
  *   gz = g * mask_in / mult   (as bpb_conv3_tc mode 1)
- * bpb_heads_bwd with g == gz == NULL computes only the parameter gradients. */
+ */
 long long bpb_heads_d8_elems(int B, int L_in, int W, int Cp, int planes);
 long long bpb_heads_dgrad_wop_elems(int W, int F, int Cp, int planes);
 int bpb_heads_pack_grad(int B, int L_in, int L_out, int W, int T, int H, int Cp, int planes,
-                        const float* dlogits, const float* dlogcounts, bpb_bf16* d8, void* stream);
+                        const float* dlogits, const float* dlogcounts, bpb_bf16* d8, float* dpb,
+                        float* dcb, void* stream);
 int bpb_prep_heads_dgrad_weights(int W, int Fw, int F, int T, int H, int Cp, const float* pw,
                                  const float* cw, bpb_bf16* w_op, int planes, void* stream);
 typedef struct {

@@ -197,15 +197,16 @@ def group_edges():
         gz = split(torch.randn((B, L_out, Fp), generator=g).to(dev), precise)
         dw = torch.empty((W, 4, Fw), dtype=torch.float32, device=dev)
         db = torch.empty((Fw,), dtype=torch.float32, device=dev)
-        ws = torch.empty((ops.input_conv_wgrad_ws_bytes(B, L_out, W, Fw) // 4,),
+        ws = torch.empty((ops.input_conv_wgrad_ws_bytes(B, L_out, W, Fp) // 4,),
                          dtype=torch.float32, device=dev)
-        ops.input_conv_wgrad(x, gz, W, Fw, dw, db, ws)
+        ops.input_conv_wgrad(x8, gz, W, Fw, dw, db, ws)
         gv = val(gz)[..., :Fw]
         xf = x.float()
         ref = torch.stack([torch.einsum("btc,btf->cf", xf[:, j:j + L_out, :], gv)
                            for j in range(W)])
         ok &= report("dw1", dw, ref, 1e-4)
         ok &= report("db1", db, gv.sum(dim=(0, 1)), 1e-4)
+        assert dw.abs().max() > 0
         # dgrad
         dx = torch.empty((B, L_in, 4), dtype=torch.float32, device=dev)
         ops.input_conv_dgrad(gz, w, L_in, dx)
@@ -276,15 +277,15 @@ def group_edges():
             mask[..., c // 64] |= maskb[..., c].long() << (c % 64)
         dpw, dpb = torch.empty_like(pw), torch.empty_like(pb)
         dcw, dcb = torch.empty_like(cw), torch.empty_like(cb)
-        ws = torch.empty((ops.heads_bwd_ws_bytes(B, L_in, W, Fw, T) // 4,), dtype=torch.float32,
-                         device=dev)
-        ops.heads_bwd(act, gap, pw, cw, dlog, dlc, dpw=dpw, dpb=dpb, dcw=dcw, dcb=dcb, ws=ws)
         planes = 2 if precise else 1
         Cp = ops.heads_cp(T, H)
         d8 = ops.heads_d8(B, L_in, W, Cp, planes, dev)
+        ws = torch.empty((ops.heads_wgrad_ws_bytes(B, L_in, W, Fp, Cp) // 4,), dtype=torch.float32,
+                         device=dev)
         w_hd = ops.heads_dgrad_wop(W, Fp, Cp, planes, dev)
         ops.prep_heads_dgrad_weights(pw, cw, Fp, Cp, w_hd, planes)
-        ops.heads_pack_grad(dlog, dlc, L_in, W, Cp, planes, d8)
+        ops.heads_pack_grad(dlog, dlc, L_in, W, Cp, planes, d8, dpb=dpb, dcb=dcb)
+        ops.heads_wgrad(act, d8, W, Fw, T, H, Cp, planes, dpw, dcw, ws)
         ops.heads_dgrad(d8, w_hd, B, L_in, W, Fp, Cp, planes, g=gpl, gz=gzp, mask_in=mask)
         aa = ae.clone().requires_grad_(True)
         pwr, pbr = pw.clone().requires_grad_(True), pb.clone().requires_grad_(True)
@@ -295,9 +296,10 @@ def group_edges():
         tolg = 3e-5 if precise else 8e-3
         ok &= report("g", val(gpl)[..., :Fw], aa.grad, tolg)
         ok &= report("gz", val(gzp)[..., :Fw], aa.grad * maskb[..., :Fw].float(), tolg)
-        ok &= report("dpw", dpw, pwr.grad, 1e-4)
+        tolw = 1e-4 if precise else 5e-3  # d8 is the loss gradient rounded to bf16 (x2 if precise)
+        ok &= report("dpw", dpw, pwr.grad, tolw)
         ok &= report("dpb", dpb, pbr.grad, 1e-4)
-        ok &= report("dcw", dcw, cwr.grad, 1e-4)
+        ok &= report("dcw", dcw, cwr.grad, tolw)
         ok &= report("dcb", dcb, cbr.grad, 1e-4)
     # adam
     n = 10007
