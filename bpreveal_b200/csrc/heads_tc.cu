@@ -1,0 +1,366 @@
+// K3 / K4 forward on tensor cores: every profile head and every counts head of the model in one
+// tcgen05 GEMM (models.py:39-49 of the reference: Conv1D(valid, width W) per head, and
+// GlobalAveragePooling1D -> Dense(1) per head).
+//
+//   logits[b,t,k]   = pb[k] + sum_{j<W} sum_c act[b,t+j,c] pw[j][c][k]          k < T (all heads)
+//   logcounts[b,h]  = cb[h] + (1/L_in) sum_t sum_c act[b,t,c] cw[c][h]
+//
+// GEMM view: M = 128 consecutive positions, N = T + H padded to 16, K = W taps x F channels.  The
+// counts heads ride along as H extra output columns whose weights are non-zero on tap 0 only
+// (the mean over positions commutes with the dense layer), so the last tower activation is read
+// exactly once.  One TMA box of 128 + W - 1 rows per tile and channel chunk feeds all W taps
+// (descriptors start at row offsets 0..W-1 of the box: SWIZZLE_128B depends on the absolute
+// shared-memory address only); weights stay resident in shared memory.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5
+// epilogue (TMEM quadrant = warp % 4): bias, coalesced fp32 logits stores, warp-shuffle reduction
+// of the counts columns into per-tile partial sums (added in tile order by a tiny second kernel:
+// deterministic, no atomics).
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <cstring>
+
+namespace bp {
+
+constexpr int kHdStages = 4;
+
+struct HeadsKParams {
+  int B, L_in, L_out, tiles_per_seq, W, KC, N, T, H;
+  int n_aplanes, n_wplanes, npass, pa_bits, pw_bits;
+  int sub_bytes, box_bytes, stages;
+  uint32_t idesc;
+  const float* pb;
+  float* logits;
+  float* cpart;  // [B][tiles_per_seq][H]
+  unsigned* dbg;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <uint32_t TMEM_COLS>
+__global__ void __launch_bounds__(192, 1)
+heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmW, const HeadsKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int b_tile = p.N * 128;
+  const int w_tiles = p.n_wplanes * p.W * p.KC;
+  const int stage_bytes = p.KC * p.n_aplanes * p.sub_bytes;
+  uint8_t* w_smem = smem;
+  uint8_t* ring = w_smem + ((static_cast<size_t>(w_tiles) * b_tile + 1023) & ~static_cast<size_t>(1023));
+  float* s_bias = reinterpret_cast<float*>(ring + static_cast<size_t>(p.stages) * stage_bytes);
+  float* s_cpart = s_bias + 256;  // [4 warps][16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_cpart + 64);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kHdStages;
+  uint64_t* acc_full = empty + kHdStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.B * p.tiles_per_seq;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = (i < p.T) ? p.pb[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(w_full, static_cast<uint32_t>(w_tiles) * b_tile);
+      for (int wp = 0; wp < p.n_wplanes; ++wp)
+        for (int j = 0; j < p.W; ++j)
+          for (int c = 0; c < p.KC; ++c)
+            tma_load_2d(&tmW, w_smem + static_cast<size_t>((wp * p.W + j) * p.KC + c) * b_tile, w_full,
+                        c * 64, (wp * p.W + j) * p.N);
+      uint32_t stage = 0, phase = 0, ntile = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ntile) {
+        const int b = tile / p.tiles_per_seq;
+        const int t0 = (tile % p.tiles_per_seq) * 128;
+        mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x2100 + stage, ntile);
+        mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.KC * p.n_aplanes * p.box_bytes));
+        uint8_t* dst = ring + static_cast<size_t>(stage) * stage_bytes;
+        for (int c = 0; c < p.KC; ++c)
+          for (int pl = 0; pl < p.n_aplanes; ++pl)
+            tma_load_3d(pl ? &tmA1 : &tmA0, dst + static_cast<size_t>(c * p.n_aplanes + pl) * p.sub_bytes,
+                        &full[stage], c * 64, t0, b);
+        if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait_wd(w_full, 0, p.dbg, 0x2300);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0, ntile = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ntile) {
+        mbar_wait_wd(&acc_empty[as], aphase ^ 1, p.dbg, 0x2400 + as, ntile);
+        mbar_wait_wd(&full[stage], phase, p.dbg, 0x2500 + stage, ntile);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * p.N;
+        const uint32_t base = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
+        uint32_t accum = 0;
+        for (int pass = 0; pass < p.npass; ++pass) {
+          const int ap = (p.pa_bits >> pass) & 1, wp = (p.pw_bits >> pass) & 1;
+          for (int c = 0; c < p.KC; ++c)
+            for (int j = 0; j < p.W; ++j) {
+              const uint32_t a_addr = base + (c * p.n_aplanes + ap) * p.sub_bytes + j * 128;
+              const uint32_t b_addr = smem_u32(w_smem) + ((wp * p.W + j) * p.KC + c) * b_tile;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
+                          umma_smem_desc(b_addr + k * 32, 0, 1024), p.idesc, accum);
+                accum = 1;
+              }
+            }
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&acc_full[as]);
+        if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    uint32_t as = 0, aphase = 0, ntile = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ntile) {
+      const int b = tile / p.tiles_per_seq;
+      const int mt = tile % p.tiles_per_seq;
+      const int t = mt * 128 + row;
+      mbar_wait_wd(&acc_full[as], aphase, p.dbg, 0x2800 + as, ntile);
+      tc_fence_after();
+      for (int n0 = 0; n0 < p.N; n0 += 16) {
+        uint32_t acc[16];
+        tmem_ld16(tmem_base + as * p.N + n0 + (static_cast<uint32_t>(q * 32) << 16), acc);
+        tmem_ld_wait();
+        if (n0 < p.T && t < p.L_out) {
+          float* dst = p.logits + (static_cast<size_t>(b) * p.L_out + t) * p.T;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + i < p.T) dst[n0 + i] = __uint_as_float(acc[i]) + s_bias[n0 + i];
+        }
+        // counts columns T .. T+H-1: deterministic sum over the 128 rows of the tile (rows beyond
+        // L_in were zero-filled by TMA and add nothing); the column test is warp-uniform
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int h = n0 + i - p.T;
+          if (h >= 0 && h < p.H) {
+            float v = __uint_as_float(acc[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_cpart[q * 16 + h] = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+      named_bar_sync(1, 128);
+      if (et < p.H && et < 16)
+        p.cpart[(static_cast<size_t>(b) * p.tiles_per_seq + mt) * p.H + et] =
+            (s_cpart[2 * 16 + et] + s_cpart[3 * 16 + et]) + (s_cpart[0 * 16 + et] + s_cpart[1 * 16 + et]);
+      named_bar_sync(1, 128);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// logcounts[b][h] = cb[h] + (sum over tiles of cpart[b][tile][h]) / L_in
+__global__ void heads_counts_finish_kernel(int B, int tiles, int H, int L_in,
+                                           const float* __restrict__ cpart,
+                                           const float* __restrict__ cb,
+                                           float* __restrict__ logcounts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, h = i % H;
+  float s = 0.f;
+  for (int tIdx = 0; tIdx < tiles; ++tIdx) s += cpart[(static_cast<size_t>(b) * tiles + tIdx) * H + h];
+  logcounts[i] = cb[h] + s / static_cast<float>(L_in);
+}
+
+// pw [W][Fw][T], cw [Fw][H] fp32 -> op [planes][W][N][KC*64] bf16 (k = channel)
+__global__ void __launch_bounds__(256)
+prep_heads_fwd_kernel(int W, int Fw, int K, int N, int T, int H, int planes,
+                      const float* __restrict__ pw, const float* __restrict__ cw,
+                      __nv_bfloat16* __restrict__ op) {
+  const long long n_el = static_cast<long long>(W) * N * K;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n_el) return;
+  const int c = static_cast<int>(i % K);
+  const int n = static_cast<int>((i / K) % N);
+  const int j = static_cast<int>(i / (static_cast<long long>(K) * N));
+  float v = 0.f;
+  if (c < Fw) {
+    if (n < T) v = pw[(static_cast<long long>(j) * Fw + c) * T + n];
+    else if (n < T + H && j == 0) v = cw[c * H + (n - T)];
+  }
+  float r = v;
+  for (int pl = 0; pl < planes; ++pl) {
+    const __nv_bfloat16 hbits = __float2bfloat16_rn(r);
+    op[pl * n_el + i] = hbits;
+    r -= __bfloat162float(hbits);
+  }
+}
+
+static int heads_n(int T, int H) { return (T + H + 15) / 16 * 16; }
+
+struct HeadsPlan {
+  int N, KC, box_rows, sub_bytes, stages;
+  size_t w_bytes, smem_bytes;
+};
+
+static bool plan_heads(int W, int F, int T, int H, int planes, HeadsPlan* pl) {
+  pl->N = heads_n(T, H);
+  pl->KC = F / 64;
+  pl->box_rows = 128 + W - 1;
+  if (pl->N > 256 || pl->box_rows > 256) return false;
+  pl->sub_bytes = (pl->box_rows * 128 + 1023) / 1024 * 1024;
+  pl->w_bytes = (static_cast<size_t>(planes) * W * pl->KC * pl->N * 128 + 1023) / 1024 * 1024;
+  const size_t fixed = 1024 + 256 * 4 + 64 * 4 + (2 * kHdStages + 5) * 8 + 16;
+  const size_t stage = static_cast<size_t>(pl->KC) * planes * pl->sub_bytes;
+  const int max_smem = max_smem_optin();
+  if (max_smem <= 0 || fixed + pl->w_bytes + stage > static_cast<size_t>(max_smem)) return false;
+  int st = static_cast<int>((static_cast<size_t>(max_smem) - fixed - pl->w_bytes) / stage);
+  if (st > kHdStages) st = kHdStages;
+  pl->stages = st;
+  pl->smem_bytes = fixed + pl->w_bytes + st * stage;
+  return true;
+}
+
+}  // namespace bp
+
+extern "C" long long bpb_heads_fwd_wop_elems(int W, int F, int T, int H, int planes) {
+  return static_cast<long long>(planes) * W * bp::heads_n(T, H) * F;
+}
+
+extern "C" int bpb_prep_heads_fwd_weights(int W, int Fw, int F, int T, int H, const float* pw,
+                                          const float* cw, bpb_bf16* w_op, int planes,
+                                          void* stream_) {
+  using namespace bp;
+  BP_REQUIRE(pw && cw && w_op && F % 64 == 0 && Fw <= F && (planes == 1 || planes == 2) && T >= 1 &&
+                 H >= 1,
+             "bpb_prep_heads_fwd_weights: bad arguments");
+  const int N = heads_n(T, H);
+  const long long n = static_cast<long long>(W) * N * F;
+  prep_heads_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
+                          static_cast<cudaStream_t>(stream_)>>>(
+      W, Fw, F, N, T, H, planes, pw, cw, reinterpret_cast<__nv_bfloat16*>(w_op));
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" long long bpb_heads_fwd_ws_bytes(int B, int L_in, int H) {
+  return static_cast<long long>(B) * ((L_in + 127) / 128) * H * 4;
+}
+
+// Returns 0 if the tensor-core kernel can run this geometry (weights + one box fit in shared
+// memory, T + H <= 256, H <= 16, W <= 129); callers fall back to bpb_heads_fwd otherwise.
+extern "C" int bpb_heads_fwd_tc_supported(int W, int F, int T, int H, int planes) {
+  bp::HeadsPlan pl;
+  return (F > 0 && F % 64 == 0 && H <= 16 && T <= 240 && bp::plan_heads(W, F, T, H, planes, &pl)) ? 0 : 1;
+}
+
+extern "C" int bpb_heads_fwd_tc(int B, int L_in, int W, int F, int T, int H,
+                                const bpb_bf16* act_hi, const bpb_bf16* act_lo,
+                                const bpb_bf16* w_op, const float* pb, const float* cb,
+                                float* logits, float* logcounts, float* ws, long long ws_bytes,
+                                void* stream_) {
+  using namespace bp;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(act_hi && w_op && pb && cb && logits && logcounts && ws, "bpb_heads_fwd_tc: NULL argument");
+  BP_REQUIRE(F > 0 && F % 64 == 0 && H >= 1 && H <= 16 && T >= 1 && T <= 240 && L_in >= W,
+             "bpb_heads_fwd_tc: bad geometry F=%d T=%d H=%d", F, T, H);
+  const int planes = act_lo ? 2 : 1;
+  HeadsPlan pl;
+  BP_REQUIRE(plan_heads(W, F, T, H, planes, &pl),
+             "bpb_heads_fwd_tc: W=%d F=%d planes=%d does not fit shared memory", W, F, planes);
+  BP_REQUIRE(ws_bytes >= bpb_heads_fwd_ws_bytes(B, L_in, H), "bpb_heads_fwd_tc: workspace too small");
+  HeadsKParams kp{};
+  kp.B = B;
+  kp.L_in = L_in;
+  kp.L_out = L_in - W + 1;
+  kp.tiles_per_seq = (L_in + 127) / 128;
+  kp.W = W;
+  kp.KC = pl.KC;
+  kp.N = pl.N;
+  kp.T = T;
+  kp.H = H;
+  kp.n_aplanes = planes;
+  kp.n_wplanes = planes;
+  kp.npass = planes == 2 ? 3 : 1;
+  kp.pa_bits = 0b010;
+  kp.pw_bits = 0b100;
+  kp.sub_bytes = pl.sub_bytes;
+  kp.box_bytes = pl.box_rows * 128;
+  kp.stages = pl.stages;
+  kp.idesc = umma_idesc_bf16(128, pl.N, 0, 0);
+  kp.pb = pb;
+  kp.logits = logits;
+  kp.cpart = ws;
+  kp.dbg = debug_buffer();
+  CUtensorMap maps[3];
+  memset(maps, 0, sizeof(maps));
+  if (!make_tmap_3d(&maps[0], act_hi, F, L_in, B, 64, pl.box_rows)) return 3;
+  if (planes == 2 && !make_tmap_3d(&maps[1], act_lo, F, L_in, B, 64, pl.box_rows)) return 3;
+  if (!make_tmap_2d(&maps[2], w_op, F, static_cast<uint64_t>(planes) * W * pl.N, 64, pl.N)) return 3;
+  const int total = B * kp.tiles_per_seq;
+  int grid = sm_count();
+  if (grid > total) grid = total;
+  const uint32_t cols = 2u * pl.N;
+#define LAUNCH_HD(C)                                                                            \
+  do {                                                                                          \
+    static bool configured = false;                                                             \
+    if (!configured) {                                                                          \
+      BP_CHECK_CUDA(cudaFuncSetAttribute(heads_fwd_tc_kernel<C>,                                \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                         max_smem_optin()));                                    \
+      configured = true;                                                                        \
+    }                                                                                           \
+    heads_fwd_tc_kernel<C><<<grid, 192, pl.smem_bytes, stream>>>(maps[0], maps[1], maps[2], kp); \
+  } while (0)
+  if (cols <= 32) LAUNCH_HD(32);
+  else if (cols <= 64) LAUNCH_HD(64);
+  else if (cols <= 128) LAUNCH_HD(128);
+  else if (cols <= 256) LAUNCH_HD(256);
+  else LAUNCH_HD(512);
+#undef LAUNCH_HD
+  BP_CHECK_CUDA(cudaGetLastError());
+  heads_counts_finish_kernel<<<(B * H + 127) / 128, 128, 0, stream>>>(B, kp.tiles_per_seq, H, L_in, ws,
+                                                                      cb, logcounts);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

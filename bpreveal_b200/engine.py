@@ -113,6 +113,11 @@ class SoloNet:
         self.w_in_planes = planes + 1
         self.w_in_op = ops.input_conv_wop(cfg.inputFilterWidth, Fp, self.w_in_planes, self.device)
         self.w_hd_op = ops.heads_dgrad_wop(cfg.outputFilterWidth, Fp, self.cp, planes, self.device)
+        # heads forward as one tcgen05 GEMM when its weights fit shared memory (else CUDA cores)
+        self.heads_tc = ops.heads_fwd_tc_supported(cfg.outputFilterWidth, Fp, cfg.T, cfg.H, planes)
+        if self.heads_tc:
+            self.w_hf_op = ops.heads_fwd_wop(cfg.outputFilterWidth, Fp, cfg.T, cfg.H, planes,
+                                             self.device)
         self.task_off = torch.tensor(np.concatenate([[0], np.cumsum(cfg.headTasks)]),
                                      dtype=torch.int32, device=self.device)
         self._ws = {}
@@ -197,6 +202,9 @@ class SoloNet:
         ops.prep_input_conv_weights(self.p["conv1_w"], cfg.Fp, self.w_in_op, self.w_in_planes)
         ops.prep_heads_dgrad_weights(self.p["prof_w"], self.p["cnt_w"], cfg.Fp, self.cp,
                                      self.w_hd_op, planes)
+        if self.heads_tc:
+            ops.prep_heads_fwd_weights(self.p["prof_w"], self.p["cnt_w"], cfg.Fp, self.w_hf_op,
+                                       planes)
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, B, kind):
@@ -212,6 +220,7 @@ class SoloNet:
         ws["logits"] = torch.empty((B, cfg.outputLength, cfg.T), dtype=torch.float32, device=dev)
         ws["gap"] = torch.empty((B, Fp), dtype=torch.float32, device=dev)
         ws["logcounts"] = torch.empty((B, cfg.H), dtype=torch.float32, device=dev)
+        ws["hf_ws"] = ops.heads_fwd_ws(B, Ls[-1], cfg.H, dev)
         if kind == "predict":
             # two ping-pong activation buffers sized for the longest layer
             ws["ping"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
@@ -289,8 +298,12 @@ class SoloNet:
                       zx_in=zx_list[i + 1] if zx_list else None, zx_div=zx_div,
                       out2=mult_list[i + 1] if mult_list else None)
             a = nxt
-        ops.heads_fwd(a, p["prof_w"], p["prof_b"], p["cnt_w"], p["cnt_b"], ws["logits"],
-                      ws["gap"], ws["logcounts"])
+        if self.heads_tc:
+            ops.heads_fwd_tc(a, self.w_hf_op, cfg.outputFilterWidth, cfg.T, cfg.H, p["prof_b"],
+                             p["cnt_b"], ws["logits"], ws["logcounts"], ws["hf_ws"])
+        else:
+            ops.heads_fwd(a, p["prof_w"], p["prof_b"], p["cnt_w"], p["cnt_b"], ws["logits"],
+                          ws["gap"], ws["logcounts"])
         return a
 
     def predict_into(self, ws):

@@ -179,6 +179,36 @@ def heads_fwd(act, pw, pb, cw, cb, logits, gap, logcounts):
                             _stream()), "bpb_heads_fwd")
 
 
+def heads_fwd_tc_supported(W, F, T, H, planes):
+    return _lib.load().bpb_heads_fwd_tc_supported(W, F, T, H, planes) == 0
+
+
+def heads_fwd_wop(W, F, T, H, planes, device):
+    n = _lib.load().bpb_heads_fwd_wop_elems(W, F, T, H, planes)
+    return torch.zeros((n,), dtype=torch.bfloat16, device=device)
+
+
+def prep_heads_fwd_weights(pw, cw, F, w_op, planes):
+    W, Fw, T = pw.shape
+    H = cw.shape[1]
+    check(_lib.load().bpb_prep_heads_fwd_weights(W, Fw, F, T, H, _p(pw), _p(cw), _p(w_op), planes,
+                                                 _stream()), "bpb_prep_heads_fwd_weights")
+
+
+def heads_fwd_ws(B, L_in, H, device):
+    n = _lib.load().bpb_heads_fwd_ws_bytes(B, L_in, H)
+    return torch.zeros((n // 4 + 1,), dtype=torch.float32, device=device)
+
+
+def heads_fwd_tc(act, w_op, W, T, H, pb, cb, logits, logcounts, ws):
+    a_hi, a_lo = _planes(act)
+    B, L_in, F = a_hi.shape
+    check(_lib.load().bpb_heads_fwd_tc(B, L_in, W, F, T, H, _p(a_hi), _p(a_lo), _p(w_op), _p(pb),
+                                       _p(cb), _p(logits), _p(logcounts), _p(ws),
+                                       ws.numel() * ws.element_size(), _stream()),
+          "bpb_heads_fwd_tc")
+
+
 def heads_wgrad_ws_bytes(B, L_in, W, F, Cp):
     n = _lib.load().bpb_heads_wgrad_ws_bytes(B, L_in, W, F, Cp)
     if n < 0:

@@ -146,6 +146,20 @@ int bpb_heads_fwd(int B, int L_in, int L_out, int W, int Fw, int F, int T, int H
                   const bpb_bf16* act_hi, const bpb_bf16* act_lo, const float* pw,
                   const float* pb, const float* cw, const float* cb, float* logits, float* gap,
                   float* logcounts, void* stream);
+/* The same forward as ONE tcgen05 GEMM (N = T + H padded to 16; the counts heads are extra output
+ * columns with weights on tap 0 only; gap is not materialised).  w_op comes from
+ * bpb_prep_heads_fwd_weights ([planes][W][N][F] bf16); ws holds per-tile partial sums of the counts
+ * columns.  bpb_heads_fwd_tc_supported returns 0 when the geometry fits shared memory; otherwise
+ * use bpb_heads_fwd (CUDA cores). */
+long long bpb_heads_fwd_wop_elems(int W, int F, int T, int H, int planes);
+int bpb_prep_heads_fwd_weights(int W, int Fw, int F, int T, int H, const float* pw,
+                               const float* cw, bpb_bf16* w_op, int planes, void* stream);
+long long bpb_heads_fwd_ws_bytes(int B, int L_in, int H);
+int bpb_heads_fwd_tc_supported(int W, int F, int T, int H, int planes);
+int bpb_heads_fwd_tc(int B, int L_in, int W, int F, int T, int H, const bpb_bf16* act_hi,
+                     const bpb_bf16* act_lo, const bpb_bf16* w_op, const float* pb,
+                     const float* cb, float* logits, float* logcounts, float* ws,
+                     long long ws_bytes, void* stream);
 /* Parameter gradients of the heads on the K7 tensor-core kernel, from the packed loss gradient
  * d8 (see below) and the last tower activations act [B][L_in][F]:
  *   dpw[j][c][k] = sum_{b,t} act[b,t+j,c] dlogits[b,t,k]

@@ -234,6 +234,20 @@ def group_edges():
         ae = val(act)[..., :Fw]
         lr = conv_cl(ae, pw) + pb
         ok &= report("logits", logits, lr, 1e-4)
+        # the same through the tensor-core kernel
+        planes_h = 2 if precise else 1
+        T_, H_ = sum(tasks), len(tasks)
+        if ops.heads_fwd_tc_supported(W, Fp, T_, H_, planes_h):
+            w_hf = ops.heads_fwd_wop(W, Fp, T_, H_, planes_h, dev)
+            ops.prep_heads_fwd_weights(pw, cw, Fp, w_hf, planes_h)
+            logits2 = torch.empty_like(logits)
+            lc2 = torch.empty_like(lc)
+            ops.heads_fwd_tc(act, w_hf, W, T_, H_, pb, cb, logits2, lc2,
+                             ops.heads_fwd_ws(B, L_in, H_, dev))
+            ok &= report("logits (tc)", logits2, lr, 2e-5 if precise else 4e-3)
+            ok &= report("logcounts (tc)", lc2, ae.mean(dim=1) @ cw + cb, 2e-5 if precise else 4e-3)
+        else:
+            print("  heads_fwd_tc not supported for this geometry", flush=True)
         gr = ae.mean(dim=1)
         ok &= report("gap", gap[:, :Fw], gr, 1e-4)
         ok &= report("logcounts", lc, gr @ cw + cb, 1e-4)
