@@ -74,6 +74,7 @@ SIGNATURES = {
     "bpb_version": (c_int, []),
     "bpb_last_error": (C.c_char_p, []),
     "bpb_device_info": (c_int, [C.POINTER(c_int)] * 3),
+    "bpb_abi_struct_size": (c_int, [c_int]),
     "bpb_debug_dump": (c_int, [C.POINTER(C.c_uint), c_int]),
     "bpb_conv3_tc": (c_int, [C.POINTER(Conv3Args), c_void_p]),
     "bpb_wgrad3_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),

@@ -154,6 +154,17 @@ int bpb_version(void) { return 1; }
 
 const char* bpb_last_error(void) { return bp::g_err; }
 
+// sizeof of the argument structs, so that a binding can verify its own layout (tests/test_abi.py)
+int bpb_abi_struct_size(int which) {
+  switch (which) {
+    case 0: return static_cast<int>(sizeof(bpb_conv3_args));
+    case 1: return static_cast<int>(sizeof(bpb_wgrad3_args));
+    case 2: return static_cast<int>(sizeof(bpb_input_conv_args));
+    case 3: return static_cast<int>(sizeof(bpb_heads_dgrad_args));
+    default: return -1;
+  }
+}
+
 int bpb_debug_dump(unsigned* out, int n) {
   if (bp::g_dbg_host == nullptr) return 0;
   if (n > 2048) n = 2048;

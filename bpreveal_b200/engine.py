@@ -150,7 +150,8 @@ class SoloNet:
         return sd
 
     def load_state(self, sd):
-        """Load a dict of numpy arrays keyed like ``oracle.init_solo_params`` (Keras layouts)."""
+        """Load a dict of numpy arrays in Keras layouts: conv1_w (W,4,F), dil{i}_w (3,F,F),
+        prof{h}_w (Wo,F,T_h), cnt{h}_w (F,1) and the matching *_b biases."""
         cfg = self.cfg
         Fn = cfg.numFilters
         p = self.p

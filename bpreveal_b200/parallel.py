@@ -1,0 +1,102 @@
+"""Host-side plumbing for one-process-per-GPU runs.
+
+Training is pure data parallelism: every rank runs forward/backward on an equal shard of the
+global batch, the single flat fp32 gradient bucket is summed with one all-reduce (NCCL over
+NVLink on GPUs; gloo in the CPU tests), scaled by 1/world inside the Adam kernel, and every rank
+applies the identical update.  Prediction and attribution shard windows into contiguous ranges
+with no communication; outputs are concatenated in rank order, which preserves the input order
+the reference guarantees (utils.py:1221-1223, interpretUtils.py:96-99 of the reference).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    """(rank, local_rank, world_size) from the torchrun environment (1 process if unset)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def init_distributed(backend=None, device=None):
+    """Join the process group described by the environment; no-op for a single process."""
+    rank, local, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl" and device is not None:
+            kw["device_id"] = device
+        dist.init_process_group(backend, **kw)
+    return rank, local, world
+
+
+def shard_range(n, rank, world):
+    """Contiguous [start, stop) of rank's share of n items (window sharding for predict / PISA):
+    the first n % world ranks get one extra item, concatenation in rank order restores the input."""
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_batch(batch_indexes, rank, world):
+    """Equal shards of one global batch.  The multinomial NLL divides by the LOCAL batch size
+    (losses.py:36-38), so the average of the ranks' means is the global mean only for equal
+    shards: a ragged tail (global batch not divisible by world) is dropped from every rank."""
+    per = len(batch_indexes) // world
+    return batch_indexes[rank * per:(rank + 1) * per]
+
+
+class EpochPlan:
+    """The per-epoch shuffle + jitter of H5BatchGenerator.refreshData (generators.py:108-122),
+    reproduced identically on every rank: one ``default_rng(1234)`` stream, per epoch
+    ``rng.shuffle(regionIndexes)`` (in place, cumulative across epochs) followed by
+    ``rng.integers(0, 2 * maxJitter, numRegions, int32)``."""
+
+    def __init__(self, numRegions, maxJitter, seed=1234):
+        self.numRegions = numRegions
+        self.maxJitter = maxJitter
+        self.rng = np.random.default_rng(seed=seed)
+        self.regionIndexes = np.arange(0, numRegions)
+
+    def next_epoch(self):
+        self.rng.shuffle(self.regionIndexes)
+        sliceCols = self.rng.integers(0, self.maxJitter * 2, size=(self.numRegions,),
+                                      dtype=np.int32)
+        return self.regionIndexes.copy(), sliceCols
+
+
+class GradAllReducer:
+    """Sum of the flat gradient bucket over ranks.  ``__call__(flat)`` is what
+    ``SoloNet.train_step(allreduce=...)`` expects; the 1/world scaling happens in the Adam
+    kernel (``grad_scale``), not here."""
+
+    def __init__(self, world):
+        self.world = world
+
+    def __call__(self, flat):
+        if self.world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        return flat
+
+
+def allreduce_scalars(values, device=None):
+    """Mean over ranks of a short list of python floats (epoch loss metrics for the callbacks)."""
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t /= dist.get_world_size()
+    return [float(v) for v in t.cpu()]
+
+
+def broadcast_object(obj, src=0):
+    """Rank ``src`` decides (learning-rate drops, early stopping, adaptive lambda); all follow."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        box = [obj]
+        dist.broadcast_object_list(box, src=src)
+        return box[0]
+    return obj

@@ -32,6 +32,9 @@ int bpb_version(void);
 const char* bpb_last_error(void);
 /* Fills SM count and compute capability of the current device. */
 int bpb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* sizeof() of the argument structs as compiled: 0 bpb_conv3_args, 1 bpb_wgrad3_args,
+ * 2 bpb_input_conv_args, 3 bpb_heads_dgrad_args (-1 otherwise); lets a binding check its layout. */
+int bpb_abi_struct_size(int which);
 /* Pipeline watchdog: kernels whose mbarrier waits time out record
  * records in a host-mapped buffer and trap.  Copies up to n (<= 2048) words: word 0 = number of
  * timed-out waits, words 8.. = records of 5 words {tag, block, thread, parity, payload}.
