@@ -1,5 +1,6 @@
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -36,6 +37,14 @@ static DevInfo& devinfo() {
 }
 int sm_count() { return devinfo().sms; }
 int max_smem_optin() { return devinfo().smem; }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("BPB_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 static unsigned* g_dbg_host = nullptr;
 static unsigned* g_dbg_dev = nullptr;

@@ -31,6 +31,26 @@ bool make_tmap_3d_strided(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t
 bool make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint32_t box0,
                   uint32_t box1);
 
+// Launch with programmatic stream serialization (PDL) unless BPB_PDL=0: the kernel's prologue
+// overlaps the tail of its predecessor; the kernel itself must call pdl_wait() before touching
+// data of earlier kernels.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                       cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #define BP_CHECK_CUDA(expr)                                                              \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

@@ -192,6 +192,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // let the next kernel of the stream start its prologue as soon as this grid's CTAs retire
+  pdl_launch_dependents();
+
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm.A[0]);
     tma_prefetch_desc(&tm.W);
@@ -216,6 +219,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  // (bias is a parameter: written only by the optimiser, never by an in-flight predecessor)
   for (int i = threadIdx.x; i < p.F; i += blockDim.x) s_bias[i] = (p.bias && i < p.bias_n) ? p.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -234,6 +238,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
                           w_smem + static_cast<size_t>((wp * p.n_taps + j) * p.KC + c) * B_TILE_BYTES,
                           w_full, c * 64, (wp * p.n_taps + j) * p.F);
       }
+      // the prepared weights are not written by any kernel that can still be in flight; the
+      // activations are: wait for the predecessor grid before the first activation load
+      pdl_wait();
       uint32_t stage = 0, phase = 0, rs = 0, rphase = 0, ntile = 0;
       TileWalk tw;
       for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
@@ -348,6 +355,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     // ------------------------------------------------------------- epilogue warps (2..)
     // EG groups of 8 warps; group g owns this CTA's tiles g, g + EG, ... (its own staging buffer
     // and named barrier), so one group's stores / barrier waits overlap the other's math.
+    pdl_wait();  // global reads (masks, multipliers) and TMA stores below
     const int grp = (warp - 2) >> 3;
     const int q = warp & 3;
     const int half = ((warp - 2) >> 2) & 1;
@@ -632,8 +640,7 @@ static int launch_conv_eg(const ConvMaps& maps, const ConvKParams& kp, size_t sm
                                        max_smem_optin()));
     configured = true;
   }
-  kern<<<grid, 64 + kEpiThreads * EG, smem_bytes, stream>>>(maps, kp);
-  BP_CHECK_CUDA(cudaGetLastError());
+  BP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + kEpiThreads * EG), smem_bytes, stream, maps, kp));
   return 0;
 }
 

@@ -73,6 +73,7 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.B * p.tiles_per_seq;
 
+  pdl_launch_dependents();
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmW);
@@ -102,6 +103,7 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           for (int c = 0; c < p.KC; ++c)
             tma_load_2d(&tmW, w_smem + static_cast<size_t>((wp * p.W + j) * p.KC + c) * b_tile, w_full,
                         c * 64, (wp * p.W + j) * p.N);
+      pdl_wait();  // the activations come from the previous kernel; the weights do not
       uint32_t stage = 0, phase = 0, ntile = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ntile) {
         const int b = tile / p.tiles_per_seq;
@@ -148,6 +150,7 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
     }
   } else {
+    pdl_wait();  // global stores below
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;
@@ -350,7 +353,8 @@ extern "C" int bpb_heads_fwd_tc(int B, int L_in, int W, int F, int T, int H,
                                          max_smem_optin()));                                    \
       configured = true;                                                                        \
     }                                                                                           \
-    heads_fwd_tc_kernel<C><<<grid, 192, pl.smem_bytes, stream>>>(maps[0], maps[1], maps[2], kp); \
+    BP_CHECK_CUDA(launch_pdl(heads_fwd_tc_kernel<C>, dim3(grid), dim3(192), pl.smem_bytes,    \
+                             stream, maps[0], maps[1], maps[2], kp));                           \
   } while (0)
   if (cols <= 32) LAUNCH_HD(32);
   else if (cols <= 64) LAUNCH_HD(64);

@@ -69,6 +69,7 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int my_kb = (kblocks - split + p.ksplit - 1) / p.ksplit;  // split < ksplit <= kblocks
   const int visits = my_kb * p.n_passes;
 
+  pdl_launch_dependents();
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmG0);
@@ -93,6 +94,8 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // everything below reads or writes global memory of earlier kernels (operands, workspace)
+  pdl_wait();
   if (warp == 0) {
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
@@ -321,8 +324,7 @@ static int launch_wgrad(const CUtensorMap* maps, const WgradKParams& kp, size_t 
                                        max_smem_optin()));
     configured = true;
   }
-  kern<<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], kp);
-  BP_CHECK_CUDA(cudaGetLastError());
+  BP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(192), smem, stream, maps[0], maps[1], maps[2], maps[3], kp));
   return 0;
 }
 
