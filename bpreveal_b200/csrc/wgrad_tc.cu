@@ -29,6 +29,9 @@ struct WgradKParams {
   int n_passes, pa_bits, pg_bits, db_mask;  // pass i: A plane (pa_bits >> i) & 1, G plane likewise
   int n_units, UG, n_groups, n_ntiles, n_items, ksplit;
   int stages;
+  int halo;        // 1: ONE TMA box of 128 + (n_taps-1)*dil rows serves every tap (NC == 1)
+  int halo_bytes;  // bytes TMA writes for the box; halo_sub: the same padded to 1024
+  int halo_sub;
   int Ncols;   // columns of the result (NT * n_ntiles)
   float* ws;   // [ksplit][(n_units * 64 + 1) * Ncols]
   unsigned* dbg;
@@ -46,8 +49,8 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int stage_tiles = NSUB + p.UG;
-  const size_t stage_bytes = static_cast<size_t>(stage_tiles) * kWgTile;
+  const size_t stage_bytes = p.halo ? static_cast<size_t>(NSUB) * kWgTile + p.halo_sub
+                                    : static_cast<size_t>(NSUB + p.UG) * kWgTile;
   uint8_t* ones = smem;
   uint8_t* ring = smem + kWgTile;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.stages * stage_bytes);
@@ -105,16 +108,22 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int b = kb / p.tiles_per_seq;
         const int t0 = (kb % p.tiles_per_seq) * 128;
         mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x1100 + stage, v);
-        mbar_expect_tx(&full[stage], static_cast<uint32_t>((NSUB + nu) * kWgTile));
+        mbar_expect_tx(&full[stage], p.halo ? static_cast<uint32_t>(NSUB * kWgTile + p.halo_bytes)
+                                            : static_cast<uint32_t>((NSUB + nu) * kWgTile));
         uint8_t* dst = ring + stage * stage_bytes;
         const CUtensorMap* mg = ((p.pg_bits >> pass) & 1) ? &tmG1 : &tmG0;
         const CUtensorMap* ma = ((p.pa_bits >> pass) & 1) ? &tmA1 : &tmA0;
         for (int s = 0; s < NSUB; ++s)
           tma_load_3d(mg, dst + s * kWgTile, &full[stage], nt * NT + s * 64, t0, b);
-        for (int i = 0; i < nu; ++i) {
-          const int u = u0 + i;
-          const int j = u / p.NC, c = u % p.NC;
-          tma_load_3d(ma, dst + (NSUB + i) * kWgTile, &full[stage], c * 64, t0 + j * p.dil, b);
+        if (p.halo) {
+          // rows t0 .. t0 + 127 + (n_taps-1)*dil of the single channel chunk: every tap at once
+          tma_load_3d(ma, dst + NSUB * kWgTile, &full[stage], 0, t0, b);
+        } else {
+          for (int i = 0; i < nu; ++i) {
+            const int u = u0 + i;
+            const int j = u / p.NC, c = u % p.NC;
+            tma_load_3d(ma, dst + (NSUB + i) * kWgTile, &full[stage], c * 64, t0 + j * p.dil, b);
+          }
         }
         if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
       }
@@ -129,7 +138,10 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tc_fence_after();
         const uint32_t g_addr = smem_u32(ring + stage * stage_bytes);
         for (int i = 0; i < nu; ++i) {
-          const uint32_t a_addr = g_addr + (NSUB + i) * kWgTile;
+          // HALO: tap i starts i*dil rows into the box (the 128-byte swizzle is a function of the
+          // absolute shared-memory address, so an MN-major operand may start on any row)
+          const uint32_t a_addr = p.halo ? g_addr + NSUB * kWgTile + (u0 + i) * p.dil * 128
+                                         : g_addr + (NSUB + i) * kWgTile;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_bf16(tmem_base + i * NT, umma_smem_desc(a_addr + k * 2048, kWgTile, 1024),
@@ -274,6 +286,7 @@ struct WgradDesc {
   const void* g_ptr[2];
   unsigned long long g_inner, g_rows, g_row_stride_bytes, g_batch_stride_bytes;
   int n_passes, pa_bits, pg_bits, db_mask;
+  bool allow_halo;
   float* ws;
   long long ws_bytes;
   WgradScatter sc;
@@ -281,10 +294,11 @@ struct WgradDesc {
 
 struct WgradPlan {
   int NT, UG, n_units, n_groups, n_ntiles, n_items, ksplit, stages;
+  int halo, halo_sub;
   size_t smem_bytes, ws_bytes;
 };
 
-static bool plan_wgrad(int B, int rows, int n_units, int Ncols, WgradPlan* pl) {
+static bool plan_wgrad(int B, int rows, int n_units, int Ncols, WgradPlan* pl, int halo_rows = 0) {
   const int NT = (Ncols % 256 == 0) ? 256 : (Ncols % 128 == 0 ? 128 : 64);
   pl->NT = NT;
   pl->n_units = n_units;
@@ -300,7 +314,11 @@ static bool plan_wgrad(int B, int rows, int n_units, int Ncols, WgradPlan* pl) {
   if (ks < 1) ks = 1;
   if (ks > kblocks) ks = kblocks;
   pl->ksplit = ks;
-  const size_t stage_bytes = static_cast<size_t>(NT / 64 + ug) * kWgTile;
+  // HALO (tower layers with one channel chunk and a dilation span <= 128 rows): one box for all taps
+  pl->halo = halo_rows > 0 && halo_rows <= 256 && pl->n_groups == 1;
+  pl->halo_sub = pl->halo ? (halo_rows * 128 + 1023) / 1024 * 1024 : 0;
+  const size_t stage_bytes = pl->halo ? static_cast<size_t>(NT / 64) * kWgTile + pl->halo_sub
+                                      : static_cast<size_t>(NT / 64 + ug) * kWgTile;
   const size_t fixed = 1024 + kWgTile + (2 * kWgMaxStages + 2) * 8 + 16;
   const int max_smem = max_smem_optin();
   if (max_smem <= 0) return false;
@@ -330,8 +348,9 @@ static int launch_wgrad(const CUtensorMap* maps, const WgradKParams& kp, size_t 
 
 static int wgrad_run(const WgradDesc& d, cudaStream_t stream) {
   WgradPlan pl;
-  BP_REQUIRE(plan_wgrad(d.B, d.rows, d.n_taps * d.NC, d.Ncols, &pl), "%s: cannot plan (no device?)",
-             d.who);
+  const int halo_rows = (d.allow_halo && d.NC == 1 && d.n_taps > 1) ? 128 + (d.n_taps - 1) * d.dil : 0;
+  BP_REQUIRE(plan_wgrad(d.B, d.rows, d.n_taps * d.NC, d.Ncols, &pl, halo_rows),
+             "%s: cannot plan (no device?)", d.who);
   BP_REQUIRE(static_cast<size_t>(d.ws_bytes) >= pl.ws_bytes, "%s: workspace too small (%lld < %zu)",
              d.who, d.ws_bytes, pl.ws_bytes);
   WgradKParams kp{};
@@ -353,6 +372,9 @@ static int wgrad_run(const WgradDesc& d, cudaStream_t stream) {
   kp.ksplit = pl.ksplit;
   kp.stages = pl.stages;
   kp.Ncols = d.Ncols;
+  kp.halo = pl.halo;
+  kp.halo_sub = pl.halo_sub;
+  kp.halo_bytes = halo_rows * 128;
   kp.ws = d.ws;
   kp.dbg = debug_buffer();
 
@@ -361,7 +383,8 @@ static int wgrad_run(const WgradDesc& d, cudaStream_t stream) {
   for (int pl_i = 0; pl_i < 2; ++pl_i) {
     if (d.a_ptr[pl_i] &&
         !make_tmap_3d_strided(&maps[pl_i], d.a_ptr[pl_i], d.a_inner, d.a_rows, d.B,
-                              d.a_row_stride_bytes, d.a_batch_stride_bytes, 64, 128))
+                              d.a_row_stride_bytes, d.a_batch_stride_bytes, 64,
+                              pl.halo ? halo_rows : 128))
       return 3;
     if (d.g_ptr[pl_i] &&
         !make_tmap_3d_strided(&maps[2 + pl_i], d.g_ptr[pl_i], d.g_inner, d.g_rows, d.B,
@@ -436,6 +459,7 @@ extern "C" int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream_) {
   d.pa_bits = 0b010;
   d.pg_bits = 0b100;
   d.db_mask = 0b101;
+  d.allow_halo = true;
   d.ws = a->ws;
   d.ws_bytes = a->ws_bytes;
   d.sc.mode = 0;
