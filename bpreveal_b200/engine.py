@@ -236,7 +236,9 @@ class SoloNet:
             ws["dlogits"] = torch.empty_like(ws["logits"])
             ws["dlogcounts"] = torch.empty_like(ws["logcounts"])
             ws["g"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
-            ws["gz"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
+            # one gz buffer per layer (no ping-pong): the parameter gradients run on a second
+            # stream and may lag the data-gradient chain by several layers
+            ws["gzl"] = [ops.new_planes(B, L, Fp, prec, dev) for L in Ls]
             nb = max([ops.wgrad3_ws_bytes(B, L, Fp, prec) for L in Ls[1:]] +
                      [ops.input_conv_wgrad_ws_bytes(B, Ls[0], cfg.inputFilterWidth, Fp),
                       ops.heads_wgrad_ws_bytes(B, Ls[-1], cfg.outputFilterWidth, Fp, self.cp)])
@@ -358,26 +360,45 @@ class SoloNet:
                          ws["losses"], ws["dlogits"], ws["dlogcounts"])
         if bias_logits is not None:
             ops.mul_f32(ws["dlogcounts"], ws["dscale"], ws["dlogcounts"])
+        # Backward.  The data-gradient chain (heads -> tower layers, each needing the previous one)
+        # runs on the current stream; every parameter gradient only needs the gz of its own layer,
+        # so they run on a side stream and fill the bubbles (prologue / tail) of the chain.  They
+        # share one split-K workspace and are therefore serialised among themselves.
         nL = cfg.numLayers
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
+
+        def fork():
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+
         gcur = self._sub(ws["g"][nL % 2], Ls[nL])
-        gzcur = self._sub(ws["gz"][nL % 2], Ls[nL])
+        gzcur = ws["gzl"][nL]
         planes = 2 if cfg.precise else 1
         ops.heads_pack_grad(ws["dlogits"], ws["dlogcounts"], Ls[nL], cfg.outputFilterWidth,
                             self.cp, planes, ws["d8"], dpb=g["prof_b"], dcb=g["cnt_b"])
-        ops.heads_wgrad(aL, ws["d8"], cfg.outputFilterWidth, cfg.numFilters, cfg.T, cfg.H,
-                        self.cp, planes, g["prof_w"], g["cnt_w"], ws["scratch"])
+        fork()
+        with torch.cuda.stream(side):
+            ops.heads_wgrad(aL, ws["d8"], cfg.outputFilterWidth, cfg.numFilters, cfg.T, cfg.H,
+                            self.cp, planes, g["prof_w"], g["cnt_w"], ws["scratch"])
         ops.heads_dgrad(ws["d8"], self.w_hd_op, ws["B"], Ls[nL], cfg.outputFilterWidth, cfg.Fp,
                         self.cp, planes, g=gcur, gz=gzcur, mask_in=ws["masks"][nL])
         for i in range(nL - 1, -1, -1):
             d = 2 ** (i + 1)
-            ops.wgrad3(ws["acts"][i], gzcur, d, g["dil_w"][i], g["dil_b"][i], ws["scratch"])
+            fork()  # gz of layer i+1 is complete
+            with torch.cuda.stream(side):
+                ops.wgrad3(ws["acts"][i], gzcur, d, g["dil_w"][i], g["dil_b"][i], ws["scratch"])
             gnext = self._sub(ws["g"][i % 2], Ls[i])
-            gznext = self._sub(ws["gz"][i % 2], Ls[i])
+            gznext = ws["gzl"][i]
             ops.conv3(gzcur, self.w_bwd[i], (0, -d, -2 * d), 1, Ls[i], resid=gcur, resid_off=-d,
                       out=gnext if i > 0 else None, out2=gznext, mask_in=ws["masks"][i])
             gcur, gzcur = gnext, gznext
-        ops.input_conv_wgrad(ws["x8"], gzcur, cfg.inputFilterWidth, cfg.numFilters, g["conv1_w"],
-                             g["conv1_b"], ws["scratch"])
+        fork()
+        with torch.cuda.stream(side):
+            ops.input_conv_wgrad(ws["x8"], gzcur, cfg.inputFilterWidth, cfg.numFilters,
+                                 g["conv1_w"], g["conv1_b"], ws["scratch"])
+        main.wait_stream(side)  # join: the optimiser needs every gradient
 
     def apply_adam(self, grad_scale=1.0):
         # the optimiser step counter lives on the device so that the update replays inside a graph
@@ -391,7 +412,32 @@ class SoloNet:
         self.step_and_lr.copy_(torch.tensor([float(step), float(lr)], dtype=torch.float32),
                                non_blocking=False)
 
-    def train_step(self, x_u8, counts, lr, use_graph=True, allreduce=None, world=1):
+    def eval_losses(self, x_u8, counts, bias_logits=None, bias_logcounts=None, use_bias=None):
+        """Forward + losses only (validation batches): returns the device vector
+        [mnll_h ..., lambda_h * mse_h ...]."""
+        self.enable_training()
+        cfg = self.cfg
+        B = x_u8.shape[0]
+        ws = self._workspace(B, "train")
+        ws["x"].copy_(x_u8, non_blocking=True)
+        ws["counts"].copy_(counts, non_blocking=True)
+        self._forward(ws, ws["x"])
+        logits, lc = ws["logits"], ws["logcounts"]
+        if bias_logits is not None:
+            if "logits_c" not in ws:
+                ws["logits_c"] = torch.empty_like(logits)
+                ws["lc_c"] = torch.empty_like(lc)
+                ws["dscale"] = torch.empty_like(lc)
+            ops.add_f32(logits, bias_logits, ws["logits_c"])
+            ops.counts_lse(use_bias, bias_logcounts, lc, ws["lc_c"], ws["dscale"])
+            logits, lc = ws["logits_c"], ws["lc_c"]
+        ops.loss_fwd_bwd(self.task_off, logits, lc, ws["counts"], self.profile_weight, self.lam,
+                         ws["losses"], None, None)
+        del cfg
+        return ws["losses"]
+
+    def train_step(self, x_u8, counts, lr, use_graph=True, allreduce=None, world=1,
+                   bias_logits=None, bias_logcounts=None, use_bias=None):
         """One optimisation step.  ``x_u8`` / ``counts`` may live on the device or in (pinned)
         host memory.  With ``allreduce`` (a callable taking the flat gradient bucket, e.g. an NCCL
         all-reduce) the step is data parallel: local forward/backward, one all-reduce of the
@@ -406,7 +452,13 @@ class SoloNet:
             self.step_and_lr[1:2].fill_(float(lr))  # stream-ordered scalar fill, only on change
             self._lr_on_device = lr
 
-        if allreduce is None:
+        if bias_logits is not None:
+            # combined model: the frozen bias outputs change every batch -> no graph replay
+            self.forward_backward_into(ws, bias_logits, bias_logcounts, use_bias)
+            if allreduce is not None:
+                allreduce(self.grads_flat)
+            self.apply_adam(grad_scale=1.0 / world)
+        elif allreduce is None:
             def body():
                 self.forward_backward_into(ws)
                 self.apply_adam()
@@ -429,6 +481,11 @@ class SoloNet:
                 allreduce(self.grads_flat)
                 body_b()
         return ws["losses"]
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     # ------------------------------------------------------------------ CUDA graphs
     def _run_graph(self, key, body):

@@ -1,0 +1,647 @@
+"""Drop-in counterparts of ``bpreveal.models`` (src/models.py of the reference).
+
+The three builders keep the reference's names, argument order and meaning
+(``soloModel`` models.py:53-56, ``transformationModel`` :226-229, ``combinedModel`` :268-272) but
+return model objects backed by the B200 engine (``engine.SoloNet``) instead of Keras graphs.  The
+objects expose the part of the Keras ``Model`` duck-type that the reference's tools touch
+(SURVEY.md 8b-2): ``name``, ``inputs`` / ``input`` / ``outputs`` / ``output`` with ``.shape``,
+``trainable``, ``compile``, ``fit``, ``predict``, ``save``, ``summary``, ``optimizer.learning_rate``,
+``get_weights`` / ``set_weights`` in Keras layer order, and the reference's layer names
+(``{name}_initial_conv``, ``{name}_conv_{i}``, ``solo_profile_{head}``, ``solo_logcounts_{head}``,
+``regress_linear_*_conv``, ... models.py:39-48, 85-104, 141-172; layers.py:35-46).
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import NetConfig, SoloNet
+
+NUM_BASES = 4  # internal/constants.py:152
+
+
+class _TensorSpec:
+    """Stand-in for a symbolic Keras tensor: only ``.shape`` and ``.name`` are consulted
+    (utils.py:881-887, models.py:339)."""
+
+    def __init__(self, shape, name):
+        self.shape = tuple(shape)
+        self.name = name
+
+    def __repr__(self):
+        return f"<TensorSpec {self.name} shape={self.shape}>"
+
+
+class _Optimizer:
+    """``keras.optimizers.Adam`` stand-in: the tools read and assign ``learning_rate``."""
+
+    def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.learning_rate = float(learning_rate)
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
+
+
+def Adam(learning_rate=0.001, **kw):  # noqa: N802  (Keras spelling)
+    return _Optimizer(learning_rate, **kw)
+
+
+class History:
+    """``keras.callbacks.History``: ``.history`` maps metric name -> list over epochs."""
+
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+    def append(self, epoch, logs):
+        self.epoch.append(epoch)
+        for k, v in logs.items():
+            self.history.setdefault(k, []).append(float(v))
+
+
+def _device(device=None):
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bpreveal_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _head_fields(headList):
+    names = [h["head-name"] for h in headList]
+    tasks = [int(h["num-tasks"]) for h in headList]
+    return names, tasks
+
+
+class Model:
+    """Behaviour shared by the three model kinds."""
+
+    useOldKeras = False  # utils.py:83 looks for this attribute
+
+    def __init__(self, name, inputLength, outputLength, headList):
+        self.name = name
+        self.headList = headList
+        self.headNames, self.headTasks = _head_fields(headList)
+        self.inputLength, self.outputLength = inputLength, outputLength
+        self.inputs = [_TensorSpec((None, inputLength, NUM_BASES), f"{name}_input")]
+        self.input = self.inputs[0]
+        self.trainable = True
+        self.stop_training = False
+        self.optimizer = None
+        self._loss_weights = None
+        self._lambdas = None
+
+    # ---- shapes -------------------------------------------------------------------------
+    def _set_outputs(self, profileNames, countsNames):
+        self.outputs = [_TensorSpec((None, self.outputLength, t), n)
+                        for t, n in zip(self.headTasks, profileNames)] + \
+                       [_TensorSpec((None, 1), n) for n in countsNames]
+        self.output = self.outputs
+        self.output_names = [o.name for o in self.outputs]
+
+    # ---- Keras-like API -----------------------------------------------------------------
+    def compile(self, optimizer=None, loss=None, loss_weights=None, metrics=None):  # noqa: A003
+        """``loss`` is accepted for signature compatibility; the losses of this path are fixed:
+        multinomial NLL per profile head, lambda-weighted MSE per counts head
+        (training.py:22-65).  ``loss_weights`` = profile weights followed by ones."""
+        del loss, metrics
+        self.optimizer = optimizer if optimizer is not None else _Optimizer()
+        H = len(self.headTasks)
+        lw = list(loss_weights) if loss_weights is not None else [1.0] * (2 * H)
+        self._loss_weights = [float(v) for v in lw[:H]]
+        lam = []
+        for h in self.headList:
+            v = h.get("INTERNAL_λ-variable", h.get("counts-loss-weight", 1.0))
+            lam.append(float(v.value if hasattr(v, "value") else v))
+        self._lambdas = lam
+
+    def set_lambdas(self, lambdas):
+        """The adaptive counts-loss weights (callbacks.py:96-389 adjust them between epochs)."""
+        self._lambdas = [float(v) for v in lambdas]
+
+    def summary(self, print_fn=print):
+        print_fn(f'Model: "{self.name}"')
+        for name, shape, n in self._layer_table():
+            print_fn(f"  {name:40s} {str(shape):24s} {n:10d}")
+        print_fn(f"Total params: {sum(r[2] for r in self._layer_table())}")
+
+    def count_params(self):
+        return sum(r[2] for r in self._layer_table())
+
+    def predict(self, x, batch_size=64, verbose=0):
+        """(n, inputLength, 4) one-hot -> [profile_h (n, Lout, T_h) ..., counts_h (n, 1) ...]
+        as numpy float32 (Keras ``predict`` contract used at utils.py:1021-1023)."""
+        del verbose
+        dev = self._device
+        xt = torch.as_tensor(np.ascontiguousarray(x)).to(device=dev, dtype=torch.uint8)
+        logits, lc = self._predict_device(xt, batch_size)
+        return self._split_outputs(logits.cpu().numpy(), lc.cpu().numpy())
+
+    def _split_outputs(self, logits, lc):
+        outs, k = [], 0
+        for t in self.headTasks:
+            outs.append(np.ascontiguousarray(logits[:, :, k:k + t]))
+            k += t
+        for h in range(len(self.headTasks)):
+            outs.append(np.ascontiguousarray(lc[:, h:h + 1]))
+        return outs
+
+    def __call__(self, x, training=False):
+        del training
+        return self.predict(x[0] if isinstance(x, (list, tuple)) else x)
+
+    # ---- training -----------------------------------------------------------------------
+    def fit(self, x, epochs=1, validation_data=None, callbacks=None, verbose=0,
+            shuffle=True, initial_epoch=0):
+        """Minimal ``Model.fit`` over ``keras.utils.Sequence``-style generators
+        (``len(gen)`` batches, ``gen[i] -> (x, (profiles..., logcounts...))``,
+        ``gen.on_epoch_end()``), as driven by training.py:168-170.
+
+        Logs per epoch: ``loss`` (weighted total), ``{output}_loss`` per output and their
+        ``val_`` twins; callbacks get ``on_train_begin / on_epoch_begin / on_epoch_end /
+        on_train_end`` with the Keras signatures and may set ``model.stop_training``."""
+        del verbose
+        if self.optimizer is None:
+            raise RuntimeError("compile() the model before fit()")
+        callbacks = list(callbacks or [])
+        hist = History()
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+            if hasattr(cb, "on_train_begin"):
+                cb.on_train_begin({})
+        self.stop_training = False
+        rng = np.random.default_rng()
+        for epoch in range(initial_epoch, epochs):
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_begin"):
+                    cb.on_epoch_begin(epoch, {})
+            order = np.arange(len(x))
+            if shuffle:
+                rng.shuffle(order)  # Keras shuffles the batch order of a Sequence by default
+            logs = self._run_epoch(x, order, train=True, prefix="")
+            if validation_data is not None:
+                logs.update(self._run_epoch(validation_data, np.arange(len(validation_data)),
+                                            train=False, prefix="val_"))
+            hist.append(epoch, logs)
+            for gen in (x, validation_data):
+                if gen is not None and hasattr(gen, "on_epoch_end"):
+                    gen.on_epoch_end()
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            if hasattr(cb, "on_train_end"):
+                cb.on_train_end({})
+        self.history = hist
+        return hist
+
+    def _run_epoch(self, gen, order, train, prefix):
+        H = len(self.headTasks)
+        sums = np.zeros(2 * H, dtype=np.float64)
+        nseq = 0
+        for bi in order:
+            xb, yb = gen[int(bi)]
+            counts = np.concatenate([np.asarray(y, dtype=np.float32) for y in yb[:H]], axis=2)
+            losses = self._step(np.asarray(xb), counts, train)
+            n = xb.shape[0]
+            sums += losses * n  # every loss is a mean over the batch (losses.py:36-38)
+            nseq += n
+        per = sums / max(nseq, 1)
+        logs = {}
+        tot = 0.0
+        for h in range(H):
+            logs[f"{prefix}{self.output_names[h]}_loss"] = per[h]
+            logs[f"{prefix}{self.output_names[H + h]}_loss"] = per[H + h]
+            tot += self._loss_weights[h] * per[h] + per[H + h]
+        logs[f"{prefix}loss"] = tot
+        return logs
+
+    # ---- weights ------------------------------------------------------------------------
+    def save(self, path):
+        """``.npz`` (native) or ``.keras`` / ``.h5`` (Keras 3 layout; needs h5py, which this image
+        lacks -- the native format is always available)."""
+        arch = self.get_config()
+        named = self.named_weights()
+        if path.endswith(".npz"):
+            np.savez(path, __config__=json.dumps(arch), **{k: v for k, v in named})
+            return
+        from . import keras_io
+        keras_io.save_keras(path, arch, named)
+
+    def named_weights(self):
+        raise NotImplementedError
+
+    def get_weights(self):
+        return [v for _, v in self.named_weights()]
+
+
+class SoloModel(Model):
+    """``soloModel``: one BPNet tower + heads on one GPU."""
+
+    def __init__(self, inputLength, outputLength, numFilters, numLayers, inputFilterWidth,
+                 outputFilterWidth, headList, modelName, precise=False, device=None, seed=None):
+        super().__init__(f"{modelName}_model", inputLength, outputLength, headList)
+        self.modelName = modelName
+        self._device = _device(device)
+        cfg = NetConfig(inputLength=inputLength, outputLength=outputLength, numFilters=numFilters,
+                        numLayers=numLayers, inputFilterWidth=inputFilterWidth,
+                        outputFilterWidth=outputFilterWidth, headTasks=self.headTasks,
+                        precise=precise)
+        self.net = SoloNet(cfg, self._device)  # raises on an inconsistent architecture
+        self.net.init_random(seed=seed if seed is not None else int.from_bytes(os.urandom(4), "little"))
+        self.inputs = [_TensorSpec((None, inputLength, NUM_BASES), f"{modelName}_input")]
+        self.input = self.inputs[0]
+        self._set_outputs([f"solo_profile_{n}" for n in self.headNames],
+                          [f"solo_logcounts_{n}" for n in self.headNames])
+
+    def get_config(self):
+        c = self.net.cfg
+        return {"kind": "solo", "modelName": self.modelName, "inputLength": c.inputLength,
+                "outputLength": c.outputLength, "numFilters": c.numFilters,
+                "numLayers": c.numLayers, "inputFilterWidth": c.inputFilterWidth,
+                "outputFilterWidth": c.outputFilterWidth,
+                "heads": [{"head-name": n, "num-tasks": t}
+                          for n, t in zip(self.headNames, self.headTasks)]}
+
+    def named_weights(self):
+        """(Keras variable path, array) in Keras layer order (models.py:85-113)."""
+        sd = self.net.state()
+        mn = self.modelName
+        out = [(f"{mn}_initial_conv/kernel", sd["conv1_w"]), (f"{mn}_initial_conv/bias", sd["conv1_b"])]
+        for i in range(self.net.cfg.numLayers):
+            out += [(f"{mn}_conv_{i}/kernel", sd[f"dil{i}_w"]), (f"{mn}_conv_{i}/bias", sd[f"dil{i}_b"])]
+        for h, n in enumerate(self.headNames):
+            out += [(f"solo_profile_{n}/kernel", sd[f"prof{h}_w"]),
+                    (f"solo_profile_{n}/bias", sd[f"prof{h}_b"])]
+            out += [(f"solo_logcounts_{n}/kernel", sd[f"cnt{h}_w"]),
+                    (f"solo_logcounts_{n}/bias", sd[f"cnt{h}_b"])]
+        return out
+
+    def set_weights(self, weights):
+        names = [k for k, _ in self.named_weights()]
+        if isinstance(weights, dict):
+            weights = [weights[k] for k in names]
+        assert len(weights) == len(names), "weight list does not match the architecture"
+        sd = {}
+        it = iter(weights)
+        sd["conv1_w"], sd["conv1_b"] = next(it), next(it)
+        for i in range(self.net.cfg.numLayers):
+            sd[f"dil{i}_w"], sd[f"dil{i}_b"] = next(it), next(it)
+        for h in range(len(self.headNames)):
+            sd[f"prof{h}_w"], sd[f"prof{h}_b"] = next(it), next(it)
+            sd[f"cnt{h}_w"], sd[f"cnt{h}_b"] = next(it), next(it)
+        self.net.load_state(sd)
+
+    def _layer_table(self):
+        return [(k, v.shape, int(v.size)) for k, v in self.named_weights()]
+
+    def _predict_device(self, xt, batch_size):
+        return self.net.predict(xt, batchSize=batch_size)
+
+    def _step(self, xb, counts, train):
+        net = self.net
+        net.enable_training()
+        net.profile_weight.copy_(torch.tensor(self._loss_weights))
+        net.lam.copy_(torch.tensor(self._lambdas))
+        if train and self.trainable:
+            losses = net.train_step(torch.as_tensor(xb), torch.as_tensor(counts),
+                                    self.optimizer.learning_rate)
+        else:
+            losses = net.eval_losses(torch.as_tensor(xb), torch.as_tensor(counts))
+        return losses.double().cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------
+# transformation model (models.py:118-265)
+# ----------------------------------------------------------------------------------------
+_ACT = {"linear": 0, "sigmoid": 1, "relu": 2}
+
+
+class TransformationModel(Model):
+    """``transformationModel``: per head, sums of ``m1 * act(m2 * u + b2) + b1`` applied to the
+    frozen solo model's profile logits and log-counts.  Parameters are scalars initialised to
+    slope 1 / offset 0 (layers.py:37-46 ``kernel_initializer="Ones"``, zero bias)."""
+
+    def __init__(self, soloModelIn, profileArchitectureSpecification,
+                 countsArchitectureSpecification, headList):
+        super().__init__("transformation_model", soloModelIn.inputLength,
+                         soloModelIn.outputLength, headList)
+        soloModelIn.trainable = False  # models.py:249
+        self.solo = soloModelIn
+        self._device = soloModelIn._device
+        self.profileSpec = profileArchitectureSpecification
+        self.countsSpec = countsArchitectureSpecification
+        for spec in (self.profileSpec, self.countsSpec):
+            if spec["name"] not in ("simple", "passthrough"):
+                raise ValueError("Currently, only simple regression is supported.")
+            for t in spec.get("types", []):
+                if t not in _ACT:
+                    raise ValueError(f"The simple layer type you gave ({t}) is not supported")
+        H = len(self.headTasks)
+        dev = self._device
+        # coefficient table [(head, kind) -> terms][4] = {m1, b1, m2, b2}
+        self.pTypes = list(self.profileSpec.get("types", [])) if self.profileSpec["name"] == "simple" else []
+        self.cTypes = list(self.countsSpec.get("types", [])) if self.countsSpec["name"] == "simple" else []
+        n_terms = H * (len(self.pTypes) + len(self.cTypes))
+        base = torch.tensor([1.0, 0.0, 1.0, 0.0], dtype=torch.float32)
+        self.coeffs = base.repeat(max(n_terms, 1), 1).to(dev).contiguous()
+        self.pAct = torch.tensor([_ACT[t] for t in self.pTypes] or [0], dtype=torch.int32, device=dev)
+        self.cAct = torch.tensor([_ACT[t] for t in self.cTypes] or [0], dtype=torch.int32, device=dev)
+        self._adam = None
+        self._set_outputs([self._out_name("profile", n, self.pTypes, f"solo_profile_{n}")
+                           for n in self.headNames],
+                          [self._out_name("logcounts", n, self.cTypes, f"solo_logcounts_{n}")
+                           for n in self.headNames])
+
+    @staticmethod
+    def _out_name(kind, head, types, passthrough):
+        if not types:
+            return passthrough
+        if len(types) > 1:
+            return f"regress_sum_{kind}_{head}"
+        t = types[0]
+        return (f"regress_linear_{kind}_{head}_r2" if t == "linear"
+                else f"{t}_out_linear_{kind}_{head}_r2")
+
+    def _rows(self, h, kind):
+        """Slice of the coefficient table holding head h's profile / counts terms."""
+        per = len(self.pTypes) + len(self.cTypes)
+        off = h * per + (0 if kind == "p" else len(self.pTypes))
+        return off, off + (len(self.pTypes) if kind == "p" else len(self.cTypes))
+
+    def get_config(self):
+        return {"kind": "transformation", "solo": self.solo.get_config(),
+                "profile": self.profileSpec, "counts": self.countsSpec}
+
+    def named_weights(self):
+        out = list(self.solo.named_weights())
+        c = self.coeffs.cpu().numpy()
+        for h, n in enumerate(self.headNames):
+            for kind, types, tag in (("p", self.pTypes, "profile"), ("c", self.cTypes, "logcounts")):
+                lo, _ = self._rows(h, kind)
+                for i, t in enumerate(types):
+                    m1, b1, m2, b2 = c[lo + i]
+                    if t == "linear":
+                        out += [(f"regress_linear_{tag}_{n}_conv/kernel", np.float32(m1).reshape(1, 1, 1)),
+                                (f"regress_linear_{tag}_{n}_conv/bias", np.float32(b1).reshape(1))]
+                    else:
+                        out += [(f"{t}_in_linear_{tag}_{n}_conv/kernel", np.float32(m2).reshape(1, 1, 1)),
+                                (f"{t}_in_linear_{tag}_{n}_conv/bias", np.float32(b2).reshape(1)),
+                                (f"{t}_out_linear_{tag}_{n}_conv/kernel", np.float32(m1).reshape(1, 1, 1)),
+                                (f"{t}_out_linear_{tag}_{n}_conv/bias", np.float32(b1).reshape(1))]
+        return out
+
+    def set_weights(self, weights):
+        names = [k for k, _ in self.named_weights()]
+        if isinstance(weights, dict):
+            weights = [weights[k] for k in names]
+        n_solo = len(self.solo.named_weights())
+        self.solo.set_weights(list(weights[:n_solo]))
+        vals = dict(zip(names[n_solo:], weights[n_solo:]))
+        c = self.coeffs.cpu().numpy().copy()
+        for h, n in enumerate(self.headNames):
+            for kind, types, tag in (("p", self.pTypes, "profile"), ("c", self.cTypes, "logcounts")):
+                lo, _ = self._rows(h, kind)
+                for i, t in enumerate(types):
+                    if t == "linear":
+                        c[lo + i, 0] = np.ravel(vals[f"regress_linear_{tag}_{n}_conv/kernel"])[0]
+                        c[lo + i, 1] = np.ravel(vals[f"regress_linear_{tag}_{n}_conv/bias"])[0]
+                    else:
+                        c[lo + i, 2] = np.ravel(vals[f"{t}_in_linear_{tag}_{n}_conv/kernel"])[0]
+                        c[lo + i, 3] = np.ravel(vals[f"{t}_in_linear_{tag}_{n}_conv/bias"])[0]
+                        c[lo + i, 0] = np.ravel(vals[f"{t}_out_linear_{tag}_{n}_conv/kernel"])[0]
+                        c[lo + i, 1] = np.ravel(vals[f"{t}_out_linear_{tag}_{n}_conv/bias"])[0]
+        self.coeffs.copy_(torch.tensor(c))
+
+    def _layer_table(self):
+        return [(k, np.shape(v), int(np.size(v))) for k, v in self.named_weights()]
+
+    # ---- forward on device tensors ------------------------------------------------------
+    def transform_device(self, logits, lc):
+        """Apply the per-head transformations to solo outputs (B, L, T) / (B, H) on the device.
+        Returns new tensors (the inputs are kept for the backward pass)."""
+        out_l = logits.clone()
+        out_c = lc.clone()
+        k = 0
+        for h, t in enumerate(self.headTasks):
+            if self.pTypes:
+                lo, hi = self._rows(h, "p")
+                u = logits[:, :, k:k + t].contiguous()
+                y = torch.empty_like(u)
+                ops.transform_fwd(u, y, self.pAct, self.coeffs[lo:hi].contiguous())
+                out_l[:, :, k:k + t] = y
+            if self.cTypes:
+                lo, hi = self._rows(h, "c")
+                u = lc[:, h:h + 1].contiguous()
+                y = torch.empty_like(u)
+                ops.transform_fwd(u, y, self.cAct, self.coeffs[lo:hi].contiguous())
+                out_c[:, h:h + 1] = y
+            k += t
+        return out_l, out_c
+
+    def _predict_device(self, xt, batch_size):
+        logits, lc = self.solo.net.predict(xt, batchSize=batch_size)
+        return self.transform_device(logits, lc)
+
+    def _step(self, xb, counts, train):
+        """One batch of trainTransformationModel: solo forward (frozen), transformations, losses,
+        gradients of the 4-vectors, Keras-Adam on them."""
+        net = self.solo.net
+        net.enable_training()
+        dev = self._device
+        xt = torch.as_tensor(xb).to(device=dev, dtype=torch.uint8)
+        ct = torch.as_tensor(counts).to(device=dev, dtype=torch.float32).contiguous()
+        logits, lc = net.predict(xt, batchSize=xt.shape[0])
+        tl, tc = self.transform_device(logits, lc)
+        B = xt.shape[0]
+        H = len(self.headTasks)
+        losses = torch.zeros((2 * H,), dtype=torch.float32, device=dev)
+        dl = torch.empty_like(tl)
+        dc = torch.empty_like(tc)
+        pw = torch.tensor(self._loss_weights, dtype=torch.float32, device=dev)
+        lam = torch.tensor(self._lambdas, dtype=torch.float32, device=dev)
+        ops.loss_fwd_bwd(net.task_off, tl.contiguous(), tc.contiguous(), ct, pw, lam, losses, dl, dc)
+        if train:
+            grads = torch.zeros_like(self.coeffs)
+            k = 0
+            for h, t in enumerate(self.headTasks):
+                if self.pTypes:
+                    lo, hi = self._rows(h, "p")
+                    g = torch.zeros((hi - lo, 4), dtype=torch.float32, device=dev)
+                    ops.transform_bwd(logits[:, :, k:k + t].contiguous(), dl[:, :, k:k + t].contiguous(),
+                                      self.pAct, self.coeffs[lo:hi].contiguous(), g)
+                    grads[lo:hi] = g
+                if self.cTypes:
+                    lo, hi = self._rows(h, "c")
+                    g = torch.zeros((hi - lo, 4), dtype=torch.float32, device=dev)
+                    ops.transform_bwd(lc[:, h:h + 1].contiguous(), dc[:, h:h + 1].contiguous(),
+                                      self.cAct, self.coeffs[lo:hi].contiguous(), g)
+                    grads[lo:hi] = g
+                k += t
+            # a linear term has no inner regression: its (m2, b2) slots are not parameters
+            for h in range(H):
+                for kind, types in (("p", self.pTypes), ("c", self.cTypes)):
+                    lo, _ = self._rows(h, kind)
+                    for i, ty in enumerate(types):
+                        if ty == "linear":
+                            grads[lo + i, 2:] = 0.0
+            if self._adam is None:
+                self._adam = {"m": torch.zeros_like(self.coeffs), "v": torch.zeros_like(self.coeffs),
+                              "sl": torch.zeros((2,), dtype=torch.float32, device=dev)}
+            a = self._adam
+            a["sl"][0] += 1.0
+            a["sl"][1] = float(self.optimizer.learning_rate)
+            flat = self.coeffs.view(-1)
+            ops.adam_step(flat, grads.view(-1).contiguous(), a["m"].view(-1), a["v"].view(-1), a["sl"])
+        del B
+        return losses.double().cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------
+# combined model (models.py:268-387)
+# ----------------------------------------------------------------------------------------
+class CombinedModel(Model):
+    """``combinedModel``: frozen (solo + transformation) bias model on the cropped input, plus a
+    trainable residual BPNet; logits add, log-counts combine as log(e^bias + e^resid) in fp64
+    where ``use-bias-counts`` (layers.py:52-75, models.py:363-380)."""
+
+    def __init__(self, residual, biasModel, headList):
+        super().__init__("combined_model", residual.inputLength, residual.outputLength, headList)
+        biasModel.trainable = False
+        self.residual = residual
+        self.bias = biasModel
+        self._device = residual._device
+        cropDiff = residual.inputLength - biasModel.inputLength
+        assert cropDiff % 2 == 0, "Cropping returns an odd number: " \
+                                  "redo your model input sizes to be even numbers."
+        assert cropDiff >= 0, "Bias model inputs are larger than residual inputs"
+        self.cropFlank = cropDiff // 2
+        assert biasModel.outputLength == residual.outputLength, \
+            "bias and residual models must predict the same output length"
+        self.useBias = torch.tensor([1 if h.get("use-bias-counts", False) else 0 for h in headList],
+                                    dtype=torch.int32, device=self._device)
+        self.inputs = residual.inputs
+        self.input = residual.input
+        self._set_outputs([f"combined_add_profile_{n}" for n in self.headNames],
+                          [f"combined_logcounts_{n}" for n in self.headNames])
+
+    def get_config(self):
+        return {"kind": "combined", "residual": self.residual.get_config(),
+                "bias": self.bias.get_config(),
+                "use-bias-counts": [bool(v) for v in self.useBias.cpu().tolist()]}
+
+    def named_weights(self):
+        return list(self.residual.named_weights()) + list(self.bias.named_weights())
+
+    def set_weights(self, weights):
+        n = len(self.residual.named_weights())
+        self.residual.set_weights(list(weights[:n]))
+        self.bias.set_weights(list(weights[n:]))
+
+    def _layer_table(self):
+        return [(k, np.shape(v), int(np.size(v))) for k, v in self.named_weights()]
+
+    def _bias_device(self, xt, batch_size):
+        f = self.cropFlank
+        xc = xt[:, f:xt.shape[1] - f, :].contiguous() if f > 0 else xt
+        return self.bias._predict_device(xc, batch_size)
+
+    def _predict_device(self, xt, batch_size):
+        bl, bc = self._bias_device(xt, batch_size)
+        rl, rc = self.residual.net.predict(xt, batchSize=batch_size)
+        out_l = torch.empty_like(rl)
+        ops.add_f32(rl, bl.contiguous(), out_l)
+        out_c = torch.empty_like(rc)
+        ops.counts_lse(self.useBias, bc.contiguous(), rc, out_c)
+        return out_l, out_c
+
+    def _step(self, xb, counts, train):
+        net = self.residual.net
+        net.enable_training()
+        dev = self._device
+        net.profile_weight.copy_(torch.tensor(self._loss_weights))
+        net.lam.copy_(torch.tensor(self._lambdas))
+        xt = torch.as_tensor(xb).to(device=dev, dtype=torch.uint8)
+        ct = torch.as_tensor(counts).to(device=dev, dtype=torch.float32)
+        bl, bc = self._bias_device(xt, xt.shape[0])
+        if train:
+            losses = net.train_step(xt, ct, self.optimizer.learning_rate, use_graph=False,
+                                    bias_logits=bl.contiguous(), bias_logcounts=bc.contiguous(),
+                                    use_bias=self.useBias)
+        else:
+            losses = net.eval_losses(xt, ct, bias_logits=bl.contiguous(),
+                                     bias_logcounts=bc.contiguous(), use_bias=self.useBias)
+        return losses.double().cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------
+# the reference's builder functions
+# ----------------------------------------------------------------------------------------
+def soloModel(inputLength, outputLength, numFilters, numLayers, inputFilterWidth,
+              outputFilterWidth, headList, modelName, **kw):
+    """models.py:53-115.  It is an error to call this with an inconsistent network structure
+    (the reference lets Keras raise; here ``NetConfig.validate`` raises ``ValueError``)."""
+    return SoloModel(inputLength, outputLength, numFilters, numLayers, inputFilterWidth,
+                     outputFilterWidth, headList, modelName, **kw)
+
+
+def transformationModel(soloModelIn, profileArchitectureSpecification,
+                        countsArchitectureSpecification, headList):
+    """models.py:226-265."""
+    return TransformationModel(soloModelIn, profileArchitectureSpecification,
+                               countsArchitectureSpecification, headList)
+
+
+def combinedModel(inputLength, outputLength, numFilters, numLayers, inputFilterWidth,
+                  outputFilterWidth, headList, biasModel, **kw):
+    """models.py:268-387.  Returns (combined, residual, biasHeads) like the reference; the third
+    element is the (frozen) bias model applied to the cropped input."""
+    kw.setdefault("device", biasModel._device)
+    residual = soloModel(inputLength, outputLength, numFilters, numLayers, inputFilterWidth,
+                         outputFilterWidth, headList, "residual", **kw)
+    combined = CombinedModel(residual, biasModel, headList)
+    return combined, residual, biasModel
+
+
+def loadModel(path, device=None, precise=False):
+    """Counterpart of ``utils.loadModel`` (utils.py:60-90) for files written by ``Model.save``."""
+    if path.endswith(".npz"):
+        z = np.load(path, allow_pickle=False)
+        arch = json.loads(str(z["__config__"]))
+        weights = {k: z[k] for k in z.files if k != "__config__"}
+    else:
+        from . import keras_io
+        arch, weights = keras_io.load_keras(path)
+    model = _build_from_config(arch, device, precise)
+    model.set_weights([weights[k] for k, _ in model.named_weights()])
+    return model
+
+
+def _build_from_config(arch, device, precise):
+    if arch["kind"] == "solo":
+        return soloModel(arch["inputLength"], arch["outputLength"], arch["numFilters"],
+                         arch["numLayers"], arch["inputFilterWidth"], arch["outputFilterWidth"],
+                         arch["heads"], arch["modelName"], device=device, precise=precise, seed=0)
+    if arch["kind"] == "transformation":
+        solo = _build_from_config(arch["solo"], device, precise)
+        return transformationModel(solo, arch["profile"], arch["counts"], arch["solo"]["heads"])
+    if arch["kind"] == "combined":
+        bias = _build_from_config(arch["bias"], device, precise)
+        r = arch["residual"]
+        heads = [dict(h, **{"use-bias-counts": u}) for h, u in zip(r["heads"], arch["use-bias-counts"])]
+        combined, _, _ = combinedModel(r["inputLength"], r["outputLength"], r["numFilters"],
+                                       r["numLayers"], r["inputFilterWidth"],
+                                       r["outputFilterWidth"], heads, bias, precise=precise, seed=0)
+        return combined
+    raise ValueError(f"unknown model kind {arch['kind']!r}")
+
+
+def lengthDifference(numLayers, inputFilterWidth, outputFilterWidth):
+    """lengthCalc.getLengthDifference (lengthCalc.py:71-123) for a solo model."""
+    return (inputFilterWidth - 1) + sum(2 * 2 ** (i + 1) for i in range(numLayers)) + \
+        (outputFilterWidth - 1)

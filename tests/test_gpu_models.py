@@ -1,0 +1,235 @@
+"""GPU: the bpreveal.models drop-in builders (soloModel / transformationModel / combinedModel)
+against the oracle restatement of models.py:53-387 and layers.py:10-75."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bpnet_oracle as O
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+HEADS = [{"head-name": "a", "num-tasks": 2, "profile-loss-weight": 1.0, "counts-loss-weight": 2.0},
+         {"head-name": "b", "num-tasks": 1, "profile-loss-weight": 1.5, "counts-loss-weight": 3.0,
+          "use-bias-counts": True}]
+
+
+def solo_state(numFilters, numLayers, wi, wo, seed):
+    return O.init_solo_params(numFilters, numLayers, wi, wo, [2, 1], seed=seed, biasScale=0.1)
+
+
+def load_solo(model, params):
+    model.net.load_state(params)
+
+
+class ArrayGen:
+    """Minimal keras.utils.Sequence look-alike (generators.py:77-90)."""
+
+    def __init__(self, x, counts, tasks, batch):
+        self.x, self.counts, self.tasks, self.batch = x, counts, tasks, batch
+
+    def __len__(self):
+        return int(np.ceil(self.x.shape[0] / self.batch))
+
+    def __getitem__(self, i):
+        s = slice(i * self.batch, min((i + 1) * self.batch, self.x.shape[0]))
+        vals, cnts, k = [], [], 0
+        for t in self.tasks:
+            v = self.counts[s, :, k:k + t]
+            vals.append(v)
+            cnts.append(np.log(v.sum(axis=(1, 2))))
+            k += t
+        return self.x[s], tuple(vals + cnts)
+
+
+def test_solo_model_duck_type_and_predict(dev):
+    from bpreveal_b200 import models
+    m = models.soloModel(52, 20, 8, 3, 3, 3, HEADS, "solo", precise=True, device=dev)
+    assert m.name == "solo_model" and m.inputs[0].shape == (None, 52, 4)
+    assert m.input.shape[1] == 52
+    assert [o.shape for o in m.outputs] == [(None, 20, 2), (None, 20, 1), (None, 1), (None, 1)]
+    assert m.output_names == ["solo_profile_a", "solo_profile_b", "solo_logcounts_a",
+                              "solo_logcounts_b"]
+    names = [k for k, _ in m.named_weights()]
+    assert names[:4] == ["solo_initial_conv/kernel", "solo_initial_conv/bias",
+                         "solo_conv_0/kernel", "solo_conv_0/bias"]
+    with pytest.raises(ValueError):
+        models.soloModel(60, 20, 8, 3, 3, 3, HEADS, "bad", device=dev)  # inconsistent lengths
+    params = solo_state(8, 3, 3, 3, seed=5)
+    load_solo(m, params)
+    x = O.synthetic_sequences(5, 52, seed=1)
+    outs = m.predict(x, batch_size=2)
+    ref_l, ref_c = Hh.oracle_forward(params, x)
+    assert [o.shape for o in outs] == [(5, 20, 2), (5, 20, 1), (5, 1), (5, 1)]
+    got_l = np.concatenate(outs[:2], axis=2)
+    got_c = np.concatenate(outs[2:], axis=1)
+    assert Hh.rel_err(got_l, ref_l) < 1e-4 and Hh.rel_err(got_c, ref_c) < 1e-4
+    lines = []
+    m.summary(print_fn=lines.append)
+    assert any("solo_profile_a/kernel" in ln for ln in lines)
+    assert m.count_params() == sum(v.size for v in params.values())
+
+
+def test_solo_fit_history_and_save_roundtrip(dev, tmp_path):
+    from bpreveal_b200 import models
+    m = models.soloModel(52, 20, 16, 3, 3, 3, HEADS, "solo", device=dev, seed=7)
+    m.compile(optimizer=models.Adam(learning_rate=0.004), loss=None,
+              loss_weights=[1.0, 1.5, 1.0, 1.0])
+    x = O.synthetic_sequences(24, 52, seed=2)
+    c = O.synthetic_profiles(24, 20, 3, seed=2, meanReads=40.0)
+    gen, val = ArrayGen(x, c, [2, 1], 8), ArrayGen(x[:8], c[:8], [2, 1], 8)
+    seen = []
+
+    class Stop:
+        def set_model(self, model):
+            self.model = model
+
+        def on_epoch_end(self, epoch, logs):
+            seen.append((epoch, logs["loss"], logs["val_loss"]))
+            if epoch == 3:
+                self.model.stop_training = True
+
+    hist = m.fit(gen, epochs=10, validation_data=val, callbacks=[Stop()], verbose=0)
+    assert len(hist.history["loss"]) == 4 and len(seen) == 4  # stopped by the callback
+    assert hist.history["loss"][-1] < hist.history["loss"][0]
+    for k in ("solo_profile_a_loss", "solo_logcounts_b_loss", "val_solo_profile_b_loss"):
+        assert k in hist.history
+    path = str(tmp_path / "m.npz")
+    m.save(path)
+    m2 = models.loadModel(path, device=dev)
+    a, b = m.predict(x[:4]), m2.predict(x[:4])
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    with pytest.raises(RuntimeError):
+        m.save(str(tmp_path / "m.keras"))  # no h5py in this image: loud, not silent
+
+
+def test_transformation_model_forward_and_training(dev):
+    from bpreveal_b200 import models
+    spec_p = {"name": "simple", "types": ["linear", "sigmoid"]}
+    spec_c = {"name": "simple", "types": ["linear"]}
+    solo = models.soloModel(52, 20, 8, 3, 3, 3, HEADS, "solo", precise=True, device=dev)
+    params = solo_state(8, 3, 3, 3, seed=5)
+    load_solo(solo, params)
+    tm = models.transformationModel(solo, spec_p, spec_c, HEADS)
+    assert solo.trainable is False and tm.name == "transformation_model"
+    # non-trivial coefficients through the Keras-named weight interface
+    rng = np.random.default_rng(3)
+    tp = O.init_transform_params(2, spec_p, spec_c)
+    for k in tp:
+        tp[k] = (tp[k] + rng.standard_normal(2) * 0.2).astype(np.float32)
+    named = dict(tm.named_weights())
+    for h, n in enumerate(["a", "b"]):
+        named[f"regress_linear_profile_{n}_conv/kernel"] = tp[f"profile{h}_linear"][0].reshape(1, 1, 1)
+        named[f"regress_linear_profile_{n}_conv/bias"] = tp[f"profile{h}_linear"][1].reshape(1)
+        named[f"sigmoid_in_linear_profile_{n}_conv/kernel"] = tp[f"profile{h}_sigmoid_in"][0].reshape(1, 1, 1)
+        named[f"sigmoid_in_linear_profile_{n}_conv/bias"] = tp[f"profile{h}_sigmoid_in"][1].reshape(1)
+        named[f"sigmoid_out_linear_profile_{n}_conv/kernel"] = tp[f"profile{h}_sigmoid_out"][0].reshape(1, 1, 1)
+        named[f"sigmoid_out_linear_profile_{n}_conv/bias"] = tp[f"profile{h}_sigmoid_out"][1].reshape(1)
+        named[f"regress_linear_logcounts_{n}_conv/kernel"] = tp[f"logcounts{h}_linear"][0].reshape(1, 1, 1)
+        named[f"regress_linear_logcounts_{n}_conv/bias"] = tp[f"logcounts{h}_linear"][1].reshape(1)
+    tm.set_weights(named)
+    x = O.synthetic_sequences(4, 52, seed=9)
+    p64 = O.to_torch(params, torch.float64)
+    tpt = {k: torch.tensor(v, dtype=torch.float64) for k, v in tp.items()}
+    po, co = O.transformation_forward(torch.tensor(x, dtype=torch.float64), p64, tpt, spec_p, spec_c)
+    outs = tm.predict(x)
+    assert Hh.rel_err(np.concatenate(outs[:2], axis=2), torch.cat(po, dim=2).numpy()) < 1e-4
+    assert Hh.rel_err(np.concatenate(outs[2:], axis=1), torch.cat(co, dim=1).numpy()) < 1e-4
+    # training moves only the regression scalars and lowers the loss
+    tm.compile(optimizer=models.Adam(learning_rate=0.05), loss_weights=[1.0, 1.0, 1.0, 1.0])
+    c = O.synthetic_profiles(16, 20, 3, seed=4, meanReads=40.0)
+    xs = O.synthetic_sequences(16, 52, seed=4)
+    before = [v.copy() for v in solo.get_weights()]
+    hist = tm.fit(ArrayGen(xs, c, [2, 1], 8), epochs=6, shuffle=False)
+    assert hist.history["loss"][-1] < hist.history["loss"][0]
+    for u, v in zip(before, solo.get_weights()):
+        assert np.array_equal(u, v)
+
+
+def test_transformation_gradients_match_oracle(dev):
+    """d loss / d (m, b) of every regression against torch autograd through the oracle."""
+    from bpreveal_b200 import models
+    spec_p = {"name": "simple", "types": ["linear", "relu"]}
+    spec_c = {"name": "simple", "types": ["sigmoid"]}
+    heads = [dict(h) for h in HEADS]
+    solo = models.soloModel(52, 20, 8, 3, 3, 3, heads, "solo", precise=True, device=dev)
+    params = solo_state(8, 3, 3, 3, seed=11)
+    load_solo(solo, params)
+    tm = models.transformationModel(solo, spec_p, spec_c, heads)
+    tm.compile(optimizer=models.Adam(learning_rate=0.0), loss_weights=[1.0, 1.5, 1.0, 1.0])
+    rng = np.random.default_rng(1)
+    c0 = tm.coeffs.cpu().numpy() + rng.standard_normal(tm.coeffs.shape).astype(np.float32) * 0.1
+    tm.coeffs.copy_(torch.tensor(c0))
+    x = O.synthetic_sequences(6, 52, seed=3)
+    counts = O.synthetic_profiles(6, 20, 3, seed=3, meanReads=30.0)
+    # oracle with the same scalars
+    tp = {}
+    for h in range(2):
+        lo, _ = tm._rows(h, "p")
+        tp[f"profile{h}_linear"] = torch.tensor(c0[lo, :2], dtype=torch.float64, requires_grad=True)
+        tp[f"profile{h}_relu_out"] = torch.tensor(c0[lo + 1, :2], dtype=torch.float64, requires_grad=True)
+        tp[f"profile{h}_relu_in"] = torch.tensor(c0[lo + 1, 2:], dtype=torch.float64, requires_grad=True)
+        lo, _ = tm._rows(h, "c")
+        tp[f"logcounts{h}_sigmoid_out"] = torch.tensor(c0[lo, :2], dtype=torch.float64, requires_grad=True)
+        tp[f"logcounts{h}_sigmoid_in"] = torch.tensor(c0[lo, 2:], dtype=torch.float64, requires_grad=True)
+    p64 = O.to_torch(params, torch.float64)
+    po, co = O.transformation_forward(torch.tensor(x, dtype=torch.float64), p64, tp, spec_p, spec_c)
+    ct = torch.tensor(counts, dtype=torch.float64)
+    trueP = [ct[:, :, 0:2], ct[:, :, 2:3]]
+    trueC = [torch.log(t.sum(dim=(1, 2))) for t in trueP]
+    tot, pl, cl = O.total_loss(po, co, trueP, trueC, [1.0, 1.5], [2.0, 3.0])
+    tot.backward()
+    # device: run one "training" step with lr 0 and read the Adam first moment = 0.1 * grad
+    losses = tm._step(x, counts, train=True)
+    got = tm._adam["m"].cpu().numpy() / 0.1
+    np.testing.assert_allclose(losses[:2], [v.item() for v in pl], rtol=1e-4)
+    for h in range(2):
+        lo, _ = tm._rows(h, "p")
+        np.testing.assert_allclose(got[lo, :2], tp[f"profile{h}_linear"].grad.numpy(), rtol=2e-3, atol=1e-4)
+        np.testing.assert_allclose(got[lo + 1, :2], tp[f"profile{h}_relu_out"].grad.numpy(), rtol=2e-3, atol=1e-4)
+        np.testing.assert_allclose(got[lo + 1, 2:], tp[f"profile{h}_relu_in"].grad.numpy(), rtol=2e-3, atol=1e-4)
+        lo, _ = tm._rows(h, "c")
+        np.testing.assert_allclose(got[lo, :2], tp[f"logcounts{h}_sigmoid_out"].grad.numpy(), rtol=2e-3, atol=1e-5)
+        np.testing.assert_allclose(got[lo, 2:], tp[f"logcounts{h}_sigmoid_in"].grad.numpy(), rtol=2e-3, atol=1e-5)
+
+
+def test_combined_model_matches_oracle_and_trains_residual_only(dev):
+    from bpreveal_b200 import models
+    vec = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden",
+                                            "oracle_vectors.npz"))
+    spec_p = {"name": "simple", "types": ["linear", "sigmoid"]}
+    spec_c = {"name": "simple", "types": ["linear"]}
+    heads = [dict(HEADS[0], **{"use-bias-counts": True}), dict(HEADS[1], **{"use-bias-counts": False})]
+    solo = models.soloModel(52, 20, 8, 3, 3, 3, heads, "solo", precise=True, device=dev)
+    load_solo(solo, {k[2:]: vec[k] for k in vec.files if k.startswith("p_")})
+    tm = models.transformationModel(solo, spec_p, spec_c, heads)
+    named = dict(tm.named_weights())
+    for h, n in enumerate(["a", "b"]):
+        for key, (kern, bias) in {
+                f"profile{h}_linear": (f"regress_linear_profile_{n}_conv/kernel", f"regress_linear_profile_{n}_conv/bias"),
+                f"profile{h}_sigmoid_in": (f"sigmoid_in_linear_profile_{n}_conv/kernel", f"sigmoid_in_linear_profile_{n}_conv/bias"),
+                f"profile{h}_sigmoid_out": (f"sigmoid_out_linear_profile_{n}_conv/kernel", f"sigmoid_out_linear_profile_{n}_conv/bias"),
+                f"logcounts{h}_linear": (f"regress_linear_logcounts_{n}_conv/kernel", f"regress_linear_logcounts_{n}_conv/bias")}.items():
+            named[kern] = vec[f"t_{key}"][0].reshape(1, 1, 1)
+            named[bias] = vec[f"t_{key}"][1].reshape(1)
+    tm.set_weights(named)
+    xr = vec["xr"]
+    comb, resid, biasHeads = models.combinedModel(xr.shape[1], 20, 8, 4, 3, 3, heads, tm,
+                                                  precise=True)
+    assert biasHeads is tm and tm.trainable is False and comb.name == "combined_model"
+    assert comb.output_names[0] == "combined_add_profile_a" and comb.cropFlank == (xr.shape[1] - 52) // 2
+    resid.net.load_state({k[2:]: vec[k] for k in vec.files if k.startswith("r_")})
+    outs = comb.predict(xr)
+    assert Hh.rel_err(np.concatenate(outs[:2], axis=2), vec["comb_logits"]) < 1e-4
+    assert Hh.rel_err(np.concatenate(outs[2:], axis=1), vec["comb_logcounts"]) < 1e-4
+    # training: bias model untouched, residual moves, loss falls
+    comb.compile(optimizer=models.Adam(learning_rate=0.004), loss_weights=[1.0, 1.0, 1.0, 1.0])
+    c = O.synthetic_profiles(xr.shape[0], 20, 3, seed=8, meanReads=40.0)
+    bias_before = [v.copy() for v in tm.get_weights()]
+    resid_before = [v.copy() for v in resid.get_weights()]
+    hist = comb.fit(ArrayGen(xr, c, [2, 1], xr.shape[0]), epochs=8, shuffle=False)
+    assert hist.history["loss"][-1] < hist.history["loss"][0]
+    for u, v in zip(bias_before, tm.get_weights()):
+        assert np.array_equal(u, v)
+    assert any(not np.array_equal(u, v) for u, v in zip(resid_before, resid.get_weights()))
