@@ -150,10 +150,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    verbose = os.environ.get("BENCH_VERBOSE", "0") != "0"
+
+    def say(msg):
+        if verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        say("process group up")
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
 
@@ -218,10 +225,14 @@ def main():
         counter["n"] += kernels_per_call.get(what, 1)
         return orig_check(rc, what)
 
-    for _ in range(warmup):
+    for i in range(warmup):
         net.train_step(batch_slice(x_dev, 0), batch_slice(c_dev, 0), lr, allreduce=allreduce,
                        world=world)
+        if i == 0:
+            torch.cuda.synchronize()
+            say("first step done")
     torch.cuda.synchronize()
+    say("warm-up done")
     # launches per step: replay the step body un-graphed once with the counter armed
     ops.check = counting_check
     net.train_step(batch_slice(x_dev, 1), batch_slice(c_dev, 1), lr, use_graph=False,
@@ -234,7 +245,9 @@ def main():
     if sampler:
         sampler.start()
     ms = timed(steps, host_io=False)
+    say(f"timed region done: {ms / steps:.3f} ms/step")
     ms_e2e = timed(steps, host_io=True)
+    say("e2e region done")
     clocks = sampler.stop() if sampler else None
     final_losses = loss_host.clone()
 
@@ -271,8 +284,8 @@ def main():
 
         for nm in names:
             wrap(nm)
-        net.train_step(batch_slice(x_dev, 0), batch_slice(c_dev, 0), lr, use_graph=False,
-                       allreduce=allreduce, world=world)
+        # local step (no collective: only rank 0 is here, a collective would wait forever)
+        net.train_step(batch_slice(x_dev, 0), batch_slice(c_dev, 0), lr, use_graph=False)
         torch.cuda.synchronize()
         for nm in names:
             setattr(ops, nm, real[nm])
