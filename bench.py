@@ -106,6 +106,64 @@ def cpu_train_rate(cfg, steps, warmup, batch):
     return batch / sec, sec, cores
 
 
+def cpu_pisa_rate(cfg, n_bases, numShuffles):
+    """The reference's PISA algorithm on the host cores (oracle port, fp32): per base a joint
+    batch [x tiled n | n shuffles] through the rescale-rule graph and back (shap.py:362-377)."""
+    import torch
+    from oracle import bpnet_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = O.init_solo_params(cfg["numFilters"], cfg["numLayers"], cfg["inputFilterWidth"],
+                                cfg["outputFilterWidth"], cfg["headTasks"], seed=1234)
+    p32 = O.to_torch(params, torch.float32)
+    xs = O.synthetic_sequences(n_bases, cfg["inputLength"], seed=5)
+    fwd = O.solo_shap_forward(p32)
+    t0 = time.perf_counter()
+    for q in range(n_bases):
+        refs = O.generate_shuffles(xs[q], numShuffles)
+        O.deepshap(xs[q], refs, fwd, lambda pr, cn: O.pisa_metric(pr, cn, 0, 0),
+                   dtype=torch.float32)
+    return n_bases / (time.perf_counter() - t0)
+
+
+def gpu_extras(net_cfg, dev, rank):
+    """Secondary measurements on one GPU: makePredictions windows/s (C2 shape, per GPU) and
+    interpretPisa bases/s (C5: 20 shuffled references per base, whole 3090-bp window)."""
+    import torch
+    from bpreveal_b200 import interpret
+    from bpreveal_b200.engine import NetConfig, SoloNet
+    out = {}
+    net = SoloNet(NetConfig(**net_cfg), dev)
+    net.init_random(seed=1234)
+    xs, _ = synth(1024, net_cfg, 777 + rank)
+    x_dev = torch.tensor(xs, device=dev)
+    net.predict(x_dev[:256], batchSize=128)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        net.predict(x_dev, batchSize=128)
+    e1.record()
+    torch.cuda.synchronize()
+    out["predict_windows_per_s"] = 3 * 1024 / (e0.elapsed_time(e1) / 1e3)
+    for label, precise in (("pisa_bases_per_s", False), ("pisa_bases_per_s_precise", True)):
+        pn = SoloNet(NetConfig(precise=precise, **net_cfg), dev)
+        pn.load_state(net.state())
+        Q, n = 3, 20
+        interpret.pisa_batch(pn, x_dev[:Q], headID=0, taskID=0, numShuffles=n)
+        torch.cuda.synchronize()
+        e0.record()
+        reps = 10
+        for r in range(reps):
+            interpret.pisa_batch(pn, x_dev[r * Q:(r + 1) * Q], headID=0, taskID=0, numShuffles=n)
+        e1.record()
+        torch.cuda.synchronize()
+        out[label] = reps * Q / (e0.elapsed_time(e1) / 1e3)
+        del pn
+        torch.cuda.empty_cache()
+    out["pisa_config"] = "C5: C1 model, 20 row-shuffled references per base, 3 bases per launch group"
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -136,6 +194,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary predict / PISA measurements")
     ap.add_argument("--precise", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -358,6 +418,15 @@ def main():
                "sample": f"3 full C1 train steps of batch {BATCH} after 1 warm-up "
                          f"({sec:.2f} s/step), fp32 torch-CPU restatement of the Keras graph"}
 
+    extras = None
+    if rank == 0 and not args.no_extras and not args.precise:
+        del net
+        torch.cuda.empty_cache()
+        extras = gpu_extras(C1, dev, rank)
+        if world == 1 and not args.no_cpu_baseline:
+            extras["pisa_cpu_bases_per_s"] = cpu_pisa_rate(C1, 2, 20)
+            extras["pisa_cpu_note"] = "oracle port of the reference algorithm, fp32 torch-CPU, 2 bases"
+
     if rank == 0:
         h2d = BATCH * (C1["inputLength"] * 4 + C1["outputLength"] * cfg.T * 4)
         line = {
@@ -379,6 +448,7 @@ def main():
             "tflops": value * TRAIN_FLOP_PER_SEQ / 1e12,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "kernel_ms_per_step": breakdown,
+            "extra": extras,
             "final_losses": [float(v) for v in final_losses],
         }
         print(json.dumps(line), flush=True)
