@@ -36,7 +36,14 @@ static DevInfo& devinfo() {
   return d[dev];
 }
 int sm_count() { return devinfo().sms; }
-int max_smem_optin() { return devinfo().smem; }
+int max_smem_optin() {
+#ifdef BPB_ROLE_PROFILE
+  // the role-profiling build keeps a small static shared array
+  return devinfo().smem > 1024 ? devinfo().smem - 1024 : devinfo().smem;
+#else
+  return devinfo().smem;
+#endif
+}
 
 bool pdl_enabled() {
   static const bool on = [] {

@@ -194,6 +194,10 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
 
   // let the next kernel of the stream start its prologue as soon as this grid's CTAs retire
   pdl_launch_dependents();
+#ifdef BPB_ROLE_PROFILE
+  const long long t_kernel_start = clock64();
+  if (threadIdx.x < 32) prof_smem()[threadIdx.x] = 0;  // published by the __syncthreads below
+#endif
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm.A[0]);
@@ -292,12 +296,53 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     if (elect_one()) {
       if (RESIDENT) mbar_wait_wd(w_full, 0, p.dbg, 0x300);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, ntile = 0;
+      // Fast path (the bf16 tower layer: 3 taps, one 64-channel chunk, one pass, resident
+      // weights): every descriptor word that does not depend on the stage is built once here, so
+      // the issue loop is 12 x (one add + one tcgen05.mma) per tile.  The single issuing thread
+      // was measured to be the bottleneck of the pipeline when it rebuilt descriptors per MMA.
+      const bool fast = RESIDENT && p.n_taps == 3 && p.KC == 1 && p.npass == 1;
+      constexpr uint32_t DHI = umma_desc_hi(1024);
+      uint32_t b_lo[3][4], a_row[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        a_row[j] = HALO ? static_cast<uint32_t>(p.tap_row[j]) * 8u : 0u;  // rows * 128 B >> 4
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          b_lo[j][k] = umma_desc_lo(smem_u32(w_smem) + j * B_TILE_BYTES + k * 32, 0);
+      }
+      const uint32_t ring_lo = smem_u32(ring) >> 4;
+      const uint32_t stage_lo = static_cast<uint32_t>(stage_bytes) >> 4;
       TileWalk tw;
       for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
         mbar_wait_wd(&acc_empty[as], aphase ^ 1, p.dbg, 0x400 + as, ntile);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * NT;
-        if (HALO) {
+        if (fast && HALO) {
+          mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
+          tc_fence_after();
+          const uint32_t a0 = ring_lo + stage * stage_lo;
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lohi(d_tmem, (a0 + a_row[j] + 2u * k) & 0x3FFFu, DHI, b_lo[j][k], DHI, IDESC,
+                             (j | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+        } else if (fast) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
+            tc_fence_after();
+            const uint32_t a0 = ring_lo + stage * stage_lo;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lohi(d_tmem, (a0 + 2u * k) & 0x3FFFu, DHI, b_lo[j][k], DHI, IDESC,
+                             (j | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+          }
+        } else if (HALO) {
           mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
           tc_fence_after();
           const uint32_t base = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
@@ -422,6 +467,17 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           }
         }
 
+#ifdef BPB_ROLE_PROFILE
+        long long tp0 = clock64();
+#define BPB_PHASE(slot)                                                            \
+  do {                                                                              \
+    const long long tnow = clock64();                                               \
+    if (lane == 0) atomicAdd(prof_smem() + (slot), static_cast<unsigned>(tnow - tp0)); \
+    tp0 = tnow;                                                                     \
+  } while (0)
+#else
+#define BPB_PHASE(slot)
+#endif
         // ---- accumulator
         if (ch == 0) {
           mbar_wait_wd(&acc_full[as], aphase, p.dbg, 0x800 + as, ntile);
@@ -436,6 +492,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
+        BPB_PHASE(9);   // acc wait + TMEM load
 
         const bool one_buf = (EG == 2) || p.nstg == 1;  // one staging buffer per writer group
         uint8_t* sb = stg + static_cast<size_t>(EG == 2 ? grp : (p.nstg == 2 ? (kc & 1) : 0)) * stg_bytes;
@@ -446,6 +503,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           named_bar_sync(bar_id, kEpiThreads);
         }
 
+        BPB_PHASE(10);  // staging buffer free (wait_read + barrier)
         float obits_lo = 0.f, obits_hi = 0.f;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -553,12 +611,11 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             }
           }
         }
-        if (IS_FWD && p.mask_out != nullptr && valid)
-          p.mask_out[(orow * chunks_per_row + (n0 >> 6)) * 2 + half] =
-              static_cast<uint32_t>(obits_lo) | (static_cast<uint32_t>(obits_hi) << 16);
 
+        BPB_PHASE(11);  // math + staging writes
         // ---- publish: generic-proxy writes -> async proxy, one barrier, one thread stores
         fence_proxy_async();
+        BPB_PHASE(12);  // proxy fence
         if (!one_buf && et == 0) tma_store_wait_read<0>();  // buffer of chunk kc-1 is free again
         named_bar_sync(bar_id, kEpiThreads);
         if (et == 0) {
@@ -572,6 +629,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           }
           tma_store_commit();
         }
+        BPB_PHASE(13);  // barrier + TMA store issue
+        // The mask goes out AFTER the proxy fence above: fence.proxy.async compiles to a
+        // MEMBAR that drains this warp's outstanding stores, and a global store issued before
+        // it would put a round trip to L2 on the critical path of every chunk.
+        if (IS_FWD && p.mask_out != nullptr && valid)
+          p.mask_out[(orow * chunks_per_row + (n0 >> 6)) * 2 + half] =
+              static_cast<uint32_t>(obits_lo) | (static_cast<uint32_t>(obits_hi) << 16);
       }
       ring_advance(as, aphase, EG, ACC);
       if (EG == 2) {
@@ -587,6 +651,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+#ifdef BPB_ROLE_PROFILE
+  if (threadIdx.x < 32 && p.dbg != nullptr && blockIdx.x < 8) {
+    unsigned v = prof_smem()[threadIdx.x];
+    if (threadIdx.x == 15) v = static_cast<unsigned>(clock64() - t_kernel_start);
+    atomicAdd(p.dbg + 1024 + 32 * blockIdx.x + threadIdx.x, v);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -74,14 +74,33 @@ static __device__ __noinline__ void mbar_timeout(unsigned* dbg, uint32_t tag, ui
     }
   }
 }
+#ifdef BPB_ROLE_PROFILE
+// Role profiling build (make PROFILE=1): cycles every thread spends inside mbarrier waits, by tag
+// group (tag >> 8), are summed per CTA into the debug buffer (words 1024 + 16*blockIdx + group).
+static __device__ __noinline__ unsigned* prof_smem() {
+  __shared__ unsigned s_prof[32];
+  return s_prof;
+}
+#endif
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, unsigned* dbg,
                                              uint32_t tag, uint32_t payload = 0) {
+#ifdef BPB_ROLE_PROFILE
+  const long long t0 = clock64();
+#endif
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     ++spins;
     if (spins == (1u << 24)) mbar_timeout(dbg, tag, parity, payload);
     if (spins == (1u << 24) + (1u << 22)) __trap();
   }
+#ifdef BPB_ROLE_PROFILE
+  if ((threadIdx.x & 31) == 0) {
+    const unsigned dt = static_cast<unsigned>(clock64() - t0);
+    unsigned* sp = prof_smem();
+    atomicAdd(sp + ((tag >> 8) & 15), dt);
+    atomicAdd(sp + 16 + ((tag >> 8) & 15), 1u);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------ TMA
@@ -159,6 +178,31 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same with the two shared-memory descriptors given as (low word, shared high word): the issue
+// loop of a persistent kernel then costs one integer add per MMA instead of rebuilding two 64-bit
+// descriptors (the single issuing thread is otherwise the pipeline's bottleneck).
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                               uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// low / high 32-bit words of umma_smem_desc()
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 }
 // All previously issued MMAs of this thread arrive on `bar` when complete (implies
 // tcgen05.fence::before_thread_sync).

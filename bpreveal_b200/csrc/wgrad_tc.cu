@@ -132,29 +132,41 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       uint32_t db_started = 0;
+      // Descriptor words that do not depend on the stage are built once: the issue loop is one
+      // integer add per MMA (the single issuing thread is otherwise the bottleneck).
+      constexpr uint32_t DHI = umma_desc_hi(1024);
+      const uint32_t lbo_bits = ((static_cast<uint32_t>(kWgTile) >> 4) & 0x3FFFu) << 16;
+      const uint32_t ring_lo = smem_u32(ring) >> 4;
+      const uint32_t stage_lo = static_cast<uint32_t>(stage_bytes) >> 4;
+      const uint32_t ones_lo = (smem_u32(ones) >> 4) | lbo_bits;
+      // offset (in 16-byte units) of unit i's A tile inside a stage
+      uint32_t a_off[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        a_off[i] = p.halo ? (NSUB * kWgTile + (u0 + i) * p.dil * 128) >> 4
+                          : ((NSUB + i) * kWgTile) >> 4;
       for (int v = 0; v < visits; ++v) {
         const int pass = v % p.n_passes;
         mbar_wait_wd(&full[stage], phase, p.dbg, 0x1500 + stage, v);
         tc_fence_after();
-        const uint32_t g_addr = smem_u32(ring + stage * stage_bytes);
-        for (int i = 0; i < nu; ++i) {
-          // HALO: tap i starts i*dil rows into the box (the 128-byte swizzle is a function of the
-          // absolute shared-memory address, so an MN-major operand may start on any row)
-          const uint32_t a_addr = p.halo ? g_addr + NSUB * kWgTile + (u0 + i) * p.dil * 128
-                                         : g_addr + (NSUB + i) * kWgTile;
+        const uint32_t g_lo = ((ring_lo + stage * stage_lo) & 0x3FFFu) | lbo_bits;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem_base + i * NT, umma_smem_desc(a_addr + k * 2048, kWgTile, 1024),
-                      umma_smem_desc(g_addr + k * 2048, kWgTile, 1024), IDESC,
-                      (v | k) != 0 ? 1u : 0u);
+        for (int i = 0; i < 4; ++i) {
+          if (i < nu) {
+            // HALO: tap i starts i*dil rows into the box (the 128-byte swizzle is a function of
+            // the absolute shared-memory address, so an MN-major operand may start on any row)
+            const uint32_t a_lo = g_lo + a_off[i];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16_lohi(tmem_base + i * NT, a_lo + k * 128u, DHI, g_lo + k * 128u, DHI, IDESC,
+                             (v | k) != 0 ? 1u : 0u);
+          }
         }
         if (do_db && ((p.db_mask >> pass) & 1)) {
-          const uint32_t o_addr = smem_u32(ones);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem_base + p.UG * NT, umma_smem_desc(o_addr + k * 2048, kWgTile, 1024),
-                      umma_smem_desc(g_addr + k * 2048, kWgTile, 1024), IDESC,
-                      (db_started | k) != 0 ? 1u : 0u);
+            umma_bf16_lohi(tmem_base + p.UG * NT, ones_lo + k * 128u, DHI, g_lo + k * 128u, DHI,
+                           IDESC, (db_started | k) != 0 ? 1u : 0u);
           db_started = 1;
         }
         umma_commit(&empty[stage]);
