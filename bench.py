@@ -148,7 +148,7 @@ def gpu_extras(net_cfg, dev, rank):
     for label, precise in (("pisa_bases_per_s", False), ("pisa_bases_per_s_precise", True)):
         pn = SoloNet(NetConfig(precise=precise, **net_cfg), dev)
         pn.load_state(net.state())
-        Q, n = 3, 20
+        Q, n = 6, 20
         interpret.pisa_batch(pn, x_dev[:Q], headID=0, taskID=0, numShuffles=n)
         torch.cuda.synchronize()
         e0.record()
@@ -160,7 +160,7 @@ def gpu_extras(net_cfg, dev, rank):
         out[label] = reps * Q / (e0.elapsed_time(e1) / 1e3)
         del pn
         torch.cuda.empty_cache()
-    out["pisa_config"] = "C5: C1 model, 20 row-shuffled references per base, 3 bases per launch group"
+    out["pisa_config"] = "C5: C1 model, 20 row-shuffled references per base, 6 bases per CUDA-graph replay"
     return out
 
 

@@ -260,16 +260,19 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
                           &full[stage], c * 64, t0 + p.box_off, b);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         } else {
-          const int nsteps = p.n_taps * p.KC * p.npass;
+          // Resident weights: one A tile per (tap, chunk, A plane), shared by every pass that
+          // multiplies that plane; streamed weights: one (A, W) tile pair per pass.
+          const int inner = RESIDENT ? p.n_aplanes : p.npass;
+          const int nsteps = p.n_taps * p.KC * inner;
           for (int step = 0; step < nsteps; ++step) {
-            const int pass = step % p.npass;
-            const int c = (step / p.npass) % p.KC;
-            const int j = step / (p.npass * p.KC);
+            const int pass = step % inner;  // RESIDENT: the A plane
+            const int c = (step / inner) % p.KC;
+            const int j = step / (inner * p.KC);
             mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
             mbar_expect_tx(&full[stage], SLAB_BYTES);
             uint8_t* dst = ring + static_cast<size_t>(stage) * SLAB_BYTES;
-            tma_load_3d(&tm.A[(p.pa_bits >> pass) & 1], dst, &full[stage], c * 64,
-                        t0 + p.tap_row[j], b);
+            tma_load_3d(&tm.A[RESIDENT ? pass : ((p.pa_bits >> pass) & 1)], dst, &full[stage],
+                        c * 64, t0 + p.tap_row[j], b);
             if (!RESIDENT) {
               const int wp = (p.pw_bits >> (2 * pass)) & 3;
               tma_load_2d(&tm.W, dst + kTileBytes, &full[stage], c * 64,
@@ -366,28 +369,41 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           umma_commit(&empty[stage]);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         } else {
-          const int nsteps = p.n_taps * p.KC * p.npass;
+          const int inner = RESIDENT ? p.n_aplanes : p.npass;
+          const int nsteps = p.n_taps * p.KC * inner;
+          uint32_t accum = 0;
           for (int step = 0; step < nsteps; ++step) {
-            const int pass = step % p.npass;
-            const int c = (step / p.npass) % p.KC;
-            const int j = step / (p.npass * p.KC);
+            const int pass = step % inner;  // RESIDENT: the A plane held by this stage
+            const int c = (step / inner) % p.KC;
+            const int j = step / (inner * p.KC);
             const int nk = (c == p.KC - 1) ? p.last_nk : 4;
             mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * SLAB_BYTES);
-            uint32_t b_addr;
             if (RESIDENT) {
-              const int wp = (p.pw_bits >> (2 * pass)) & 3;
-              b_addr = smem_u32(w_smem) + ((wp * p.n_taps + j) * p.KC + c) * B_TILE_BYTES;
-            } else {
-              b_addr = a_addr + kTileBytes;
-            }
+              for (int ps = 0; ps < p.npass; ++ps) {
+                if (((p.pa_bits >> ps) & 1) != pass) continue;
+                const int wp = (p.pw_bits >> (2 * ps)) & 3;
+                const uint32_t b_addr =
+                    smem_u32(w_smem) + ((wp * p.n_taps + j) * p.KC + c) * B_TILE_BYTES;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < nk)
-                umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
-                          umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC,
-                          (step | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  if (k < nk) {
+                    umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
+                              umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, accum);
+                    accum = 1;
+                  }
+              }
+            } else {
+              const uint32_t b_addr = a_addr + kTileBytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nk) {
+                  umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
+                            umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, accum);
+                  accum = 1;
+                }
+            }
             umma_commit(&empty[stage]);
             if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
           }

@@ -160,6 +160,7 @@ class SoloNet:
         def t(a):
             return torch.as_tensor(np.asarray(a, dtype=np.float32), device=dev)
 
+        self._rf_twin = None  # cached receptive-field twin of interpret.pisa_batch is stale now
         self.params.flat.zero_()
         p["conv1_w"].copy_(t(sd["conv1_w"]))
         p["conv1_b"].copy_(t(sd["conv1_b"]))
@@ -402,6 +403,7 @@ class SoloNet:
 
     def apply_adam(self, grad_scale=1.0):
         # the optimiser step counter lives on the device so that the update replays inside a graph
+        self._rf_twin = None
         self.step_and_lr[0:1].add_(1.0)
         ops.adam_step(self.params.flat, self.grads_flat, self.adam_m, self.adam_v,
                       self.step_and_lr, grad_scale=grad_scale)

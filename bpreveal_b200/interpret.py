@@ -36,25 +36,111 @@ def make_references(x_u8, numShuffles, seed=355687):
     return refs
 
 
-def pisa_batch(net, x_u8, headID, taskID, numShuffles, refs_u8=None, hypothetical=False):
+def _receptive_field_net(net):
+    """PISA asks for the attribution of ONE output position (the leftmost logit), which only sees
+    the first inputLength - outputLength + 1 input bases (the reference stores exactly that slice:
+    interpretPisa.py:45, 'receptive field').  The convolutions are 'valid', so running the same
+    weights on that prefix with outputLength 1 gives bit-identical logits and multipliers at
+    ~2/3 of the work.  The cropped twin shares nothing mutable with ``net``; it is rebuilt when
+    the weights changed (``net.step``)."""
+    from .engine import NetConfig, SoloNet
+    cfg = net.cfg
+    twin = getattr(net, "_rf_twin", None)
+    if twin is None or twin[0] != net.step:
+        rf = cfg.inputLength - cfg.outputLength + 1
+        c2 = NetConfig(inputLength=rf, outputLength=1, numFilters=cfg.numFilters,
+                       numLayers=cfg.numLayers, inputFilterWidth=cfg.inputFilterWidth,
+                       outputFilterWidth=cfg.outputFilterWidth, headTasks=list(cfg.headTasks),
+                       precise=cfg.precise)
+        t = SoloNet(c2, net.device)
+        t.load_state(net.state())
+        twin = (net.step, t)
+        net._rf_twin = twin
+    return twin[1]
+
+
+def pisa_batch(net, x_u8, headID, taskID, numShuffles, refs_u8=None, hypothetical=False,
+               use_graph=True, crop=True):
     """PISA attributions of Q query windows (interpretPisa.py:153-166: metric = leftmost logit).
 
-    Returns (phi (Q, Lin, 4) fp32, input_predictions (Q,), shuffle_predictions (Q, n))."""
+    Returns (phi (Q, Lin, 4) fp32, input_predictions (Q,), shuffle_predictions (Q, n)); phi is
+    zero beyond the receptive field of output position 0.
+
+    With ``crop`` the network is evaluated on the receptive field only (exact, see
+    ``_receptive_field_net``).  With the standard shuffled references the whole computation --
+    reference generation, the two forward passes, the rescale backward and the combiner, ~45
+    launches -- is captured once per (Q, numShuffles, head, task) as a CUDA graph and replayed:
+    the launches are shorter than the Python launch path, so eager execution is host-bound."""
     cfg = net.cfg
-    Q = x_u8.shape[0]
+    Q, Lin = x_u8.shape[0], cfg.inputLength
     x_u8 = x_u8.contiguous()
-    if refs_u8 is None:
-        refs_u8 = make_references(x_u8, numShuffles)
     col = int(sum(cfg.headTasks[:headID])) + taskID
+    run = _receptive_field_net(net) if (crop and cfg.outputLength > 1) else net
+    rf = run.cfg.inputLength
+    dev = x_u8.device
 
     def dlogits_fn(wx, wr):
         wr["dlogits"].zero_()
         wr["dlogcounts"].zero_()
         wr["dlogits"][:, 0, col] = 1.0
 
-    dx, wx, wr = net.shap_batch(x_u8, refs_u8, dlogits_fn)
-    phi = torch.empty((Q, cfg.inputLength, 4), dtype=torch.float32, device=x_u8.device)
-    ops.shap_combine(x_u8, refs_u8, dx, phi, hypothetical)
+    def compute(x_full, refs_full, phi_full, xc, rc, phic):
+        """x_full/refs_full: whole windows; xc/rc/phic: receptive-field buffers (== the full ones
+        when not cropping)."""
+        if rf != Lin:
+            xc.copy_(x_full[:, :rf])
+            rc.copy_(refs_full[:, :rf])
+        dx, wx, wr = run.shap_batch(xc, rc, dlogits_fn)
+        ops.shap_combine(xc, rc, dx, phic, hypothetical)
+        if rf != Lin:
+            phi_full.zero_()
+            phi_full[:, :rf].copy_(phic)
+        return wx, wr
+
+    def buffers():
+        R = Q * numShuffles
+        st = {"x": torch.zeros((Q, Lin, 4), dtype=torch.uint8, device=dev),
+              "refs": torch.empty((R, Lin, 4), dtype=torch.uint8, device=dev),
+              "phi": torch.empty((Q, Lin, 4), dtype=torch.float32, device=dev)}
+        if rf != Lin:
+            st["xc"] = torch.empty((Q, rf, 4), dtype=torch.uint8, device=dev)
+            st["rc"] = torch.empty((R, rf, 4), dtype=torch.uint8, device=dev)
+            st["phic"] = torch.empty((Q, rf, 4), dtype=torch.float32, device=dev)
+        else:
+            st["xc"], st["rc"], st["phic"] = st["x"], st["refs"], st["phi"]
+        return st
+
+    if refs_u8 is not None or not use_graph:
+        st = buffers()
+        st["x"].copy_(x_u8)
+        st["refs"].copy_(refs_u8 if refs_u8 is not None else make_references(x_u8, numShuffles))
+        wx, wr = compute(st["x"], st["refs"], st["phi"], st["xc"], st["rc"], st["phic"])
+        phi = st["phi"]
+    else:
+        key = ("pisa", Q, numShuffles, col, bool(hypothetical), rf)
+        # cached on the network that actually runs: a rebuilt receptive-field twin (new weights)
+        # takes its graphs -- which hold pointers into its buffers -- with it
+        st = run._graphs.get(key)
+        if st is None:
+            st = buffers()
+            st["perm"] = torch.as_tensor(shuffle_indices(Lin, numShuffles), device=dev).contiguous()
+
+            def body():
+                ops.shuffle_rows(st["x"], st["perm"], st["refs"])
+                st["wx"], st["wr"] = compute(st["x"], st["refs"], st["phi"], st["xc"], st["rc"],
+                                             st["phic"])
+
+            st["x"].copy_(x_u8)
+            body()  # eager warm-up (allocates workspaces, configures kernels)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            st["graph"] = g
+            run._graphs[key] = st
+        st["x"].copy_(x_u8)
+        st["graph"].replay()
+        phi, wx, wr = st["phi"].clone(), st["wx"], st["wr"]
     vx = wx["logits"][:, 0, col].clone()
     vr = wr["logits"][:, 0, col].reshape(Q, numShuffles).clone()
     return phi, vx, vr

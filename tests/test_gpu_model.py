@@ -143,3 +143,29 @@ def test_pisa_shap_parity(dev, name, cfg, precise):
         lhs = phis[q].sum()
         rhs = vx[q] - vr[q].mean()
         assert abs(lhs - rhs) <= (2e-3 if precise else 5e-2) * max(abs(rhs), scale), (lhs, rhs)
+
+
+def test_pisa_receptive_field_crop_and_graph_are_exact(dev):
+    """Evaluating PISA on the receptive field of output position 0 only, and replaying it as a
+    CUDA graph, reproduces the eager whole-window computation (the convolutions are 'valid')."""
+    from bpreveal_b200 import interpret
+    cfg = Hh.mid_cfg()
+    net, params = build(cfg, True, dev, scale=2.0)
+    Q, n = 2, 5
+    xs = torch.tensor(O.synthetic_sequences(2 * Q, cfg["inputLength"], seed=33), device=dev)
+    full = interpret.pisa_batch(net, xs[:Q], 0, 1, n, use_graph=False, crop=False)
+    fast = interpret.pisa_batch(net, xs[:Q], 0, 1, n)            # first call: eager warm-up
+    again = interpret.pisa_batch(net, xs[Q:], 0, 1, n)           # graph replay on other inputs
+    full2 = interpret.pisa_batch(net, xs[Q:], 0, 1, n, use_graph=False, crop=False)
+    rf = cfg["inputLength"] - cfg["outputLength"] + 1
+    for a, b in ((full, fast), (full2, again)):
+        scale = a[0].abs().max().item()
+        assert (a[0] - b[0]).abs().max().item() <= 1e-5 * scale
+        assert b[0][:, rf:].abs().max().item() == 0.0
+        assert torch.allclose(a[1], b[1], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(a[2], b[2], rtol=1e-5, atol=1e-6)
+    # new weights invalidate the cached twin
+    net.load_state(Hh.oracle_params(cfg, seed=99))
+    other = interpret.pisa_batch(net, xs[:Q], 0, 1, n)
+    ref = interpret.pisa_batch(net, xs[:Q], 0, 1, n, use_graph=False, crop=False)
+    assert (other[0] - ref[0]).abs().max().item() <= 1e-5 * ref[0].abs().max().item()
