@@ -245,7 +245,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       // the prepared weights are not written by any kernel that can still be in flight; the
       // activations are: wait for the predecessor grid before the first activation load
       pdl_wait();
-      uint32_t stage = 0, phase = 0, rs = 0, rphase = 0, ntile = 0;
+      // The residual ring is split into EG sub-rings, one per epilogue group (tile i belongs to
+      // group i % EG): a slot is then always consumed by the same warps, which observe every
+      // phase of its mbarrier.  (A consumer that skipped phases cannot tell "the phase I skipped
+      // is still in flight" from "my phase completed" -- seen as a rare deadlock.)
+      const uint32_t RG = static_cast<uint32_t>(p.rstages) / EG;
+      uint32_t stage = 0, phase = 0, ntile = 0;
+      uint32_t rsg[2] = {0, 0}, rphg[2] = {0, 0};
       TileWalk tw;
       for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
         const int nt = tw.nt, b = tw.b;
@@ -282,14 +288,17 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           }
         }
         if (RING_RESID) {
+          const uint32_t g = (EG == 2) ? (ntile & 1u) : 0u;
           for (int ch = 0; ch < NCH; ++ch) {
+            const uint32_t rs = g * RG + rsg[g];
+            const uint32_t rphase = rphg[g];
             mbar_wait_wd(&rempty[rs], rphase ^ 1, p.dbg, 0x200 + rs, ntile);
             mbar_expect_tx(&rfull[rs], static_cast<uint32_t>(rstage_bytes));
             uint8_t* dst = rring + static_cast<size_t>(rs) * rstage_bytes;
             for (int pl = 0; pl < PLANES; ++pl)
               tma_load_3d(&tm.R[pl], dst + pl * kTileBytes, &rfull[rs], nt * NT + ch * 64,
                           t0 + p.resid_off, b);
-            if (++rs == static_cast<uint32_t>(p.rstages)) { rs = 0; rphase ^= 1; }
+            if (++rsg[g] == RG) { rsg[g] = 0; rphg[g] ^= 1; }
           }
         }
       }
@@ -424,13 +433,14 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     const int et = threadIdx.x - 64 - grp * kEpiThreads;
     const int bar_id = 1 + grp;
     const int chunks_per_row = p.F >> 6;
+    const uint32_t RG = static_cast<uint32_t>(p.rstages) / EG;  // this group's residual sub-ring
+    const uint32_t rbase = static_cast<uint32_t>(grp) * RG;
     uint32_t as = 0, aphase = 0, rs = 0, rphase = 0, hs = 0, hphase = 0, kc = 0;
     TileWalk tw;
     tw.init(p);
     if (EG == 2 && grp == 1 && tw.b < p.B) {
       tw.next(p);
       ring_advance(as, aphase, 1, ACC);
-      ring_advance(rs, rphase, NCH, p.rstages);
       ring_advance(hs, hphase, 1, p.stages);
     }
     uint32_t ntile = grp;
@@ -454,16 +464,16 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         uint4 rr[4], rl[4];
         if (RESID) {
           if (RING_RESID) {
-            mbar_wait_wd(&rfull[rs], rphase, p.dbg, 0x600 + rs, ntile);
-            const uint8_t* src = rring + static_cast<size_t>(rs) * rstage_bytes;
+            mbar_wait_wd(&rfull[rbase + rs], rphase, p.dbg, 0x600 + rbase + rs, ntile);
+            const uint8_t* src = rring + static_cast<size_t>(rbase + rs) * rstage_bytes;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               rr[g] = lds128(src + sw128(row, cq + g));
               if (PLANES == 2) rl[g] = lds128(src + kTileBytes + sw128(row, cq + g));
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&rempty[rs]);
-            ring_advance(rs, rphase, 1, p.rstages);
+            if (lane == 0) mbar_arrive(&rempty[rbase + rs]);
+            ring_advance(rs, rphase, 1, RG);
           } else {
             if (ch == 0) mbar_wait_wd(&full[hs], hphase, p.dbg, 0x700 + hs, ntile);
             // n_ntiles == 1 in HALO mode, so the chunk index is the channel-chunk index
@@ -657,7 +667,6 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       if (EG == 2) {
         // skip the other group's tile
         tw.next(p);
-        if (RING_RESID) ring_advance(rs, rphase, NCH, p.rstages);
       }
     }
     if (et == 0) tma_store_wait_all<0>();

@@ -389,6 +389,58 @@ def group_bench():
     return True
 
 
+def group_bench512():
+    """C4-like layers (F=512, 9262-bp activations): the tensor-bound regime."""
+    B, Fn = 8, 512
+    for (L, d) in [(9262, 2), (9000, 64), (6000, 1024)]:
+        x = torch.randn((B, L, Fn), device=dev)
+        w = torch.randn((3, Fn, Fn), device=dev) / 40
+        xin = split(x, False)
+        fwd, bwd = prep_w(w, Fn, False)
+        L_out = L - 2 * d
+        out = ops.new_planes(B, L_out, Fn, False, dev)
+        mask = torch.zeros((B, L_out, Fn // 64), dtype=torch.int64, device=dev)
+        bias = torch.zeros((Fn,), device=dev)
+        dw = torch.empty((3, Fn, Fn), dtype=torch.float32, device=dev)
+        db = torch.empty((Fn,), dtype=torch.float32, device=dev)
+        ws = torch.empty((ops.wgrad3_ws_bytes(B, L_out, Fn, False) // 4,), dtype=torch.float32,
+                         device=dev)
+        gin = ops.new_planes(B, L, Fn, False, dev)
+        gz2 = ops.new_planes(B, L, Fn, False, dev)
+        mask_in = torch.zeros((B, L, Fn // 64), dtype=torch.int64, device=dev)
+
+        def f_fwd():
+            ops.conv3(xin, fwd, (0, d, 2 * d), 0, L_out, bias=bias, resid=xin, resid_off=d,
+                      out=out, mask_out=mask)
+
+        def f_bwd():
+            ops.conv3(out, bwd, (0, -d, -2 * d), 1, L, resid=out, resid_off=-d, out=gin,
+                      out2=gz2, mask_in=mask_in)
+
+        def f_wg():
+            ops.wgrad3(xin, out, d, dw, db, ws)
+
+        for name, fn in (("fwd", f_fwd), ("dgrad", f_bwd), ("wgrad", f_wg)):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(5):
+                    fn()
+            gr.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 5 * 1e3
+            fl = 2.0 * B * L_out * 3 * Fn * Fn
+            print(f"F=512 L={L} d={d} {name}: {us:.1f} us  {fl / us / 1e6:.1f} TFLOP/s", flush=True)
+    return True
+
+
 def group_stress():
     """Every C1 tower layer shape, forward and backward, many launches (races show up here)."""
     B, Fn = 64, 64
@@ -435,7 +487,7 @@ def group_stress():
 
 if __name__ == "__main__":
     groups = {"conv_fwd": group_conv_fwd, "conv_bwd": group_conv_bwd, "wgrad": group_wgrad,
-              "edges": group_edges, "bench": group_bench, "stress": group_stress}
+              "edges": group_edges, "bench": group_bench, "stress": group_stress, "bench512": group_bench512}
     allok = True
     for name in sys.argv[1:]:
         print(f"=== {name}", flush=True)
@@ -445,6 +497,9 @@ if __name__ == "__main__":
         except Exception as e:  # noqa: BLE001
             import traceback
             traceback.print_exc()
+            from bpreveal_b200 import _lib
+            for rec in _lib.debug_dump()[:24]:
+                print("  watchdog: tag=0x%x block=%d thread=%d parity=%d tile=%d" % rec, flush=True)
             r = False
         allok &= bool(r)
         print(f"=== {name} -> {'PASS' if r else 'FAIL'} ({time.time() - t0:.1f}s)", flush=True)
