@@ -160,6 +160,31 @@ def gpu_extras(net_cfg, dev, rank):
         out[label] = reps * Q / (e0.elapsed_time(e1) / 1e3)
         del pn
         torch.cuda.empty_cache()
+    # C4: the wide model (512 filters, 11 dilated layers, 25/75 filters, 9286 -> 1000 bp), the
+    # tensor-bound regime of the same kernels; 407 GFLOP per sequence and training step
+    c4 = dict(inputLength=9286, outputLength=1000, numFilters=512, numLayers=11,
+              inputFilterWidth=25, outputFilterWidth=75, headTasks=[2])
+    wide = SoloNet(NetConfig(**c4), dev)
+    wide.init_random(seed=1234)
+    Bw = 16
+    xw, cw_ = synth(Bw, c4, 99 + rank)
+    xw_d, cw_d = torch.tensor(xw, device=dev), torch.tensor(cw_, device=dev)
+    for _ in range(3):
+        wide.train_step(xw_d, cw_d, 0.004)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        wide.train_step(xw_d, cw_d, 0.004)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3 / 10
+    flop_fwd = 2.0 * (25 * 4 * 512 * 9262 + 3 * 512 * 512 * sum(
+        9262 - sum(2 * 2 ** (k + 1) for k in range(i + 1)) for i in range(11)) + 75 * 512 * 2 * 1000)
+    out["c4_wide_train_seq_per_s"] = Bw / sec
+    out["c4_wide_train_tflops"] = 3 * flop_fwd * Bw / sec / 1e12
+    out["c4_config"] = "C4: F=512, 11 dilated layers, 25/75, 9286->1000 bp, batch 16, bf16"
+    del wide
+    torch.cuda.empty_cache()
     out["pisa_config"] = "C5: C1 model, 20 row-shuffled references per base, 6 bases per CUDA-graph replay"
     return out
 

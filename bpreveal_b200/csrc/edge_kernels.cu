@@ -73,45 +73,52 @@ heads_fwd_kernel(int L_in, int L_out, int W, int Fw, int F, int T,
                  float* __restrict__ logits, float* __restrict__ gap) {
   extern __shared__ float sm[];
   const int rows = 128 + W - 1;
-  const int stride = Fw + 1;
-  float* sa = sm;  // [rows][Fw+1] fp32 (hi+lo summed)
+  constexpr int CH = 64;        // channels staged per pass (any number of filters fits)
+  constexpr int stride = CH + 1;
+  float* sa = sm;  // [rows][CH+1] fp32 (hi+lo summed)
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 128;
-  for (int i = threadIdx.x; i < rows * Fw; i += blockDim.x) {
-    const int r = i / Fw, c = i % Fw;
-    const int t = t0 + r;
-    float v = 0.f;
-    if (t < L_in) {
-      const size_t idx = (static_cast<size_t>(b) * L_in + t) * F + c;
-      v = bf16_at(act_hi + idx);
-      if (act_lo) v += bf16_at(act_lo + idx);
-    }
-    sa[r * stride + c] = v;
-  }
-  __syncthreads();
-  // global average pool partial sums over this block's own 128 rows
-  if (gap) {
-    for (int c = threadIdx.x; c < Fw; c += blockDim.x) {
-      float s = 0.f;
-      for (int r = 0; r < 128; ++r) s += sa[r * stride + c];  // rows >= L_in are zero
-      atomicAdd(gap + static_cast<size_t>(b) * F + c, s / static_cast<float>(L_in));
-    }
-  }
   const int t = t0 + threadIdx.x;
-  if (t < L_out) {
-    float acc[TP];
+  float acc[TP];
 #pragma unroll
-    for (int k = 0; k < TP; ++k) acc[k] = (k < T) ? pb[k] : 0.f;
-    for (int j = 0; j < W; ++j) {
-      const float* ar = sa + (threadIdx.x + j) * stride;
-      const float* wr = pw + static_cast<size_t>(j) * Fw * T;
-      for (int c = 0; c < Fw; ++c) {
-        const float a = ar[c];
-#pragma unroll
-        for (int k = 0; k < TP; ++k)
-          if (k < T) acc[k] = fmaf(a, __ldg(wr + c * T + k), acc[k]);
+  for (int k = 0; k < TP; ++k) acc[k] = (k < T) ? pb[k] : 0.f;
+  for (int c0 = 0; c0 < Fw; c0 += CH) {
+    const int nc = min(CH, Fw - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * nc; i += blockDim.x) {
+      const int r = i / nc, c = i % nc;
+      const int tt = t0 + r;
+      float v = 0.f;
+      if (tt < L_in) {
+        const size_t idx = (static_cast<size_t>(b) * L_in + tt) * F + c0 + c;
+        v = bf16_at(act_hi + idx);
+        if (act_lo) v += bf16_at(act_lo + idx);
+      }
+      sa[r * stride + c] = v;
+    }
+    __syncthreads();
+    // global average pool partial sums over this block's own 128 rows
+    if (gap) {
+      for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < 128; ++r) s += sa[r * stride + c];  // rows >= L_in are zero
+        atomicAdd(gap + static_cast<size_t>(b) * F + c0 + c, s / static_cast<float>(L_in));
       }
     }
+    if (t < L_out) {
+      for (int j = 0; j < W; ++j) {
+        const float* ar = sa + (threadIdx.x + j) * stride;
+        const float* wr = pw + (static_cast<size_t>(j) * Fw + c0) * T;
+        for (int c = 0; c < nc; ++c) {
+          const float a = ar[c];
+#pragma unroll
+          for (int k = 0; k < TP; ++k)
+            if (k < T) acc[k] = fmaf(a, __ldg(wr + c * T + k), acc[k]);
+        }
+      }
+    }
+  }
+  if (t < L_out) {
     float* lo = logits + (static_cast<size_t>(b) * L_out + t) * T;
 #pragma unroll
     for (int k = 0; k < TP; ++k)
@@ -166,9 +173,8 @@ extern "C" int bpb_heads_fwd(int B, int L_in, int L_out, int W, int Fw, int F, i
              "bpb_heads_fwd: NULL argument");
   BP_REQUIRE(T >= 1 && T <= 16, "bpb_heads_fwd: total tasks T=%d must be in 1..16", T);
   BP_REQUIRE(L_out == L_in - W + 1, "bpb_heads_fwd: L_out must be L_in - W + 1");
-  const size_t smem = static_cast<size_t>(128 + W - 1) * (Fw + 1) * 4;
-  BP_REQUIRE(smem <= 200 * 1024, "bpb_heads_fwd: tile does not fit shared memory (W=%d Fw=%d)", W,
-             Fw);
+  const size_t smem = static_cast<size_t>(128 + W - 1) * 65 * 4;  // 64-channel staging passes
+  BP_REQUIRE(smem <= 200 * 1024, "bpb_heads_fwd: filter width W=%d too large", W);
   BP_CHECK_CUDA(cudaMemsetAsync(gap, 0, static_cast<size_t>(B) * F * 4, stream));
   dim3 grid((L_in + 127) / 128, B);
   const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(act_hi);

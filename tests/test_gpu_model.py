@@ -15,6 +15,8 @@ CASES = [
     ("tiny2heads", Hh.tiny_cfg(headTasks=[1, 3], numFilters=16)),
     ("mid", Hh.mid_cfg()),
     ("mid128", Hh.mid_cfg(numFilters=128, numLayers=3, outputLength=150, headTasks=[2, 2])),
+    # the wide regime of C4 in miniature: N tiles of 256 with streamed weights, width-75 heads
+    ("wide256", Hh.mid_cfg(numFilters=256, numLayers=3, outputLength=60, outputFilterWidth=75)),
 ]
 
 
