@@ -69,7 +69,10 @@ def test_loss_and_gradients(dev, name, cfg, precise):
         assert abs(losses[H + h] - cl[h]) <= (1e-3 if precise else 3e-2) * abs(cl[h]) + 1e-5, \
             (h, losses[H + h], cl[h])
     got = net.state(net.grads_flat)
-    gtol = 2e-3 if precise else 8e-2
+    # precise path: activations carry 16 mantissa bits (hi + lo bf16 planes), so pre-activations
+    # within ~1e-5 of zero can land on the other side of the ReLU than in the fp64 oracle; each
+    # such flip moves a gradient entry by one term.  K = 3 * 256 doubles the chance per element.
+    gtol = (2e-3 if cfg["numFilters"] <= 128 else 5e-3) if precise else 8e-2
     gscale = max(np.abs(v).max() for v in grads.values())
     for k in grads:
         # relative to the tensor's own magnitude, floored by the global gradient scale (the profile
