@@ -206,8 +206,12 @@ class Model:
         nseq = 0
         for bi in order:
             xb, yb = gen[int(bi)]
-            counts = np.concatenate([np.asarray(y, dtype=np.float32) for y in yb[:H]], axis=2)
-            losses = self._step(np.asarray(xb), counts, train)
+            if isinstance(xb, torch.Tensor):  # device-resident generator: stay on the device
+                counts = yb[0] if H == 1 else torch.cat(list(yb[:H]), dim=2)
+            else:
+                counts = np.concatenate([np.asarray(y, dtype=np.float32) for y in yb[:H]], axis=2)
+                xb = np.asarray(xb)
+            losses = self._step(xb, counts, train)
             n = xb.shape[0]
             sums += losses * n  # every loss is a mean over the batch (losses.py:36-38)
             nseq += n
