@@ -24,24 +24,36 @@ namespace bp {
 constexpr int kWgTile = 128 * 128;  // bytes of one [128 x 64] bf16 tile
 constexpr int kWgMaxStages = 8;
 
+constexpr int kWgMaxJobs = 12;
+
+// One launch serves up to kWgMaxJobs independent contractions of the same shape class (all tower
+// layers of a step): job j owns the CTAs [cta_begin[j], cta_begin[j+1]) -- a share of the SMs
+// proportional to its position tiles -- so that split-K partials, prologue and tail are paid once
+// per step instead of once per layer.
 struct WgradKParams {
-  int B, L_out, tiles_per_seq, F, NC, dil;
+  int B, NC;
   int n_passes, pa_bits, pg_bits, db_mask;  // pass i: A plane (pa_bits >> i) & 1, G plane likewise
-  int n_units, UG, n_groups, n_ntiles, n_items, ksplit;
-  int stages;
-  int halo;        // 1: ONE TMA box of 128 + (n_taps-1)*dil rows serves every tap (NC == 1)
-  int halo_bytes;  // bytes TMA writes for the box; halo_sub: the same padded to 1024
-  int halo_sub;
+  int n_units, UG, n_groups, n_ntiles, n_items;
+  int stages, stage_bytes;
   int Ncols;   // columns of the result (NT * n_ntiles)
-  float* ws;   // [ksplit][(n_units * 64 + 1) * Ncols]
+  int n_jobs;
+  int cta_begin[kWgMaxJobs + 1];
+  int tiles_per_seq[kWgMaxJobs];
+  int dil[kWgMaxJobs];
+  int halo[kWgMaxJobs];        // 1: ONE TMA box of 128 + (n_taps-1)*dil rows serves every tap
+  int halo_bytes[kWgMaxJobs];  // bytes TMA writes for that box
+  long long ws_off[kWgMaxJobs];  // float offset of the job's [ksplit][(n_units*64+1)*Ncols] partials
+  float* ws;
   unsigned* dbg;
+};
+
+struct WgradMaps {
+  CUtensorMap A[2][kWgMaxJobs], G[2][kWgMaxJobs];
 };
 
 template <int NT>
 __global__ void __launch_bounds__(192, 1)
-wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1,
-                 const WgradKParams p) {
+wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   constexpr int NSUB = NT / 64;
   constexpr uint32_t IDESC = umma_idesc_bf16(64, NT, 1, 1);
   constexpr uint32_t TMEM_COLS = 512;
@@ -49,8 +61,7 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const size_t stage_bytes = p.halo ? static_cast<size_t>(NSUB) * kWgTile + p.halo_sub
-                                    : static_cast<size_t>(NSUB + p.UG) * kWgTile;
+  const size_t stage_bytes = static_cast<size_t>(p.stage_bytes);
   uint8_t* ones = smem;
   uint8_t* ring = smem + kWgTile;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.stages * stage_bytes);
@@ -61,21 +72,32 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int item = blockIdx.x % p.n_items;
-  const int split = blockIdx.x / p.n_items;
+  int job = 0;
+  while (job + 1 < p.n_jobs && static_cast<int>(blockIdx.x) >= p.cta_begin[job + 1]) ++job;
+  const int local = blockIdx.x - p.cta_begin[job];
+  const int ksplit = (p.cta_begin[job + 1] - p.cta_begin[job]) / p.n_items;
+  const int tiles_per_seq = p.tiles_per_seq[job];
+  const int dil = p.dil[job];
+  const bool halo = p.halo[job] != 0;
+  const CUtensorMap* tmA0 = &tm.A[0][job];
+  const CUtensorMap* tmA1 = &tm.A[1][job];
+  const CUtensorMap* tmG0 = &tm.G[0][job];
+  const CUtensorMap* tmG1 = &tm.G[1][job];
+  const int item = local % p.n_items;
+  const int split = local / p.n_items;
   const int grp = item / p.n_ntiles;
   const int nt = item % p.n_ntiles;
   const int u0 = grp * p.UG;
   const int nu = min(p.UG, p.n_units - u0);
   const bool do_db = (grp == 0);
-  const int kblocks = p.B * p.tiles_per_seq;
-  const int my_kb = (kblocks - split + p.ksplit - 1) / p.ksplit;  // split < ksplit <= kblocks
+  const int kblocks = p.B * tiles_per_seq;
+  const int my_kb = (kblocks - split + ksplit - 1) / ksplit;  // split < ksplit <= kblocks
   const int visits = my_kb * p.n_passes;
 
   pdl_launch_dependents();
   if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmG0);
+    tma_prefetch_desc(tmA0);
+    tma_prefetch_desc(tmG0);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -103,26 +125,26 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int v = 0; v < visits; ++v) {
-        const int kb = split + (v / p.n_passes) * p.ksplit;
+        const int kb = split + (v / p.n_passes) * ksplit;
         const int pass = v % p.n_passes;
-        const int b = kb / p.tiles_per_seq;
-        const int t0 = (kb % p.tiles_per_seq) * 128;
+        const int b = kb / tiles_per_seq;
+        const int t0 = (kb % tiles_per_seq) * 128;
         mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x1100 + stage, v);
-        mbar_expect_tx(&full[stage], p.halo ? static_cast<uint32_t>(NSUB * kWgTile + p.halo_bytes)
-                                            : static_cast<uint32_t>((NSUB + nu) * kWgTile));
+        mbar_expect_tx(&full[stage], halo ? static_cast<uint32_t>(NSUB * kWgTile + p.halo_bytes[job])
+                                          : static_cast<uint32_t>((NSUB + nu) * kWgTile));
         uint8_t* dst = ring + stage * stage_bytes;
-        const CUtensorMap* mg = ((p.pg_bits >> pass) & 1) ? &tmG1 : &tmG0;
-        const CUtensorMap* ma = ((p.pa_bits >> pass) & 1) ? &tmA1 : &tmA0;
+        const CUtensorMap* mg = ((p.pg_bits >> pass) & 1) ? tmG1 : tmG0;
+        const CUtensorMap* ma = ((p.pa_bits >> pass) & 1) ? tmA1 : tmA0;
         for (int s = 0; s < NSUB; ++s)
           tma_load_3d(mg, dst + s * kWgTile, &full[stage], nt * NT + s * 64, t0, b);
-        if (p.halo) {
+        if (halo) {
           // rows t0 .. t0 + 127 + (n_taps-1)*dil of the single channel chunk: every tap at once
           tma_load_3d(ma, dst + NSUB * kWgTile, &full[stage], 0, t0, b);
         } else {
           for (int i = 0; i < nu; ++i) {
             const int u = u0 + i;
             const int j = u / p.NC, c = u % p.NC;
-            tma_load_3d(ma, dst + (NSUB + i) * kWgTile, &full[stage], c * 64, t0 + j * p.dil, b);
+            tma_load_3d(ma, dst + (NSUB + i) * kWgTile, &full[stage], c * 64, t0 + j * dil, b);
           }
         }
         if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
@@ -143,8 +165,8 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t a_off[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        a_off[i] = p.halo ? (NSUB * kWgTile + (u0 + i) * p.dil * 128) >> 4
-                          : ((NSUB + i) * kWgTile) >> 4;
+        a_off[i] = halo ? (NSUB * kWgTile + (u0 + i) * dil * 128) >> 4
+                        : ((NSUB + i) * kWgTile) >> 4;
       for (int v = 0; v < visits; ++v) {
         const int pass = v % p.n_passes;
         mbar_wait_wd(&full[stage], phase, p.dbg, 0x1500 + stage, v);
@@ -180,7 +202,7 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     mbar_wait_wd(acc_full, 0, p.dbg, 0x1800, 0);
     tc_fence_after();
     const size_t rows = static_cast<size_t>(p.n_units) * 64;
-    float* wsp = p.ws + static_cast<size_t>(split) * (rows + 1) * p.Ncols;
+    float* wsp = p.ws + p.ws_off[job] + static_cast<size_t>(split) * (rows + 1) * p.Ncols;
     for (int i = 0; i < nu; ++i) {
       const int u = u0 + i;
       // M=64 accumulators occupy lanes 0-15 of each TMEM quadrant: row = 16*q + lane.
@@ -255,12 +277,29 @@ __device__ __forceinline__ void wgrad_scatter(const WgradScatter& sc, long long 
   }
 }
 
-// out[i] = sum_s ws[s][i] in a fixed order (deterministic).  One block owns 32 consecutive outputs;
-// warp w adds the splits s = w, w + 8, ... (each a coalesced 128-byte read, four independent
-// chains), then the eight warp partials are added in warp order.
+struct WgradReduceJobs {
+  int n_jobs;
+  int ksplit[kWgMaxJobs];
+  long long ws_off[kWgMaxJobs];
+  float* o0[kWgMaxJobs];
+  float* o1[kWgMaxJobs];
+  float* o2[kWgMaxJobs];
+  WgradScatter sc;  // shared geometry; o0/o1/o2 come from the per-job arrays
+};
+
+// out[i] = sum_s ws[s][i] in a fixed order (deterministic).  One block owns 32 consecutive outputs
+// of job blockIdx.y; warp w adds the splits s = w, w + 8, ... (each a coalesced 128-byte read, four
+// independent chains), then the eight warp partials are added in warp order.
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, const WgradScatter sc) {
+wgrad_reduce_kernel(const float* __restrict__ ws_all, const WgradReduceJobs jobs) {
   __shared__ float part[8][32];
+  const int job = blockIdx.y;
+  const float* ws = ws_all + jobs.ws_off[job];
+  const int ksplit = jobs.ksplit[job];
+  WgradScatter sc = jobs.sc;
+  sc.o0 = jobs.o0[job];
+  sc.o1 = jobs.o1[job];
+  sc.o2 = jobs.o2[job];
   const long long n = (static_cast<long long>(sc.rows) + 1) * sc.cols;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = static_cast<long long>(blockIdx.x) * 32 + lane;
@@ -285,7 +324,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, const WgradScatter
   }
 }
 
-// One launch: out[u*64 + m][n] = sum over positions of A_u[pos][m] * G[pos][n], u = (tap, chunk).
+// One contraction: out[u*64 + m][n] = sum over positions of A_u[pos][m] * G[pos][n], u = (tap, chunk).
 struct WgradDesc {
   const char* who;
   int B, rows;      // sequences, positions per sequence (the K extent)
@@ -305,12 +344,18 @@ struct WgradDesc {
 };
 
 struct WgradPlan {
-  int NT, UG, n_units, n_groups, n_ntiles, n_items, ksplit, stages;
-  int halo, halo_sub;
-  size_t smem_bytes, ws_bytes;
+  int NT, UG, n_units, n_groups, n_ntiles, n_items, stages;
+  int ksplit[kWgMaxJobs];
+  int halo[kWgMaxJobs], halo_rows[kWgMaxJobs];
+  long long ws_off[kWgMaxJobs];
+  size_t stage_bytes, smem_bytes, ws_bytes;
+  int grid;
 };
 
-static bool plan_wgrad(int B, int rows, int n_units, int Ncols, WgradPlan* pl, int halo_rows = 0) {
+// Jobs must agree on n_units and Ncols (the same layer shape); rows / dilation may differ.
+static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_in, int n_units,
+                       int Ncols, WgradPlan* pl) {
+  if (n_jobs < 1 || n_jobs > kWgMaxJobs) return false;
   const int NT = (Ncols % 256 == 0) ? 256 : (Ncols % 128 == 0 ? 128 : 64);
   pl->NT = NT;
   pl->n_units = n_units;
@@ -321,31 +366,70 @@ static bool plan_wgrad(int B, int rows, int n_units, int Ncols, WgradPlan* pl, i
   pl->n_groups = (n_units + ug - 1) / ug;
   pl->n_ntiles = Ncols / NT;
   pl->n_items = pl->n_groups * pl->n_ntiles;
-  const int kblocks = B * ((rows + 127) / 128);
-  int ks = sm_count() / pl->n_items;
-  if (ks < 1) ks = 1;
-  if (ks > kblocks) ks = kblocks;
-  pl->ksplit = ks;
-  // HALO (tower layers with one channel chunk and a dilation span <= 128 rows): one box for all taps
-  pl->halo = halo_rows > 0 && halo_rows <= 256 && pl->n_groups == 1;
-  pl->halo_sub = pl->halo ? (halo_rows * 128 + 1023) / 1024 * 1024 : 0;
-  const size_t stage_bytes = pl->halo ? static_cast<size_t>(NT / 64) * kWgTile + pl->halo_sub
-                                      : static_cast<size_t>(NT / 64 + ug) * kWgTile;
+  const int sms = sm_count();
+  if (sms <= 0) return false;
+  // split-K factors: the SMs are shared between the jobs in proportion to their position tiles
+  long long total_kb = 0;
+  int kb[kWgMaxJobs];
+  for (int j = 0; j < n_jobs; ++j) {
+    kb[j] = B * ((rows[j] + 127) / 128);
+    total_kb += kb[j];
+  }
+  int budget = sms / pl->n_items;  // splits available in total
+  if (budget < n_jobs) budget = n_jobs;
+  int used = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    int ks = static_cast<int>(static_cast<long long>(budget) * kb[j] / total_kb);
+    if (ks < 1) ks = 1;
+    if (ks > kb[j]) ks = kb[j];
+    pl->ksplit[j] = ks;
+    used += ks;
+  }
+  // hand the remainder to the largest jobs
+  for (int guard = 0; used < budget && guard < 4 * kWgMaxJobs; ++guard) {
+    int best = -1;
+    double best_load = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+      const double load = static_cast<double>(kb[j]) / pl->ksplit[j];
+      if (pl->ksplit[j] < kb[j] && load > best_load) { best_load = load; best = j; }
+    }
+    if (best < 0) break;
+    ++pl->ksplit[best];
+    ++used;
+  }
+  pl->grid = used * pl->n_items;
+  // staging: HALO (one box for all taps) where the dilation span allows it, else one tile per unit
+  size_t stage = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    const int hr = halo_rows_in ? halo_rows_in[j] : 0;
+    pl->halo[j] = hr > 0 && hr <= 256 && pl->n_groups == 1;
+    pl->halo_rows[j] = pl->halo[j] ? hr : 0;
+    const size_t sb = pl->halo[j]
+                          ? static_cast<size_t>(NT / 64) * kWgTile + (hr * 128 + 1023) / 1024 * 1024
+                          : static_cast<size_t>(NT / 64 + ug) * kWgTile;
+    if (sb > stage) stage = sb;
+  }
+  pl->stage_bytes = stage;
   const size_t fixed = 1024 + kWgTile + (2 * kWgMaxStages + 2) * 8 + 16;
   const int max_smem = max_smem_optin();
   if (max_smem <= 0) return false;
-  int stages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / stage_bytes);
+  int stages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / stage);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   if (stages < 1) return false;
   pl->stages = stages;
-  pl->smem_bytes = fixed + stages * stage_bytes;
-  pl->ws_bytes = static_cast<size_t>(ks) * (static_cast<size_t>(n_units) * 64 + 1) * Ncols *
-                 sizeof(float);
+  pl->smem_bytes = fixed + stages * stage;
+  const long long per_split = (static_cast<long long>(n_units) * 64 + 1) * Ncols;
+  long long off = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    pl->ws_off[j] = off;
+    off += per_split * pl->ksplit[j];
+  }
+  pl->ws_bytes = static_cast<size_t>(off) * sizeof(float);
   return true;
 }
 
 template <int NT>
-static int launch_wgrad(const CUtensorMap* maps, const WgradKParams& kp, size_t smem, int grid,
+static int launch_wgrad(const WgradMaps& maps, const WgradKParams& kp, size_t smem, int grid,
                         cudaStream_t stream) {
   auto kern = wgrad3_tc_kernel<NT>;
   static bool configured = false;
@@ -354,74 +438,101 @@ static int launch_wgrad(const CUtensorMap* maps, const WgradKParams& kp, size_t 
                                        max_smem_optin()));
     configured = true;
   }
-  BP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(192), smem, stream, maps[0], maps[1], maps[2], maps[3], kp));
+  BP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(192), smem, stream, maps, kp));
   return 0;
 }
 
-static int wgrad_run(const WgradDesc& d, cudaStream_t stream) {
+// All descs share shape class (n_taps, NC, Ncols, passes, scatter mode); d[0].ws is the workspace.
+static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
+  const WgradDesc& d0 = d[0];
+  BP_REQUIRE(n_jobs >= 1 && n_jobs <= kWgMaxJobs, "%s: %d jobs (1..%d supported)", d0.who, n_jobs,
+             kWgMaxJobs);
+  int rows[kWgMaxJobs], halo_rows[kWgMaxJobs];
+  for (int j = 0; j < n_jobs; ++j) {
+    BP_REQUIRE(d[j].n_taps == d0.n_taps && d[j].NC == d0.NC && d[j].Ncols == d0.Ncols &&
+                   d[j].B == d0.B && d[j].n_passes == d0.n_passes,
+               "%s: every job of one launch must have the same layer shape", d0.who);
+    rows[j] = d[j].rows;
+    halo_rows[j] = (d[j].allow_halo && d[j].NC == 1 && d[j].n_taps > 1)
+                       ? 128 + (d[j].n_taps - 1) * d[j].dil : 0;
+  }
   WgradPlan pl;
-  const int halo_rows = (d.allow_halo && d.NC == 1 && d.n_taps > 1) ? 128 + (d.n_taps - 1) * d.dil : 0;
-  BP_REQUIRE(plan_wgrad(d.B, d.rows, d.n_taps * d.NC, d.Ncols, &pl, halo_rows),
-             "%s: cannot plan (no device?)", d.who);
-  BP_REQUIRE(static_cast<size_t>(d.ws_bytes) >= pl.ws_bytes, "%s: workspace too small (%lld < %zu)",
-             d.who, d.ws_bytes, pl.ws_bytes);
+  BP_REQUIRE(plan_wgrad(n_jobs, d0.B, rows, halo_rows, d0.n_taps * d0.NC, d0.Ncols, &pl),
+             "%s: cannot plan (no device?)", d0.who);
+  BP_REQUIRE(static_cast<size_t>(d0.ws_bytes) >= pl.ws_bytes, "%s: workspace too small (%lld < %zu)",
+             d0.who, d0.ws_bytes, pl.ws_bytes);
   WgradKParams kp{};
-  kp.B = d.B;
-  kp.L_out = d.rows;
-  kp.tiles_per_seq = (d.rows + 127) / 128;
-  kp.F = d.Ncols;
-  kp.NC = d.NC;
-  kp.dil = d.dil;
-  kp.n_passes = d.n_passes;
-  kp.pa_bits = d.pa_bits;
-  kp.pg_bits = d.pg_bits;
-  kp.db_mask = d.db_mask;
+  kp.B = d0.B;
+  kp.NC = d0.NC;
+  kp.n_passes = d0.n_passes;
+  kp.pa_bits = d0.pa_bits;
+  kp.pg_bits = d0.pg_bits;
+  kp.db_mask = d0.db_mask;
   kp.n_units = pl.n_units;
   kp.UG = pl.UG;
   kp.n_groups = pl.n_groups;
   kp.n_ntiles = pl.n_ntiles;
   kp.n_items = pl.n_items;
-  kp.ksplit = pl.ksplit;
   kp.stages = pl.stages;
-  kp.Ncols = d.Ncols;
-  kp.halo = pl.halo;
-  kp.halo_sub = pl.halo_sub;
-  kp.halo_bytes = halo_rows * 128;
-  kp.ws = d.ws;
+  kp.stage_bytes = static_cast<int>(pl.stage_bytes);
+  kp.Ncols = d0.Ncols;
+  kp.n_jobs = n_jobs;
+  kp.ws = d0.ws;
   kp.dbg = debug_buffer();
 
-  CUtensorMap maps[4];
-  memset(maps, 0, sizeof(maps));
-  for (int pl_i = 0; pl_i < 2; ++pl_i) {
-    if (d.a_ptr[pl_i] &&
-        !make_tmap_3d_strided(&maps[pl_i], d.a_ptr[pl_i], d.a_inner, d.a_rows, d.B,
-                              d.a_row_stride_bytes, d.a_batch_stride_bytes, 64,
-                              pl.halo ? halo_rows : 128))
-      return 3;
-    if (d.g_ptr[pl_i] &&
-        !make_tmap_3d_strided(&maps[2 + pl_i], d.g_ptr[pl_i], d.g_inner, d.g_rows, d.B,
-                              d.g_row_stride_bytes, d.g_batch_stride_bytes, 64, 128))
-      return 3;
+  static thread_local WgradMaps maps;  // 6 KB: too large for the stack frame of every caller
+  memset(&maps, 0, sizeof(maps));
+  WgradReduceJobs rj{};
+  rj.n_jobs = n_jobs;
+  rj.sc = d0.sc;
+  rj.sc.rows = pl.n_units * 64;
+  rj.sc.cols = d0.Ncols;
+  int cta = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    kp.cta_begin[j] = cta;
+    cta += pl.ksplit[j] * pl.n_items;
+    kp.tiles_per_seq[j] = (d[j].rows + 127) / 128;
+    kp.dil[j] = d[j].dil;
+    kp.halo[j] = pl.halo[j];
+    kp.halo_bytes[j] = pl.halo_rows[j] * 128;
+    kp.ws_off[j] = pl.ws_off[j];
+    rj.ksplit[j] = pl.ksplit[j];
+    rj.ws_off[j] = pl.ws_off[j];
+    rj.o0[j] = d[j].sc.o0;
+    rj.o1[j] = d[j].sc.o1;
+    rj.o2[j] = d[j].sc.o2;
+    for (int pl_i = 0; pl_i < 2; ++pl_i) {
+      if (d[j].a_ptr[pl_i] &&
+          !make_tmap_3d_strided(&maps.A[pl_i][j], d[j].a_ptr[pl_i], d[j].a_inner, d[j].a_rows,
+                                d[j].B, d[j].a_row_stride_bytes, d[j].a_batch_stride_bytes, 64,
+                                pl.halo[j] ? pl.halo_rows[j] : 128))
+        return 3;
+      if (d[j].g_ptr[pl_i] &&
+          !make_tmap_3d_strided(&maps.G[pl_i][j], d[j].g_ptr[pl_i], d[j].g_inner, d[j].g_rows,
+                                d[j].B, d[j].g_row_stride_bytes, d[j].g_batch_stride_bytes, 64, 128))
+        return 3;
+    }
   }
-  const int grid = pl.n_items * pl.ksplit;
+  kp.cta_begin[n_jobs] = cta;
   int rc;
-  if (pl.NT == 64) rc = launch_wgrad<64>(maps, kp, pl.smem_bytes, grid, stream);
-  else if (pl.NT == 128) rc = launch_wgrad<128>(maps, kp, pl.smem_bytes, grid, stream);
-  else rc = launch_wgrad<256>(maps, kp, pl.smem_bytes, grid, stream);
+  if (pl.NT == 64) rc = launch_wgrad<64>(maps, kp, pl.smem_bytes, pl.grid, stream);
+  else if (pl.NT == 128) rc = launch_wgrad<128>(maps, kp, pl.smem_bytes, pl.grid, stream);
+  else rc = launch_wgrad<256>(maps, kp, pl.smem_bytes, pl.grid, stream);
   if (rc) return rc;
 
-  WgradScatter sc = d.sc;
-  sc.rows = pl.n_units * 64;
-  sc.cols = d.Ncols;
-  const long long n = (static_cast<long long>(sc.rows) + 1) * sc.cols;
-  wgrad_reduce_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, stream>>>(d.ws, pl.ksplit, sc);
+  const long long n = (static_cast<long long>(rj.sc.rows) + 1) * rj.sc.cols;
+  dim3 rgrid(static_cast<unsigned>((n + 31) / 32), static_cast<unsigned>(n_jobs));
+  wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(d0.ws, rj);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-static long long wgrad_ws_bytes(const char* who, int B, int rows, int n_units, int Ncols) {
+static int wgrad_run(const WgradDesc& d, cudaStream_t stream) { return wgrad_run(&d, 1, stream); }
+
+static long long wgrad_ws_bytes(const char* who, int n_jobs, int B, const int* rows, int n_units,
+                                int Ncols) {
   WgradPlan pl;
-  if (Ncols <= 0 || Ncols % 64 != 0 || !plan_wgrad(B, rows, n_units, Ncols, &pl)) {
+  if (Ncols <= 0 || Ncols % 64 != 0 || !plan_wgrad(n_jobs, B, rows, nullptr, n_units, Ncols, &pl)) {
     set_error("%s: unsupported geometry or no CUDA device", who);
     return -1;
   }
@@ -434,20 +545,19 @@ static int window_kc(int W, int C) { return (W * C + 63) / 64; }
 
 extern "C" long long bpb_wgrad3_ws_bytes(int B, int L_out, int F, int precise) {
   (void)precise;
-  return bp::wgrad_ws_bytes("bpb_wgrad3_ws_bytes", B, L_out, F > 0 ? 3 * (F / 64) : 0, F);
+  return bp::wgrad_ws_bytes("bpb_wgrad3_ws_bytes", 1, B, &L_out, F > 0 ? 3 * (F / 64) : 0, F);
 }
 
-extern "C" int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream_) {
+static int fill_wgrad3_desc(const char* who, const bpb_wgrad3_args* a, bp::WgradDesc* out) {
   using namespace bp;
-  BP_REQUIRE(a != nullptr, "bpb_wgrad3_tc: null args");
-  BP_REQUIRE(a->F > 0 && a->F % 64 == 0, "bpb_wgrad3_tc: F=%d must be a positive multiple of 64",
-             a->F);
-  BP_REQUIRE(a->act_hi && a->gz_hi && a->dw && a->ws, "bpb_wgrad3_tc: NULL tensor");
+  BP_REQUIRE(a != nullptr, "%s: null args", who);
+  BP_REQUIRE(a->F > 0 && a->F % 64 == 0, "%s: F=%d must be a positive multiple of 64", who, a->F);
+  BP_REQUIRE(a->act_hi && a->gz_hi && a->dw, "%s: NULL tensor", who);
   BP_REQUIRE((a->act_lo != nullptr) == (a->gz_lo != nullptr),
-             "bpb_wgrad3_tc: act_lo and gz_lo must both be given or both be NULL");
+             "%s: act_lo and gz_lo must both be given or both be NULL", who);
   const bool precise = a->act_lo != nullptr;
   WgradDesc d{};
-  d.who = "bpb_wgrad3_tc";
+  d.who = who;
   d.B = a->B;
   d.rows = a->L_out;
   d.n_taps = 3;
@@ -477,11 +587,41 @@ extern "C" int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream_) {
   d.sc.mode = 0;
   d.sc.o0 = a->dw;
   d.sc.o1 = a->db;
-  return wgrad_run(d, static_cast<cudaStream_t>(stream_));
+  *out = d;
+  return 0;
+}
+
+extern "C" int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream_) {
+  bp::WgradDesc d;
+  if (int rc = fill_wgrad3_desc("bpb_wgrad3_tc", a, &d)) return rc;
+  BP_REQUIRE(a->ws != nullptr, "bpb_wgrad3_tc: NULL workspace");
+  return bp::wgrad_run(d, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" long long bpb_wgrad3_multi_ws_bytes(int n_layers, int B, const int* L_out, int F) {
+  if (n_layers < 1 || n_layers > bp::kWgMaxJobs || L_out == nullptr) {
+    bp::set_error("bpb_wgrad3_multi_ws_bytes: 1..%d layers", bp::kWgMaxJobs);
+    return -1;
+  }
+  return bp::wgrad_ws_bytes("bpb_wgrad3_multi_ws_bytes", n_layers, B, L_out,
+                            F > 0 ? 3 * (F / 64) : 0, F);
+}
+
+extern "C" int bpb_wgrad3_multi(const bpb_wgrad3_args* layers, int n_layers, float* ws,
+                                long long ws_bytes, void* stream_) {
+  using namespace bp;
+  BP_REQUIRE(layers != nullptr && ws != nullptr && n_layers >= 1 && n_layers <= kWgMaxJobs,
+             "bpb_wgrad3_multi: 1..%d layers and a workspace are required", kWgMaxJobs);
+  WgradDesc d[kWgMaxJobs];
+  for (int i = 0; i < n_layers; ++i)
+    if (int rc = fill_wgrad3_desc("bpb_wgrad3_multi", &layers[i], &d[i])) return rc;
+  d[0].ws = ws;
+  d[0].ws_bytes = ws_bytes;
+  return wgrad_run(d, n_layers, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" long long bpb_input_conv_wgrad_ws_bytes(int B, int L_out, int W, int F) {
-  return bp::wgrad_ws_bytes("bpb_input_conv_wgrad_ws_bytes", B, L_out, bp::window_kc(W, 8), F);
+  return bp::wgrad_ws_bytes("bpb_input_conv_wgrad_ws_bytes", 1, B, &L_out, bp::window_kc(W, 8), F);
 }
 
 extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, int F,
@@ -527,7 +667,7 @@ extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, i
 }
 
 extern "C" long long bpb_heads_wgrad_ws_bytes(int B, int L_in, int W, int F, int Cp) {
-  return bp::wgrad_ws_bytes("bpb_heads_wgrad_ws_bytes", B, L_in, F > 0 ? F / 64 : 0,
+  return bp::wgrad_ws_bytes("bpb_heads_wgrad_ws_bytes", 1, B, &L_in, F > 0 ? F / 64 : 0,
                             bp::window_kc(W, Cp) * 64);
 }
 

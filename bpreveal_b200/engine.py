@@ -237,10 +237,11 @@ class SoloNet:
             ws["dlogits"] = torch.empty_like(ws["logits"])
             ws["dlogcounts"] = torch.empty_like(ws["logcounts"])
             ws["g"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
-            # one gz buffer per layer (no ping-pong): the parameter gradients run on a second
-            # stream and may lag the data-gradient chain by several layers
+            # one gz buffer per layer (no ping-pong): the tower weight gradients are computed
+            # together after the data-gradient chain
             ws["gzl"] = [ops.new_planes(B, L, Fp, prec, dev) for L in Ls]
             nb = max([ops.wgrad3_ws_bytes(B, L, Fp, prec) for L in Ls[1:]] +
+                     ([ops.wgrad3_multi_ws_bytes(B, Ls[1:], Fp)] if 0 < len(Ls) - 1 <= 12 else []) +
                      [ops.input_conv_wgrad_ws_bytes(B, Ls[0], cfg.inputFilterWidth, Fp),
                       ops.heads_wgrad_ws_bytes(B, Ls[-1], cfg.outputFilterWidth, Fp, self.cp)])
             ws["scratch"] = torch.empty((nb // 4 + 4,), dtype=torch.float32, device=dev)
@@ -361,45 +362,36 @@ class SoloNet:
                          ws["losses"], ws["dlogits"], ws["dlogcounts"])
         if bias_logits is not None:
             ops.mul_f32(ws["dlogcounts"], ws["dscale"], ws["dlogcounts"])
-        # Backward.  The data-gradient chain (heads -> tower layers, each needing the previous one)
-        # runs on the current stream; every parameter gradient only needs the gz of its own layer,
-        # so they run on a side stream and fill the bubbles (prologue / tail) of the chain.  They
-        # share one split-K workspace and are therefore serialised among themselves.
+        # Backward.  The data-gradient chain comes first (heads -> tower layers, each needing the
+        # previous one) and leaves one gz buffer per layer; every tower weight gradient is then
+        # computed by ONE split-K launch (bpb_wgrad3_multi) instead of one launch + reduction per
+        # layer.
         nL = cfg.numLayers
-        main = torch.cuda.current_stream()
-        side = self._side_stream()
-
-        def fork():
-            ev = torch.cuda.Event()
-            ev.record(main)
-            side.wait_event(ev)
-
         gcur = self._sub(ws["g"][nL % 2], Ls[nL])
         gzcur = ws["gzl"][nL]
         planes = 2 if cfg.precise else 1
         ops.heads_pack_grad(ws["dlogits"], ws["dlogcounts"], Ls[nL], cfg.outputFilterWidth,
                             self.cp, planes, ws["d8"], dpb=g["prof_b"], dcb=g["cnt_b"])
-        fork()
-        with torch.cuda.stream(side):
-            ops.heads_wgrad(aL, ws["d8"], cfg.outputFilterWidth, cfg.numFilters, cfg.T, cfg.H,
-                            self.cp, planes, g["prof_w"], g["cnt_w"], ws["scratch"])
+        ops.heads_wgrad(aL, ws["d8"], cfg.outputFilterWidth, cfg.numFilters, cfg.T, cfg.H,
+                        self.cp, planes, g["prof_w"], g["cnt_w"], ws["scratch"])
         ops.heads_dgrad(ws["d8"], self.w_hd_op, ws["B"], Ls[nL], cfg.outputFilterWidth, cfg.Fp,
                         self.cp, planes, g=gcur, gz=gzcur, mask_in=ws["masks"][nL])
         for i in range(nL - 1, -1, -1):
             d = 2 ** (i + 1)
-            fork()  # gz of layer i+1 is complete
-            with torch.cuda.stream(side):
-                ops.wgrad3(ws["acts"][i], gzcur, d, g["dil_w"][i], g["dil_b"][i], ws["scratch"])
             gnext = self._sub(ws["g"][i % 2], Ls[i])
             gznext = ws["gzl"][i]
             ops.conv3(gzcur, self.w_bwd[i], (0, -d, -2 * d), 1, Ls[i], resid=gcur, resid_off=-d,
                       out=gnext if i > 0 else None, out2=gznext, mask_in=ws["masks"][i])
             gcur, gzcur = gnext, gznext
-        fork()
-        with torch.cuda.stream(side):
-            ops.input_conv_wgrad(ws["x8"], gzcur, cfg.inputFilterWidth, cfg.numFilters,
-                                 g["conv1_w"], g["conv1_b"], ws["scratch"])
-        main.wait_stream(side)  # join: the optimiser needs every gradient
+        if 0 < nL <= 12:
+            ops.wgrad3_multi([(ws["acts"][i], ws["gzl"][i + 1], 2 ** (i + 1), g["dil_w"][i],
+                               g["dil_b"][i]) for i in range(nL)], ws["scratch"])
+        else:
+            for i in range(nL):
+                ops.wgrad3(ws["acts"][i], ws["gzl"][i + 1], 2 ** (i + 1), g["dil_w"][i],
+                           g["dil_b"][i], ws["scratch"])
+        ops.input_conv_wgrad(ws["x8"], ws["gzl"][0], cfg.inputFilterWidth, cfg.numFilters,
+                             g["conv1_w"], g["conv1_b"], ws["scratch"])
 
     def apply_adam(self, grad_scale=1.0):
         # the optimiser step counter lives on the device so that the update replays inside a graph
@@ -483,11 +475,6 @@ class SoloNet:
                 allreduce(self.grads_flat)
                 body_b()
         return ws["losses"]
-
-    def _side_stream(self):
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        return self._side
 
     # ------------------------------------------------------------------ CUDA graphs
     def _run_graph(self, key, body):

@@ -143,6 +143,30 @@ def input_conv_fwd(x8, w_op, w_planes, W, Fw, bias, F, out, mask_out=None, z_out
     check(lib.bpb_input_conv_fwd(C.byref(a), _stream()), "bpb_input_conv_fwd")
 
 
+def wgrad3_multi_ws_bytes(B, L_outs, F):
+    arr = (C.c_int * len(L_outs))(*L_outs)
+    n = _lib.load().bpb_wgrad3_multi_ws_bytes(len(L_outs), B, arr, F)
+    if n < 0:
+        check(1, "bpb_wgrad3_multi_ws_bytes")
+    return n
+
+
+def wgrad3_multi(layers, ws):
+    """layers: list of (act planes, gz planes, dilation, dw, db) -- every tower layer of a step in
+    one launch (bpb_wgrad3_multi)."""
+    lib = _lib.load()
+    arr = (Wgrad3Args * len(layers))()
+    for a, (act, gz, dil, dw, db) in zip(arr, layers):
+        a_hi, a_lo = _planes(act)
+        g_hi, g_lo = _planes(gz)
+        B, L_in, F = a_hi.shape
+        a.B, a.L_in, a.L_out, a.F, a.dil = B, L_in, g_hi.shape[1], F, dil
+        a.act_hi, a.act_lo, a.gz_hi, a.gz_lo = _p(a_hi), _p(a_lo), _p(g_hi), _p(g_lo)
+        a.dw, a.db = _p(dw), _p(db)
+    check(lib.bpb_wgrad3_multi(arr, len(layers), _p(ws), ws.numel() * ws.element_size(),
+                               _stream()), "bpb_wgrad3_multi")
+
+
 def input_conv_wgrad_ws_bytes(B, L_out, W, F):
     n = _lib.load().bpb_input_conv_wgrad_ws_bytes(B, L_out, W, F)
     if n < 0:

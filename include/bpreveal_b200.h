@@ -96,6 +96,13 @@ typedef struct {
 } bpb_wgrad3_args;
 long long bpb_wgrad3_ws_bytes(int B, int L_out, int F, int precise);
 int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream);
+/* The same for up to 12 layers of one network (same B and F) in ONE launch: the SMs are shared
+ * between the layers in proportion to their position tiles, so the split-K partials, the kernel
+ * prologue / tail and the reduction are paid once per step instead of once per layer.  The ws /
+ * ws_bytes fields of the individual layers are ignored; every layer's dw / db is overwritten. */
+long long bpb_wgrad3_multi_ws_bytes(int n_layers, int B, const int* host_L_out, int F);
+int bpb_wgrad3_multi(const bpb_wgrad3_args* host_layers, int n_layers, float* ws,
+                     long long ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1: input convolution on one-hot DNA (models.py:85-90) as a tcgen05 GEMM.
