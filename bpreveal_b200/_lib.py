@@ -117,6 +117,7 @@ SIGNATURES = {
     "bpb_add_f32": (c_int, [c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bpb_mul_f32": (c_int, [c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bpb_shuffle_rows": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bpb_flat_profile_seed": (c_int, [c_int] * 4 + [c_void_p] * 7),
     "bpb_shap_combine": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                  c_void_p]),
     "bpb_counts_lse": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

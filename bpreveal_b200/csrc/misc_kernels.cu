@@ -471,3 +471,87 @@ extern "C" int bpb_shuffle_rows(int Q, int n, int L, const uint8_t* x, const int
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// interpretFlat profile metric (interpretFlat.py:187-237) under DeepSHAP (shap.py:642-678).
+//   l~ = logits[:, :, selected tasks] - mean over the (L x tasks) block
+//   metric v = sum_j softmax(stop_gradient(l~))_j * l~_j
+// The product of two varying tensors takes the 2-input rule: the multiplier of the query-half l~
+// is (p_x + p_r) / 2, zero where |l~_x - l~_r| < 1e-7; the stop-gradient branch contributes
+// nothing; the mean-normalisation is linear, so dlogits_j = m_j - mean(m) on the selected
+// columns.  One block per (query, reference) pair.
+// ------------------------------------------------------------------------------------------
+namespace bp {
+__global__ void __launch_bounds__(256)
+flat_profile_seed_kernel(int n, int L, int T, const int* __restrict__ sel,
+                         const float* __restrict__ lx_all, const float* __restrict__ lr_all,
+                         float* __restrict__ dlogits, float* __restrict__ vx,
+                         float* __restrict__ vr) {
+  __shared__ float scratch[32];
+  const int r = blockIdx.x;
+  const int q = r / n;
+  const float* lx = lx_all + static_cast<size_t>(q) * L * T;
+  const float* lr = lr_all + static_cast<size_t>(r) * L * T;
+  float* dl = dlogits + static_cast<size_t>(r) * L * T;
+  const int N = L * T;
+  float sx = 0.f, sr = 0.f, mxx = -INFINITY, mxr = -INFINITY;
+  int cnt = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    if (sel[i % T]) {
+      sx += lx[i]; sr += lr[i];
+      mxx = fmaxf(mxx, lx[i]); mxr = fmaxf(mxr, lr[i]);
+      ++cnt;
+    }
+  sx = block_reduce(sx, SumF(), scratch);
+  sr = block_reduce(sr, SumF(), scratch);
+  mxx = block_reduce(mxx, MaxF(), scratch);
+  mxr = block_reduce(mxr, MaxF(), scratch);
+  const float J = block_reduce(static_cast<float>(cnt), SumF(), scratch);
+  const float mean_x = sx / J, mean_r = sr / J;
+  float ex = 0.f, er = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    if (sel[i % T]) {
+      ex += __expf(lx[i] - mxx);
+      er += __expf(lr[i] - mxr);
+    }
+  ex = block_reduce(ex, SumF(), scratch);
+  er = block_reduce(er, SumF(), scratch);
+  float sm = 0.f, ax = 0.f, ar = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    if (sel[i % T]) {
+      const float px = __expf(lx[i] - mxx) / ex, pr = __expf(lr[i] - mxr) / er;
+      const float tx = lx[i] - mean_x, tr = lr[i] - mean_r;
+      sm += (fabsf(tx - tr) < 1e-7f) ? 0.f : 0.5f * (px + pr);
+      ax += px * tx;
+      ar += pr * tr;
+    }
+  sm = block_reduce(sm, SumF(), scratch);
+  ax = block_reduce(ax, SumF(), scratch);
+  ar = block_reduce(ar, SumF(), scratch);
+  const float mbar = sm / J;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float g = 0.f;
+    if (sel[i % T]) {
+      const float px = __expf(lx[i] - mxx) / ex, pr = __expf(lr[i] - mxr) / er;
+      const float tx = lx[i] - mean_x, tr = lr[i] - mean_r;
+      g = ((fabsf(tx - tr) < 1e-7f) ? 0.f : 0.5f * (px + pr)) - mbar;
+    }
+    dl[i] = g;
+  }
+  if (threadIdx.x == 0) {
+    if (vr) vr[r] = ar;
+    if (vx && r % n == 0) vx[q] = ax;
+  }
+}
+}  // namespace bp
+
+extern "C" int bpb_flat_profile_seed(int Q, int n, int L, int T, const int* sel,
+                                     const float* logits_x, const float* logits_r,
+                                     float* dlogits, float* vx, float* vr, void* stream_) {
+  BP_REQUIRE(sel && logits_x && logits_r && dlogits && Q > 0 && n > 0,
+             "bpb_flat_profile_seed: bad argument");
+  bp::flat_profile_seed_kernel<<<Q * n, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      n, L, T, sel, logits_x, logits_r, dlogits, vx, vr);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

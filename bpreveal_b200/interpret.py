@@ -144,3 +144,42 @@ def pisa_batch(net, x_u8, headID, taskID, numShuffles, refs_u8=None, hypothetica
     vx = wx["logits"][:, 0, col].clone()
     vr = wr["logits"][:, 0, col].reshape(Q, numShuffles).clone()
     return phi, vx, vr
+
+
+def flat_batch(net, x_u8, headID, numShuffles, kind="profile", taskIDs=None, refs_u8=None):
+    """interpretFlat hypothetical contribution scores (interpretFlat.py:187-312,
+    interpretUtils.py:1295-1312) of Q windows for one head.
+
+    kind "profile": the weighted mean-normalised logits of ``taskIDs`` (default: every task of the
+    head); kind "counts": the head's log-counts.  Returns (hyp_scores (Q, Lin, 4) fp32,
+    metric on the queries (Q,), metric on the shuffles (Q, n))."""
+    cfg = net.cfg
+    Q = x_u8.shape[0]
+    x_u8 = x_u8.contiguous()
+    dev = x_u8.device
+    if refs_u8 is None:
+        refs_u8 = make_references(x_u8, numShuffles)
+    k0 = int(sum(cfg.headTasks[:headID]))
+    tasks = list(range(cfg.headTasks[headID])) if taskIDs is None else list(taskIDs)
+    sel = torch.zeros((cfg.T,), dtype=torch.int32, device=dev)
+    for t in tasks:
+        sel[k0 + t] = 1
+    vals = {}
+
+    def dlogits_fn(wx, wr):
+        wr["dlogits"].zero_()
+        wr["dlogcounts"].zero_()
+        if kind == "counts":
+            wr["dlogcounts"][:, headID] = 1.0
+            vals["x"] = wx["logcounts"][:, headID].clone()
+            vals["r"] = wr["logcounts"][:, headID].reshape(Q, numShuffles).clone()
+        else:
+            vx = torch.empty((Q,), dtype=torch.float32, device=dev)
+            vr = torch.empty((Q * numShuffles,), dtype=torch.float32, device=dev)
+            ops.flat_profile_seed(sel, wx["logits"], wr["logits"], wr["dlogits"], vx, vr)
+            vals["x"], vals["r"] = vx, vr.reshape(Q, numShuffles)
+
+    dx, _, _ = net.shap_batch(x_u8, refs_u8, dlogits_fn)
+    hyp = torch.empty((Q, cfg.inputLength, 4), dtype=torch.float32, device=dev)
+    ops.shap_combine(x_u8, refs_u8, dx, hyp, True)
+    return hyp, vals["x"], vals["r"]

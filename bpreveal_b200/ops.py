@@ -374,6 +374,14 @@ def shuffle_rows(x, perm, refs):
           "bpb_shuffle_rows")
 
 
+def flat_profile_seed(sel, logits_x, logits_r, dlogits, vx=None, vr=None):
+    Q, L, T = logits_x.shape
+    n = logits_r.shape[0] // Q
+    check(_lib.load().bpb_flat_profile_seed(Q, n, L, T, _p(sel), _p(logits_x), _p(logits_r),
+                                            _p(dlogits), _p(vx), _p(vr), _stream()),
+          "bpb_flat_profile_seed")
+
+
 def shap_combine(x, refs, mult, phi, hypothetical=False):
     Q, L, _ = x.shape
     n = refs.shape[0] // Q

@@ -279,6 +279,14 @@ int bpb_counts_lse(int B, int H, const int* use_bias, const float* bias_lc, cons
  * ------------------------------------------------------------------------------------------ */
 int bpb_shuffle_rows(int Q, int n, int L, const uint8_t* x, const int* perm, uint8_t* refs,
                      void* stream);
+/* Seeds of the interpretFlat profile metric (interpretFlat.py:187-237) under the DeepSHAP
+ * 2-input rule (shap.py:642-678): for pair (q, r) of query logits_x [Q][L][T] and reference
+ * logits_r [Q*n][L][T], over the columns with sel[k] != 0,
+ *   dlogits[r] = m - mean(m),  m = (softmax(l~_x) + softmax(l~_r)) / 2  (0 where |l~_x - l~_r| < 1e-7)
+ * and the metric values vx [Q], vr [Q*n] (either may be NULL). */
+int bpb_flat_profile_seed(int Q, int n, int L, int T, const int* sel, const float* logits_x,
+                          const float* logits_r, float* dlogits, float* vx, float* vr,
+                          void* stream);
 int bpb_shap_combine(int Q, int n, int L, const uint8_t* x, const uint8_t* refs,
                      const float* mult, int hypothetical, float* phi, void* stream);
 

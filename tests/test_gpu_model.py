@@ -174,3 +174,33 @@ def test_pisa_receptive_field_crop_and_graph_are_exact(dev):
     other = interpret.pisa_batch(net, xs[:Q], 0, 1, n)
     ref = interpret.pisa_batch(net, xs[:Q], 0, 1, n, use_graph=False, crop=False)
     assert (other[0] - ref[0]).abs().max().item() <= 1e-5 * ref[0].abs().max().item()
+
+
+@pytest.mark.parametrize("precise", [False, True])
+def test_flat_hypothetical_scores_parity(dev, precise):
+    """interpretFlat profile / counts metrics with the hypothetical-contribution combiner
+    (interpretFlat.py:187-312, interpretUtils.py:1295-1312) against the oracle."""
+    from bpreveal_b200 import interpret
+    cfg = Hh.tiny_cfg(headTasks=[2, 1])
+    net, params = build(cfg, precise, dev, scale=1.5)
+    Q, n = 2, 6
+    xs = O.synthetic_sequences(Q, cfg["inputLength"], seed=5)
+    p64 = O.to_torch(params, torch.float64)
+    xt = torch.tensor(xs, device=dev)
+    hyp_p, vx_p, vr_p = interpret.flat_batch(net, xt, 0, n, kind="profile", taskIDs=[0, 1])
+    hyp_c, vx_c, vr_c = interpret.flat_batch(net, xt, 1, n, kind="counts")
+    tol = 3e-3 if precise else 6e-2
+    for q in range(Q):
+        refs = O.generate_shuffles(xs[q], n)
+        ref_p, val_p, rv_p = O.deepshap(xs[q], refs, O.solo_shap_forward(p64),
+                                        lambda pr, cn: O.profile_metric(pr, cn, 0, [0, 1], shap=True),
+                                        hypothetical=True)
+        ref_c, val_c, rv_c = O.deepshap(xs[q], refs, O.solo_shap_forward(p64),
+                                        lambda pr, cn: O.counts_metric(pr, cn, 1), hypothetical=True)
+        for got, ref in ((hyp_p[q], ref_p), (hyp_c[q], ref_c)):
+            scale = np.abs(ref).max()
+            assert np.abs(got.cpu().numpy() - ref).max() <= tol * scale
+        assert abs(vx_p[q].item() - val_p) <= (1e-3 if precise else 5e-2) * max(1.0, abs(val_p))
+        assert abs(vx_c[q].item() - val_c) <= (1e-4 if precise else 3e-2) * max(1.0, abs(val_c))
+        assert np.abs(vr_c[q].cpu().numpy() - rv_c).max() <= (1e-4 if precise else 3e-2) * max(
+            1.0, np.abs(rv_c).max())
