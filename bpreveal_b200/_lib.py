@@ -81,6 +81,7 @@ SIGNATURES = {
     "bpb_wgrad3_tc": (c_int, [C.POINTER(Wgrad3Args), c_void_p]),
     "bpb_wgrad3_multi_ws_bytes": (c_ll, [c_int, c_int, C.POINTER(c_int), c_int]),
     "bpb_wgrad3_multi": (c_int, [C.POINTER(Wgrad3Args), c_int, c_void_p, c_ll, c_void_p]),
+    "bpb_x8_elems": (c_ll, [c_int, c_int]),
     "bpb_onehot_expand": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "bpb_input_conv_wop_elems": (c_ll, [c_int, c_int, c_int]),
     "bpb_prep_input_conv_weights": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int,

@@ -52,6 +52,15 @@ struct ConvKParams {
   // operand planes: pass i multiplies A plane (pa_bits >> i) & 1 with W plane (pw_bits >> 2i) & 3
   int npass, pa_bits, pw_bits, n_aplanes, n_wplanes;
   int step_b, step_mt, step_nt;  // gridDim.x tiles expressed as (sequences, M tiles, N tiles)
+  // STRIP staging (window convolutions over a 16-byte-per-position tensor, resident weights): the
+  // A operand of a tile is the raw strip of 127 + 2*nk16 positions; a NON-swizzled K-major UMMA
+  // descriptor (LBO 16 B, SBO 128 B) reads the implicit im2col matrix straight out of it.
+  int strip;         // 1: STRIP staging
+  int strip_bytes;   // bytes copied per (tile, A plane)
+  int strip_stride;  // the same padded to 1024
+  int nk16;          // K = 16 * nk16
+  long long a_batch_bytes;      // STRIP: byte stride between sequences
+  const uint8_t* a_base[2];     // STRIP: the A planes
   int tap_row[3];  // SLAB: row offset of tap j relative to t0; HALO: row of tap j inside the box
   int box_off;     // HALO: first box row = t0 + box_off
   int sub_bytes;   // HALO: bytes of one (chunk, plane) box, padded to 1024
@@ -169,7 +178,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
   const int w_tiles = RESIDENT ? p.n_wplanes * p.n_taps * p.KC : 0;
-  const int stage_bytes = HALO ? p.KC * p.n_aplanes * p.sub_bytes : SLAB_BYTES;
+  const int stage_bytes = HALO ? p.KC * p.n_aplanes * p.sub_bytes
+                               : (p.strip ? p.n_aplanes * p.strip_stride : SLAB_BYTES);
   const int n_out = p.has_out + p.has_out2;
   const int stg_bytes = n_out * PLANES * kTileBytes;
   const int rstage_bytes = PLANES * kTileBytes;
@@ -265,6 +275,16 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               tma_load_3d(&tm.A[pl], dst + static_cast<size_t>(c * p.n_aplanes + pl) * p.sub_bytes,
                           &full[stage], c * 64, t0 + p.box_off, b);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+        } else if (RESIDENT && p.strip) {
+          mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
+          mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.n_aplanes * p.strip_bytes));
+          uint8_t* dst = ring + static_cast<size_t>(stage) * stage_bytes;
+          for (int pl = 0; pl < p.n_aplanes; ++pl)
+            bulk_load_1d(dst + pl * p.strip_stride,
+                         p.a_base[pl] + static_cast<size_t>(b) * p.a_batch_bytes +
+                             static_cast<size_t>(t0) * 16,
+                         static_cast<uint32_t>(p.strip_bytes), &full[stage]);
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         } else {
           // Resident weights: one A tile per (tap, chunk, A plane), shared by every pass that
           // multiplies that plane; streamed weights: one (A, W) tile pair per pass.
@@ -354,6 +374,28 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             umma_commit(&empty[stage]);
             if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
           }
+        } else if (RESIDENT && p.strip) {
+          mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
+          tc_fence_after();
+          const uint32_t a0 = (ring_lo + stage * stage_lo) & 0x3FFFu;
+          // no-swizzle K-major: LBO = 16 B (next core matrix along K), SBO = 128 B (along M)
+          constexpr uint32_t A_HI = (128u >> 4) | (1u << 14);
+          constexpr uint32_t A_LBO = (16u >> 4) << 16;
+          uint32_t accum = 0;
+          for (int ps = 0; ps < p.npass; ++ps) {
+            const uint32_t ap = (p.pa_bits >> ps) & 1;
+            const uint32_t wp = (p.pw_bits >> (2 * ps)) & 3;
+            const uint32_t a_pl = a0 + ap * (static_cast<uint32_t>(p.strip_stride) >> 4);
+            const uint32_t b_pl = smem_u32(w_smem) + wp * p.KC * B_TILE_BYTES;
+            for (int k = 0; k < p.nk16; ++k) {
+              const uint32_t b_addr = b_pl + (k >> 2) * B_TILE_BYTES + (k & 3) * 32;
+              umma_bf16_lohi(d_tmem, ((a_pl + 2u * k) & 0x3FFFu) | A_LBO, A_HI,
+                             umma_desc_lo(b_addr, 0), DHI, IDESC, accum);
+              accum = 1;
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         } else if (HALO) {
           mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
           tc_fence_after();
@@ -718,7 +760,14 @@ struct ConvDesc {
   int zx_div;
   float* z_out;
   bool allow_halo;
+  bool allow_strip;  // window convolution over a 16-byte-per-position tensor (n_taps == 1)
 };
+
+// BPB_STRIP=0 disables STRIP staging (falls back to overlapping-row TMA boxes).
+static const bool g_strip_enabled = [] {
+  const char* e = getenv("BPB_STRIP");
+  return !(e && e[0] == '0');
+}();
 
 // Tuning knob (BPB_EPI_GROUPS=1|2, default 2): number of 8-warp epilogue groups on the bf16 path.
 static int g_epi_groups = [] {
@@ -834,6 +883,13 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   const bool two_groups = (n_planes == 1) && g_epi_groups == 2;
   const int r_hi = two_groups ? 4 : 3;
 
+  // STRIP staging: resident weights, one tap, rows one 16-byte position apart
+  const int nk16 = (d.KC - 1) * 4 + d.last_nk;
+  const int strip_bytes = (127 + 2 * nk16) * 16;
+  // multiple of 1024 so that everything carved after the ring keeps the swizzle-atom alignment
+  const int strip_stride = (strip_bytes + 1023) / 1024 * 1024;
+  const bool strip_ok = !RESID && d.allow_strip && can_reside && d.n_taps == 1 &&
+                        d.a_row_stride_bytes == 16 && g_strip_enabled;
   bool halo = false, resident = false;
   int stages = 0, rstages = 0, nstg = 0;
   size_t stage_bytes = 0;
@@ -850,6 +906,8 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
       rows = kTileM + span;
       sb = static_cast<size_t>(d.KC) * d.n_aplanes *
            ((static_cast<size_t>(rows) * 128 + 1023) / 1024 * 1024);
+    } else if (want_res && strip_ok) {
+      sb = static_cast<size_t>(d.n_aplanes) * strip_stride;
     } else {
       sb = kTileBytes + (want_res ? 0 : b_tile);
     }
@@ -875,6 +933,15 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
               try_plan(false, false, 1, 2, 2);
   BP_REQUIRE(planned, "%s: not enough shared memory for F=%d planes=%d", d.who, F, n_planes);
   kp.stages = stages;
+  if (resident && !halo && strip_ok) {
+    kp.strip = 1;
+    kp.strip_bytes = strip_bytes;
+    kp.strip_stride = strip_stride;
+    kp.nk16 = nk16;
+    kp.a_batch_bytes = static_cast<long long>(d.a_batch_stride_bytes);
+    kp.a_base[0] = static_cast<const uint8_t*>(d.a_ptr[0]);
+    kp.a_base[1] = static_cast<const uint8_t*>(d.a_ptr[1]);
+  }
   kp.rstages = rstages > 0 ? rstages : 1;
   kp.ring_resid = rstages > 0 ? 1 : 0;
   kp.nstg = nstg;

@@ -12,6 +12,10 @@
 
 namespace bp {
 
+// STRIP staging reads whole strips of 127 + 2*nk16 positions, also for the last tile of the last
+// sequence: window tensors (x8, d8 planes) carry this many spare elements at their end.
+constexpr long long kStripPadElems = 8 * 512;
+
 __global__ void __launch_bounds__(256)
 onehot_expand_kernel(long long n_pos, const uint32_t* __restrict__ x, uint4* __restrict__ x8) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -59,6 +63,7 @@ heads_pack_grad_kernel(int B, int L_in, int L_out, int W, int T, int H, int Cp, 
   const long long n_el = static_cast<long long>(B) * Lp * Cp;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n_el) return;
+  const long long plane_stride = n_el + kStripPadElems;  // see bpb_heads_d8_elems
   const int ch = static_cast<int>(i % Cp);
   const int r = static_cast<int>((i / Cp) % Lp);
   const int b = static_cast<int>(i / (static_cast<long long>(Cp) * Lp));
@@ -69,7 +74,7 @@ heads_pack_grad_kernel(int B, int L_in, int L_out, int W, int T, int H, int Cp, 
   } else if (ch < T + H) {
     v = dlc[b * H + (ch - T)] / static_cast<float>(L_in);
   }
-  store_split(d8, n_el, planes, i, v);
+  store_split(d8, plane_stride, planes, i, v);
 }
 
 // Bias gradients of the heads in fp32 (they are sums of terms that cancel almost exactly -- the
@@ -136,6 +141,10 @@ extern "C" int bpb_onehot_expand(int B, int L, const uint8_t* x, bpb_bf16* x8, v
       n, reinterpret_cast<const uint32_t*>(x), reinterpret_cast<uint4*>(x8));
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" long long bpb_x8_elems(int B, int L) {
+  return static_cast<long long>(B) * L * 8 + bp::kStripPadElems;
 }
 
 extern "C" long long bpb_input_conv_wop_elems(int W, int F, int planes) {
@@ -207,11 +216,16 @@ extern "C" int bpb_input_conv_fwd(const bpb_input_conv_args* a, void* stream_) {
   d.zx_div = a->zx_div;
   d.z_out = a->z_out;
   d.allow_halo = false;
+  d.allow_strip = true;  // x8 must be padded by bpb_strip_pad_elems() elements at its end
   return conv_run<false>(d, static_cast<cudaStream_t>(stream_));
 }
 
+static long long d8_plane_elems(int B, int L_in, int W, int Cp) {
+  return static_cast<long long>(B) * (L_in + W - 1) * Cp + bp::kStripPadElems;
+}
+
 extern "C" long long bpb_heads_d8_elems(int B, int L_in, int W, int Cp, int planes) {
-  return static_cast<long long>(planes) * B * (L_in + W - 1) * Cp;
+  return planes * d8_plane_elems(B, L_in, W, Cp);
 }
 
 extern "C" long long bpb_heads_dgrad_wop_elems(int W, int F, int Cp, int planes) {
@@ -299,5 +313,6 @@ extern "C" int bpb_heads_dgrad_tc(const bpb_heads_dgrad_args* a, void* stream_) 
   d.mult[0] = a->mult_hi;
   d.mult[1] = a->mult_lo;
   d.allow_halo = false;
+  d.allow_strip = true;  // taken when Cp == 8 (16 bytes per position)
   return conv_run<false>(d, static_cast<cudaStream_t>(stream_));
 }

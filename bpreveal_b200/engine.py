@@ -218,7 +218,7 @@ class SoloNet:
         Ls = cfg.lengths()
         ws = {"B": B}
         ws["x"] = torch.zeros((B, cfg.inputLength, 4), dtype=torch.uint8, device=dev)
-        ws["x8"] = torch.zeros((B, cfg.inputLength, 8), dtype=torch.bfloat16, device=dev)
+        ws["x8"] = ops.new_x8(B, cfg.inputLength, dev)
         ws["logits"] = torch.empty((B, cfg.outputLength, cfg.T), dtype=torch.float32, device=dev)
         ws["gap"] = torch.empty((B, Fp), dtype=torch.float32, device=dev)
         ws["logcounts"] = torch.empty((B, cfg.H), dtype=torch.float32, device=dev)

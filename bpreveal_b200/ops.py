@@ -109,6 +109,13 @@ def wgrad3(act, gz, dil, dw, db, ws):
     check(lib.bpb_wgrad3_tc(C.byref(a), _stream()), "bpb_wgrad3_tc")
 
 
+def new_x8(B, L, device):
+    """bf16 [B, L, 8] view of a buffer with the spare tail the STRIP-staged kernels read into."""
+    n = _lib.load().bpb_x8_elems(B, L)
+    flat = torch.zeros((n,), dtype=torch.bfloat16, device=device)
+    return flat[:B * L * 8].view(B, L, 8)
+
+
 def onehot_expand(x, x8):
     """u8 one-hot [B, L, 4] -> bf16 [B, L, 8] (the tcgen05 operand of the input convolution)."""
     B, L, nb = x.shape

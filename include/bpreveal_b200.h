@@ -117,6 +117,7 @@ int bpb_wgrad3_multi(const bpb_wgrad3_args* host_layers, int n_layers, float* ws
  * Optional outputs: relu mask bits, fp32 z (attribution of the query), rescale multiplier
  * against zx_in (attribution of a shuffled reference).
  * ------------------------------------------------------------------------------------------ */
+long long bpb_x8_elems(int B, int L); /* B*L*8 plus the spare tail that whole-strip reads need */
 int bpb_onehot_expand(int B, int L, const uint8_t* x, bpb_bf16* x8, void* stream);
 long long bpb_input_conv_wop_elems(int W, int F, int planes);
 int bpb_prep_input_conv_weights(int W, int Fw, int F, const float* w, bpb_bf16* w_op, int planes,
@@ -185,7 +186,8 @@ int bpb_heads_wgrad_tc(int B, int L_in, int W, int Fw, int F, int T, int H, int 
 /* Data gradient of the heads on tensor cores.  bpb_heads_pack_grad writes
  *   d8[b, r, ch] = dlogits[b, r-(W-1), ch]  (ch < T, zero outside the profile)
  *                = dlogcounts[b, ch-T] / L_in  (T <= ch < T+H, every row)        bf16 planes
- * as [planes][B][L_in+W-1][Cp] (Cp a multiple of 8 >= T+H); bpb_prep_heads_dgrad_weights lays the
+ * as [planes][B][L_in+W-1][Cp] (Cp a multiple of 8 >= T+H; each plane is followed by a spare tail,
+ * bpb_heads_d8_elems() is the size of the whole buffer and the lo plane starts at its middle); bpb_prep_heads_dgrad_weights lays the
  * profile / counts kernels out as the matching GEMM operand
  * (with dpb != NULL it also writes the heads' bias gradients dpb[k] = sum dlogits[b,t,k] and
  * dcb[h] = sum_b dlogcounts[b,h] in fp32: their terms cancel almost exactly, so they are not

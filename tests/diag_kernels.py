@@ -175,7 +175,7 @@ def group_edges():
         mask = torch.zeros((B, L_out, Fp // 64), dtype=torch.int64, device=dev)
         z = torch.empty((B, L_out, Fp), dtype=torch.float32, device=dev)
         planes = 2 if precise else 1
-        x8 = torch.zeros((B, L_in, 8), dtype=torch.bfloat16, device=dev)
+        x8 = ops.new_x8(B, L_in, dev)
         ops.onehot_expand(x, x8)
         assert torch.equal(x8[..., :4].float(), x.float()) and x8[..., 4:].abs().max() == 0
         w_op = ops.input_conv_wop(W, Fp, planes, dev)
