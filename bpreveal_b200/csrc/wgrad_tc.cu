@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace bp {
 
 constexpr int kWgTile = 128 * 128;  // bytes of one [128 x 64] bf16 tile
@@ -42,6 +44,12 @@ struct WgradKParams {
   int dil[kWgMaxJobs];
   int halo[kWgMaxJobs];        // 1: ONE TMA box of 128 + (n_taps-1)*dil rows serves every tap
   int halo_bytes[kWgMaxJobs];  // bytes TMA writes for that box
+  // STRIP staging of the A operand (window gradients over a 16-byte-per-position tensor): the raw
+  // strip of 128 + 8*n_units positions is copied once per position tile and read through
+  // NON-swizzled MN-major descriptors (LBO 128 B along K, SBO 16 B along MN), unit u at +128*u B.
+  int strip, strip_bytes;
+  long long a_batch_bytes;
+  const uint8_t* a_base;
   long long ws_off[kWgMaxJobs];  // float offset of the job's [ksplit][(n_units*64+1)*Ncols] partials
   float* ws;
   unsigned* dbg;
@@ -130,14 +138,21 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
         const int b = kb / tiles_per_seq;
         const int t0 = (kb % tiles_per_seq) * 128;
         mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x1100 + stage, v);
-        mbar_expect_tx(&full[stage], halo ? static_cast<uint32_t>(NSUB * kWgTile + p.halo_bytes[job])
-                                          : static_cast<uint32_t>((NSUB + nu) * kWgTile));
+        mbar_expect_tx(&full[stage],
+                       p.strip ? static_cast<uint32_t>(NSUB * kWgTile + p.strip_bytes)
+                       : halo  ? static_cast<uint32_t>(NSUB * kWgTile + p.halo_bytes[job])
+                               : static_cast<uint32_t>((NSUB + nu) * kWgTile));
         uint8_t* dst = ring + stage * stage_bytes;
         const CUtensorMap* mg = ((p.pg_bits >> pass) & 1) ? tmG1 : tmG0;
         const CUtensorMap* ma = ((p.pa_bits >> pass) & 1) ? tmA1 : tmA0;
         for (int s = 0; s < NSUB; ++s)
           tma_load_3d(mg, dst + s * kWgTile, &full[stage], nt * NT + s * 64, t0, b);
-        if (halo) {
+        if (p.strip) {
+          bulk_load_1d(dst + NSUB * kWgTile,
+                       p.a_base + static_cast<size_t>(b) * p.a_batch_bytes +
+                           static_cast<size_t>(t0) * 16,
+                       static_cast<uint32_t>(p.strip_bytes), &full[stage]);
+        } else if (halo) {
           // rows t0 .. t0 + 127 + (n_taps-1)*dil of the single channel chunk: every tap at once
           tma_load_3d(ma, dst + NSUB * kWgTile, &full[stage], 0, t0, b);
         } else {
@@ -165,8 +180,14 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
       uint32_t a_off[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        a_off[i] = halo ? (NSUB * kWgTile + (u0 + i) * dil * 128) >> 4
-                        : ((NSUB + i) * kWgTile) >> 4;
+        a_off[i] = p.strip ? (NSUB * kWgTile + (u0 + i) * 128) >> 4
+                  : halo  ? (NSUB * kWgTile + (u0 + i) * dil * 128) >> 4
+                          : ((NSUB + i) * kWgTile) >> 4;
+      // STRIP: no swizzle, LBO = 128 B (8 positions along K), SBO = 16 B (8 elements along MN),
+      // K advances by 16 positions = 256 B per MMA
+      const uint32_t a_lbo = p.strip ? ((128u >> 4) << 16) : lbo_bits;
+      const uint32_t a_hi = p.strip ? ((16u >> 4) | (1u << 14)) : DHI;
+      const uint32_t a_kstep = p.strip ? (256u >> 4) : 128u;
       for (int v = 0; v < visits; ++v) {
         const int pass = v % p.n_passes;
         mbar_wait_wd(&full[stage], phase, p.dbg, 0x1500 + stage, v);
@@ -177,11 +198,11 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
           if (i < nu) {
             // HALO: tap i starts i*dil rows into the box (the 128-byte swizzle is a function of
             // the absolute shared-memory address, so an MN-major operand may start on any row)
-            const uint32_t a_lo = g_lo + a_off[i];
+            const uint32_t a_lo = (((ring_lo + stage * stage_lo) & 0x3FFFu) + a_off[i]) | a_lbo;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_bf16_lohi(tmem_base + i * NT, a_lo + k * 128u, DHI, g_lo + k * 128u, DHI, IDESC,
-                             (v | k) != 0 ? 1u : 0u);
+              umma_bf16_lohi(tmem_base + i * NT, a_lo + k * a_kstep, a_hi, g_lo + k * 128u, DHI,
+                             IDESC, (v | k) != 0 ? 1u : 0u);
           }
         }
         if (do_db && ((p.db_mask >> pass) & 1)) {
@@ -338,6 +359,7 @@ struct WgradDesc {
   unsigned long long g_inner, g_rows, g_row_stride_bytes, g_batch_stride_bytes;
   int n_passes, pa_bits, pg_bits, db_mask;
   bool allow_halo;
+  bool allow_strip;  // A rows are one 16-byte position apart (n_taps == 1, single A plane)
   float* ws;
   long long ws_bytes;
   WgradScatter sc;
@@ -354,7 +376,7 @@ struct WgradPlan {
 
 // Jobs must agree on n_units and Ncols (the same layer shape); rows / dilation may differ.
 static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_in, int n_units,
-                       int Ncols, WgradPlan* pl) {
+                       int Ncols, WgradPlan* pl, bool strip = false) {
   if (n_jobs < 1 || n_jobs > kWgMaxJobs) return false;
   const int NT = (Ncols % 256 == 0) ? 256 : (Ncols % 128 == 0 ? 128 : 64);
   pl->NT = NT;
@@ -404,7 +426,10 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
     const int hr = halo_rows_in ? halo_rows_in[j] : 0;
     pl->halo[j] = hr > 0 && hr <= 256 && pl->n_groups == 1;
     pl->halo_rows[j] = pl->halo[j] ? hr : 0;
-    const size_t sb = pl->halo[j]
+    const size_t sb = (strip && pl->n_groups == 1)
+                          ? static_cast<size_t>(NT / 64) * kWgTile +
+                                ((128 + 8 * n_units) * 16 + 1023) / 1024 * 1024
+                      : pl->halo[j]
                           ? static_cast<size_t>(NT / 64) * kWgTile + (hr * 128 + 1023) / 1024 * 1024
                           : static_cast<size_t>(NT / 64 + ug) * kWgTile;
     if (sb > stage) stage = sb;
@@ -456,8 +481,14 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
     halo_rows[j] = (d[j].allow_halo && d[j].NC == 1 && d[j].n_taps > 1)
                        ? 128 + (d[j].n_taps - 1) * d[j].dil : 0;
   }
+  static const bool strip_enabled = [] {
+    const char* e = getenv("BPB_STRIP");
+    return !(e && e[0] == '0');
+  }();
+  const bool want_strip = strip_enabled && n_jobs == 1 && d0.allow_strip && d0.n_taps == 1 &&
+                          d0.a_row_stride_bytes == 16 && d0.a_ptr[1] == nullptr && d0.NC <= 4;
   WgradPlan pl;
-  BP_REQUIRE(plan_wgrad(n_jobs, d0.B, rows, halo_rows, d0.n_taps * d0.NC, d0.Ncols, &pl),
+  BP_REQUIRE(plan_wgrad(n_jobs, d0.B, rows, halo_rows, d0.n_taps * d0.NC, d0.Ncols, &pl, want_strip),
              "%s: cannot plan (no device?)", d0.who);
   BP_REQUIRE(static_cast<size_t>(d0.ws_bytes) >= pl.ws_bytes, "%s: workspace too small (%lld < %zu)",
              d0.who, d0.ws_bytes, pl.ws_bytes);
@@ -477,6 +508,12 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
   kp.stage_bytes = static_cast<int>(pl.stage_bytes);
   kp.Ncols = d0.Ncols;
   kp.n_jobs = n_jobs;
+  if (want_strip && pl.n_groups == 1) {
+    kp.strip = 1;
+    kp.strip_bytes = (128 + 8 * pl.n_units) * 16;
+    kp.a_batch_bytes = static_cast<long long>(d0.a_batch_stride_bytes);
+    kp.a_base = static_cast<const uint8_t*>(d0.a_ptr[0]);
+  }
   kp.ws = d0.ws;
   kp.dbg = debug_buffer();
 
@@ -656,6 +693,7 @@ extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, i
   d.pa_bits = 0;
   d.pg_bits = 0b10;
   d.db_mask = 0b11;
+  d.allow_strip = true;  // x8 carries the spare tail (bpb_x8_elems)
   d.ws = ws;
   d.ws_bytes = ws_bytes;
   d.sc.mode = 1;
