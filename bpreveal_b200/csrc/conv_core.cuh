@@ -52,6 +52,10 @@ struct ConvKParams {
   // operand planes: pass i multiplies A plane (pa_bits >> i) & 1 with W plane (pw_bits >> 2i) & 3
   int npass, pa_bits, pw_bits, n_aplanes, n_wplanes;
   int step_b, step_mt, step_nt;  // gridDim.x tiles expressed as (sequences, M tiles, N tiles)
+  // ceil(2^32 / n_ntiles) and ceil(2^32 / tiles_per_seq) (0 when the divisor is 1): the first
+  // tile of a CTA is found with two multiply-highs instead of three integer divisions, which
+  // sat on the single-thread start-up chain of every launch
+  unsigned inv_ntiles, inv_tiles_per_seq;
   // STRIP staging (window convolutions over a 16-byte-per-position tensor, resident weights): the
   // A operand of a tile is the raw strip of 127 + 2*nk16 positions; a NON-swizzled K-major UMMA
   // descriptor (LBO 16 B, SBO 128 B) reads the implicit im2col matrix straight out of it.
@@ -137,10 +141,12 @@ __device__ __forceinline__ float gt0_flag(float v) {
 struct TileWalk {
   int b, mt, nt;
   __device__ __forceinline__ void init(const ConvKParams& p) {
-    const int tile = blockIdx.x;
-    nt = tile % p.n_ntiles;
-    mt = (tile / p.n_ntiles) % p.tiles_per_seq;
-    b = tile / (p.n_ntiles * p.tiles_per_seq);
+    const unsigned tile = blockIdx.x;  // < 2^16, divisors < 2^16: the multiply-high is exact
+    const unsigned t1 = p.inv_ntiles ? __umulhi(tile, p.inv_ntiles) : tile;
+    nt = static_cast<int>(tile - t1 * static_cast<unsigned>(p.n_ntiles));
+    const unsigned bb = p.inv_tiles_per_seq ? __umulhi(t1, p.inv_tiles_per_seq) : t1;
+    mt = static_cast<int>(t1 - bb * static_cast<unsigned>(p.tiles_per_seq));
+    b = static_cast<int>(bb);
   }
   __device__ __forceinline__ void next(const ConvKParams& p) {
     nt += p.step_nt;
@@ -209,52 +215,73 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   if (threadIdx.x < 32) prof_smem()[threadIdx.x] = 0;  // published by the __syncthreads below
 #endif
 
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tm.A[0]);
-    tma_prefetch_desc(&tm.W);
-    if (p.n_aplanes == 2) tma_prefetch_desc(&tm.A[1]);
-    if (p.has_out) tma_prefetch_desc(&tm.O[0]);
-    if (p.has_out2) tma_prefetch_desc(&tm.P[0]);
-    if (RING_RESID) tma_prefetch_desc(&tm.R[0]);
-    for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full[i], 1);
+  if (warp == 0) {
+    // one lane per barrier (pair): the prologue is on the critical path of every launch
+    static_assert(kMaxStages <= 16 && kMaxRStages <= 7, "lane map of the barrier initialisation");
+    if (lane < p.stages) {
+      mbar_init(&full[lane], 1);
       // HALO forward: the box is released by the MMA commit AND by the 8 epilogue warps
-      mbar_init(&empty[i], (HALO && IS_FWD && RESID) ? 9 : 1);
+      mbar_init(&empty[lane], (HALO && IS_FWD && RESID) ? 9 : 1);
+    } else if (lane >= 16 && lane < 16 + ACC) {
+      mbar_init(&acc_full[lane - 16], 1);
+      mbar_init(&acc_empty[lane - 16], 8);
+    } else if (lane >= 24 && lane < 24 + kMaxRStages) {
+      mbar_init(&rfull[lane - 24], 1);
+      mbar_init(&rempty[lane - 24], 8);
+    } else if (lane == 20) {
+      tma_prefetch_desc(&tm.A[0]);
+      tma_prefetch_desc(&tm.W);
+      if (p.n_aplanes == 2) tma_prefetch_desc(&tm.A[1]);
+    } else if (lane == 21) {
+      if (p.has_out) tma_prefetch_desc(&tm.O[0]);
+      if (p.has_out2) tma_prefetch_desc(&tm.P[0]);
+      if (RING_RESID) tma_prefetch_desc(&tm.R[0]);
     }
-    for (int i = 0; i < ACC; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 8);
-    }
-    for (int i = 0; i < kMaxRStages; ++i) {
-      mbar_init(&rfull[i], 1);
-      mbar_init(&rempty[i], 8);
-    }
-    mbar_init(w_full, 1);
     fence_barrier_init();
+    // Split barrier: the producer needs nothing from the other warps (not even the TMEM base),
+    // so it only ARRIVES and issues its first loads while TMEM is still being allocated; the
+    // memory latency of the first tile is the longest link of the start-up chain.
+    __syncwarp();
+    named_bar_arrive(8, blockDim.x);
+  } else {
+    if (warp == 1) {
+      // The resident weights are fetched by the MMA warp (their only reader), off the
+      // producer's chain: they are parameters, never written by an in-flight predecessor.
+      if (elect_one()) {
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+        if (RESIDENT) {
+          mbar_expect_tx(w_full, static_cast<uint32_t>(w_tiles) * B_TILE_BYTES);
+          for (int wp = 0; wp < p.n_wplanes; ++wp)
+            for (int j = 0; j < p.n_taps; ++j)
+              for (int c = 0; c < p.KC; ++c)
+                tma_load_2d(&tm.W,
+                            w_smem + static_cast<size_t>((wp * p.n_taps + j) * p.KC + c) * B_TILE_BYTES,
+                            w_full, c * 64, (wp * p.n_taps + j) * p.F);
+        }
+      }
+      __syncwarp();
+      tmem_alloc<TMEM_COLS>(tmem_slot);
+    }
+    tc_fence_before();
+    named_bar_sync(8, blockDim.x);
+    tc_fence_after();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
-  // (bias is a parameter: written only by the optimiser, never by an in-flight predecessor)
-  for (int i = threadIdx.x; i < p.F; i += blockDim.x) s_bias[i] = (p.bias && i < p.bias_n) ? p.bias[i] : 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = (warp == 0) ? 0u : *tmem_slot;
+#ifdef BPB_ROLE_PROFILE
+#define BPB_STAMP(slot) prof_smem()[slot] = static_cast<unsigned>(clock64() - t_kernel_start)
+  if (threadIdx.x == 0) BPB_STAMP(20);
+#else
+#define BPB_STAMP(slot)
+#endif
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (elect_one()) {
-      if (RESIDENT) {
-        mbar_expect_tx(w_full, static_cast<uint32_t>(w_tiles) * B_TILE_BYTES);
-        for (int wp = 0; wp < p.n_wplanes; ++wp)
-          for (int j = 0; j < p.n_taps; ++j)
-            for (int c = 0; c < p.KC; ++c)
-              tma_load_2d(&tm.W,
-                          w_smem + static_cast<size_t>((wp * p.n_taps + j) * p.KC + c) * B_TILE_BYTES,
-                          w_full, c * 64, (wp * p.n_taps + j) * p.F);
-      }
-      // the prepared weights are not written by any kernel that can still be in flight; the
-      // activations are: wait for the predecessor grid before the first activation load
+      // the activations are written by the predecessor grid: wait for it before the first load
+      BPB_STAMP(25);
       pdl_wait();
+      BPB_STAMP(21);
       // The residual ring is split into EG sub-rings, one per epilogue group (tile i belongs to
       // group i % EG): a slot is then always consumed by the same warps, which observe every
       // phase of its mbarrier.  (A consumer that skipped phases cannot tell "the phase I skipped
@@ -267,13 +294,16 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         const int nt = tw.nt, b = tw.b;
         const int t0 = tw.mt * kTileM;
         if (HALO) {
+          if (ntile == 0) BPB_STAMP(29);
           mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
           mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.KC * p.n_aplanes * p.box_bytes));
+          if (ntile == 0) BPB_STAMP(30);
           uint8_t* dst = ring + static_cast<size_t>(stage) * stage_bytes;
           for (int c = 0; c < p.KC; ++c)
             for (int pl = 0; pl < p.n_aplanes; ++pl)
               tma_load_3d(&tm.A[pl], dst + static_cast<size_t>(c * p.n_aplanes + pl) * p.sub_bytes,
                           &full[stage], c * 64, t0 + p.box_off, b);
+          if (ntile == 0) BPB_STAMP(26);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         } else if (RESIDENT && p.strip) {
           mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
@@ -284,6 +314,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
                          p.a_base[pl] + static_cast<size_t>(b) * p.a_batch_bytes +
                              static_cast<size_t>(t0) * 16,
                          static_cast<uint32_t>(p.strip_bytes), &full[stage]);
+          if (ntile == 0) BPB_STAMP(26);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         } else {
           // Resident weights: one A tile per (tap, chunk, A plane), shared by every pass that
@@ -327,6 +358,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     // ------------------------------------------------------------- MMA issuer
     if (elect_one()) {
       if (RESIDENT) mbar_wait_wd(w_full, 0, p.dbg, 0x300);
+      BPB_STAMP(28);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, ntile = 0;
       // Fast path (the bf16 tower layer: 3 taps, one 64-channel chunk, one pass, resident
       // weights): every descriptor word that does not depend on the stage is built once here, so
@@ -351,6 +383,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         const uint32_t d_tmem = tmem_base + as * NT;
         if (fast && HALO) {
           mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
+#ifdef BPB_ROLE_PROFILE
+          if (ntile == 0) BPB_STAMP(27);
+#endif
           tc_fence_after();
           const uint32_t a0 = ring_lo + stage * stage_lo;
 #pragma unroll
@@ -467,6 +502,12 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     // ------------------------------------------------------------- epilogue warps (2..)
     // EG groups of 8 warps; group g owns this CTA's tiles g, g + EG, ... (its own staging buffer
     // and named barrier), so one group's stores / barrier waits overlap the other's math.
+    // The bias is a parameter: written only by the optimiser, never by an in-flight predecessor,
+    // so it is fetched before the dependency wait -- and by the warps that use it, off the
+    // producer's and the MMA issuer's start-up path.
+    for (int i = static_cast<int>(threadIdx.x) - 64; i < p.F; i += EG * kEpiThreads)
+      s_bias[i] = (p.bias && i < p.bias_n) ? p.bias[i] : 0.f;
+    named_bar_sync(7, EG * kEpiThreads);
     pdl_wait();  // global reads (masks, multipliers) and TMA stores below
     const int grp = (warp - 2) >> 3;
     const int q = warp & 3;
@@ -550,6 +591,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         if (ch == 0) {
           mbar_wait_wd(&acc_full[as], aphase, p.dbg, 0x800 + as, ntile);
           tc_fence_after();
+#ifdef BPB_ROLE_PROFILE
+          if (et == 0 && ntile == 0) BPB_STAMP(22);
+#endif
         }
         uint32_t acc[32];
         tmem_ld32(tmem_base + as * NT + ch * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16),
@@ -711,7 +755,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         tw.next(p);
       }
     }
+#ifdef BPB_ROLE_PROFILE
+    if (et == 0 && grp == 0) BPB_STAMP(23);
+#endif
     if (et == 0) tma_store_wait_all<0>();
+#ifdef BPB_ROLE_PROFILE
+    if (et == 0 && grp == 0) BPB_STAMP(24);
+#endif
   }
 
   tc_fence_before();
@@ -986,6 +1036,13 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   kp.step_nt = grid % kp.n_ntiles;
   kp.step_mt = (grid / kp.n_ntiles) % kp.tiles_per_seq;
   kp.step_b = grid / (kp.n_ntiles * kp.tiles_per_seq);
+  auto inv32 = [](int d) -> unsigned {
+    return d <= 1 ? 0u : static_cast<unsigned>(((1ull << 32) + static_cast<unsigned>(d) - 1) / static_cast<unsigned>(d));
+  };
+  BP_REQUIRE(grid < 65536 && kp.n_ntiles < 65536 && kp.tiles_per_seq < 65536,
+             "%s: tile counts out of range", d.who);
+  kp.inv_ntiles = inv32(kp.n_ntiles);
+  kp.inv_tiles_per_seq = inv32(kp.tiles_per_seq);
 
   switch (d.epi) {
     case EPI_FWD:

@@ -279,6 +279,10 @@ __device__ __forceinline__ void pdl_wait() {
 }
 
 // ------------------------------------------------------------------ misc helpers
+// Arrive without waiting (the producer side of a split barrier; pairs with named_bar_sync).
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -48,6 +48,8 @@ _lib.load().bpb_debug_dump(buf0, 2048)
 N = 10
 for _ in range(N):
     ops.conv3(xin, fwd, (0, d, 2 * d), 0, L_out, bias=bias, resid=xin, resid_off=d, out=out, mask_out=mask)
+    if os.environ.get("ROLES_SYNC"):
+        torch.cuda.synchronize()
 torch.cuda.synchronize()
 buf1 = (C.c_uint * 2048)()
 _lib.load().bpb_debug_dump(buf1, 2048)
@@ -64,3 +66,6 @@ for cta in range(2):
             continue
         parts.append(f"{nm}={(buf1[base + g] - buf0[base + g]) / N:.0f}cyc/{n}waits")
     print(f"  cta{cta}: total={tot:.0f}cyc  " + "  ".join(parts))
+    st = [(buf1[base + s] - buf0[base + s]) / N for s in range(20, 31)]
+    print(f"     stamps: prologue_done={st[0]:.0f} pdl_wait_done={st[1]:.0f} first_acc={st[2]:.0f} "
+          f"epi_done={st[3]:.0f} stores_drained={st[4]:.0f} w_issued={st[5]:.0f} a_issued={st[6]:.0f} a_landed={st[7]:.0f} w_landed={st[8]:.0f} loop_entered={st[9]:.0f} expect_done={st[10]:.0f}")
