@@ -304,7 +304,7 @@ def main():
     orig_check = ops.check
 
     kernels_per_call = {"bpb_wgrad3_tc": 2, "bpb_wgrad3_multi": 2, "bpb_input_conv_wgrad": 2, "bpb_heads_fwd": 2,
-                        "bpb_heads_wgrad_tc": 2, "bpb_heads_pack_grad": 2}
+                        "bpb_heads_wgrad_tc": 2, "bpb_heads_pack_grad": 2, "bpb_heads_fwd_tc": 2}
 
     def counting_check(rc, what):
         counter["n"] += kernels_per_call.get(what, 1)
@@ -351,7 +351,7 @@ def main():
         real = {}
         names = ["conv3", "wgrad3", "wgrad3_multi", "onehot_expand", "input_conv_fwd", "input_conv_wgrad",
                  "heads_fwd", "heads_fwd_tc", "heads_wgrad", "heads_dgrad", "heads_pack_grad",
-                 "loss_fwd_bwd", "prep_heads_fwd_weights",
+                 "loss_fwd_bwd", "loss_fwd_bwd_pack", "prep_heads_fwd_weights",
                  "adam_step", "prep_conv3_weights", "prep_input_conv_weights",
                  "prep_heads_dgrad_weights"]
 

@@ -218,21 +218,24 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   if (warp == 0) {
     // one lane per barrier (pair): the prologue is on the critical path of every launch
     static_assert(kMaxStages <= 16 && kMaxRStages <= 7, "lane map of the barrier initialisation");
-    if (lane < p.stages) {
-      mbar_init(&full[lane], 1);
+    // branch-free lane map: lanes 0..15 ring stages, 16..19 accumulators, 24..27 residual ring
+    {
+      const bool is_ring = lane < p.stages;
+      const bool is_acc = lane >= 16 && lane < 16 + ACC;
+      const bool is_res = lane >= 24 && lane < 24 + kMaxRStages;
+      uint64_t* b0 = is_ring ? &full[lane] : is_acc ? &acc_full[lane - 16] : &rfull[lane - 24];
+      uint64_t* b1 = is_ring ? &empty[lane] : is_acc ? &acc_empty[lane - 16] : &rempty[lane - 24];
       // HALO forward: the box is released by the MMA commit AND by the 8 epilogue warps
-      mbar_init(&empty[lane], (HALO && IS_FWD && RESID) ? 9 : 1);
-    } else if (lane >= 16 && lane < 16 + ACC) {
-      mbar_init(&acc_full[lane - 16], 1);
-      mbar_init(&acc_empty[lane - 16], 8);
-    } else if (lane >= 24 && lane < 24 + kMaxRStages) {
-      mbar_init(&rfull[lane - 24], 1);
-      mbar_init(&rempty[lane - 24], 8);
-    } else if (lane == 20) {
+      const uint32_t c1 = is_ring ? ((HALO && IS_FWD && RESID) ? 9u : 1u) : 8u;
+      if (is_ring || is_acc || is_res) {
+        mbar_init(b0, 1);
+        mbar_init(b1, c1);
+      }
+    }
+    if (lane == 20) {
       tma_prefetch_desc(&tm.A[0]);
       tma_prefetch_desc(&tm.W);
       if (p.n_aplanes == 2) tma_prefetch_desc(&tm.A[1]);
-    } else if (lane == 21) {
       if (p.has_out) tma_prefetch_desc(&tm.O[0]);
       if (p.has_out2) tma_prefetch_desc(&tm.P[0]);
       if (RING_RESID) tma_prefetch_desc(&tm.R[0]);
@@ -421,11 +424,22 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             const uint32_t ap = (p.pa_bits >> ps) & 1;
             const uint32_t wp = (p.pw_bits >> (2 * ps)) & 3;
             const uint32_t a_pl = a0 + ap * (static_cast<uint32_t>(p.strip_stride) >> 4);
-            const uint32_t b_pl = smem_u32(w_smem) + wp * p.KC * B_TILE_BYTES;
-            for (int k = 0; k < p.nk16; ++k) {
-              const uint32_t b_addr = b_pl + (k >> 2) * B_TILE_BYTES + (k & 3) * 32;
-              umma_bf16_lohi(d_tmem, ((a_pl + 2u * k) & 0x3FFFu) | A_LBO, A_HI,
-                             umma_desc_lo(b_addr, 0), DHI, IDESC, accum);
+            // one add per MMA on the issuing thread: the descriptors advance by constants (A: 32 B
+            // per K step; W: 32 B inside a 64-wide chunk tile, then on to the next tile)
+            uint32_t a_lo = a_pl | A_LBO;
+            uint32_t b_lo = umma_desc_lo(smem_u32(w_smem) + wp * p.KC * B_TILE_BYTES, 0);
+            const int nk4 = p.nk16 >> 2, nkr = p.nk16 & 3;
+            for (int k4 = 0; k4 < nk4; ++k4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_lohi(d_tmem, a_lo + 2u * k, A_HI, b_lo + 2u * k, DHI, IDESC, accum);
+                accum = 1;
+              }
+              a_lo += 8u;
+              b_lo += static_cast<uint32_t>(B_TILE_BYTES) >> 4;
+            }
+            for (int k = 0; k < nkr; ++k) {
+              umma_bf16_lohi(d_tmem, a_lo + 2u * k, A_HI, b_lo + 2u * k, DHI, IDESC, accum);
               accum = 1;
             }
           }

@@ -131,17 +131,23 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         uint32_t accum = 0;
         for (int pass = 0; pass < p.npass; ++pass) {
           const int ap = (p.pa_bits >> pass) & 1, wp = (p.pw_bits >> pass) & 1;
-          for (int c = 0; c < p.KC; ++c)
+          // W x 4 MMAs per chunk issued by ONE thread: the descriptor words advance by constants
+          // (A: one box row = 128 B per tap, W: one tile per tap), two adds per tap
+          constexpr uint32_t DHI = umma_desc_hi(1024);
+          for (int c = 0; c < p.KC; ++c) {
+            uint32_t a_lo = umma_desc_lo(base + (c * p.n_aplanes + ap) * p.sub_bytes, 0);
+            uint32_t b_lo = umma_desc_lo(smem_u32(w_smem) + ((wp * p.W) * p.KC + c) * b_tile, 0);
+            const uint32_t b_step = (static_cast<uint32_t>(p.KC) * b_tile) >> 4;
             for (int j = 0; j < p.W; ++j) {
-              const uint32_t a_addr = base + (c * p.n_aplanes + ap) * p.sub_bytes + j * 128;
-              const uint32_t b_addr = smem_u32(w_smem) + ((wp * p.W + j) * p.KC + c) * b_tile;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
-                          umma_smem_desc(b_addr + k * 32, 0, 1024), p.idesc, accum);
+                umma_bf16_lohi(d_tmem, a_lo + 2u * k, DHI, b_lo + 2u * k, DHI, p.idesc, accum);
                 accum = 1;
               }
+              a_lo += 8u;
+              b_lo += b_step;
             }
+          }
         }
         umma_commit(&empty[stage]);
         umma_commit(&acc_full[as]);

@@ -1,23 +1,34 @@
 // K5 (fused log-softmax / multinomial NLL / log-counts MSE forward+backward), K9 (Keras Adam),
 // weight re-layout for the tcgen05 kernels, the epoch jitter gather that replaces libslide, and
 // the scalar regressions of the transformation / combined models.
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace bp {
 
+// Block-wide reduction in a fixed order (deterministic): butterfly inside each warp, then the
+// first warp combines the (up to 32) warp results with a second butterfly (lanes beyond the warp
+// count contribute the identity `id`).
+// Every thread returns the result.  (A loop over the warp results in EVERY thread costs a
+// thousand shared-memory reads per call with 32 warps -- measured 1.7k cycles per reduction.)
 template <typename T, typename Op>
-__device__ __forceinline__ T block_reduce(T v, Op op, T* scratch) {
+__device__ __forceinline__ T block_reduce(T v, Op op, T* scratch, T id) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  __syncthreads();  // scratch may still be read by the previous call
   if (lane == 0) scratch[warp] = v;
   __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-  v = scratch[0];
-  for (int i = 1; i < nw; ++i) v = op(v, scratch[i]);
-  return v;
+  if (warp == 0) {
+    T w = lane < nw ? scratch[lane] : id;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = op(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (lane == 0) scratch[0] = w;
+  }
+  __syncthreads();
+  return scratch[0];
 }
 
 struct SumF { __device__ float operator()(float a, float b) const { return a + b; } };
@@ -28,7 +39,7 @@ struct SumD { __device__ double operator()(double a, double b) const { return a 
 // K5.  losses.py:15-39 (tfp Multinomial.log_prob over the flattened L*T_h block of one head),
 // losses.py:42-63 + Keras sum_over_batch_size.  One block per (sequence, head).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 loss_kernel(int B, int L, int T, int H, const int* __restrict__ task_off,
             const float* __restrict__ logits, const float* __restrict__ logcounts,
             const float* __restrict__ counts, const float* __restrict__ logcounts_true,
@@ -53,16 +64,16 @@ loss_kernel(int B, int L, int T, int H, const int* __restrict__ task_off,
     sLg += lgammaf(k + 1.f);
     sKl += static_cast<double>(k) * l;
   }
-  mx = block_reduce(mx, MaxF(), scratch_f);
-  sN = block_reduce(sN, SumD(), scratch_d);
-  sLg = block_reduce(sLg, SumD(), scratch_d);
-  sKl = block_reduce(sKl, SumD(), scratch_d);
+  mx = block_reduce(mx, MaxF(), scratch_f, -INFINITY);
+  sN = block_reduce(sN, SumD(), scratch_d, 0.0);
+  sLg = block_reduce(sLg, SumD(), scratch_d, 0.0);
+  sKl = block_reduce(sKl, SumD(), scratch_d, 0.0);
   float se = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int idx = (i / Th) * T + k0 + (i % Th);
     se += __expf(lg[idx] - mx);
   }
-  se = block_reduce(se, SumF(), scratch_f);
+  se = block_reduce(se, SumF(), scratch_f, 0.f);
   const float lse = mx + logf(se);
   const float N = static_cast<float>(sN);
   const float invB = 1.f / static_cast<float>(B);
@@ -82,6 +93,281 @@ loss_kernel(int B, int L, int T, int H, const int* __restrict__ task_off,
       dl[idx] = wh * (N * __expf(lg[idx] - lse) - ct[idx]);
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// K5 + packing, one launch: the losses of K5, and the loss gradient written straight into the
+// packed bf16 tensor d8 that the heads' tensor-core kernels read (bpb_heads_pack_grad's layout),
+// the heads' bias gradients and the loss sums reduced over the batch in a FIXED order by the last
+// block to finish (no float atomics, no memset node).  One block per (sequence, head), one
+// thread per profile row.
+// ------------------------------------------------------------------------------------------
+// (hi, lo) += (eh, el) with the rounding error of hi + eh kept in lo (Knuth two-sum; no fast-math
+// reassociation is enabled for this library, so the compiler keeps the sequence as written)
+__device__ __forceinline__ void two_sum_acc(float& hi, float& lo, float eh, float el) {
+  const float t = __fadd_rn(hi, eh);
+  const float bp = __fadd_rn(t, -hi);
+  const float err = __fadd_rn(__fadd_rn(hi, -__fadd_rn(t, -bp)), __fadd_rn(eh, -bp));
+  hi = t;
+  lo = __fadd_rn(lo, __fadd_rn(err, el));
+}
+
+// Block-wide reduction of N per-thread float partials through shared memory, accumulated in
+// double by ONE warp per quantity (lane j takes elements j, j+32, ... in four chains, a
+// butterfly joins the lanes): fixed order, and no double-precision work in the 1024-thread part
+// of the kernel.  Quantity 0 is a maximum when MAX0.  `buf` holds N * blockDim.x floats; the
+// results land in res (double) and res_f (float), valid after the call for every thread.
+template <int N, bool MAX0>
+__device__ __forceinline__ void block_reduce_smem(const float (&v)[N], int n_used, float* buf,
+                                                  double* res, float* res_f) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockDim.x;
+  __syncthreads();  // buf / res may still be read by the previous call
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (i < n_used) buf[i * nt + threadIdx.x] = v[i];
+  __syncthreads();
+  if (warp < n_used) {
+    // The sums are carried as unevaluated float pairs (hi + lo, error-free two-sum): ~48
+    // mantissa bits without touching the FP64 pipe, whose latency dominated this kernel when
+    // the chains were double adds.
+    const float* src = buf + warp * nt;
+    if (MAX0 && warp == 0) {
+      float m = -INFINITY;
+      for (int j = lane; j < nt; j += 32) m = fmaxf(m, src[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) {
+        res[0] = static_cast<double>(m);
+        res_f[0] = m;
+      }
+    } else {
+      float hi[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = lane; j < nt; j += 128) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float e = (j + 32 * q < nt) ? src[j + 32 * q] : 0.f;
+          two_sum_acc(hi[q], lo[q], e, 0.f);
+        }
+      }
+      two_sum_acc(hi[0], lo[0], hi[1], lo[1]);
+      two_sum_acc(hi[2], lo[2], hi[3], lo[3]);
+      two_sum_acc(hi[0], lo[0], hi[2], lo[2]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float eh = __shfl_xor_sync(0xffffffffu, hi[0], o);
+        const float el = __shfl_xor_sync(0xffffffffu, lo[0], o);
+        two_sum_acc(hi[0], lo[0], eh, el);
+      }
+      if (lane == 0) {
+        res[warp] = static_cast<double>(hi[0]) + static_cast<double>(lo[0]);
+        res_f[warp] = hi[0] + lo[0];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+constexpr int kLossMaxTh = 8;  // tasks per head handled by the fused kernel
+
+// lgamma for the total count of a region: Stirling's series from x = 16 up (next term < 1e-16),
+// the library routine below (it is several thousand cycles of one thread on the critical path)
+__device__ __forceinline__ double lgamma_total(double x) {
+  if (x < 16.0) return lgamma(x);
+  const double xi = 1.0 / x, x2 = xi * xi;
+  const double corr = xi * (1.0 / 12.0 - x2 * (1.0 / 360.0 - x2 * (1.0 / 1260.0 - x2 * (1.0 / 1680.0 -
+                      x2 * (1.0 / 1188.0)))));
+  return (x - 0.5) * log(x) - x + 0.91893853320467274178 + corr;
+}
+
+struct LossPack {
+  int L_in, W, Cp, planes;
+  long long plane_stride;  // elements between the bf16 remainder planes of d8
+  __nv_bfloat16* d8;
+  float *dpb, *dcb;
+  float* ws;  // [B][2H] loss terms | [B][T] profile-bias terms | [B][H] dlogcounts | counter
+  unsigned* dbg;
+};
+
+__global__ void __launch_bounds__(1024)
+loss_pack_kernel(int B, int L, int T, int H, const int* __restrict__ task_off,
+                 const float* __restrict__ logits, const float* __restrict__ logcounts,
+                 const float* __restrict__ counts, const float* __restrict__ logcounts_true,
+                 const float* __restrict__ profile_weight, const float* __restrict__ lambda,
+                 float* __restrict__ losses, float* __restrict__ dlogits,
+                 float* __restrict__ dlogcounts, const LossPack pk) {
+  __shared__ float red_buf[kLossMaxTh * 1024];
+  __shared__ double red_res[kLossMaxTh];
+  __shared__ float red_res_f[kLossMaxTh];
+  __shared__ float s_dlc;
+  __shared__ int s_last;
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int k0 = task_off[h];
+  const int Th = task_off[h + 1] - k0;
+  // scalars of this (sequence, head): fetched now so that their latency hides behind pass 1
+  const float w_prof = profile_weight[h], lam_h = lambda[h], lc_pred = logcounts[b * H + h];
+  const float lc_true = logcounts_true ? logcounts_true[b * H + h] : 0.f;
+  const float* lg = logits + static_cast<size_t>(b) * L * T + k0;
+  const float* ct = counts + static_cast<size_t>(b) * L * T + k0;
+  float* part_loss = pk.ws;
+  float* part_pb = part_loss + static_cast<size_t>(B) * 2 * H;
+  float* part_dlc = part_pb + static_cast<size_t>(B) * T;
+  unsigned* counter = reinterpret_cast<unsigned*>(part_dlc + static_cast<size_t>(B) * H);
+#ifdef BPB_ROLE_PROFILE
+  const long long t_start = clock64();
+  __shared__ unsigned lp_st[16];
+#define LP_STAMP(slot) \
+  if (threadIdx.x == 0) lp_st[slot] = static_cast<unsigned>(clock64() - t_start)
+#else
+#define LP_STAMP(slot)
+#endif
+
+  // the thread's first row stays in registers for the three passes (L <= 1024: its only row)
+  float l0[kLossMaxTh], c0[kLossMaxTh];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < kLossMaxTh; ++c) {
+    const bool on = c < Th && tid < L;
+    l0[c] = on ? lg[tid * T + c] : 0.f;
+    c0[c] = on ? ct[tid * T + c] : 0.f;
+  }
+  float mx = -INFINITY;
+  // per-thread partials in float (a thread owns L / 1024 rows), batch sums in double
+  float sN = 0.f, sLg = 0.f, sKl = 0.f;
+  for (int t = tid; t < L; t += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < kLossMaxTh; ++c)
+      if (c < Th) {
+        const float l = (t == tid) ? l0[c] : lg[t * T + c];
+        const float k = (t == tid) ? c0[c] : ct[t * T + c];
+        mx = fmaxf(mx, l);
+        sN += k;
+        sLg += lgammaf(k + 1.f);
+        sKl = fmaf(k, l, sKl);
+      }
+  }
+  LP_STAMP(1);
+  double dN, dLg, dKl;
+  {
+    const float v4[4] = {mx, sN, sLg, sKl};
+    block_reduce_smem<4, true>(v4, 4, red_buf, red_res, red_res_f);
+    mx = red_res_f[0];
+    dN = red_res[1]; dLg = red_res[2]; dKl = red_res[3];  // (used by thread 0 only)
+  }
+  const float N = red_res_f[1];
+  LP_STAMP(2);
+  float se = 0.f;
+  for (int t = tid; t < L; t += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < kLossMaxTh; ++c)
+      if (c < Th) se += __expf(((t == tid) ? l0[c] : lg[t * T + c]) - mx);
+  }
+  {
+    const float v1[1] = {se};
+    block_reduce_smem<1, false>(v1, 1, red_buf, red_res, red_res_f);
+    se = red_res_f[0];
+  }
+  LP_STAMP(3);
+  const float lse = mx + logf(se);
+  const float invB = 1.f / static_cast<float>(B);
+  if (threadIdx.x == 0) {
+    const double logp = lgamma_total(dN + 1.0) - dLg + dKl - dN * static_cast<double>(lse);
+    const float y = logcounts_true ? lc_true : logf(N);
+    const float d = lc_pred - y;
+    const float dlc = 2.f * lam_h * d * invB;
+    part_loss[(static_cast<size_t>(b) * 2) * H + h] = static_cast<float>(-logp) * invB;
+    part_loss[(static_cast<size_t>(b) * 2 + 1) * H + h] = lam_h * d * d * invB;
+    part_dlc[b * H + h] = dlc;
+    if (dlogcounts) dlogcounts[b * H + h] = dlc;
+    s_dlc = dlc;
+  }
+  __syncthreads();
+  LP_STAMP(4);
+
+  // gradient wrt the logits: fp32 copy (optional), packed bf16 planes, per-task sums
+  const int Lp = pk.L_in + pk.W - 1;
+  const float wh = w_prof * invB;
+  float csum[kLossMaxTh];
+#pragma unroll
+  for (int c = 0; c < kLossMaxTh; ++c) csum[c] = 0.f;
+  for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    const long long row = (static_cast<long long>(b) * Lp + t + pk.W - 1) * pk.Cp + k0;
+#pragma unroll
+    for (int c = 0; c < kLossMaxTh; ++c)
+      if (c < Th) {
+        const float l = (t == tid) ? l0[c] : lg[t * T + c];
+        const float k = (t == tid) ? c0[c] : ct[t * T + c];
+        const float dl = wh * (N * __expf(l - lse) - k);
+        if (dlogits) dlogits[(static_cast<size_t>(b) * L + t) * T + k0 + c] = dl;
+        csum[c] += dl;
+        float r = dl;
+        for (int pl = 0; pl < pk.planes; ++pl) {
+          const __nv_bfloat16 hv = __float2bfloat16_rn(r);
+          pk.d8[pl * pk.plane_stride + row + c] = hv;
+          r -= __bfloat162float(hv);
+        }
+      }
+  }
+  LP_STAMP(5);
+  // the counts gradient rides on every row of its own channel (tap 0 of the heads' data gradient)
+  {
+    const float v = s_dlc / static_cast<float>(pk.L_in);
+    for (int r0 = threadIdx.x; r0 < Lp; r0 += blockDim.x) {
+      const long long idx = (static_cast<long long>(b) * Lp + r0) * pk.Cp + T + h;
+      float r = v;
+      for (int pl = 0; pl < pk.planes; ++pl) {
+        const __nv_bfloat16 hv = __float2bfloat16_rn(r);
+        pk.d8[pl * pk.plane_stride + idx] = hv;
+        r -= __bfloat162float(hv);
+      }
+    }
+  }
+  LP_STAMP(6);
+  {
+    block_reduce_smem<kLossMaxTh, false>(csum, Th, red_buf, red_res, red_res_f);
+    if (threadIdx.x < Th) part_pb[static_cast<size_t>(b) * T + k0 + threadIdx.x] = red_res_f[threadIdx.x];
+  }
+
+  // last block to finish adds the per-sequence terms in sequence order
+  LP_STAMP(7);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(counter, 1u);
+    s_last = (ticket == gridDim.x * gridDim.y - 1u);
+  }
+  __syncthreads();
+  LP_STAMP(8);
+  if (s_last) {
+    __threadfence();
+    // one warp per output (round-robin): lane j adds sequences j, j+32, ... then a butterfly --
+    // a fixed order, with the B loads of an output in flight together
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int o = warp; o < 2 * H + T + H; o += nw) {
+      const float* src;
+      int stride, col;
+      if (o < 2 * H) { src = part_loss; stride = 2 * H; col = o; }
+      else if (o < 2 * H + T) { src = part_pb; stride = T; col = o - 2 * H; }
+      else { src = part_dlc; stride = H; col = o - 2 * H - T; }
+      float tot = 0.f;
+      for (int bb = lane; bb < B; bb += 32) tot += __ldcg(src + static_cast<size_t>(bb) * stride + col);
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, sh);
+      if (lane == 0) {
+        if (o < 2 * H) losses[o] = tot;
+        else if (o < 2 * H + T) { if (pk.dpb) pk.dpb[col] = tot; }
+        else if (pk.dcb) pk.dcb[col] = tot;
+      }
+    }
+    if (threadIdx.x == 0) *counter = 0u;  // ready for the next launch
+    LP_STAMP(9);
+  }
+#ifdef BPB_ROLE_PROFILE
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && pk.dbg)
+    for (int i = 1; i < 9; ++i) atomicAdd(pk.dbg + 1024 + i, lp_st[i]);
+  if (threadIdx.x == 0 && s_last && pk.dbg) atomicAdd(pk.dbg + 1024 + 9, lp_st[9] - lp_st[8]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -154,7 +440,7 @@ log_row_sums_kernel(const float* __restrict__ vals, float* __restrict__ out, int
   const float* v = vals + static_cast<size_t>(blockIdx.x) * n_per_row;
   float s = 0.f;
   for (int i = threadIdx.x; i < n_per_row; i += blockDim.x) s += v[i];
-  s = block_reduce(s, SumF(), scratch);
+  s = block_reduce(s, SumF(), scratch, 0.f);
   if (threadIdx.x == 0) out[blockIdx.x] = logf(s);
 }
 
@@ -209,10 +495,10 @@ transform_bwd_kernel(long long n, const float* __restrict__ u, const float* __re
         g3 += d * m1 * df;
       }
     }
-    g0 = block_reduce(g0, SumF(), scratch);
-    g1 = block_reduce(g1, SumF(), scratch);
-    g2 = block_reduce(g2, SumF(), scratch);
-    g3 = block_reduce(g3, SumF(), scratch);
+    g0 = block_reduce(g0, SumF(), scratch, 0.f);
+    g1 = block_reduce(g1, SumF(), scratch, 0.f);
+    g2 = block_reduce(g2, SumF(), scratch, 0.f);
+    g3 = block_reduce(g3, SumF(), scratch, 0.f);
     if (threadIdx.x == 0) {
       atomicAdd(&dcoeffs[4 * t], g0);
       atomicAdd(&dcoeffs[4 * t + 1], g1);
@@ -277,9 +563,63 @@ extern "C" int bpb_loss_fwd_bwd(int B, int L, int T, int H, const int* task_off,
   BP_REQUIRE(B > 0 && L > 0 && T > 0 && H > 0, "bpb_loss_fwd_bwd: bad sizes");
   BP_CHECK_CUDA(cudaMemsetAsync(losses, 0, static_cast<size_t>(2) * H * sizeof(float), stream));
   dim3 grid(B, H);
-  loss_kernel<<<grid, 256, 0, stream>>>(B, L, T, H, task_off, logits, logcounts, counts,
+  // one block per (sequence, head) is all the parallelism the reductions allow, so the block is
+  // as wide as it can be: the kernel is bound by the latency of its serial passes
+  loss_kernel<<<grid, 1024, 0, stream>>>(B, L, T, H, task_off, logits, logcounts, counts,
                                         logcounts_true, profile_weight, lambda, losses, dlogits,
                                         dlogcounts);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+extern "C" long long bpb_loss_pack_ws_elems(int B, int T, int H) {
+  return static_cast<long long>(B) * (2 * H + T + H) + 4;
+}
+
+extern "C" int bpb_loss_fwd_bwd_pack(int B, int L, int T, int H, const int* task_off,
+                                     const float* logits, const float* logcounts,
+                                     const float* counts, const float* logcounts_true,
+                                     const float* profile_weight, const float* lambda,
+                                     float* losses, float* dlogits, float* dlogcounts, int L_in,
+                                     int W, int Cp, int planes, bpb_bf16* d8, float* dpb,
+                                     float* dcb, float* ws, const int* host_task_off,
+                                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(task_off && logits && logcounts && counts && profile_weight && lambda && losses &&
+                 d8 && ws && host_task_off,
+             "bpb_loss_fwd_bwd_pack: NULL argument");
+  BP_REQUIRE(B > 0 && L > 0 && T > 0 && H > 0, "bpb_loss_fwd_bwd_pack: bad sizes");
+  BP_REQUIRE(Cp % 8 == 0 && Cp >= T + H && L == L_in - W + 1 && (planes == 1 || planes == 2),
+             "bpb_loss_fwd_bwd_pack: bad geometry (Cp=%d must be a multiple of 8 >= T+H=%d)", Cp,
+             T + H);
+  BP_REQUIRE(2 * H + T + H <= 1024, "bpb_loss_fwd_bwd_pack: too many heads / tasks");
+  for (int h = 0; h < H; ++h)
+    BP_REQUIRE(host_task_off[h + 1] - host_task_off[h] >= 1 &&
+                   host_task_off[h + 1] - host_task_off[h] <= kLossMaxTh,
+               "bpb_loss_fwd_bwd_pack: head %d has %d tasks (1..%d supported; use bpb_loss_fwd_bwd + "
+               "bpb_heads_pack_grad)", h, host_task_off[h + 1] - host_task_off[h], kLossMaxTh);
+  LossPack pk{};
+  pk.L_in = L_in;
+  pk.W = W;
+  pk.Cp = Cp;
+  pk.planes = planes;
+  // same buffer layout as bpb_heads_pack_grad / bpb_heads_d8_elems: each plane has a spare tail
+  pk.plane_stride = static_cast<long long>(B) * (L_in + W - 1) * Cp + 8 * 512;
+  pk.d8 = reinterpret_cast<__nv_bfloat16*>(d8);
+  pk.dpb = dpb;
+  pk.dcb = dcb;
+  pk.ws = ws;
+  pk.dbg = debug_buffer();
+  dim3 grid(B, H);
+  static const int n_threads = [] {
+    const char* e = getenv("BPB_LOSS_THREADS");
+    const int v = e ? atoi(e) : 1024;
+    return (v == 256 || v == 512 || v == 1024) ? v : 1024;
+  }();
+  loss_pack_kernel<<<grid, n_threads, 0, stream>>>(B, L, T, H, task_off, logits, logcounts, counts,
+                                             logcounts_true, profile_weight, lambda, losses,
+                                             dlogits, dlogcounts, pk);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -502,11 +842,11 @@ flat_profile_seed_kernel(int n, int L, int T, const int* __restrict__ sel,
       mxx = fmaxf(mxx, lx[i]); mxr = fmaxf(mxr, lr[i]);
       ++cnt;
     }
-  sx = block_reduce(sx, SumF(), scratch);
-  sr = block_reduce(sr, SumF(), scratch);
-  mxx = block_reduce(mxx, MaxF(), scratch);
-  mxr = block_reduce(mxr, MaxF(), scratch);
-  const float J = block_reduce(static_cast<float>(cnt), SumF(), scratch);
+  sx = block_reduce(sx, SumF(), scratch, 0.f);
+  sr = block_reduce(sr, SumF(), scratch, 0.f);
+  mxx = block_reduce(mxx, MaxF(), scratch, -INFINITY);
+  mxr = block_reduce(mxr, MaxF(), scratch, -INFINITY);
+  const float J = block_reduce(static_cast<float>(cnt), SumF(), scratch, 0.f);
   const float mean_x = sx / J, mean_r = sr / J;
   float ex = 0.f, er = 0.f;
   for (int i = threadIdx.x; i < N; i += blockDim.x)
@@ -514,8 +854,8 @@ flat_profile_seed_kernel(int n, int L, int T, const int* __restrict__ sel,
       ex += __expf(lx[i] - mxx);
       er += __expf(lr[i] - mxr);
     }
-  ex = block_reduce(ex, SumF(), scratch);
-  er = block_reduce(er, SumF(), scratch);
+  ex = block_reduce(ex, SumF(), scratch, 0.f);
+  er = block_reduce(er, SumF(), scratch, 0.f);
   float sm = 0.f, ax = 0.f, ar = 0.f;
   for (int i = threadIdx.x; i < N; i += blockDim.x)
     if (sel[i % T]) {
@@ -525,9 +865,9 @@ flat_profile_seed_kernel(int n, int L, int T, const int* __restrict__ sel,
       ax += px * tx;
       ar += pr * tr;
     }
-  sm = block_reduce(sm, SumF(), scratch);
-  ax = block_reduce(ax, SumF(), scratch);
-  ar = block_reduce(ar, SumF(), scratch);
+  sm = block_reduce(sm, SumF(), scratch, 0.f);
+  ax = block_reduce(ax, SumF(), scratch, 0.f);
+  ar = block_reduce(ar, SumF(), scratch, 0.f);
   const float mbar = sm / J;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     float g = 0.f;

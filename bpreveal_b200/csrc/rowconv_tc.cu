@@ -89,7 +89,26 @@ heads_bias_grad_kernel(long long n_rows, int T, int B, int H, const float* __res
   const int o = blockIdx.x;
   float s = 0.f;
   if (o < T) {
-    for (long long r = threadIdx.x; r < n_rows; r += blockDim.x) s += dlogits[r * T + o];
+    if ((T == 1 || T == 2 || T == 4) && (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0) {
+      // coalesced 16-byte reads of the whole [rows][T] array, many in flight: element e belongs
+      // to channel e % T, and T divides 4
+      const long long n = n_rows * T, n4 = n >> 2;
+      const float4* p4 = reinterpret_cast<const float4*>(dlogits);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+      for (long long e = threadIdx.x; e < n4; e += blockDim.x) {
+        const float4 v = __ldg(p4 + e);
+        s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+      }
+      if (T == 1) s = (s0 + s1) + (s2 + s3);
+      else if (T == 2) s = (o == 0) ? s0 + s2 : s1 + s3;
+      else s = (o == 0) ? s0 : (o == 1) ? s1 : (o == 2) ? s2 : s3;
+      if (threadIdx.x == 0)
+        for (long long e = n4 << 2; e < n; ++e)
+          if (static_cast<int>(e % T) == o) s += dlogits[e];
+    } else {
+      for (long long r = threadIdx.x; r < n_rows; r += blockDim.x) s += dlogits[r * T + o];
+    }
   } else {
     for (int b = threadIdx.x; b < B; b += blockDim.x) s += dlc[b * H + (o - T)];
   }

@@ -80,6 +80,13 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef BPB_ROLE_PROFILE
+  const long long t_kernel_start = clock64();
+  if (threadIdx.x < 32) prof_smem()[threadIdx.x] = 0;
+#define WG_STAMP(slot) prof_smem()[slot] = static_cast<unsigned>(clock64() - t_kernel_start)
+#else
+#define WG_STAMP(slot)
+#endif
   int job = 0;
   while (job + 1 < p.n_jobs && static_cast<int>(blockIdx.x) >= p.cta_begin[job + 1]) ++job;
   const int local = blockIdx.x - p.cta_begin[job];
@@ -126,9 +133,11 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) WG_STAMP(20);
 
   // everything below reads or writes global memory of earlier kernels (operands, workspace)
   pdl_wait();
+  if (threadIdx.x == 0) WG_STAMP(21);
   if (warp == 0) {
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
@@ -191,6 +200,9 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
       for (int v = 0; v < visits; ++v) {
         const int pass = v % p.n_passes;
         mbar_wait_wd(&full[stage], phase, p.dbg, 0x1500 + stage, v);
+#ifdef BPB_ROLE_PROFILE
+        if (v == 0) WG_STAMP(22);
+#endif
         tc_fence_after();
         const uint32_t g_lo = ((ring_lo + stage * stage_lo) & 0x3FFFu) | lbo_bits;
 #pragma unroll
@@ -216,12 +228,14 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
         if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
       }
       umma_commit(acc_full);
+      WG_STAMP(23);
     }
   } else {
     // epilogue: TMEM partial sums -> workspace slice of this split
     const int q = warp & 3;
     mbar_wait_wd(acc_full, 0, p.dbg, 0x1800, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) WG_STAMP(24);
     const size_t rows = static_cast<size_t>(p.n_units) * 64;
     float* wsp = p.ws + p.ws_off[job] + static_cast<size_t>(split) * (rows + 1) * p.Ncols;
     for (int i = 0; i < nu; ++i) {
@@ -259,6 +273,14 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+#ifdef BPB_ROLE_PROFILE
+  if (threadIdx.x < 32 && p.dbg != nullptr && blockIdx.x < 8) {
+    unsigned v = prof_smem()[threadIdx.x];
+    if (threadIdx.x == 15) v = static_cast<unsigned>(clock64() - t_kernel_start);
+    if (threadIdx.x == 16) v = static_cast<unsigned>(visits);
+    atomicAdd(p.dbg + 1024 + 32 * blockIdx.x + threadIdx.x, v);
+  }
+#endif
 }
 
 // Scatter of one reduced element into the caller's Keras-layout gradient tensors.

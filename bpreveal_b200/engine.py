@@ -12,6 +12,8 @@ import dataclasses
 import math
 
 import numpy as np
+import os
+
 import torch
 
 from . import ops
@@ -110,7 +112,7 @@ class SoloNet:
         self.cp = ops.heads_cp(cfg.T, cfg.H)
         # K1 weights as 2 (bf16 path) / 3 (precise path) bf16 remainder planes: the first layer's
         # pre-activations (and so its ReLU mask) stay fp32-accurate at the cost of K = 8 W extra MMAs
-        self.w_in_planes = planes + 1
+        self.w_in_planes = planes + int(os.environ.get("BPB_W1_EXTRA", "1"))
         self.w_in_op = ops.input_conv_wop(cfg.inputFilterWidth, Fp, self.w_in_planes, self.device)
         self.w_hd_op = ops.heads_dgrad_wop(cfg.outputFilterWidth, Fp, self.cp, planes, self.device)
         # heads forward as one tcgen05 GEMM when its weights fit shared memory (else CUDA cores)
@@ -118,8 +120,8 @@ class SoloNet:
         if self.heads_tc:
             self.w_hf_op = ops.heads_fwd_wop(cfg.outputFilterWidth, Fp, cfg.T, cfg.H, planes,
                                              self.device)
-        self.task_off = torch.tensor(np.concatenate([[0], np.cumsum(cfg.headTasks)]),
-                                     dtype=torch.int32, device=self.device)
+        self.host_task_off = [int(v) for v in np.concatenate([[0], np.cumsum(cfg.headTasks)])]
+        self.task_off = torch.tensor(self.host_task_off, dtype=torch.int32, device=self.device)
         self._ws = {}
         self._graphs = {}
 
@@ -247,6 +249,7 @@ class SoloNet:
             ws["scratch"] = torch.empty((nb // 4 + 4,), dtype=torch.float32, device=dev)
             ws["d8"] = ops.heads_d8(B, Ls[-1], cfg.outputFilterWidth, self.cp,
                                     2 if prec else 1, dev)
+            ws["loss_ws"] = ops.loss_pack_ws(B, cfg.T, cfg.H, dev)
         if kind == "shap_x":
             ws["z"] = [torch.empty((B, L, Fp), dtype=torch.float32, device=dev) for L in Ls]
         if kind == "shap_r":
@@ -358,20 +361,30 @@ class SoloNet:
             ops.add_f32(logits, bias_logits, ws["logits_c"])
             ops.counts_lse(use_bias, bias_logcounts, lc, ws["lc_c"], ws["dscale"])
             logits, lc = ws["logits_c"], ws["lc_c"]
-        ops.loss_fwd_bwd(self.task_off, logits, lc, ws["counts"], self.profile_weight, self.lam,
-                         ws["losses"], ws["dlogits"], ws["dlogcounts"])
+        nL = cfg.numLayers
+        planes = 2 if cfg.precise else 1
+        # solo model: losses, packed loss gradient and the heads' bias gradients in ONE launch
+        fused = bias_logits is None and max(cfg.headTasks) <= 8
+        if fused:
+            ops.loss_fwd_bwd_pack(self.task_off, self.host_task_off, logits, lc, ws["counts"],
+                                  self.profile_weight, self.lam, ws["losses"], Ls[nL],
+                                  cfg.outputFilterWidth, self.cp, planes, ws["d8"], ws["loss_ws"],
+                                  dlogits=ws["dlogits"], dlogcounts=ws["dlogcounts"],
+                                  dpb=g["prof_b"], dcb=g["cnt_b"])
+        else:
+            ops.loss_fwd_bwd(self.task_off, logits, lc, ws["counts"], self.profile_weight,
+                             self.lam, ws["losses"], ws["dlogits"], ws["dlogcounts"])
         if bias_logits is not None:
             ops.mul_f32(ws["dlogcounts"], ws["dscale"], ws["dlogcounts"])
         # Backward.  The data-gradient chain comes first (heads -> tower layers, each needing the
         # previous one) and leaves one gz buffer per layer; every tower weight gradient is then
         # computed by ONE split-K launch (bpb_wgrad3_multi) instead of one launch + reduction per
         # layer.
-        nL = cfg.numLayers
         gcur = self._sub(ws["g"][nL % 2], Ls[nL])
         gzcur = ws["gzl"][nL]
-        planes = 2 if cfg.precise else 1
-        ops.heads_pack_grad(ws["dlogits"], ws["dlogcounts"], Ls[nL], cfg.outputFilterWidth,
-                            self.cp, planes, ws["d8"], dpb=g["prof_b"], dcb=g["cnt_b"])
+        if not fused:
+            ops.heads_pack_grad(ws["dlogits"], ws["dlogcounts"], Ls[nL], cfg.outputFilterWidth,
+                                self.cp, planes, ws["d8"], dpb=g["prof_b"], dcb=g["cnt_b"])
         ops.heads_wgrad(aL, ws["d8"], cfg.outputFilterWidth, cfg.numFilters, cfg.T, cfg.H,
                         self.cp, planes, g["prof_w"], g["cnt_w"], ws["scratch"])
         ops.heads_dgrad(ws["d8"], self.w_hd_op, ws["B"], Ls[nL], cfg.outputFilterWidth, cfg.Fp,

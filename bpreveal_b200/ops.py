@@ -312,6 +312,28 @@ def loss_fwd_bwd(task_off, logits, logcounts, counts, profile_weight, lam, losse
                                _p(dlogits), _p(dlogcounts), _stream()), "bpb_loss_fwd_bwd")
 
 
+def loss_pack_ws(B, T, H, device):
+    """Zero-filled scratch of bpb_loss_fwd_bwd_pack (one per stream; the calls keep it consistent)."""
+    n = _lib.load().bpb_loss_pack_ws_elems(B, T, H)
+    return torch.zeros((n,), dtype=torch.float32, device=device)
+
+
+def loss_fwd_bwd_pack(task_off, host_task_off, logits, logcounts, counts, profile_weight, lam, losses,
+                      L_in, W, Cp, planes, d8, ws, dlogits=None, dlogcounts=None, dpb=None, dcb=None,
+                      logcounts_true=None):
+    """K5 + bpb_heads_pack_grad in one launch; ``d8`` must have been zero-filled once
+    (``heads_d8``), ``host_task_off`` is a sequence of ints."""
+    lib = _lib.load()
+    B, L, T = logits.shape
+    H = logcounts.shape[1]
+    hto = (C.c_int * (H + 1))(*[int(v) for v in host_task_off])
+    check(lib.bpb_loss_fwd_bwd_pack(B, L, T, H, _p(task_off), _p(logits), _p(logcounts), _p(counts),
+                                    _p(logcounts_true), _p(profile_weight), _p(lam), _p(losses),
+                                    _p(dlogits), _p(dlogcounts), L_in, W, Cp, planes, _p(d8),
+                                    _p(dpb), _p(dcb), _p(ws), hto, _stream()),
+          "bpb_loss_fwd_bwd_pack")
+
+
 def adam_step(param, grad, m, v, step_and_lr, beta1=0.9, beta2=0.999, eps=1e-7, grad_scale=1.0):
     lib = _lib.load()
     check(lib.bpb_adam_step(param.numel(), _p(param), _p(grad), _p(m), _p(v), _p(step_and_lr),

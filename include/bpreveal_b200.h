@@ -231,6 +231,22 @@ int bpb_loss_fwd_bwd(int B, int L, int T, int H, const int* task_off, const floa
                      const float* profile_weight, const float* lambda, float* losses,
                      float* dlogits, float* dlogcounts, void* stream);
 
+/* K5 and bpb_heads_pack_grad in one launch (the training step's path): same losses and gradients,
+ * the gradient written straight into the packed tensor d8 (layout of bpb_heads_pack_grad,
+ * bpb_heads_d8_elems() elements; the caller zero-fills d8 ONCE -- only its T+H live channels are
+ * written here), the heads' bias gradients dpb [T], dcb [H] (nullable) and the loss sums reduced
+ * over the batch in sequence order by the last block to finish (deterministic; no atomics on
+ * floats).  dlogits may be NULL.  ws: bpb_loss_pack_ws_elems() floats, zero-filled once by the
+ * caller and then owned by these calls (one buffer per stream).  host_task_off is the HOST copy of
+ * task_off (heads of 1..8 tasks). */
+long long bpb_loss_pack_ws_elems(int B, int T, int H);
+int bpb_loss_fwd_bwd_pack(int B, int L, int T, int H, const int* task_off, const float* logits,
+                          const float* logcounts, const float* counts, const float* logcounts_true,
+                          const float* profile_weight, const float* lambda, float* losses,
+                          float* dlogits, float* dlogcounts, int L_in, int W, int Cp, int planes,
+                          bpb_bf16* d8, float* dpb, float* dcb, float* ws, const int* host_task_off,
+                          void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K9: Keras-semantics Adam over one flat fp32 bucket:
  *   m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)

@@ -204,3 +204,44 @@ def test_flat_hypothetical_scores_parity(dev, precise):
         assert abs(vx_c[q].item() - val_c) <= (1e-4 if precise else 3e-2) * max(1.0, abs(val_c))
         assert np.abs(vr_c[q].cpu().numpy() - rv_c).max() <= (1e-4 if precise else 3e-2) * max(
             1.0, np.abs(rv_c).max())
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_fused_loss_pack_matches_separate_kernels(dev, planes):
+    """bpb_loss_fwd_bwd_pack == bpb_loss_fwd_bwd + bpb_heads_pack_grad (bit-equal d8 and dlogits;
+    batch sums in a different but fixed order), also on a second call (scratch state is reset)."""
+    from bpreveal_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, L, W, tasks = 5, 37, 7, [2, 3]
+    T, H = sum(tasks), len(tasks)
+    L_in, Cp = L + W - 1, ops.heads_cp(T, H)
+    toff_h = [0, 2, 5]
+    toff = torch.tensor(toff_h, dtype=torch.int32, device=dev)
+    logits = torch.randn((B, L, T), generator=g).to(dev) * 2
+    counts = torch.poisson(torch.rand((B, L, T), generator=g) * 4).to(dev)
+    lc = torch.randn((B, H), generator=g).to(dev)
+    pw = torch.tensor([1.0, 0.7], device=dev)
+    lam = torch.tensor([2.0, 3.5], device=dev)
+    losses_a = torch.zeros((2 * H,), device=dev)
+    dl_a, dlc_a = torch.empty_like(logits), torch.empty_like(lc)
+    ops.loss_fwd_bwd(toff, logits, lc, counts, pw, lam, losses_a, dl_a, dlc_a)
+    d8_a = ops.heads_d8(B, L_in, W, Cp, planes, dev)
+    dpb_a, dcb_a = torch.empty((T,), device=dev), torch.empty((H,), device=dev)
+    ops.heads_pack_grad(dl_a, dlc_a, L_in, W, Cp, planes, d8_a, dpb=dpb_a, dcb=dcb_a)
+    ws = ops.loss_pack_ws(B, T, H, dev)
+    d8_b = ops.heads_d8(B, L_in, W, Cp, planes, dev)
+    for _ in range(2):
+        losses_b = torch.full((2 * H,), float("nan"), device=dev)
+        dl_b, dlc_b = torch.empty_like(logits), torch.empty_like(lc)
+        dpb_b, dcb_b = torch.empty((T,), device=dev), torch.empty((H,), device=dev)
+        ops.loss_fwd_bwd_pack(toff, toff_h, logits, lc, counts, pw, lam, losses_b, L_in, W, Cp,
+                              planes, d8_b, ws, dlogits=dl_b, dlogcounts=dlc_b, dpb=dpb_b, dcb=dcb_b)
+        torch.cuda.synchronize()
+        # (the two kernels add the softmax denominator in different orders)
+        assert torch.allclose(dl_a, dl_b, rtol=1e-4, atol=1e-5 * float(dl_a.abs().max()))
+        assert torch.equal(dlc_a, dlc_b)
+        assert torch.allclose(d8_a.float(), d8_b.float(), rtol=1e-2, atol=1e-4 * float(dl_a.abs().max()))
+        assert torch.allclose(losses_a, losses_b, rtol=1e-5)
+        scale = dl_a.abs().sum(dim=(0, 1))
+        assert ((dpb_a - dpb_b).abs() <= 1e-5 * scale).all()
+        assert torch.allclose(dcb_a, dcb_b, rtol=1e-5, atol=1e-6)
