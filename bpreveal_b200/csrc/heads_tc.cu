@@ -31,6 +31,7 @@ struct HeadsKParams {
   int sub_bytes, box_bytes, stages;
   uint32_t idesc;
   const float* pb;
+  const uint8_t* w_image;  // the prepared weights: the shared-memory image, copied in one piece
   float* logits;
   float* cpart;  // [B][tiles_per_seq][H]
   unsigned* dbg;
@@ -74,9 +75,15 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const int total_tiles = p.B * p.tiles_per_seq;
 
   pdl_launch_dependents();
+#ifdef BPB_ROLE_PROFILE
+  const long long t_kernel_start = clock64();
+  if (threadIdx.x < 32) prof_smem()[threadIdx.x] = 0;
+#define HD_STAMP(slot) prof_smem()[slot] = static_cast<unsigned>(clock64() - t_kernel_start)
+#else
+#define HD_STAMP(slot)
+#endif
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmW);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -94,15 +101,16 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) HD_STAMP(20);
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(w_full, static_cast<uint32_t>(w_tiles) * b_tile);
-      for (int wp = 0; wp < p.n_wplanes; ++wp)
-        for (int j = 0; j < p.W; ++j)
-          for (int c = 0; c < p.KC; ++c)
-            tma_load_2d(&tmW, w_smem + static_cast<size_t>((wp * p.W + j) * p.KC + c) * b_tile, w_full,
-                        c * 64, (wp * p.W + j) * p.N);
+      // bpb_prep_heads_fwd_weights writes the swizzled shared-memory image, so ONE bulk copy
+      // brings every tap in (issuing a tensor load per tap cost ~150 cycles each on this thread,
+      // at the head of the kernel's critical path)
+      bulk_load_1d(w_smem, p.w_image, static_cast<uint32_t>(w_tiles) * b_tile, w_full);
+      HD_STAMP(21);
       pdl_wait();  // the activations come from the previous kernel; the weights do not
       uint32_t stage = 0, phase = 0, ntile = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ntile) {
@@ -121,10 +129,14 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 1) {
     if (elect_one()) {
       mbar_wait_wd(w_full, 0, p.dbg, 0x2300);
+      HD_STAMP(22);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, ntile = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ntile) {
         mbar_wait_wd(&acc_empty[as], aphase ^ 1, p.dbg, 0x2400 + as, ntile);
         mbar_wait_wd(&full[stage], phase, p.dbg, 0x2500 + stage, ntile);
+#ifdef BPB_ROLE_PROFILE
+        if (ntile == 0) HD_STAMP(23);
+#endif
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * p.N;
         const uint32_t base = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
@@ -151,9 +163,13 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         umma_commit(&empty[stage]);
         umma_commit(&acc_full[as]);
+#ifdef BPB_ROLE_PROFILE
+        if (ntile == 0) HD_STAMP(24);
+#endif
         if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
+      HD_STAMP(25);
     }
   } else {
     pdl_wait();  // global stores below
@@ -166,6 +182,9 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int mt = tile % p.tiles_per_seq;
       const int t = mt * 128 + row;
       mbar_wait_wd(&acc_full[as], aphase, p.dbg, 0x2800 + as, ntile);
+#ifdef BPB_ROLE_PROFILE
+      if (ntile == 0 && et == 0) HD_STAMP(26);
+#endif
       tc_fence_after();
       for (int n0 = 0; n0 < p.N; n0 += 16) {
         uint32_t acc[16];
@@ -206,6 +225,13 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+#ifdef BPB_ROLE_PROFILE
+  if (threadIdx.x < 32 && p.dbg != nullptr && blockIdx.x < 8) {
+    unsigned v = prof_smem()[threadIdx.x];
+    if (threadIdx.x == 15) v = static_cast<unsigned>(clock64() - t_kernel_start);
+    atomicAdd(p.dbg + 1024 + 32 * blockIdx.x + threadIdx.x, v);
+  }
+#endif
 }
 
 // logcounts[b][h] = cb[h] + (sum over tiles of cpart[b][tile][h]) / L_in
@@ -221,7 +247,8 @@ __global__ void heads_counts_finish_kernel(int B, int tiles, int H, int L_in,
   logcounts[i] = cb[h] + s / static_cast<float>(L_in);
 }
 
-// pw [W][Fw][T], cw [Fw][H] fp32 -> op [planes][W][N][KC*64] bf16 (k = channel)
+// pw [W][Fw][T], cw [Fw][H] fp32 -> op: bf16 image of the kernel's shared-memory operand,
+// [planes][W][KC] tiles of N rows x 64 channels
 __global__ void __launch_bounds__(256)
 prep_heads_fwd_kernel(int W, int Fw, int K, int N, int T, int H, int planes,
                       const float* __restrict__ pw, const float* __restrict__ cw,
@@ -237,10 +264,16 @@ prep_heads_fwd_kernel(int W, int Fw, int K, int N, int T, int H, int planes,
     if (n < T) v = pw[(static_cast<long long>(j) * Fw + c) * T + n];
     else if (n < T + H && j == 0) v = cw[c * H + (n - T)];
   }
+  // destination: tile (plane, tap, 64-channel chunk) of N rows x 128 B, 16-byte chunks XOR-ed
+  // with the row (the 128-byte swizzle of a tile whose base is 1024-aligned in shared memory)
+  const int KC = K >> 6;
+  const int cc = c & 63;
+  const long long in_tile = static_cast<long long>(n) * 64 + (((cc >> 3) ^ (n & 7)) << 3) + (cc & 7);
   float r = v;
   for (int pl = 0; pl < planes; ++pl) {
     const __nv_bfloat16 hbits = __float2bfloat16_rn(r);
-    op[pl * n_el + i] = hbits;
+    const long long tile = (static_cast<long long>(pl) * W + j) * KC + (c >> 6);
+    op[tile * (static_cast<long long>(N) * 64) + in_tile] = hbits;
     r -= __bfloat162float(hbits);
   }
 }
@@ -338,6 +371,7 @@ extern "C" int bpb_heads_fwd_tc(int B, int L_in, int W, int F, int T, int H,
   kp.stages = pl.stages;
   kp.idesc = umma_idesc_bf16(128, pl.N, 0, 0);
   kp.pb = pb;
+  kp.w_image = reinterpret_cast<const uint8_t*>(w_op);
   kp.logits = logits;
   kp.cpart = ws;
   kp.dbg = debug_buffer();

@@ -159,7 +159,8 @@ int bpb_heads_fwd(int B, int L_in, int L_out, int W, int Fw, int F, int T, int H
                   float* logcounts, void* stream);
 /* The same forward as ONE tcgen05 GEMM (N = T + H padded to 16; the counts heads are extra output
  * columns with weights on tap 0 only; gap is not materialised).  w_op comes from
- * bpb_prep_heads_fwd_weights ([planes][W][N][F] bf16); ws holds per-tile partial sums of the counts
+ * bpb_prep_heads_fwd_weights (an opaque bf16 image of the kernel's shared-memory operand:
+ * [planes][W][F/64] tiles of N x 64, 128-byte swizzled); ws holds per-tile partial sums of the counts
  * columns.  bpb_heads_fwd_tc_supported returns 0 when the geometry fits shared memory; otherwise
  * use bpb_heads_fwd (CUDA cores). */
 long long bpb_heads_fwd_wop_elems(int W, int F, int T, int H, int planes);

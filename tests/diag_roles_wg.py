@@ -110,3 +110,16 @@ for _ in range(10):
     torch.cuda.synchronize()
 b1 = snapshot()
 print("loss_pack block 0 stamps (cycles):", [(b1[1024 + i] - b0[1024 + i]) // 10 for i in range(1, 10)])
+
+
+b0 = snapshot()
+for _ in range(10):
+    ops.heads_fwd_tc(aL, net.w_hf_op, cfg.outputFilterWidth, cfg.T, cfg.H, net.p["prof_b"],
+                     net.p["cnt_b"], ws["logits"], ws["logcounts"], ws["hf_ws"])
+    torch.cuda.synchronize()
+b1 = snapshot()
+for cta in range(2):
+    base = 1024 + 32 * cta
+    d = [(b1[base + i] - b0[base + i]) // 10 for i in range(32)]
+    print(f"heads_fwd_tc cta{cta}: total={d[15]} prologue={d[20]} w_issued={d[21]} w_landed={d[22]} "
+          f"first_full={d[23]} first_mma_issued={d[24]} mma_all_issued={d[25]} first_acc={d[26]}")
