@@ -352,7 +352,7 @@ def main():
         names = ["conv3", "wgrad3", "wgrad3_multi", "onehot_expand", "input_conv_fwd", "input_conv_wgrad",
                  "heads_fwd", "heads_fwd_tc", "heads_wgrad", "heads_dgrad", "heads_pack_grad",
                  "loss_fwd_bwd", "loss_fwd_bwd_pack", "prep_heads_fwd_weights",
-                 "adam_step", "prep_conv3_weights", "prep_input_conv_weights",
+                 "adam_step", "adam_prep_step", "prep_conv3_weights", "prep_input_conv_weights",
                  "prep_heads_dgrad_weights"]
 
         def wrap(name):
@@ -397,7 +397,7 @@ def main():
         agg = {}
         counts = {}
         for key in dict.fromkeys(c[0] for c in calls):
-            if key in ("adam_step", "prep_conv3_weights", "prep_input_conv_weights",
+            if key in ("adam_step", "adam_prep_step", "prep_conv3_weights", "prep_input_conv_weights",
                        "prep_heads_dgrad_weights", "prep_heads_fwd_weights"):
                 continue  # replaying the optimiser would train; they are ~10 us together
             agg[key], counts[key] = time_family(key)

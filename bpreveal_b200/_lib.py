@@ -69,6 +69,17 @@ class HeadsDgradArgs(C.Structure):
     ]
 
 
+class PrepTable(C.Structure):
+    _fields_ = [
+        ("off_dil_w", c_ll), ("off_conv1_w", c_ll), ("off_prof_w", c_ll), ("off_cnt_w", c_ll),
+        ("n_layers", c_int), ("F", c_int), ("Fw", c_int), ("W_in", c_int), ("W_out", c_int),
+        ("T", c_int), ("H", c_int), ("Cp", c_int), ("planes", c_int), ("in_planes", c_int),
+        ("N_heads", c_int),
+        ("w_fwd", c_void_p), ("w_bwd", c_void_p), ("w_in_op", c_void_p), ("w_hd_op", c_void_p),
+        ("w_hf_op", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/bpreveal_b200.h one to one.
 SIGNATURES = {
     "bpb_version": (c_int, []),
@@ -107,6 +118,8 @@ SIGNATURES = {
     "bpb_loss_pack_ws_elems": (c_ll, [c_int] * 3),
     "bpb_loss_fwd_bwd_pack": (c_int, [c_int] * 4 + [c_void_p] * 10 + [c_int] * 4 + [c_void_p] * 6),
     "bpb_adam_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 + [c_void_p]),
+    "bpb_adam_prep_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 +
+                           [C.POINTER(PrepTable), c_void_p]),
     "bpb_prep_conv3_weights": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                        c_void_p]),
     "bpb_slide_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -177,6 +177,7 @@ int bpb_abi_struct_size(int which) {
     case 1: return static_cast<int>(sizeof(bpb_wgrad3_args));
     case 2: return static_cast<int>(sizeof(bpb_input_conv_args));
     case 3: return static_cast<int>(sizeof(bpb_heads_dgrad_args));
+    case 4: return static_cast<int>(sizeof(bpb_prep_table));
     default: return -1;
   }
 }

@@ -377,10 +377,15 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
                             float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ step_and_lr, float b1, float b2, float eps,
                             float gscale) {
-  const double step = static_cast<double>(step_and_lr[0]);
-  const float lr = step_and_lr[1];
-  const float alpha = static_cast<float>(static_cast<double>(lr) * sqrt(1.0 - pow((double)b2, step)) /
-                                         (1.0 - pow((double)b1, step)));
+  // bias-corrected step size: double-precision pow is long and slow, one thread per block does it
+  __shared__ float s_alpha;
+  if (threadIdx.x == 0) {
+    const double step = static_cast<double>(step_and_lr[0]);
+    s_alpha = static_cast<float>(static_cast<double>(step_and_lr[1]) *
+                                 sqrt(1.0 - pow((double)b2, step)) / (1.0 - pow((double)b1, step)));
+  }
+  __syncthreads();
+  const float alpha = s_alpha;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float gi = g[i] * gscale;
@@ -389,6 +394,120 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
     m[i] = mi;
     v[i] = vi;
     p[i] -= alpha * mi / (sqrtf(vi) + eps);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// K9 + operand refresh, one launch: the Adam update of every parameter, and each updated weight
+// scattered straight into the bf16 operand layouts the tensor-core kernels read (what
+// bpb_prep_conv3_weights / bpb_prep_input_conv_weights / bpb_prep_heads_dgrad_weights /
+// bpb_prep_heads_fwd_weights produce: same formulas, bit-equal results).  The padding entries of
+// those layouts are never written: they stay zero from allocation.  The step counter lives in
+// state[0] and is advanced by the last block to finish (state[2] is its ticket counter).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scatter_planes(__nv_bfloat16* dst, long long plane_stride,
+                                               int planes, long long idx, float v) {
+  float r = v;
+  for (int pl = 0; pl < planes; ++pl) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(r);
+    dst[pl * plane_stride + idx] = h;
+    r -= __bfloat162float(h);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
+                 float* __restrict__ m, float* __restrict__ v, float* __restrict__ state, float b1,
+                 float b2, float eps, float gscale, const bpb_prep_table tb) {
+  // bias-corrected step size: double-precision pow is long and slow, one thread per block does it
+  __shared__ float s_alpha;
+  const float step_f = state[0] + 1.f;
+  if (threadIdx.x == 0) {
+    const double step = static_cast<double>(step_f);
+    s_alpha = static_cast<float>(static_cast<double>(state[1]) * sqrt(1.0 - pow((double)b2, step)) /
+                                 (1.0 - pow((double)b1, step)));
+  }
+  __syncthreads();
+  const float alpha = s_alpha;
+  const long long F = tb.F;
+  const long long per = 3 * F * F;
+  const long long n_dil = per * tb.n_layers;
+  const long long n_c1 = static_cast<long long>(tb.W_in) * 4 * tb.Fw;
+  const long long n_pw = static_cast<long long>(tb.W_out) * tb.Fw * tb.T;
+  const long long n_cw = static_cast<long long>(tb.Fw) * tb.H;
+  const long long K_in = (tb.W_in * 8 + 63) / 64 * 64;
+  const long long K_hd = (tb.W_out * tb.Cp + 63) / 64 * 64;
+  const int KC = tb.F >> 6;
+  __nv_bfloat16* w_fwd = reinterpret_cast<__nv_bfloat16*>(tb.w_fwd);
+  __nv_bfloat16* w_bwd = reinterpret_cast<__nv_bfloat16*>(tb.w_bwd);
+  __nv_bfloat16* w_in_op = reinterpret_cast<__nv_bfloat16*>(tb.w_in_op);
+  __nv_bfloat16* w_hd_op = reinterpret_cast<__nv_bfloat16*>(tb.w_hd_op);
+  __nv_bfloat16* w_hf_op = reinterpret_cast<__nv_bfloat16*>(tb.w_hf_op);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+    m[i] = mi;
+    v[i] = vi;
+    const float w = p[i] - alpha * mi / (sqrtf(vi) + eps);
+    p[i] = w;
+    long long r = i - tb.off_dil_w;
+    if (r >= 0 && r < n_dil) {
+      const long long l = r / per, rr = r % per;
+      const long long j = rr / (F * F), cin = (rr / F) % F, cout = rr % F;
+      const long long base = l * tb.planes * per;
+      scatter_planes(w_fwd, per, tb.planes, base + (j * F + cout) * F + cin, w);
+      scatter_planes(w_bwd, per, tb.planes, base + (j * F + cin) * F + cout, w);
+      continue;
+    }
+    r = i - tb.off_conv1_w;
+    if (r >= 0 && r < n_c1) {
+      const long long j = r / (4 * tb.Fw), c4 = (r / tb.Fw) % 4, nn = r % tb.Fw;
+      scatter_planes(w_in_op, F * K_in, tb.in_planes, nn * K_in + j * 8 + c4, w);
+      continue;
+    }
+    r = i - tb.off_prof_w;
+    int j = -1, c = 0, col = 0;
+    if (r >= 0 && r < n_pw) {
+      j = static_cast<int>(r / (static_cast<long long>(tb.Fw) * tb.T));
+      c = static_cast<int>((r / tb.T) % tb.Fw);
+      col = static_cast<int>(r % tb.T);
+    } else {
+      r = i - tb.off_cnt_w;
+      if (r >= 0 && r < n_cw) {
+        j = 0;
+        c = static_cast<int>(r / tb.H);
+        col = tb.T + static_cast<int>(r % tb.H);
+      }
+    }
+    if (j >= 0) {
+      // heads' data-gradient operand [F][K_hd], k = (W_out-1-j)*Cp + col (counts ride on tap 0,
+      // which is j' = 0 there as well)
+      const long long jp = (col < tb.T) ? (tb.W_out - 1 - j) : 0;
+      scatter_planes(w_hd_op, F * K_hd, tb.planes, c * K_hd + jp * tb.Cp + col, w);
+      if (w_hf_op != nullptr) {
+        const int cc = c & 63;
+        const long long in_tile = static_cast<long long>(col) * 64 + (((cc >> 3) ^ (col & 7)) << 3) + (cc & 7);
+        float rem = w;
+        for (int pl = 0; pl < tb.planes; ++pl) {
+          const __nv_bfloat16 hb = __float2bfloat16_rn(rem);
+          const long long tile = (static_cast<long long>(pl) * tb.W_out + j) * KC + (c >> 6);
+          w_hf_op[tile * (static_cast<long long>(tb.N_heads) * 64) + in_tile] = hb;
+          rem -= __bfloat162float(hb);
+        }
+      }
+    }
+  }
+  // advance the step counter once every block has read it
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ticket = reinterpret_cast<unsigned*>(state + 2);
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+      *ticket = 0u;
+      state[0] = step_f;
+    }
   }
 }
 
@@ -632,6 +751,27 @@ extern "C" int bpb_adam_step(long long n, float* param, const float* grad, float
   if (n <= 0) return 0;
   adam_kernel<<<ew_blocks(n), 256, 0, stream>>>(n, param, grad, m, v, step_and_lr, beta1, beta2,
                                                 eps, grad_scale);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+extern "C" int bpb_adam_prep_step(long long n, float* param, const float* grad, float* m, float* v,
+                                  float* state, float beta1, float beta2, float eps,
+                                  float grad_scale, const bpb_prep_table* table, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(param && grad && m && v && state && table, "bpb_adam_prep_step: NULL argument");
+  const bpb_prep_table& t = *table;
+  BP_REQUIRE(t.F > 0 && t.F % 64 == 0 && t.Fw > 0 && t.Fw <= t.F && t.n_layers >= 0 &&
+                 (t.planes == 1 || t.planes == 2) && t.in_planes >= 1 && t.in_planes <= 3 &&
+                 t.Cp % 8 == 0 && t.Cp >= t.T + t.H,
+             "bpb_adam_prep_step: bad table");
+  BP_REQUIRE(t.w_in_op && t.w_hd_op && (t.n_layers == 0 || (t.w_fwd && t.w_bwd)) &&
+                 (t.w_hf_op == nullptr || t.N_heads >= t.T + t.H),
+             "bpb_adam_prep_step: missing operand buffers");
+  if (n <= 0) return 0;
+  adam_prep_kernel<<<ew_blocks(n), 256, 0, stream>>>(n, param, grad, m, v, state, beta1, beta2, eps,
+                                                     grad_scale, t);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -101,7 +101,8 @@ class SoloNet:
         self.grads_flat = None
         self.adam_m = None
         self.adam_v = None
-        self.step_and_lr = torch.zeros((2,), dtype=torch.float32, device=self.device)
+        # {step, lr, ticket word of bpb_adam_prep_step, pad}
+        self.step_and_lr = torch.zeros((4,), dtype=torch.float32, device=self.device)
         self.step = 0
         planes = 2 if cfg.precise else 1
         Fp, L = cfg.Fp, cfg.numLayers
@@ -409,15 +410,32 @@ class SoloNet:
     def apply_adam(self, grad_scale=1.0):
         # the optimiser step counter lives on the device so that the update replays inside a graph
         self._rf_twin = None
-        self.step_and_lr[0:1].add_(1.0)
-        ops.adam_step(self.params.flat, self.grads_flat, self.adam_m, self.adam_v,
-                      self.step_and_lr, grad_scale=grad_scale)
-        self.refresh_weights()
+        # Adam, the step increment and the refresh of every bf16 operand layout: one launch
+        ops.adam_prep_step(self.params.flat, self.grads_flat, self.adam_m, self.adam_v,
+                           self.step_and_lr, self._prep_table(), grad_scale=grad_scale)
+
+    def _prep_table(self):
+        if getattr(self, "_ptab", None) is None:
+            from . import _lib
+            cfg, off = self.cfg, self.params.offsets
+            t = _lib.PrepTable()
+            t.off_dil_w, t.off_conv1_w = off["dil_w"][0], off["conv1_w"][0]
+            t.off_prof_w, t.off_cnt_w = off["prof_w"][0], off["cnt_w"][0]
+            t.n_layers, t.F, t.Fw = cfg.numLayers, cfg.Fp, cfg.numFilters
+            t.W_in, t.W_out, t.T, t.H, t.Cp = (cfg.inputFilterWidth, cfg.outputFilterWidth, cfg.T,
+                                               cfg.H, self.cp)
+            t.planes, t.in_planes = (2 if cfg.precise else 1), self.w_in_planes
+            t.N_heads = (cfg.T + cfg.H + 15) // 16 * 16
+            t.w_fwd, t.w_bwd = self.w_fwd.data_ptr(), self.w_bwd.data_ptr()
+            t.w_in_op, t.w_hd_op = self.w_in_op.data_ptr(), self.w_hd_op.data_ptr()
+            t.w_hf_op = self.w_hf_op.data_ptr() if self.heads_tc else None
+            self._ptab = t
+        return self._ptab
 
     def set_step(self, step, lr):
         self.step = step
-        self.step_and_lr.copy_(torch.tensor([float(step), float(lr)], dtype=torch.float32),
-                               non_blocking=False)
+        self.step_and_lr[:2].copy_(torch.tensor([float(step), float(lr)], dtype=torch.float32),
+                                   non_blocking=False)
 
     def eval_losses(self, x_u8, counts, bias_logits=None, bias_logcounts=None, use_bias=None):
         """Forward + losses only (validation batches): returns the device vector

@@ -340,6 +340,16 @@ def adam_step(param, grad, m, v, step_and_lr, beta1=0.9, beta2=0.999, eps=1e-7, 
                             beta1, beta2, eps, grad_scale, _stream()), "bpb_adam_step")
 
 
+def adam_prep_step(param, grad, m, v, state, table, beta1=0.9, beta2=0.999, eps=1e-7,
+                   grad_scale=1.0):
+    """Adam + refresh of every bf16 operand layout in one launch; ``state`` is the device vector
+    {step, lr, ticket} (the kernel advances step), ``table`` a ``_lib.PrepTable``."""
+    lib = _lib.load()
+    check(lib.bpb_adam_prep_step(param.numel(), _p(param), _p(grad), _p(m), _p(v), _p(state),
+                                 beta1, beta2, eps, grad_scale, C.byref(table), _stream()),
+          "bpb_adam_prep_step")
+
+
 def prep_conv3_weights(w, F, fwd, bwd, precise):
     """w: [3, Fw, Fw] or [layers, 3, Fw, Fw] fp32 -> fwd/bwd [layers, planes, 3, F, F] bf16."""
     lib = _lib.load()

@@ -33,7 +33,8 @@ const char* bpb_last_error(void);
 /* Fills SM count and compute capability of the current device. */
 int bpb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* sizeof() of the argument structs as compiled: 0 bpb_conv3_args, 1 bpb_wgrad3_args,
- * 2 bpb_input_conv_args, 3 bpb_heads_dgrad_args (-1 otherwise); lets a binding check its layout. */
+ * 2 bpb_input_conv_args, 3 bpb_heads_dgrad_args, 4 bpb_prep_table (-1 otherwise); lets a binding
+ * check its layout. */
 int bpb_abi_struct_size(int which);
 /* Pipeline watchdog: kernels whose mbarrier waits time out record
  * records in a host-mapped buffer and trap.  Copies up to n (<= 2048) words: word 0 = number of
@@ -257,6 +258,27 @@ int bpb_loss_fwd_bwd_pack(int B, int L, int T, int H, const int* task_off, const
 int bpb_adam_step(long long n, float* param, const float* grad, float* m, float* v,
                   const float* step_and_lr, float beta1, float beta2, float eps, float grad_scale,
                   void* stream);
+
+/* K9 and the four bpb_prep_* refreshes in one launch (the training step's path).  The table says
+ * where the weight tensors live in the flat bucket (element offsets; Keras layouts, dil_w padded
+ * to [layers][3][F][F]) and where their bf16 operand layouts go; every updated weight is written
+ * to its operand positions (bit-equal to the bpb_prep_* kernels; padding entries are not touched
+ * and must be zero from allocation).  state = {float step, float lr, uint32 ticket (zero)}: the
+ * update uses step + 1 and the kernel stores step + 1 back (no separate increment launch). */
+typedef struct {
+  long long off_dil_w, off_conv1_w, off_prof_w, off_cnt_w;
+  int n_layers, F, Fw, W_in, W_out, T, H, Cp;
+  int planes;    /* bf16 remainder planes of the tower / heads operands (1 | 2) */
+  int in_planes; /* ... of the input convolution operand (bpb_prep_input_conv_weights) */
+  int N_heads;   /* padded column count of the heads-forward image (16 * ceil((T+H)/16)) */
+  bpb_bf16 *w_fwd, *w_bwd; /* bpb_prep_conv3_weights outputs */
+  bpb_bf16* w_in_op;       /* bpb_prep_input_conv_weights output */
+  bpb_bf16* w_hd_op;       /* bpb_prep_heads_dgrad_weights output */
+  bpb_bf16* w_hf_op;       /* bpb_prep_heads_fwd_weights output, or NULL */
+} bpb_prep_table;
+int bpb_adam_prep_step(long long n, float* param, const float* grad, float* m, float* v,
+                       float* state, float beta1, float beta2, float eps, float grad_scale,
+                       const bpb_prep_table* table, void* stream);
 
 /* fp32 Keras conv kernels [layers][3][Fw][Fw] -> padded bf16 operand layouts of bpb_conv3_tc:
  *   fwd[l][p][j][n][c] = w[l][j][c][n]   and   bwd[l][p][j][n][c] = w[l][j][n][c]   (each

@@ -245,3 +245,49 @@ def test_fused_loss_pack_matches_separate_kernels(dev, planes):
         scale = dl_a.abs().sum(dim=(0, 1))
         assert ((dpb_a - dpb_b).abs() <= 1e-5 * scale).all()
         assert torch.allclose(dcb_a, dcb_b, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("precise", [False, True])
+def test_fused_adam_refresh_matches_separate_kernels(dev, precise):
+    """bpb_adam_prep_step == bpb_adam_step + the four bpb_prep_* kernels, bit for bit (parameters,
+    moments and every bf16 operand layout), and it advances the device step counter."""
+    from bpreveal_b200 import ops
+    cfg = dict(CASES[1][1])  # two heads
+    net, _ = build(cfg, precise, dev, scale=1.0)
+    net.enable_training()
+    g = torch.Generator().manual_seed(9)
+    net.set_step(3, 0.004)
+    net.grads_flat.copy_(torch.randn(net.grads_flat.shape, generator=g).to(dev) * 0.1)
+    # padded entries of the bucket carry no gradient
+    mask = torch.zeros_like(net.params.flat)
+    for k, v in net.params.views(mask).items():
+        if k == "dil_w":
+            v[:, :, :net.cfg.numFilters, :net.cfg.numFilters] = 1
+        elif k == "dil_b":
+            v[:, :net.cfg.numFilters] = 1
+        else:
+            v.fill_(1)
+    net.grads_flat.mul_(mask)
+    net.adam_m.copy_(torch.randn(net.adam_m.shape, generator=g).to(dev) * 0.01 * mask)
+    net.adam_v.copy_(torch.rand(net.adam_v.shape, generator=g).to(dev) * 0.01 * mask)
+    names = ["w_fwd", "w_bwd", "w_in_op", "w_hd_op"] + (["w_hf_op"] if net.heads_tc else [])
+    saved = {k: t.clone() for k, t in (("p", net.params.flat), ("m", net.adam_m), ("v", net.adam_v))}
+    # separate kernels
+    sl = net.step_and_lr.clone()
+    sl[0] += 1
+    ops.adam_step(net.params.flat, net.grads_flat, net.adam_m, net.adam_v, sl)
+    net.refresh_weights()
+    torch.cuda.synchronize()
+    ref = {k: getattr(net, k).clone() for k in names}
+    ref.update(p=net.params.flat.clone(), m=net.adam_m.clone(), v=net.adam_v.clone())
+    # fused kernel from the same state, operand buffers scrambled where they will be rewritten
+    net.params.flat.copy_(saved["p"])
+    net.adam_m.copy_(saved["m"])
+    net.adam_v.copy_(saved["v"])
+    net.apply_adam()
+    torch.cuda.synchronize()
+    assert float(net.step_and_lr[0]) == 4.0
+    assert torch.equal(net.params.flat, ref["p"])
+    assert torch.equal(net.adam_m, ref["m"]) and torch.equal(net.adam_v, ref["v"])
+    for k in names:
+        assert torch.equal(getattr(net, k).view(torch.int16), ref[k].view(torch.int16)), k
