@@ -421,13 +421,20 @@ def main():
             peaks = json.load(open(pk_path))
         peak = peaks.get("hbm_gbs", 6650.0)
         achieved = conv_fwd_bytes / (conv_fwd_t / 1e3) / 1e9 if conv_fwd_t > 0 else 0.0
+        # DRAM bytes per launch of this kernel from the committed ncu capture (bench.py cannot run
+        # under ncu); only quoted for the workload the capture was taken on
+        traffic, traffic_src = None, None
+        tr_path = os.path.join(ROOT, "profiles", "conv_fwd_traffic_r1.json")
+        if os.path.exists(tr_path) and not args.precise:
+            tr = json.load(open(tr_path))
+            traffic, traffic_src = tr["dram_bytes_per_launch"], "profiles/conv_fwd_traffic_r1.json (ncu --set full)"
         roof = {"bound": "hbm",
                 "kernel": "conv_tc_kernel, forward of the 9 dilated residual layers of one step "
                           "(CUDA graph of the 9 launches replayed 20x between CUDA events)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks
                 else "fallback 6650 GB/s",
-                "traffic": None, "launches": conv_fwd_n,
+                "traffic": traffic, "traffic_source": traffic_src, "launches": conv_fwd_n,
                 "avg_launch_us": conv_fwd_t / max(conv_fwd_n, 1) * 1e3,
                 "algorithmic_bytes_per_launch": conv_fwd_bytes / max(conv_fwd_n, 1),
                 "share_of_step": conv_fwd_t / tot if tot else None,
