@@ -117,6 +117,14 @@ class Model:
             lam.append(float(v.value if hasattr(v, "value") else v))
         self._lambdas = lam
 
+    def _push_weights(self, net):
+        """Loss weights -> device vectors of the engine, only when they changed."""
+        key = (tuple(self._loss_weights), tuple(self._lambdas))
+        if getattr(self, "_pushed", None) != (id(net), key):
+            net.profile_weight.copy_(torch.tensor(self._loss_weights))
+            net.lam.copy_(torch.tensor(self._lambdas))
+            self._pushed = (id(net), key)
+
     def set_lambdas(self, lambdas):
         """The adaptive counts-loss weights (callbacks.py:96-389 adjust them between epochs)."""
         self._lambdas = [float(v) for v in lambdas]
@@ -185,13 +193,15 @@ class Model:
             if validation_data is not None:
                 logs.update(self._run_epoch(validation_data, np.arange(len(validation_data)),
                                             train=False, prefix="val_"))
-            hist.append(epoch, logs)
             for gen in (x, validation_data):
                 if gen is not None and hasattr(gen, "on_epoch_end"):
                     gen.on_epoch_end()
             for cb in callbacks:
                 if hasattr(cb, "on_epoch_end"):
                     cb.on_epoch_end(epoch, logs)
+            # Keras' History runs after the user callbacks: it records the logs as they left them
+            # (FixLossCallback's totals, ReduceLROnPlateau's learning_rate)
+            hist.append(epoch, logs)
             if self.stop_training:
                 break
         for cb in callbacks:
@@ -200,9 +210,21 @@ class Model:
         self.history = hist
         return hist
 
+    def _refresh_lambdas(self):
+        """Pick up counts-loss weights changed between epochs through the heads'
+        ``INTERNAL_λ-variable`` (training.buildLosses / callbacks.ApplyAdaptiveCountsLoss)."""
+        if self._lambdas is None:
+            return
+        for i, h in enumerate(self.headList):
+            v = h.get("INTERNAL_λ-variable")
+            if v is not None:
+                self._lambdas[i] = float(v.read_value() if hasattr(v, "read_value") else v)
+
     def _run_epoch(self, gen, order, train, prefix):
         H = len(self.headTasks)
+        self._refresh_lambdas()
         sums = np.zeros(2 * H, dtype=np.float64)
+        sums_dev = None  # losses stay on the device until the epoch ends (one read-back)
         nseq = 0
         for bi in order:
             xb, yb = gen[int(bi)]
@@ -213,14 +235,24 @@ class Model:
                 xb = np.asarray(xb)
             losses = self._step(xb, counts, train)
             n = xb.shape[0]
-            sums += losses * n  # every loss is a mean over the batch (losses.py:36-38)
+            # every loss is a mean over the batch (losses.py:36-38)
+            if isinstance(losses, torch.Tensor):
+                sums_dev = losses * n if sums_dev is None else sums_dev + losses * n
+            else:
+                sums += losses * n
             nseq += n
+        if sums_dev is not None:
+            sums += sums_dev.cpu().numpy()
         per = sums / max(nseq, 1)
         logs = {}
         tot = 0.0
         for h in range(H):
             logs[f"{prefix}{self.output_names[h]}_loss"] = per[h]
             logs[f"{prefix}{self.output_names[H + h]}_loss"] = per[H + h]
+            # the metric names Keras derives from metrics=losses, which the reference's callbacks
+            # match by regex (callbacks.py:56-59): unweighted MNLL, lambda-weighted MSE
+            logs[f"{prefix}{self.output_names[h]}_multinomial_nll"] = per[h]
+            logs[f"{prefix}{self.output_names[H + h]}_reweightable_mse"] = per[H + h]
             tot += self._loss_weights[h] * per[h] + per[H + h]
         logs[f"{prefix}loss"] = tot
         return logs
@@ -310,14 +342,13 @@ class SoloModel(Model):
     def _step(self, xb, counts, train):
         net = self.net
         net.enable_training()
-        net.profile_weight.copy_(torch.tensor(self._loss_weights))
-        net.lam.copy_(torch.tensor(self._lambdas))
+        self._push_weights(net)
         if train and self.trainable:
             losses = net.train_step(torch.as_tensor(xb), torch.as_tensor(counts),
                                     self.optimizer.learning_rate)
         else:
             losses = net.eval_losses(torch.as_tensor(xb), torch.as_tensor(counts))
-        return losses.double().cpu().numpy()
+        return losses.double()  # a copy: the engine reuses its loss buffer next step
 
 
 # ----------------------------------------------------------------------------------------
@@ -568,8 +599,7 @@ class CombinedModel(Model):
         net = self.residual.net
         net.enable_training()
         dev = self._device
-        net.profile_weight.copy_(torch.tensor(self._loss_weights))
-        net.lam.copy_(torch.tensor(self._lambdas))
+        self._push_weights(net)
         xt = torch.as_tensor(xb).to(device=dev, dtype=torch.uint8)
         ct = torch.as_tensor(counts).to(device=dev, dtype=torch.float32)
         bl, bc = self._bias_device(xt, xt.shape[0])
@@ -580,7 +610,7 @@ class CombinedModel(Model):
         else:
             losses = net.eval_losses(xt, ct, bias_logits=bl.contiguous(),
                                      bias_logcounts=bc.contiguous(), use_bias=self.useBias)
-        return losses.double().cpu().numpy()
+        return losses.double()
 
 
 # ----------------------------------------------------------------------------------------

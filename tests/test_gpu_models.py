@@ -277,3 +277,46 @@ def test_device_batch_generator_matches_reference_semantics(dev):
     m.compile(optimizer=models.Adam(learning_rate=0.004), loss_weights=[1.0, 1.0, 1.0, 1.0])
     hist = m.fit(gen, epochs=3)
     assert hist.history["loss"][-1] < hist.history["loss"][0]
+
+
+def test_train_model_with_the_reference_callback_set(dev, tmp_path):
+    """training.trainModel = buildLosses + getCallbacks + fit, as trainSoloModel.py:174-190 drives
+    it: adaptive counts-loss weights reach the kernels, the logs carry the metric names the
+    reference's callbacks match, the checkpoint and the history file are written."""
+    import copy
+    import json
+    from bpreveal_b200 import models, training
+    heads = copy.deepcopy(HEADS)
+    heads[0]["counts-loss-frac-target"] = 0.2
+    losses, weights = training.buildLosses(heads)
+    m = models.soloModel(52, 20, 16, 3, 3, 3, heads, "solo", device=dev, seed=7)
+    m.compile(optimizer=models.Adam(learning_rate=0.004), loss=losses, loss_weights=weights)
+    x = O.synthetic_sequences(32, 52, seed=3)
+    c = O.synthetic_profiles(32, 20, 3, seed=3, meanReads=40.0)
+    gen, val = ArrayGen(x, c, [2, 1], 8), ArrayGen(x[:16], c[:16], [2, 1], 8)
+    prefix = str(tmp_path / "solo")
+    hist = training.trainModel(m, gen, val, epochs=5, earlyStop=10, outputPrefix=prefix,
+                               plateauPatience=10, heads=heads,
+                               checkpointSuffix=".checkpoint.npz")
+    h = hist.history
+    for k in ("solo_profile_a_multinomial_nll", "val_solo_logcounts_b_reweightable_mse",
+              "learning_rate", "loss", "val_loss"):
+        assert len(h[k]) == 5, k
+    # FixLossCallback: loss = sum of the metrics, without the profile weight 1.5 of head b
+    e = 4
+    tot = sum(h[f"solo_profile_{n}_multinomial_nll"][e] + h[f"solo_logcounts_{n}_reweightable_mse"][e]
+              for n in "ab")
+    assert h["loss"][e] == pytest.approx(tot, rel=1e-12)
+    lam = h["counts-loss-weight"]
+    assert lam["a"][0] == 2.0 and lam["b"] == [3.0] * 5
+    # after epoch 0 the weight jumps to t p / (c_raw (1 - t)) computed from the validation losses
+    p0, c0 = h["val_solo_profile_a_multinomial_nll"][0], h["val_solo_logcounts_a_reweightable_mse"][0]
+    want = 0.2 * p0 / ((c0 / 2.0) * 0.8)
+    want = min(max(want, 2.0 / 10), 2.0 * 10)
+    assert lam["a"][1] == pytest.approx(want, rel=1e-6)
+    # ... and the kernels used it: the device-side weight is the one of the last epoch
+    assert float(m.net.lam[0]) == pytest.approx(lam["a"][4], rel=1e-6)
+    m2 = models.loadModel(prefix + ".checkpoint.npz", device=dev)
+    assert m2.predict(x[:2])[0].shape == (2, 20, 2)
+    name = training.saveHistory(hist, {"settings": {"output-prefix": prefix}, "heads": heads})
+    assert json.load(open(name, encoding="utf-8"))["counts-loss-weight"]["a"][0] == 2.0
