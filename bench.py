@@ -331,6 +331,7 @@ def main():
         sampler.start()
     ms = timed(steps, host_io=False)
     say(f"timed region done: {ms / steps:.3f} ms/step")
+    timed(max(warmup, 3), host_io=True)  # warm-up of the host-input path (staging slots, copy stream)
     ms_e2e = timed(steps, host_io=True)
     say("e2e region done")
     clocks = sampler.stop() if sampler else None

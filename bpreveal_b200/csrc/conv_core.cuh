@@ -40,6 +40,7 @@ constexpr int kTileM = 128;
 constexpr int kTileBytes = kTileM * 128;  // [128 x 64] bf16
 constexpr int kMaxStages = 12;
 constexpr int kMaxRStages = 4;
+constexpr int kMaxAcc = 6;
 constexpr int kEpiThreads = 256;
 
 enum { EPI_FWD = 0, EPI_FWD_Z = 1, EPI_FWD_R = 2, EPI_BWD_MASK = 3, EPI_BWD_MULT = 4 };
@@ -167,9 +168,12 @@ __device__ __forceinline__ void ring_advance(uint32_t& idx, uint32_t& phase, uin
 template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID>
 __global__ void __launch_bounds__(64 + kEpiThreads * EG, 1)
 conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
-  constexpr int ACC = (NT <= 128) ? 4 : 2;
+  // accumulator stages: a multiple of the group count, so a stage (and its mbarriers) always
+  // belongs to the same epilogue group
+  constexpr int ACC = (EG == 3) ? ((NT <= 64) ? 6 : 3) : ((NT <= 128) ? 4 : 2);
+  static_assert(ACC <= kMaxAcc && ACC * NT <= 512, "TMEM accumulator stages");
   constexpr int NCH = NT / 64;
-  constexpr uint32_t TMEM_COLS = ACC * NT;
+  constexpr uint32_t TMEM_COLS = (ACC * NT <= 128) ? 128 : (ACC * NT <= 256 ? 256 : 512);
   constexpr int B_TILE_BYTES = NT * 128;
   constexpr int SLAB_BYTES = kTileBytes + (RESIDENT ? 0 : B_TILE_BYTES);
   constexpr uint32_t IDESC = umma_idesc_bf16(128, NT, 0, 0);
@@ -199,8 +203,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   uint64_t* full = bars;
   uint64_t* empty = full + kMaxStages;
   uint64_t* acc_full = empty + kMaxStages;
-  uint64_t* acc_empty = acc_full + 4;
-  uint64_t* rfull = acc_empty + 4;
+  uint64_t* acc_empty = acc_full + kMaxAcc;
+  uint64_t* rfull = acc_empty + kMaxAcc;
   uint64_t* rempty = rfull + kMaxRStages;
   uint64_t* w_full = rempty + kMaxRStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
@@ -217,7 +221,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
 
   if (warp == 0) {
     // one lane per barrier (pair): the prologue is on the critical path of every launch
-    static_assert(kMaxStages <= 16 && kMaxRStages <= 7, "lane map of the barrier initialisation");
+    static_assert(kMaxStages <= 16 && kMaxAcc <= 8 && kMaxRStages <= 6,
+                  "lane map of the barrier initialisation");
     // branch-free lane map: lanes 0..15 ring stages, 16..19 accumulators, 24..27 residual ring
     {
       const bool is_ring = lane < p.stages;
@@ -232,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         mbar_init(b1, c1);
       }
     }
-    if (lane == 20) {
+    if (lane == 31) {
       tma_prefetch_desc(&tm.A[0]);
       tma_prefetch_desc(&tm.W);
       if (p.n_aplanes == 2) tma_prefetch_desc(&tm.A[1]);
@@ -291,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       // is still in flight" from "my phase completed" -- seen as a rare deadlock.)
       const uint32_t RG = static_cast<uint32_t>(p.rstages) / EG;
       uint32_t stage = 0, phase = 0, ntile = 0;
-      uint32_t rsg[2] = {0, 0}, rphg[2] = {0, 0};
+      uint32_t rsg[3] = {0, 0, 0}, rphg[3] = {0, 0, 0};
       TileWalk tw;
       for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
         const int nt = tw.nt, b = tw.b;
@@ -342,7 +347,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           }
         }
         if (RING_RESID) {
-          const uint32_t g = (EG == 2) ? (ntile & 1u) : 0u;
+          const uint32_t g = (EG > 1) ? (ntile % EG) : 0u;
           for (int ch = 0; ch < NCH; ++ch) {
             const uint32_t rs = g * RG + rsg[g];
             const uint32_t rphase = rphg[g];
@@ -535,7 +540,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     uint32_t as = 0, aphase = 0, rs = 0, rphase = 0, hs = 0, hphase = 0, kc = 0;
     TileWalk tw;
     tw.init(p);
-    if (EG == 2 && grp == 1 && tw.b < p.B) {
+    for (int skip = 0; skip < grp && tw.b < p.B; ++skip) {  // this group's first tile
       tw.next(p);
       ring_advance(as, aphase, 1, ACC);
       ring_advance(hs, hphase, 1, p.stages);
@@ -620,8 +625,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         }
         BPB_PHASE(9);   // acc wait + TMEM load
 
-        const bool one_buf = (EG == 2) || p.nstg == 1;  // one staging buffer per writer group
-        uint8_t* sb = stg + static_cast<size_t>(EG == 2 ? grp : (p.nstg == 2 ? (kc & 1) : 0)) * stg_bytes;
+        const bool one_buf = (EG >= 2) || p.nstg == 1;  // one staging buffer per writer group
+        uint8_t* sb = stg + static_cast<size_t>(EG >= 2 ? grp : (p.nstg == 2 ? (kc & 1) : 0)) * stg_bytes;
         uint8_t* sb2 = sb + static_cast<size_t>(p.has_out * PLANES) * kTileBytes;
         if (one_buf) {
           // single staging buffer: the previous chunk's stores must have read it
@@ -764,10 +769,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               static_cast<uint32_t>(obits_lo) | (static_cast<uint32_t>(obits_hi) << 16);
       }
       ring_advance(as, aphase, EG, ACC);
-      if (EG == 2) {
-        // skip the other group's tile
-        tw.next(p);
-      }
+      // skip the other groups' tiles
+      for (int skip = 1; skip < EG && tw.b < p.B; ++skip) tw.next(p);
     }
 #ifdef BPB_ROLE_PROFILE
     if (et == 0 && grp == 0) BPB_STAMP(23);
@@ -833,9 +836,16 @@ static const bool g_strip_enabled = [] {
   return !(e && e[0] == '0');
 }();
 
-// Tuning knob (BPB_EPI_GROUPS=1|2, default 2): number of 8-warp epilogue groups on the bf16 path.
+// Tuning knob (BPB_EPI_GROUPS=1|2|3, default 2): most 8-warp epilogue groups used on the bf16 path.
+// Three groups (-DBPB_ENABLE_EG3, F = 64 with resident weights) were measured SLOWER than two on
+// C1 (forward 123 vs 105 us per step, data gradient 156 vs 136): 72 instead of 96 registers per
+// thread, three staging buffers leave a shorter operand ring, and the math phases of the groups
+// already compete for issue slots.  The kernel stays general; the instantiation is off.
 static int g_epi_groups = [] {
   const char* e = getenv("BPB_EPI_GROUPS");
+#ifdef BPB_ENABLE_EG3
+  if (e && e[0] == '3') return 3;
+#endif
   return (e && e[0] == '1') ? 1 : 2;
 }();
 
@@ -857,7 +867,13 @@ static int launch_conv_eg(const ConvMaps& maps, const ConvKParams& kp, size_t sm
 template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, bool RESID>
 static int launch_conv(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
                        cudaStream_t stream) {
-  if (PLANES == 1 && kp.nstg == 2 && kp.epi_groups == 2 && (kp.rstages % 2 == 0 || !kp.ring_resid))
+#ifdef BPB_ENABLE_EG3
+  if constexpr (NT == 64 && RESIDENT)
+    if (PLANES == 1 && kp.nstg == 3 && kp.epi_groups >= 3 &&
+        (kp.rstages % 3 == 0 || !kp.ring_resid))
+      return launch_conv_eg<EPI, NT, RESIDENT, 1, HALO, 3, RESID>(maps, kp, smem_bytes, grid, stream);
+#endif
+  if (PLANES == 1 && kp.nstg == 2 && kp.epi_groups >= 2 && (kp.rstages % 2 == 0 || !kp.ring_resid))
     return launch_conv_eg<EPI, NT, RESIDENT, 1, HALO, 2, RESID>(maps, kp, smem_bytes, grid, stream);
   return launch_conv_eg<EPI, NT, RESIDENT, PLANES, HALO, 1, RESID>(maps, kp, smem_bytes, grid, stream);
 }
@@ -938,13 +954,14 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   const size_t b_tile = static_cast<size_t>(NT) * 128;
   const size_t w_res = static_cast<size_t>(d.n_wplanes) * d.n_taps * d.KC * b_tile;
   const size_t fixed = 1024 /*align slack*/ + static_cast<size_t>(F) * 4 +
-                       (2 * kMaxStages + 8 + 2 * kMaxRStages + 1) * 8 + 16;
+                       (2 * kMaxStages + 2 * kMaxAcc + 2 * kMaxRStages + 1) * 8 + 16;
   const bool can_reside = (kp.n_ntiles == 1) && (NT <= 128);
   // With two epilogue groups (bf16 path, two staging buffers) the residual ring must have an EVEN
   // number of slots: a slot is then always consumed by the same group.  With an odd ring a group
   // would skip every other phase of a slot's mbarrier, and a parity wait cannot tell "the phase I
   // skipped is still in flight" from "my phase is complete" (observed as a rare deadlock).
-  const bool two_groups = (n_planes == 1) && g_epi_groups == 2;
+  const bool two_groups = (n_planes == 1) && g_epi_groups >= 2;
+  const bool three_groups = (n_planes == 1) && g_epi_groups >= 3 && NT == 64;
   const int r_hi = two_groups ? 4 : 3;
 
   // STRIP staging: resident weights, one tap, rows one 16-byte position apart
@@ -980,6 +997,7 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
     if (want_halo && st > 6) st = 6;
     // same-group ownership of every HALO box slot as well
     if (want_halo && two_groups && is_fwd && want_nstg == 2 && st > 2 && (st & 1)) st -= 1;
+    if (want_halo && is_fwd && want_nstg == 3) st -= st % 3;
     if (st < min_stages) return false;
     halo = want_halo; resident = want_res; nstg = want_nstg; rstages = ring_resid ? want_rst : 0;
     stages = st; stage_bytes = sb; box_rows = rows;
@@ -988,7 +1006,12 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   const bool halo_ok = RESID && d.allow_halo && can_reside && span <= 128 && span > 0 &&
                        d.last_nk == 4;
   bool planned = false;
-  if (halo_ok) planned = try_plan(true, true, 2, r_hi, 3) || try_plan(true, true, 2, 2, 2);
+  // Three epilogue groups (3 staging buffers, residual sub-rings of one slot) when shared memory
+  // still leaves a useful operand ring; the weights must be resident (F = 64 towers).
+  if (three_groups && halo_ok) planned = try_plan(true, true, 3, 3, is_fwd ? 3 : 2);
+  if (!planned && three_groups && can_reside && !strip_ok) planned = try_plan(false, true, 3, 3, 6);
+  if (!planned && three_groups && can_reside && strip_ok) planned = try_plan(false, true, 3, 3, 3);
+  if (!planned && halo_ok) planned = try_plan(true, true, 2, r_hi, 3) || try_plan(true, true, 2, 2, 2);
   if (!planned && can_reside)
     planned = try_plan(false, true, 2, r_hi, 4) || try_plan(false, true, 2, 2, 3) ||
               try_plan(false, true, 1, 2, 3);

@@ -470,8 +470,7 @@ class SoloNet:
         self.enable_training()
         B = x_u8.shape[0]
         ws = self._workspace(B, "train")
-        ws["x"].copy_(x_u8, non_blocking=True)
-        ws["counts"].copy_(counts, non_blocking=True)
+        self._stage_inputs(ws, x_u8, counts)
         self.step += 1
         if lr != getattr(self, "_lr_on_device", None):
             self.step_and_lr[1:2].fill_(float(lr))  # stream-ordered scalar fill, only on change
@@ -506,6 +505,39 @@ class SoloNet:
                 allreduce(self.grads_flat)
                 body_b()
         return ws["losses"]
+
+    def _stage_inputs(self, ws, x_u8, counts):
+        """Inputs -> the fixed device buffers the step's CUDA graph reads.  Host inputs go through
+        two staging slots filled on a copy stream, so the host-to-device copy of step i+1
+        overlaps the kernels of step i (the call returns as soon as the work is enqueued); the
+        compute stream then moves the slot into place with a device copy (~1 us)."""
+        if x_u8.is_cuda and counts.is_cuda:
+            ws["x"].copy_(x_u8, non_blocking=True)
+            ws["counts"].copy_(counts, non_blocking=True)
+            return
+        st = ws.get("h2d")
+        if st is None:
+            st = {"x": [torch.empty_like(ws["x"]) for _ in range(2)],
+                  "c": [torch.empty_like(ws["counts"]) for _ in range(2)],
+                  "ready": [torch.cuda.Event() for _ in range(2)],
+                  "free": [torch.cuda.Event() for _ in range(2)],
+                  "k": 0, "stream": torch.cuda.Stream(device=self.device)}
+            ws["h2d"] = st
+            cur0 = torch.cuda.current_stream(self.device)
+            for ev in st["free"]:
+                ev.record(cur0)
+        k = st["k"]
+        st["k"] = k ^ 1
+        cs, cur = st["stream"], torch.cuda.current_stream(self.device)
+        cs.wait_event(st["free"][k])  # the slot's previous contents have been moved out
+        with torch.cuda.stream(cs):
+            st["x"][k].copy_(x_u8, non_blocking=True)
+            st["c"][k].copy_(counts, non_blocking=True)
+            st["ready"][k].record(cs)
+        cur.wait_event(st["ready"][k])
+        ws["x"].copy_(st["x"][k], non_blocking=True)
+        ws["counts"].copy_(st["c"][k], non_blocking=True)
+        st["free"][k].record(cur)
 
     # ------------------------------------------------------------------ CUDA graphs
     def _run_graph(self, key, body):
