@@ -17,6 +17,14 @@ CASES = [
     ("mid128", Hh.mid_cfg(numFilters=128, numLayers=3, outputLength=150, headTasks=[2, 2])),
     # the wide regime of C4 in miniature: N tiles of 256 with streamed weights, width-75 heads
     ("wide256", Hh.mid_cfg(numFilters=256, numLayers=3, outputLength=60, outputFilterWidth=75)),
+    # ragged everything: F = 24 (zero-padded to 64), even filter widths, an output length that is
+    # not a multiple of the 128-row tile, a head of 9 tasks (beyond the fused loss kernel's 8, so
+    # the step takes the separate loss / pack kernels) next to a single-task head
+    ("ragged", Hh.mid_cfg(numFilters=24, numLayers=2, outputLength=131, inputFilterWidth=4,
+                          outputFilterWidth=10, headTasks=[1, 9])),
+    # no dilated layers at all: input convolution straight into the heads
+    ("nolayers", Hh.mid_cfg(numFilters=16, numLayers=0, outputLength=40, inputFilterWidth=7,
+                            outputFilterWidth=5, headTasks=[2])),
 ]
 
 
