@@ -117,6 +117,7 @@ SIGNATURES = {
     "bpb_loss_fwd_bwd": (c_int, [c_int] * 4 + [c_void_p] * 11),
     "bpb_loss_pack_ws_elems": (c_ll, [c_int] * 3),
     "bpb_loss_fwd_bwd_pack": (c_int, [c_int] * 4 + [c_void_p] * 10 + [c_int] * 4 + [c_void_p] * 6),
+    "bpb_ushuffle_ohe": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, C.c_uint]),
     "bpb_adam_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 + [c_void_p]),
     "bpb_adam_prep_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 +
                            [C.POINTER(PrepTable), c_void_p]),

@@ -27,9 +27,19 @@ def shuffle_indices(length, numShuffles, seed=355687):
     return _PERM_CACHE[key]
 
 
-def make_references(x_u8, numShuffles, seed=355687):
-    """(Q, L, 4) u8 on device -> (Q*numShuffles, L, 4) shuffled references on device."""
+def make_references(x_u8, numShuffles, seed=355687, kmerSize=1):
+    """(Q, L, 4) u8 on device -> (Q*numShuffles, L, 4) shuffled references on device.
+
+    kmerSize 1: the same row permutations for every query (interpretUtils.py:1216-1222, on the
+    device).  kmerSize > 1: k-let preserving shuffles of every query, the generator re-seeded per
+    query as the reference does (interpretUtils.py:1223-1225) -- host code, like the reference's
+    ushuffle, bit-identical to it (``bpb_ushuffle_ohe``)."""
     Q, L, _ = x_u8.shape
+    if kmerSize > 1:
+        xh = x_u8.cpu().numpy()
+        refs = np.concatenate([ops.ushuffle_ohe(xh[q], kmerSize, numShuffles, seed)
+                               for q in range(Q)], axis=0)
+        return torch.as_tensor(refs, device=x_u8.device)
     perm = torch.as_tensor(shuffle_indices(L, numShuffles, seed), device=x_u8.device)
     refs = torch.empty((Q * numShuffles, L, 4), dtype=torch.uint8, device=x_u8.device)
     ops.shuffle_rows(x_u8.contiguous(), perm.contiguous(), refs)
@@ -60,7 +70,7 @@ def _receptive_field_net(net):
 
 
 def pisa_batch(net, x_u8, headID, taskID, numShuffles, refs_u8=None, hypothetical=False,
-               use_graph=True, crop=True):
+               use_graph=True, crop=True, kmerSize=1):
     """PISA attributions of Q query windows (interpretPisa.py:153-166: metric = leftmost logit).
 
     Returns (phi (Q, Lin, 4) fp32, input_predictions (Q,), shuffle_predictions (Q, n)); phi is
@@ -74,6 +84,8 @@ def pisa_batch(net, x_u8, headID, taskID, numShuffles, refs_u8=None, hypothetica
     cfg = net.cfg
     Q, Lin = x_u8.shape[0], cfg.inputLength
     x_u8 = x_u8.contiguous()
+    if refs_u8 is None and kmerSize > 1:
+        refs_u8 = make_references(x_u8, numShuffles, kmerSize=kmerSize)
     col = int(sum(cfg.headTasks[:headID])) + taskID
     run = _receptive_field_net(net) if (crop and cfg.outputLength > 1) else net
     rf = run.cfg.inputLength
@@ -146,7 +158,8 @@ def pisa_batch(net, x_u8, headID, taskID, numShuffles, refs_u8=None, hypothetica
     return phi, vx, vr
 
 
-def flat_batch(net, x_u8, headID, numShuffles, kind="profile", taskIDs=None, refs_u8=None):
+def flat_batch(net, x_u8, headID, numShuffles, kind="profile", taskIDs=None, refs_u8=None,
+               kmerSize=1):
     """interpretFlat hypothetical contribution scores (interpretFlat.py:187-312,
     interpretUtils.py:1295-1312) of Q windows for one head.
 
@@ -158,7 +171,7 @@ def flat_batch(net, x_u8, headID, numShuffles, kind="profile", taskIDs=None, ref
     x_u8 = x_u8.contiguous()
     dev = x_u8.device
     if refs_u8 is None:
-        refs_u8 = make_references(x_u8, numShuffles)
+        refs_u8 = make_references(x_u8, numShuffles, kmerSize=kmerSize)
     k0 = int(sum(cfg.headTasks[:headID]))
     tasks = list(range(cfg.headTasks[headID])) if taskIDs is None else list(taskIDs)
     sel = torch.zeros((cfg.T,), dtype=torch.int32, device=dev)

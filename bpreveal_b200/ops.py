@@ -340,6 +340,19 @@ def adam_step(param, grad, m, v, step_and_lr, beta1=0.9, beta2=0.999, eps=1e-7, 
                             beta1, beta2, eps, grad_scale, _stream()), "bpb_adam_step")
 
 
+def ushuffle_ohe(x, kmerSize, numShuffles, seed=355687):
+    """(L, A) one-hot numpy array (A <= 8) -> (numShuffles, L, A) uint8 k-let preserving shuffles
+    (host; ushuffle.shuffleOHE of the reference, bit-identical for the same seed)."""
+    import numpy as np
+    x = np.ascontiguousarray(x, dtype=np.uint8)
+    L, A = x.shape
+    out = np.empty((numShuffles, L, A), dtype=np.uint8)
+    check(_lib.load().bpb_ushuffle_ohe(x.ctypes.data, out.ctypes.data, A, L, int(kmerSize),
+                                       int(numShuffles), int(seed) & 0xFFFFFFFF),
+          "bpb_ushuffle_ohe")
+    return out
+
+
 def adam_prep_step(param, grad, m, v, state, table, beta1=0.9, beta2=0.999, eps=1e-7,
                    grad_scale=1.0):
     """Adam + refresh of every bf16 operand layout in one launch; ``state`` is the device vector

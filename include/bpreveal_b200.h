@@ -312,6 +312,15 @@ int bpb_mul_f32(long long n, const float* a, const float* b, float* out, void* s
 int bpb_counts_lse(int B, int H, const int* use_bias, const float* bias_lc, const float* resid_lc,
                    float* out, float* dresid_scale, void* stream);
 
+/* k-let preserving shuffles of a one-hot sequence (HOST pointers, host code -- the reference's
+ * internal/libushuffle.c:59-344 runs on the host too): the DeepSHAP references for kmer-size > 1
+ * (ushuffle.shuffleOHE, interpretUtils.py:1223-1225).  host_in [length][alphabet] (alphabet <= 8,
+ * any non-zero byte is hot), host_out [numShuffles][length][alphabet] 0/1 bytes.  Draws from a
+ * restatement of glibc's random() seeded with `seed` at the start of the call, in the reference's
+ * order: the output is bit-identical to the reference's for the same seed. */
+int bpb_ushuffle_ohe(const unsigned char* host_in, unsigned char* host_out, int alphabet, int length,
+                     int kmerSize, int numShuffles, unsigned seed);
+
 /* ------------------------------------------------------------------------------------------
  * DeepSHAP plumbing (interpretUtils.py:1216-1312, shap.py:26-30).
  * bpb_shuffle_rows: refs[q*n + r, t, :] = x[q, perm[r*L + t], :]  (x u8 [Q][L][4], perm int32 [n][L])
