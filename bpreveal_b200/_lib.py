@@ -109,6 +109,10 @@ SIGNATURES = {
     "bpb_heads_wgrad_tc": (c_int, [c_int] * 8 + [c_void_p] * 7 + [c_ll, c_void_p]),
     "bpb_input_conv_dgrad": (c_int, [c_int] * 6 + [c_void_p] * 5),
     "bpb_heads_fwd": (c_int, [c_int] * 8 + [c_void_p] * 10),
+    "bpb_input_dgrad_wop_elems": (c_ll, [c_int] * 3),
+    "bpb_input_conv_dgrad_tc_supported": (c_int, [c_int] * 3),
+    "bpb_prep_input_dgrad_weights": (c_int, [c_int] * 3 + [c_void_p] * 2 + [c_int, c_void_p]),
+    "bpb_input_conv_dgrad_tc": (c_int, [c_int] * 5 + [c_void_p] * 5),
     "bpb_heads_fwd_wop_elems": (c_ll, [c_int] * 5),
     "bpb_prep_heads_fwd_weights": (c_int, [c_int] * 5 + [c_void_p] * 3 + [c_int, c_void_p]),
     "bpb_heads_fwd_ws_bytes": (c_ll, [c_int] * 3),

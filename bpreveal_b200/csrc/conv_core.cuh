@@ -678,7 +678,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               for (int i = 0; i < 8; ++i) {
                 const float din = zx[i] - v[i];
                 const float dout = fmaxf(zx[i], 0.f) - fmaxf(v[i], 0.f);
-                o2[i] = (fabsf(din) < 1e-6f) ? (zx[i] > 0.f ? 1.f : 0.f) : dout / din;
+                // approximate division (2 ulp): the multiplier is stored in bf16 planes, and a
+                // full-precision divide was a third of this epilogue's instructions
+                o2[i] = (fabsf(din) < 1e-6f) ? (zx[i] > 0.f ? 1.f : 0.f) : __fdividef(dout, din);
               }
             }
             if (EPI == EPI_FWD_Z) {

@@ -29,6 +29,7 @@ struct HeadsKParams {
   int B, L_in, L_out, tiles_per_seq, W, KC, N, T, H;
   int n_aplanes, n_wplanes, npass, pa_bits, pw_bits;
   int sub_bytes, box_bytes, stages;
+  int row_shift;  // the box of tile t0 starts at row t0 + row_shift (negative rows read as zero)
   uint32_t idesc;
   const float* pb;
   const uint8_t* w_image;  // the prepared weights: the shared-memory image, copied in one piece
@@ -96,7 +97,8 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = (i < p.T) ? p.pb[i] : 0.f;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    s_bias[i] = (i < p.T && p.pb != nullptr) ? p.pb[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -122,7 +124,7 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         for (int c = 0; c < p.KC; ++c)
           for (int pl = 0; pl < p.n_aplanes; ++pl)
             tma_load_3d(pl ? &tmA1 : &tmA0, dst + static_cast<size_t>(c * p.n_aplanes + pl) * p.sub_bytes,
-                        &full[stage], c * 64, t0, b);
+                        &full[stage], c * 64, t0 + p.row_shift, b);
         if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
       }
     }
@@ -250,7 +252,7 @@ __global__ void heads_counts_finish_kernel(int B, int tiles, int H, int L_in,
 // pw [W][Fw][T], cw [Fw][H] fp32 -> op: bf16 image of the kernel's shared-memory operand,
 // [planes][W][KC] tiles of N rows x 64 channels
 __global__ void __launch_bounds__(256)
-prep_heads_fwd_kernel(int W, int Fw, int K, int N, int T, int H, int planes,
+prep_heads_fwd_kernel(int W, int Fw, int K, int N, int T, int H, int planes, int flip_input_conv,
                       const float* __restrict__ pw, const float* __restrict__ cw,
                       __nv_bfloat16* __restrict__ op) {
   const long long n_el = static_cast<long long>(W) * N * K;
@@ -261,8 +263,15 @@ prep_heads_fwd_kernel(int W, int Fw, int K, int N, int T, int H, int planes,
   const int j = static_cast<int>(i / (static_cast<long long>(K) * N));
   float v = 0.f;
   if (c < Fw) {
-    if (n < T) v = pw[(static_cast<long long>(j) * Fw + c) * T + n];
-    else if (n < T + H && j == 0) v = cw[c * H + (n - T)];
+    if (flip_input_conv) {
+      // transposed input convolution: pw is the Keras kernel [W][4][Fw]; tap j of this operand is
+      // tap W-1-j of the forward filter, column n the input channel, row c the filter
+      if (n < T) v = pw[(static_cast<long long>(W - 1 - j) * T + n) * Fw + c];
+    } else if (n < T) {
+      v = pw[(static_cast<long long>(j) * Fw + c) * T + n];
+    } else if (n < T + H && j == 0) {
+      v = cw[c * H + (n - T)];
+    }
   }
   // destination: tile (plane, tap, 64-channel chunk) of N rows x 128 B, 16-byte chunks XOR-ed
   // with the row (the 128-byte swizzle of a tile whose base is 1024-aligned in shared memory)
@@ -320,7 +329,30 @@ extern "C" int bpb_prep_heads_fwd_weights(int W, int Fw, int F, int T, int H, co
   const long long n = static_cast<long long>(W) * N * F;
   prep_heads_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
                           static_cast<cudaStream_t>(stream_)>>>(
-      W, Fw, F, N, T, H, planes, pw, cw, reinterpret_cast<__nv_bfloat16*>(w_op));
+      W, Fw, F, N, T, H, planes, 0, pw, cw, reinterpret_cast<__nv_bfloat16*>(w_op));
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" long long bpb_input_dgrad_wop_elems(int W, int F, int planes) {
+  return bpb_heads_fwd_wop_elems(W, F, 4, 0, planes);
+}
+
+extern "C" int bpb_input_conv_dgrad_tc_supported(int W, int F, int planes) {
+  bp::HeadsPlan pl;
+  return (F > 0 && F % 64 == 0 && bp::plan_heads(W, F, 4, 0, planes, &pl)) ? 0 : 1;
+}
+
+extern "C" int bpb_prep_input_dgrad_weights(int W, int Fw, int F, const float* w, bpb_bf16* w_op,
+                                            int planes, void* stream_) {
+  using namespace bp;
+  BP_REQUIRE(w && w_op && F % 64 == 0 && Fw <= F && (planes == 1 || planes == 2),
+             "bpb_prep_input_dgrad_weights: bad arguments");
+  const int N = heads_n(4, 0);
+  const long long n = static_cast<long long>(W) * N * F;
+  prep_heads_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
+                          static_cast<cudaStream_t>(stream_)>>>(
+      W, Fw, F, N, 4, 0, planes, 1, w, nullptr, reinterpret_cast<__nv_bfloat16*>(w_op));
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -336,26 +368,27 @@ extern "C" int bpb_heads_fwd_tc_supported(int W, int F, int T, int H, int planes
   return (F > 0 && F % 64 == 0 && H <= 16 && T <= 240 && bp::plan_heads(W, F, T, H, planes, &pl)) ? 0 : 1;
 }
 
-extern "C" int bpb_heads_fwd_tc(int B, int L_in, int W, int F, int T, int H,
-                                const bpb_bf16* act_hi, const bpb_bf16* act_lo,
-                                const bpb_bf16* w_op, const float* pb, const float* cb,
-                                float* logits, float* logcounts, float* ws, long long ws_bytes,
-                                void* stream_) {
+// One launch of the window GEMM.  full = 0: the heads ('valid' correlation, L_out = L_in - W + 1,
+// tiles cover L_in because the counts columns sum over every input row); full = 1: 'full'
+// correlation of L_in + W - 1 output rows (the box starts W - 1 rows early; rows outside the
+// sequence read as zero through TMA's out-of-bounds fill) -- the transposed input convolution.
+static int heads_fwd_run(const char* who, int full, int B, int L_in, int W, int F, int T, int H,
+                         const bpb_bf16* act_hi, const bpb_bf16* act_lo, const bpb_bf16* w_op,
+                         const float* pb, const float* cb, float* logits, float* logcounts,
+                         float* ws, long long ws_bytes, void* stream_) {
   using namespace bp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BP_REQUIRE(act_hi && w_op && pb && cb && logits && logcounts && ws, "bpb_heads_fwd_tc: NULL argument");
-  BP_REQUIRE(F > 0 && F % 64 == 0 && H >= 1 && H <= 16 && T >= 1 && T <= 240 && L_in >= W,
-             "bpb_heads_fwd_tc: bad geometry F=%d T=%d H=%d", F, T, H);
   const int planes = act_lo ? 2 : 1;
   HeadsPlan pl;
   BP_REQUIRE(plan_heads(W, F, T, H, planes, &pl),
-             "bpb_heads_fwd_tc: W=%d F=%d planes=%d does not fit shared memory", W, F, planes);
-  BP_REQUIRE(ws_bytes >= bpb_heads_fwd_ws_bytes(B, L_in, H), "bpb_heads_fwd_tc: workspace too small");
+             "%s: W=%d F=%d planes=%d does not fit shared memory", who, W, F, planes);
+  BP_REQUIRE(H == 0 || ws_bytes >= bpb_heads_fwd_ws_bytes(B, L_in, H), "%s: workspace too small", who);
   HeadsKParams kp{};
   kp.B = B;
   kp.L_in = L_in;
-  kp.L_out = L_in - W + 1;
-  kp.tiles_per_seq = (L_in + 127) / 128;
+  kp.L_out = full ? L_in + W - 1 : L_in - W + 1;
+  kp.row_shift = full ? -(W - 1) : 0;
+  kp.tiles_per_seq = ((full ? kp.L_out : L_in) + 127) / 128;
   kp.W = W;
   kp.KC = pl.KC;
   kp.N = pl.N;
@@ -403,8 +436,35 @@ extern "C" int bpb_heads_fwd_tc(int B, int L_in, int W, int F, int T, int H,
   else LAUNCH_HD(512);
 #undef LAUNCH_HD
   BP_CHECK_CUDA(cudaGetLastError());
-  heads_counts_finish_kernel<<<(B * H + 127) / 128, 128, 0, stream>>>(B, kp.tiles_per_seq, H, L_in, ws,
-                                                                      cb, logcounts);
-  BP_CHECK_CUDA(cudaGetLastError());
+  if (H > 0) {
+    heads_counts_finish_kernel<<<(B * H + 127) / 128, 128, 0, stream>>>(B, kp.tiles_per_seq, H, L_in,
+                                                                        ws, cb, logcounts);
+    BP_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
+}
+
+extern "C" int bpb_heads_fwd_tc(int B, int L_in, int W, int F, int T, int H,
+                                const bpb_bf16* act_hi, const bpb_bf16* act_lo,
+                                const bpb_bf16* w_op, const float* pb, const float* cb,
+                                float* logits, float* logcounts, float* ws, long long ws_bytes,
+                                void* stream_) {
+  BP_REQUIRE(act_hi && w_op && pb && cb && logits && logcounts && ws, "bpb_heads_fwd_tc: NULL argument");
+  BP_REQUIRE(F > 0 && F % 64 == 0 && H >= 1 && H <= 16 && T >= 1 && T <= 240 && L_in >= W,
+             "bpb_heads_fwd_tc: bad geometry F=%d T=%d H=%d", F, T, H);
+  return heads_fwd_run("bpb_heads_fwd_tc", 0, B, L_in, W, F, T, H, act_hi, act_lo, w_op, pb, cb, logits,
+                       logcounts, ws, ws_bytes, stream_);
+}
+
+// Data gradient of the input convolution wrt the one-hot input (attribution only) as the same
+// window GEMM: dx[b,t,c] = sum_j sum_n gz[b,t-j,n] w[j][c][n], a 'full' correlation with the
+// tap-reversed, transposed filter (bpb_prep_input_dgrad_weights).
+extern "C" int bpb_input_conv_dgrad_tc(int B, int L_in, int L_out, int W, int F,
+                                       const bpb_bf16* gz_hi, const bpb_bf16* gz_lo,
+                                       const bpb_bf16* w_op, float* dx, void* stream_) {
+  BP_REQUIRE(gz_hi && w_op && dx, "bpb_input_conv_dgrad_tc: NULL argument");
+  BP_REQUIRE(F > 0 && F % 64 == 0 && L_out == L_in - W + 1 && L_out >= 1,
+             "bpb_input_conv_dgrad_tc: bad geometry");
+  return heads_fwd_run("bpb_input_conv_dgrad_tc", 1, B, L_out, W, F, 4, 0, gz_hi, gz_lo, w_op, nullptr,
+                       nullptr, dx, nullptr, nullptr, 0, stream_);
 }

@@ -116,6 +116,8 @@ class SoloNet:
         self.w_in_planes = planes + int(os.environ.get("BPB_W1_EXTRA", "1"))
         self.w_in_op = ops.input_conv_wop(cfg.inputFilterWidth, Fp, self.w_in_planes, self.device)
         self.w_hd_op = ops.heads_dgrad_wop(cfg.outputFilterWidth, Fp, self.cp, planes, self.device)
+        # transposed input convolution (attribution only), refreshed where it is used
+        self.w_id_op = ops.input_dgrad_wop(cfg.inputFilterWidth, Fp, planes, self.device)
         # heads forward as one tcgen05 GEMM when its weights fit shared memory (else CUDA cores)
         self.heads_tc = ops.heads_fwd_tc_supported(cfg.outputFilterWidth, Fp, cfg.T, cfg.H, planes)
         if self.heads_tc:
@@ -591,5 +593,12 @@ class SoloNet:
             ops.conv3(gzcur, self.w_bwd[i], (0, -d, -2 * d), 1, Ls[i], resid=gcur, resid_off=-d,
                       out=gnext if i > 0 else None, out2=gznext, mult=wr["mult"][i])
             gcur, gzcur = gnext, gznext
-        ops.input_conv_dgrad(gzcur, p["conv1_w"], cfg.inputLength, wr["dx"])
+        planes_id = 2 if cfg.precise else 1
+        if ops.input_conv_dgrad_tc_supported(cfg.inputFilterWidth, cfg.Fp, planes_id):
+            # transposed input convolution on tensor cores (its operand is rebuilt here: it is
+            # only needed for attribution, 3 us, and always matches the current weights)
+            ops.prep_input_dgrad_weights(p["conv1_w"], cfg.Fp, self.w_id_op, planes_id)
+            ops.input_conv_dgrad_tc(gzcur, self.w_id_op, cfg.inputFilterWidth, wr["dx"])
+        else:
+            ops.input_conv_dgrad(gzcur, p["conv1_w"], cfg.inputLength, wr["dx"])
         return wr["dx"], wx, wr

@@ -199,6 +199,30 @@ def input_conv_dgrad(gz, w, L_in, dx):
                                    _stream()), "bpb_input_conv_dgrad")
 
 
+def input_conv_dgrad_tc_supported(W, F, planes):
+    return _lib.load().bpb_input_conv_dgrad_tc_supported(W, F, planes) == 0
+
+
+def input_dgrad_wop(W, F, planes, device):
+    n = _lib.load().bpb_input_dgrad_wop_elems(W, F, planes)
+    return torch.zeros((n,), dtype=torch.bfloat16, device=device)
+
+
+def prep_input_dgrad_weights(w, F, w_op, planes):
+    W, _, Fw = w.shape
+    check(_lib.load().bpb_prep_input_dgrad_weights(W, Fw, F, _p(w), _p(w_op), planes, _stream()),
+          "bpb_prep_input_dgrad_weights")
+
+
+def input_conv_dgrad_tc(gz, w_op, W, dx):
+    """dx (B, L_in, 4) fp32 <- gz planes (B, L_out, F) through the tensor-core window GEMM."""
+    g_hi, g_lo = _planes(gz)
+    B, L_out, F = g_hi.shape
+    check(_lib.load().bpb_input_conv_dgrad_tc(B, L_out + W - 1, L_out, W, F, _p(g_hi), _p(g_lo),
+                                              _p(w_op), _p(dx), _stream()),
+          "bpb_input_conv_dgrad_tc")
+
+
 def heads_fwd(act, pw, pb, cw, cb, logits, gap, logcounts):
     lib = _lib.load()
     a_hi, a_lo = _planes(act)

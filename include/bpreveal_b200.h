@@ -158,6 +158,19 @@ int bpb_heads_fwd(int B, int L_in, int L_out, int W, int Fw, int F, int T, int H
                   const bpb_bf16* act_hi, const bpb_bf16* act_lo, const float* pw,
                   const float* pb, const float* cw, const float* cb, float* logits, float* gap,
                   float* logcounts, void* stream);
+/* Data gradient of the input convolution wrt the one-hot input (attribution only; TF gradient of
+ * models.py:85-90) on the same window-GEMM kernel as bpb_heads_fwd_tc, as a 'full' correlation:
+ *   dx[b,t,c] = sum_j sum_n gz[b,t-j,n] w[j][c][n]      dx fp32 [B][L_in][4], gz bf16 [B][L_out][F]
+ * w_op (bpb_input_dgrad_wop_elems elements) is the tap-reversed, transposed filter laid out by
+ * bpb_prep_input_dgrad_weights from the Keras kernel w [W][4][Fw].  _supported returns 0 when the
+ * geometry fits shared memory; otherwise use bpb_input_conv_dgrad (CUDA cores, fp32 weights). */
+long long bpb_input_dgrad_wop_elems(int W, int F, int planes);
+int bpb_input_conv_dgrad_tc_supported(int W, int F, int planes);
+int bpb_prep_input_dgrad_weights(int W, int Fw, int F, const float* w, bpb_bf16* w_op, int planes,
+                                 void* stream);
+int bpb_input_conv_dgrad_tc(int B, int L_in, int L_out, int W, int F, const bpb_bf16* gz_hi,
+                            const bpb_bf16* gz_lo, const bpb_bf16* w_op, float* dx, void* stream);
+
 /* The same forward as ONE tcgen05 GEMM (N = T + H padded to 16; the counts heads are extra output
  * columns with weights on tap 0 only; gap is not materialised).  w_op comes from
  * bpb_prep_heads_fwd_weights (an opaque bf16 image of the kernel's shared-memory operand:
