@@ -148,13 +148,15 @@ def gpu_extras(net_cfg, dev, rank):
     for label, precise in (("pisa_bases_per_s", False), ("pisa_bases_per_s_precise", True)):
         pn = SoloNet(NetConfig(precise=precise, **net_cfg), dev)
         pn.load_state(net.state())
-        Q, n = 6, 20
+        Q, n = 24, 20
         interpret.pisa_batch(pn, x_dev[:Q], headID=0, taskID=0, numShuffles=n)
         torch.cuda.synchronize()
         e0.record()
-        reps = 10
+        reps = 6
+        nq = x_dev.shape[0] // Q
         for r in range(reps):
-            interpret.pisa_batch(pn, x_dev[r * Q:(r + 1) * Q], headID=0, taskID=0, numShuffles=n)
+            o = (r % nq) * Q
+            interpret.pisa_batch(pn, x_dev[o:o + Q], headID=0, taskID=0, numShuffles=n)
         e1.record()
         torch.cuda.synchronize()
         out[label] = reps * Q / (e0.elapsed_time(e1) / 1e3)
@@ -185,7 +187,7 @@ def gpu_extras(net_cfg, dev, rank):
     out["c4_config"] = "C4: F=512, 11 dilated layers, 25/75, 9286->1000 bp, batch 16, bf16"
     del wide
     torch.cuda.empty_cache()
-    out["pisa_config"] = "C5: C1 model, 20 row-shuffled references per base, 6 bases per CUDA-graph replay"
+    out["pisa_config"] = "C5: C1 model, 20 row-shuffled references per base, 24 bases per CUDA-graph replay"
     return out
 
 
