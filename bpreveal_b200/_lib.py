@@ -127,6 +127,8 @@ SIGNATURES = {
                            [C.POINTER(PrepTable), c_void_p]),
     "bpb_prep_conv3_weights": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                        c_void_p]),
+    "bpb_onehot_encode": (c_int, [c_ll] + [c_void_p] * 4),
+    "bpb_logits_to_profile": (c_int, [c_int] * 4 + [c_void_p] * 5),
     "bpb_slide_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p]),
     "bpb_slide_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -511,6 +511,54 @@ adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Prediction-side helpers.
+// utils.py:420-486 oneHotEncode: ASCII bases -> [n][4] uint8, columns A C G T, upper or lower
+// case, anything else all-zero (allowN) -- the caller learns how many bytes were not ACGT.
+// utils.py:523-572 logitsToProfile: softmax over the L x T_h block of one head times
+// exp(logcounts), one block per (sequence, head).
+// ------------------------------------------------------------------------------------------
+__global__ void onehot_encode_kernel(long long n, const uint8_t* __restrict__ seq,
+                                     uint32_t* __restrict__ out, unsigned long long* n_other) {
+  unsigned other = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint8_t c = seq[i] & 0xDF;  // fold case
+    uint32_t w = 0;
+    if (c == 'A') w = 0x00000001u;
+    else if (c == 'C') w = 0x00000100u;
+    else if (c == 'G') w = 0x00010000u;
+    else if (c == 'T') w = 0x01000000u;
+    else ++other;
+    out[i] = w;  // four uint8 {A, C, G, T}, little endian
+  }
+  if (n_other != nullptr && other) atomicAdd(n_other, static_cast<unsigned long long>(other));
+}
+
+__global__ void __launch_bounds__(256)
+logits_to_profile_kernel(int L, int T, int H, const int* __restrict__ task_off,
+                         const float* __restrict__ logits, const float* __restrict__ logcounts,
+                         float* __restrict__ profile) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int k0 = task_off[h], Th = task_off[h + 1] - k0;
+  const float* lg = logits + static_cast<size_t>(b) * L * T + k0;
+  float* pr = profile + static_cast<size_t>(b) * L * T + k0;
+  const int n = L * Th;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, lg[(i / Th) * T + (i % Th)]);
+  mx = block_reduce(mx, MaxF(), scratch, -INFINITY);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) se += expf(lg[(i / Th) * T + (i % Th)] - mx);
+  se = block_reduce(se, SumF(), scratch, 0.f);
+  const float scale = expf(logcounts[b * H + h]) / se;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int idx = (i / Th) * T + (i % Th);
+    pr[idx] = expf(lg[idx] - mx) * scale;
+  }
+}
+
 // fp32 Keras kernels [layers][3][Fw][Fw] (tap, cin, cout) -> bf16 operand layouts
 // [layers][planes][3][F][F]
 __global__ void prep_conv3_kernel(int n_layers, int Fw, int F, const float* __restrict__ w,
@@ -772,6 +820,32 @@ extern "C" int bpb_adam_prep_step(long long n, float* param, const float* grad, 
   if (n <= 0) return 0;
   adam_prep_kernel<<<ew_blocks(n), 256, 0, stream>>>(n, param, grad, m, v, state, beta1, beta2, eps,
                                                      grad_scale, t);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+extern "C" int bpb_onehot_encode(long long n, const unsigned char* seq, unsigned char* onehot,
+                                 unsigned long long* n_other, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(seq && onehot, "bpb_onehot_encode: NULL argument");
+  BP_REQUIRE((reinterpret_cast<uintptr_t>(onehot) & 3) == 0, "bpb_onehot_encode: onehot must be 4-byte aligned");
+  if (n <= 0) return 0;
+  if (n_other) BP_CHECK_CUDA(cudaMemsetAsync(n_other, 0, sizeof(unsigned long long), stream));
+  onehot_encode_kernel<<<ew_blocks(n), 256, 0, stream>>>(n, seq, reinterpret_cast<uint32_t*>(onehot),
+                                                         n_other);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bpb_logits_to_profile(int B, int L, int T, int H, const int* task_off,
+                                     const float* logits, const float* logcounts, float* profile,
+                                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(task_off && logits && logcounts && profile, "bpb_logits_to_profile: NULL argument");
+  BP_REQUIRE(B > 0 && L > 0 && T > 0 && H > 0, "bpb_logits_to_profile: bad sizes");
+  dim3 grid(B, H);
+  logits_to_profile_kernel<<<grid, 256, 0, stream>>>(L, T, H, task_off, logits, logcounts, profile);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -396,6 +396,33 @@ def prep_conv3_weights(w, F, fwd, bwd, precise):
                                      1 if precise else 0, _stream()), "bpb_prep_conv3_weights")
 
 
+def onehot_encode(seq_bytes, allowN=False):
+    """uint8 tensor of ASCII bases (any shape, on the device) -> (..., 4) uint8 one-hot
+    (utils.oneHotEncode); raises like the reference when allowN is False and a byte is not ACGT."""
+    seq_bytes = seq_bytes.contiguous()
+    out = torch.empty(seq_bytes.shape + (4,), dtype=torch.uint8, device=seq_bytes.device)
+    cnt = torch.zeros((1,), dtype=torch.int64, device=seq_bytes.device)
+    check(_lib.load().bpb_onehot_encode(seq_bytes.numel(), _p(seq_bytes), _p(out), _p(cnt), _stream()),
+          "bpb_onehot_encode")
+    if not allowN and int(cnt.item()) != 0:
+        raise AssertionError("Sequence contains unrecognized nucleotides. Maybe your sequence "
+                             "contains 'N'?")
+    return out
+
+
+def logits_to_profile(task_off, logits, logcounts, profile=None):
+    """(B, L, T) logits, (B, H) log-counts -> (B, L, T) predicted profiles (utils.logitsToProfile
+    applied to every head of every sequence)."""
+    B, L, T = logits.shape
+    H = logcounts.shape[1]
+    if profile is None:
+        profile = torch.empty_like(logits)
+    check(_lib.load().bpb_logits_to_profile(B, L, T, H, _p(task_off), _p(logits.contiguous()),
+                                            _p(logcounts.contiguous()), _p(profile), _stream()),
+          "bpb_logits_to_profile")
+    return profile
+
+
 def slide_u8(src, dst, row_idx, col_idx):
     lib = _lib.load()
     rows, src_cols, depth = src.shape

@@ -299,6 +299,17 @@ int bpb_adam_prep_step(long long n, float* param, const float* grad, float* m, f
 int bpb_prep_conv3_weights(int n_layers, int Fw, int F, const float* w, bpb_bf16* fwd,
                            bpb_bf16* bwd, int precise, void* stream);
 
+/* Prediction-side helpers (device pointers).
+ * bpb_onehot_encode: ASCII bases seq[n] -> onehot [n][4] uint8, columns A C G T, either case,
+ *   anything else all-zero (utils.py:420-486 with allowN); *n_other (device, nullable) receives the
+ *   number of bytes that were not ACGT, so the caller can enforce allowN = False.
+ * bpb_logits_to_profile: profile[b,:,tasks of head h] = softmax over the L x T_h block of the
+ *   head's logits times exp(logcounts[b,h]) (utils.py:523-572, for a whole batch). */
+int bpb_onehot_encode(long long n, const unsigned char* seq, unsigned char* onehot,
+                      unsigned long long* n_other, void* stream);
+int bpb_logits_to_profile(int B, int L, int T, int H, const int* task_off, const float* logits,
+                          const float* logcounts, float* profile, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Epoch jitter / shuffle gather (generators.py:129-138, libslide.c:44-91):
  *   dst[row_idx[r]] = src[r, col_idx[r] : col_idx[r] + dst_cols]

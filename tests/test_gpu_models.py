@@ -320,3 +320,38 @@ def test_train_model_with_the_reference_callback_set(dev, tmp_path):
     assert m2.predict(x[:2])[0].shape == (2, 20, 2)
     name = training.saveHistory(hist, {"settings": {"output-prefix": prefix}, "heads": heads})
     assert json.load(open(name, encoding="utf-8"))["counts-loss-weight"]["a"][0] == 2.0
+
+
+def test_prediction_side_kernels(dev):
+    """bpb_onehot_encode == utils.oneHotEncode (docstring matrix utils.py:456-464, case folding, N ->
+    zeros, allowN = False raises) and bpb_logits_to_profile == utils.logitsToProfile per head."""
+    from bpreveal_b200 import ops
+    seq = "ACGTTTacgtNnRx"
+    b = torch.tensor(list(seq.encode("ascii")), dtype=torch.uint8, device=dev)
+    want = np.array([[c.upper() == a for a in "ACGT"] for c in seq], dtype=np.uint8)
+    got = ops.onehot_encode(b, allowN=True).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[:6], [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1],
+                                    [0, 0, 0, 1], [0, 0, 0, 1]])
+    with pytest.raises(AssertionError):
+        ops.onehot_encode(b)
+    ops.onehot_encode(b[:10])  # pure ACGT passes the strict check
+    big = torch.randint(0, 256, (3, 1000), dtype=torch.uint8, device=dev)
+    gb = ops.onehot_encode(big, allowN=True).cpu().numpy()
+    up = np.char.upper(big.cpu().numpy().astype(np.uint8).view("S1"))
+    for i, a in enumerate(b"ACGT"):
+        assert np.array_equal(gb[..., i], (up == bytes([a])).astype(np.uint8))
+    # logitsToProfile for a batch with two heads of 2 and 1 tasks
+    g = torch.Generator().manual_seed(1)
+    logits = (torch.randn((5, 37, 3), generator=g) * 3).to(dev)
+    lc = torch.randn((5, 2), generator=g).to(dev)
+    toff = torch.tensor([0, 2, 3], dtype=torch.int32, device=dev)
+    prof = ops.logits_to_profile(toff, logits, lc).cpu().numpy().astype(np.float64)
+    lg, lcn = logits.cpu().numpy().astype(np.float64), lc.cpu().numpy().astype(np.float64)
+    for bi in range(5):
+        for h, (k0, k1) in enumerate(((0, 2), (2, 3))):
+            blk = lg[bi, :, k0:k1]
+            e = np.exp(blk - blk.max())
+            ref = e / e.sum() * np.exp(lcn[bi, h])
+            assert np.allclose(prof[bi, :, k0:k1], ref, rtol=2e-5, atol=1e-9)
+            assert np.isclose(prof[bi, :, k0:k1].sum(), np.exp(lcn[bi, h]), rtol=1e-5)
