@@ -305,7 +305,7 @@ def main():
     lib = __import__("bpreveal_b200._lib", fromlist=["_lib"])
     orig_check = ops.check
 
-    kernels_per_call = {"bpb_wgrad3_tc": 2, "bpb_wgrad3_multi": 2, "bpb_input_conv_wgrad": 2, "bpb_heads_fwd": 2,
+    kernels_per_call = {"bpb_wgrad3_tc": 2, "bpb_wgrad3_multi": 2, "bpb_wgrad_tower_input": 2, "bpb_input_conv_wgrad": 2, "bpb_heads_fwd": 2,
                         "bpb_heads_wgrad_tc": 2, "bpb_heads_pack_grad": 2, "bpb_heads_fwd_tc": 2}
 
     def counting_check(rc, what):
@@ -352,7 +352,7 @@ def main():
     if rank == 0:
         calls = []
         real = {}
-        names = ["conv3", "wgrad3", "wgrad3_multi", "onehot_expand", "input_conv_fwd", "input_conv_wgrad",
+        names = ["conv3", "wgrad3", "wgrad3_multi", "wgrad_tower_input", "onehot_expand", "input_conv_fwd", "input_conv_wgrad",
                  "heads_fwd", "heads_fwd_tc", "heads_wgrad", "heads_dgrad", "heads_pack_grad",
                  "loss_fwd_bwd", "loss_fwd_bwd_pack", "prep_heads_fwd_weights",
                  "adam_step", "adam_prep_step", "prep_conv3_weights", "prep_input_conv_weights",

@@ -35,7 +35,8 @@ constexpr int kWgMaxJobs = 12;
 struct WgradKParams {
   int B, NC;
   int n_passes, pa_bits, pg_bits, db_mask;  // pass i: A plane (pa_bits >> i) & 1, G plane likewise
-  int n_units, UG, n_groups, n_ntiles, n_items;
+  int n_units, UG, n_groups, n_ntiles, n_items;  // n_units = the largest job's
+  int n_units_j[kWgMaxJobs];  // units (tap x chunk) of job j; jobs may differ when n_groups == 1
   int stages, stage_bytes;
   int Ncols;   // columns of the result (NT * n_ntiles)
   int n_jobs;
@@ -47,9 +48,9 @@ struct WgradKParams {
   // STRIP staging of the A operand (window gradients over a 16-byte-per-position tensor): the raw
   // strip of 128 + 8*n_units positions is copied once per position tile and read through
   // NON-swizzled MN-major descriptors (LBO 128 B along K, SBO 16 B along MN), unit u at +128*u B.
-  int strip, strip_bytes;
-  long long a_batch_bytes;
-  const uint8_t* a_base;
+  int strip[kWgMaxJobs], strip_bytes[kWgMaxJobs];
+  long long a_batch_bytes[kWgMaxJobs];
+  const uint8_t* a_base[kWgMaxJobs];
   long long ws_off[kWgMaxJobs];  // float offset of the job's [ksplit][(n_units*64+1)*Ncols] partials
   float* ws;
   unsigned* dbg;
@@ -102,8 +103,10 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   const int split = local / p.n_items;
   const int grp = item / p.n_ntiles;
   const int nt = item % p.n_ntiles;
+  const int n_units = p.n_units_j[job];
+  const bool strip = p.strip[job] != 0;
   const int u0 = grp * p.UG;
-  const int nu = min(p.UG, p.n_units - u0);
+  const int nu = min(p.UG, n_units - u0);
   const bool do_db = (grp == 0);
   const int kblocks = p.B * tiles_per_seq;
   const int my_kb = (kblocks - split + ksplit - 1) / ksplit;  // split < ksplit <= kblocks
@@ -148,7 +151,7 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
         const int t0 = (kb % tiles_per_seq) * 128;
         mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x1100 + stage, v);
         mbar_expect_tx(&full[stage],
-                       p.strip ? static_cast<uint32_t>(NSUB * kWgTile + p.strip_bytes)
+                       strip ? static_cast<uint32_t>(NSUB * kWgTile + p.strip_bytes[job])
                        : halo  ? static_cast<uint32_t>(NSUB * kWgTile + p.halo_bytes[job])
                                : static_cast<uint32_t>((NSUB + nu) * kWgTile));
         uint8_t* dst = ring + stage * stage_bytes;
@@ -156,11 +159,11 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
         const CUtensorMap* ma = ((p.pa_bits >> pass) & 1) ? tmA1 : tmA0;
         for (int s = 0; s < NSUB; ++s)
           tma_load_3d(mg, dst + s * kWgTile, &full[stage], nt * NT + s * 64, t0, b);
-        if (p.strip) {
+        if (strip) {
           bulk_load_1d(dst + NSUB * kWgTile,
-                       p.a_base + static_cast<size_t>(b) * p.a_batch_bytes +
+                       p.a_base[job] + static_cast<size_t>(b) * p.a_batch_bytes[job] +
                            static_cast<size_t>(t0) * 16,
-                       static_cast<uint32_t>(p.strip_bytes), &full[stage]);
+                       static_cast<uint32_t>(p.strip_bytes[job]), &full[stage]);
         } else if (halo) {
           // rows t0 .. t0 + 127 + (n_taps-1)*dil of the single channel chunk: every tap at once
           tma_load_3d(ma, dst + NSUB * kWgTile, &full[stage], 0, t0, b);
@@ -189,14 +192,14 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
       uint32_t a_off[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        a_off[i] = p.strip ? (NSUB * kWgTile + (u0 + i) * 128) >> 4
+        a_off[i] = strip ? (NSUB * kWgTile + (u0 + i) * 128) >> 4
                   : halo  ? (NSUB * kWgTile + (u0 + i) * dil * 128) >> 4
                           : ((NSUB + i) * kWgTile) >> 4;
       // STRIP: no swizzle, LBO = 128 B (8 positions along K), SBO = 16 B (8 elements along MN),
       // K advances by 16 positions = 256 B per MMA
-      const uint32_t a_lbo = p.strip ? ((128u >> 4) << 16) : lbo_bits;
-      const uint32_t a_hi = p.strip ? ((16u >> 4) | (1u << 14)) : DHI;
-      const uint32_t a_kstep = p.strip ? (256u >> 4) : 128u;
+      const uint32_t a_lbo = strip ? ((128u >> 4) << 16) : lbo_bits;
+      const uint32_t a_hi = strip ? ((16u >> 4) | (1u << 14)) : DHI;
+      const uint32_t a_kstep = strip ? (256u >> 4) : 128u;
       for (int v = 0; v < visits; ++v) {
         const int pass = v % p.n_passes;
         mbar_wait_wd(&full[stage], phase, p.dbg, 0x1500 + stage, v);
@@ -236,7 +239,7 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
     mbar_wait_wd(acc_full, 0, p.dbg, 0x1800, 0);
     tc_fence_after();
     if (threadIdx.x == 64) WG_STAMP(24);
-    const size_t rows = static_cast<size_t>(p.n_units) * 64;
+    const size_t rows = static_cast<size_t>(n_units) * 64;
     float* wsp = p.ws + p.ws_off[job] + static_cast<size_t>(split) * (rows + 1) * p.Ncols;
     for (int i = 0; i < nu; ++i) {
       const int u = u0 + i;
@@ -324,10 +327,7 @@ struct WgradReduceJobs {
   int n_jobs;
   int ksplit[kWgMaxJobs];
   long long ws_off[kWgMaxJobs];
-  float* o0[kWgMaxJobs];
-  float* o1[kWgMaxJobs];
-  float* o2[kWgMaxJobs];
-  WgradScatter sc;  // shared geometry; o0/o1/o2 come from the per-job arrays
+  WgradScatter sc[kWgMaxJobs];  // per-job geometry and outputs
 };
 
 // out[i] = sum_s ws[s][i] in a fixed order (deterministic).  One block owns 32 consecutive outputs
@@ -339,10 +339,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws_all, const WgradReduceJobs jobs
   const int job = blockIdx.y;
   const float* ws = ws_all + jobs.ws_off[job];
   const int ksplit = jobs.ksplit[job];
-  WgradScatter sc = jobs.sc;
-  sc.o0 = jobs.o0[job];
-  sc.o1 = jobs.o1[job];
-  sc.o2 = jobs.o2[job];
+  const WgradScatter sc = jobs.sc[job];
   const long long n = (static_cast<long long>(sc.rows) + 1) * sc.cols;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = static_cast<long long>(blockIdx.x) * 32 + lane;
@@ -389,6 +386,7 @@ struct WgradDesc {
 
 struct WgradPlan {
   int NT, UG, n_units, n_groups, n_ntiles, n_items, stages;
+  int n_units_j[kWgMaxJobs];
   int ksplit[kWgMaxJobs];
   int halo[kWgMaxJobs], halo_rows[kWgMaxJobs];
   long long ws_off[kWgMaxJobs];
@@ -396,34 +394,48 @@ struct WgradPlan {
   int grid;
 };
 
-// Jobs must agree on n_units and Ncols (the same layer shape); rows / dilation may differ.
-static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_in, int n_units,
-                       int Ncols, WgradPlan* pl, bool strip = false) {
+// Jobs must agree on Ncols; rows / dilation may differ, and so may the unit count (and the STRIP
+// staging of the A operand) as long as every job fits one accumulator group.
+static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_in,
+                       const int* n_units_j, int Ncols, WgradPlan* pl,
+                       const bool* strip_j = nullptr) {
   if (n_jobs < 1 || n_jobs > kWgMaxJobs) return false;
   const int NT = (Ncols % 256 == 0) ? 256 : (Ncols % 128 == 0 ? 128 : 64);
   pl->NT = NT;
+  int n_units = 0;
+  bool uniform = true;
+  for (int j = 0; j < n_jobs; ++j) {
+    pl->n_units_j[j] = n_units_j[j];
+    if (n_units_j[j] > n_units) n_units = n_units_j[j];
+    if (n_units_j[j] != n_units_j[0]) uniform = false;
+  }
   pl->n_units = n_units;
   int ug = 512 / NT - 1;  // one accumulator slot is reserved for the bias-gradient unit
   if (ug > n_units) ug = n_units;
   if (ug > 4) ug = 4;
   pl->UG = ug;
   pl->n_groups = (n_units + ug - 1) / ug;
+  if (!uniform && pl->n_groups != 1) return false;
   pl->n_ntiles = Ncols / NT;
   pl->n_items = pl->n_groups * pl->n_ntiles;
   const int sms = sm_count();
   if (sms <= 0) return false;
   // split-K factors: the SMs are shared between the jobs in proportion to their position tiles
-  long long total_kb = 0;
+  // (a STRIP-staged job is bound by its MMAs -- units + 1 groups of 8 per position tile -- where a
+  // tower job is bound by HBM: measured ~1.7k against ~1.4k cycles per tile, hence the weight)
+  double total_kb = 0;
   int kb[kWgMaxJobs];
+  double cost[kWgMaxJobs];
   for (int j = 0; j < n_jobs; ++j) {
     kb[j] = B * ((rows[j] + 127) / 128);
-    total_kb += kb[j];
+    cost[j] = kb[j] * ((strip_j && strip_j[j] && n_jobs > 1) ? 1.25 : 1.0);
+    total_kb += cost[j];
   }
   int budget = sms / pl->n_items;  // splits available in total
   if (budget < n_jobs) budget = n_jobs;
   int used = 0;
   for (int j = 0; j < n_jobs; ++j) {
-    int ks = static_cast<int>(static_cast<long long>(budget) * kb[j] / total_kb);
+    int ks = static_cast<int>(budget * cost[j] / total_kb);
     if (ks < 1) ks = 1;
     if (ks > kb[j]) ks = kb[j];
     pl->ksplit[j] = ks;
@@ -434,7 +446,7 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
     int best = -1;
     double best_load = 0;
     for (int j = 0; j < n_jobs; ++j) {
-      const double load = static_cast<double>(kb[j]) / pl->ksplit[j];
+      const double load = cost[j] / pl->ksplit[j];
       if (pl->ksplit[j] < kb[j] && load > best_load) { best_load = load; best = j; }
     }
     if (best < 0) break;
@@ -448,12 +460,13 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
     const int hr = halo_rows_in ? halo_rows_in[j] : 0;
     pl->halo[j] = hr > 0 && hr <= 256 && pl->n_groups == 1;
     pl->halo_rows[j] = pl->halo[j] ? hr : 0;
-    const size_t sb = (strip && pl->n_groups == 1)
+    const size_t sb = (strip_j && strip_j[j] && pl->n_groups == 1)
                           ? static_cast<size_t>(NT / 64) * kWgTile +
-                                ((128 + 8 * n_units) * 16 + 1023) / 1024 * 1024
+                                ((128 + 8 * n_units_j[j]) * 16 + 1023) / 1024 * 1024
                       : pl->halo[j]
                           ? static_cast<size_t>(NT / 64) * kWgTile + (hr * 128 + 1023) / 1024 * 1024
-                          : static_cast<size_t>(NT / 64 + ug) * kWgTile;
+                          : static_cast<size_t>(NT / 64 + (n_units_j[j] < ug ? n_units_j[j] : ug)) *
+                                kWgTile;
     if (sb > stage) stage = sb;
   }
   pl->stage_bytes = stage;
@@ -465,9 +478,9 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
   if (stages < 1) return false;
   pl->stages = stages;
   pl->smem_bytes = fixed + stages * stage;
-  const long long per_split = (static_cast<long long>(n_units) * 64 + 1) * Ncols;
   long long off = 0;
   for (int j = 0; j < n_jobs; ++j) {
+    const long long per_split = (static_cast<long long>(n_units_j[j]) * 64 + 1) * Ncols;
     pl->ws_off[j] = off;
     off += per_split * pl->ksplit[j];
   }
@@ -489,16 +502,18 @@ static int launch_wgrad(const WgradMaps& maps, const WgradKParams& kp, size_t sm
   return 0;
 }
 
-// All descs share shape class (n_taps, NC, Ncols, passes, scatter mode); d[0].ws is the workspace.
+// All descs share Ncols, batch and passes; the unit structure (taps x chunks, STRIP staging) and the
+// scatter of the result may differ per job; d[0].ws is the workspace.
 static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
   const WgradDesc& d0 = d[0];
   BP_REQUIRE(n_jobs >= 1 && n_jobs <= kWgMaxJobs, "%s: %d jobs (1..%d supported)", d0.who, n_jobs,
              kWgMaxJobs);
   int rows[kWgMaxJobs], halo_rows[kWgMaxJobs];
   for (int j = 0; j < n_jobs; ++j) {
-    BP_REQUIRE(d[j].n_taps == d0.n_taps && d[j].NC == d0.NC && d[j].Ncols == d0.Ncols &&
-                   d[j].B == d0.B && d[j].n_passes == d0.n_passes,
-               "%s: every job of one launch must have the same layer shape", d0.who);
+    BP_REQUIRE(d[j].Ncols == d0.Ncols && d[j].B == d0.B && d[j].n_passes == d0.n_passes &&
+                   d[j].pa_bits == d0.pa_bits && d[j].pg_bits == d0.pg_bits &&
+                   d[j].db_mask == d0.db_mask,
+               "%s: every job of one launch must have the same columns, batch and passes", d0.who);
     rows[j] = d[j].rows;
     halo_rows[j] = (d[j].allow_halo && d[j].NC == 1 && d[j].n_taps > 1)
                        ? 128 + (d[j].n_taps - 1) * d[j].dil : 0;
@@ -507,10 +522,18 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
     const char* e = getenv("BPB_STRIP");
     return !(e && e[0] == '0');
   }();
-  const bool want_strip = strip_enabled && n_jobs == 1 && d0.allow_strip && d0.n_taps == 1 &&
-                          d0.a_row_stride_bytes == 16 && d0.a_ptr[1] == nullptr && d0.NC <= 4;
+  bool want_strip[kWgMaxJobs];
+  int units[kWgMaxJobs];
+  for (int j = 0; j < n_jobs; ++j) {
+    want_strip[j] = strip_enabled && d[j].allow_strip && d[j].n_taps == 1 &&
+                    d[j].a_row_stride_bytes == 16 && d[j].a_ptr[1] == nullptr && d[j].NC <= 4;
+    units[j] = d[j].n_taps * d[j].NC;
+    // a job that is not STRIP-staged is addressed through the shared (taps, chunks) decoding
+    BP_REQUIRE(want_strip[j] || (d[j].n_taps == d0.n_taps && d[j].NC == d0.NC) || n_jobs == 1,
+               "%s: jobs of one launch must share the tap structure unless STRIP-staged", d0.who);
+  }
   WgradPlan pl;
-  BP_REQUIRE(plan_wgrad(n_jobs, d0.B, rows, halo_rows, d0.n_taps * d0.NC, d0.Ncols, &pl, want_strip),
+  BP_REQUIRE(plan_wgrad(n_jobs, d0.B, rows, halo_rows, units, d0.Ncols, &pl, want_strip),
              "%s: cannot plan (no device?)", d0.who);
   BP_REQUIRE(static_cast<size_t>(d0.ws_bytes) >= pl.ws_bytes, "%s: workspace too small (%lld < %zu)",
              d0.who, d0.ws_bytes, pl.ws_bytes);
@@ -530,12 +553,6 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
   kp.stage_bytes = static_cast<int>(pl.stage_bytes);
   kp.Ncols = d0.Ncols;
   kp.n_jobs = n_jobs;
-  if (want_strip && pl.n_groups == 1) {
-    kp.strip = 1;
-    kp.strip_bytes = (128 + 8 * pl.n_units) * 16;
-    kp.a_batch_bytes = static_cast<long long>(d0.a_batch_stride_bytes);
-    kp.a_base = static_cast<const uint8_t*>(d0.a_ptr[0]);
-  }
   kp.ws = d0.ws;
   kp.dbg = debug_buffer();
 
@@ -543,9 +560,7 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
   memset(&maps, 0, sizeof(maps));
   WgradReduceJobs rj{};
   rj.n_jobs = n_jobs;
-  rj.sc = d0.sc;
-  rj.sc.rows = pl.n_units * 64;
-  rj.sc.cols = d0.Ncols;
+  long long n_max = 0;
   int cta = 0;
   for (int j = 0; j < n_jobs; ++j) {
     kp.cta_begin[j] = cta;
@@ -555,11 +570,20 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
     kp.halo[j] = pl.halo[j];
     kp.halo_bytes[j] = pl.halo_rows[j] * 128;
     kp.ws_off[j] = pl.ws_off[j];
+    kp.n_units_j[j] = units[j];
+    if (want_strip[j] && pl.n_groups == 1) {
+      kp.strip[j] = 1;
+      kp.strip_bytes[j] = (128 + 8 * units[j]) * 16;
+      kp.a_batch_bytes[j] = static_cast<long long>(d[j].a_batch_stride_bytes);
+      kp.a_base[j] = static_cast<const uint8_t*>(d[j].a_ptr[0]);
+    }
     rj.ksplit[j] = pl.ksplit[j];
     rj.ws_off[j] = pl.ws_off[j];
-    rj.o0[j] = d[j].sc.o0;
-    rj.o1[j] = d[j].sc.o1;
-    rj.o2[j] = d[j].sc.o2;
+    rj.sc[j] = d[j].sc;
+    rj.sc[j].rows = units[j] * 64;
+    rj.sc[j].cols = d[j].Ncols;
+    const long long n_j = (static_cast<long long>(rj.sc[j].rows) + 1) * rj.sc[j].cols;
+    if (n_j > n_max) n_max = n_j;
     for (int pl_i = 0; pl_i < 2; ++pl_i) {
       if (d[j].a_ptr[pl_i] &&
           !make_tmap_3d_strided(&maps.A[pl_i][j], d[j].a_ptr[pl_i], d[j].a_inner, d[j].a_rows,
@@ -579,8 +603,7 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
   else rc = launch_wgrad<256>(maps, kp, pl.smem_bytes, pl.grid, stream);
   if (rc) return rc;
 
-  const long long n = (static_cast<long long>(rj.sc.rows) + 1) * rj.sc.cols;
-  dim3 rgrid(static_cast<unsigned>((n + 31) / 32), static_cast<unsigned>(n_jobs));
+  dim3 rgrid(static_cast<unsigned>((n_max + 31) / 32), static_cast<unsigned>(n_jobs));
   wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(d0.ws, rj);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -588,14 +611,22 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
 
 static int wgrad_run(const WgradDesc& d, cudaStream_t stream) { return wgrad_run(&d, 1, stream); }
 
-static long long wgrad_ws_bytes(const char* who, int n_jobs, int B, const int* rows, int n_units,
-                                int Ncols) {
+static long long wgrad_ws_bytes(const char* who, int n_jobs, int B, const int* rows,
+                                const int* n_units_j, int Ncols) {
   WgradPlan pl;
-  if (Ncols <= 0 || Ncols % 64 != 0 || !plan_wgrad(n_jobs, B, rows, nullptr, n_units, Ncols, &pl)) {
+  if (Ncols <= 0 || Ncols % 64 != 0 || n_jobs < 1 || n_jobs > kWgMaxJobs ||
+      !plan_wgrad(n_jobs, B, rows, nullptr, n_units_j, Ncols, &pl)) {
     set_error("%s: unsupported geometry or no CUDA device", who);
     return -1;
   }
   return static_cast<long long>(pl.ws_bytes);
+}
+
+static long long wgrad_ws_bytes(const char* who, int n_jobs, int B, const int* rows, int n_units,
+                                int Ncols) {
+  int units[kWgMaxJobs];
+  for (int j = 0; j < kWgMaxJobs; ++j) units[j] = n_units;
+  return wgrad_ws_bytes(who, n_jobs, B, rows, units, Ncols);
 }
 
 static int window_kc(int W, int C) { return (W * C + 63) / 64; }
@@ -683,16 +714,12 @@ extern "C" long long bpb_input_conv_wgrad_ws_bytes(int B, int L_out, int W, int 
   return bp::wgrad_ws_bytes("bpb_input_conv_wgrad_ws_bytes", 1, B, &L_out, bp::window_kc(W, 8), F);
 }
 
-extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, int F,
-                                    const bpb_bf16* x8, const bpb_bf16* gz_hi,
-                                    const bpb_bf16* gz_lo, float* dw, float* db, float* ws,
-                                    long long ws_bytes, void* stream_) {
+static bp::WgradDesc input_conv_wgrad_desc(const char* who, int B, int L_in, int L_out, int W, int Fw,
+                                           int F, const bpb_bf16* x8, const bpb_bf16* gz_hi,
+                                           const bpb_bf16* gz_lo, float* dw, float* db) {
   using namespace bp;
-  BP_REQUIRE(x8 && gz_hi && dw && ws, "bpb_input_conv_wgrad: NULL argument");
-  BP_REQUIRE(F > 0 && F % 64 == 0 && Fw <= F && L_out == L_in - W + 1,
-             "bpb_input_conv_wgrad: bad geometry");
   WgradDesc d{};
-  d.who = "bpb_input_conv_wgrad";
+  d.who = who;
   d.B = B;
   d.rows = L_out;
   d.n_taps = 1;
@@ -716,14 +743,72 @@ extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, i
   d.pg_bits = 0b10;
   d.db_mask = 0b11;
   d.allow_strip = true;  // x8 carries the spare tail (bpb_x8_elems)
-  d.ws = ws;
-  d.ws_bytes = ws_bytes;
   d.sc.mode = 1;
   d.sc.W = W;
   d.sc.Fw = Fw;
   d.sc.o0 = dw;
   d.sc.o1 = db;
+  return d;
+}
+
+extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, int F,
+                                    const bpb_bf16* x8, const bpb_bf16* gz_hi,
+                                    const bpb_bf16* gz_lo, float* dw, float* db, float* ws,
+                                    long long ws_bytes, void* stream_) {
+  using namespace bp;
+  BP_REQUIRE(x8 && gz_hi && dw && ws, "bpb_input_conv_wgrad: NULL argument");
+  BP_REQUIRE(F > 0 && F % 64 == 0 && Fw <= F && L_out == L_in - W + 1,
+             "bpb_input_conv_wgrad: bad geometry");
+  WgradDesc d = input_conv_wgrad_desc("bpb_input_conv_wgrad", B, L_in, L_out, W, Fw, F, x8, gz_hi,
+                                      gz_lo, dw, db);
+  d.ws = ws;
+  d.ws_bytes = ws_bytes;
   return wgrad_run(d, static_cast<cudaStream_t>(stream_));
+}
+
+// The tower layers of a step AND the input convolution in one launch (bf16 path; the jobs differ
+// in their unit structure: 3 tap units HALO/SLAB-staged vs ceil(8W/64) window units STRIP-staged).
+extern "C" long long bpb_wgrad_tower_input_ws_bytes(int n_layers, int B, const int* L_out, int F,
+                                                    int L_out0, int W) {
+  using namespace bp;
+  if (n_layers < 1 || n_layers + 1 > kWgMaxJobs || L_out == nullptr || F <= 0 || F % 64 != 0) {
+    set_error("bpb_wgrad_tower_input_ws_bytes: 1..%d layers, F a multiple of 64", kWgMaxJobs - 1);
+    return -1;
+  }
+  int rows[kWgMaxJobs], units[kWgMaxJobs];
+  for (int j = 0; j < n_layers; ++j) {
+    rows[j] = L_out[j];
+    units[j] = 3 * (F / 64);
+  }
+  rows[n_layers] = L_out0;
+  units[n_layers] = window_kc(W, 8);
+  return wgrad_ws_bytes("bpb_wgrad_tower_input_ws_bytes", n_layers + 1, B, rows, units, F);
+}
+
+extern "C" int bpb_wgrad_tower_input(const bpb_wgrad3_args* layers, int n_layers, int L_in0,
+                                     int L_out0, int W, int Fw, const bpb_bf16* x8,
+                                     const bpb_bf16* gz0_hi, float* dw1, float* db1, float* ws,
+                                     long long ws_bytes, void* stream_) {
+  using namespace bp;
+  BP_REQUIRE(layers != nullptr && ws != nullptr && n_layers >= 1 && n_layers + 1 <= kWgMaxJobs,
+             "bpb_wgrad_tower_input: 1..%d layers and a workspace are required", kWgMaxJobs - 1);
+  BP_REQUIRE(x8 && gz0_hi && dw1, "bpb_wgrad_tower_input: NULL argument");
+  WgradDesc d[kWgMaxJobs];
+  for (int i = 0; i < n_layers; ++i) {
+    if (int rc = fill_wgrad3_desc("bpb_wgrad_tower_input", &layers[i], &d[i])) return rc;
+    BP_REQUIRE(layers[i].act_lo == nullptr, "bpb_wgrad_tower_input: bf16 path only");
+  }
+  const int F = layers[0].F, B = layers[0].B;
+  BP_REQUIRE(Fw <= F && L_out0 == L_in0 - W + 1, "bpb_wgrad_tower_input: bad input-conv geometry");
+  d[n_layers] = input_conv_wgrad_desc("bpb_wgrad_tower_input", B, L_in0, L_out0, W, Fw, F, x8,
+                                      gz0_hi, nullptr, dw1, db1);
+  // single pass: only bit 0 of the plane selectors is read; align them with the tower's
+  d[n_layers].pa_bits = d[0].pa_bits;
+  d[n_layers].pg_bits = d[0].pg_bits;
+  d[n_layers].db_mask = d[0].db_mask;
+  d[0].ws = ws;
+  d[0].ws_bytes = ws_bytes;
+  return wgrad_run(d, n_layers + 1, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" long long bpb_heads_wgrad_ws_bytes(int B, int L_in, int W, int F, int Cp) {

@@ -245,7 +245,11 @@ class SoloNet:
             # one gz buffer per layer (no ping-pong): the tower weight gradients are computed
             # together after the data-gradient chain
             ws["gzl"] = [ops.new_planes(B, L, Fp, prec, dev) for L in Ls]
-            nb = max([ops.wgrad3_ws_bytes(B, L, Fp, prec) for L in Ls[1:]] +
+            joint = -1
+            if not prec and 0 < len(Ls) - 1 <= 11:
+                joint = ops.wgrad_tower_input_ws_bytes(B, Ls[1:], Fp, Ls[0], cfg.inputFilterWidth)
+            ws["wg_joint"] = joint > 0
+            nb = max([max(joint, 0)] + [ops.wgrad3_ws_bytes(B, L, Fp, prec) for L in Ls[1:]] +
                      ([ops.wgrad3_multi_ws_bytes(B, Ls[1:], Fp)] if 0 < len(Ls) - 1 <= 12 else []) +
                      [ops.input_conv_wgrad_ws_bytes(B, Ls[0], cfg.inputFilterWidth, Fp),
                       ops.heads_wgrad_ws_bytes(B, Ls[-1], cfg.outputFilterWidth, Fp, self.cp)])
@@ -399,6 +403,13 @@ class SoloNet:
             ops.conv3(gzcur, self.w_bwd[i], (0, -d, -2 * d), 1, Ls[i], resid=gcur, resid_off=-d,
                       out=gnext if i > 0 else None, out2=gznext, mask_in=ws["masks"][i])
             gcur, gzcur = gnext, gznext
+        if ws.get("wg_joint"):
+            # tower layers + input convolution: one split-K launch and one reduction
+            ops.wgrad_tower_input([(ws["acts"][i], ws["gzl"][i + 1], 2 ** (i + 1), g["dil_w"][i],
+                                    g["dil_b"][i]) for i in range(nL)], ws["x8"], ws["gzl"][0],
+                                  cfg.inputFilterWidth, cfg.numFilters, g["conv1_w"],
+                                  g["conv1_b"], ws["scratch"])
+            return
         if 0 < nL <= 12:
             ops.wgrad3_multi([(ws["acts"][i], ws["gzl"][i + 1], 2 ** (i + 1), g["dil_w"][i],
                                g["dil_b"][i]) for i in range(nL)], ws["scratch"])

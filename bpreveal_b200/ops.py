@@ -174,6 +174,31 @@ def wgrad3_multi(layers, ws):
                                _stream()), "bpb_wgrad3_multi")
 
 
+def wgrad_tower_input_ws_bytes(B, L_outs, F, L_out0, W):
+    """Workspace of ``wgrad_tower_input``; -1 when tower and input conv cannot share a launch."""
+    arr = (C.c_int * len(L_outs))(*L_outs)
+    return _lib.load().bpb_wgrad_tower_input_ws_bytes(len(L_outs), B, arr, F, L_out0, W)
+
+
+def wgrad_tower_input(layers, x8, gz0, W, Fw, dw1, db1, ws):
+    """Every tower weight gradient of a step and the input convolution's in one launch (bf16
+    path).  layers as in ``wgrad3_multi``; gz0 = gradient planes at the input conv's output."""
+    lib = _lib.load()
+    arr = (Wgrad3Args * len(layers))()
+    for a, (act, gz, dil, dw, db) in zip(arr, layers):
+        a_hi, a_lo = _planes(act)
+        g_hi, g_lo = _planes(gz)
+        B, L_in, F = a_hi.shape
+        a.B, a.L_in, a.L_out, a.F, a.dil = B, L_in, g_hi.shape[1], F, dil
+        a.act_hi, a.act_lo, a.gz_hi, a.gz_lo = _p(a_hi), _p(a_lo), _p(g_hi), _p(g_lo)
+        a.dw, a.db = _p(dw), _p(db)
+    g0_hi, _ = _planes(gz0)
+    check(lib.bpb_wgrad_tower_input(arr, len(layers), x8.shape[1], g0_hi.shape[1], W, Fw, _p(x8),
+                                    _p(g0_hi), _p(dw1), _p(db1), _p(ws),
+                                    ws.numel() * ws.element_size(), _stream()),
+          "bpb_wgrad_tower_input")
+
+
 def input_conv_wgrad_ws_bytes(B, L_out, W, F):
     n = _lib.load().bpb_input_conv_wgrad_ws_bytes(B, L_out, W, F)
     if n < 0:
