@@ -103,9 +103,9 @@ SIGNATURES = {
     "bpb_heads_pack_grad": (c_int, [c_int] * 8 + [c_void_p] * 6),
     "bpb_prep_heads_dgrad_weights": (c_int, [c_int] * 6 + [c_void_p] * 3 + [c_int, c_void_p]),
     "bpb_heads_dgrad_tc": (c_int, [C.POINTER(HeadsDgradArgs), c_void_p]),
-    "bpb_wgrad_tower_input_ws_bytes": (c_ll, [c_int, c_int, c_void_p, c_int, c_int, c_int]),
+    "bpb_wgrad_tower_input_ws_bytes": (c_ll, [c_int, c_int, c_void_p] + [c_int] * 5),
     "bpb_wgrad_tower_input": (c_int, [C.POINTER(Wgrad3Args), c_int, c_int, c_int, c_int, c_int] +
-                              [c_void_p] * 5 + [c_ll, c_void_p]),
+                              [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 5 + [c_ll, c_void_p]),
     "bpb_input_conv_wgrad_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "bpb_input_conv_wgrad": (c_int, [c_int] * 6 + [c_void_p] * 6 + [c_ll, c_void_p]),
     "bpb_heads_wgrad_ws_bytes": (c_ll, [c_int] * 5),

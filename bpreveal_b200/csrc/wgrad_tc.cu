@@ -311,6 +311,13 @@ __device__ __forceinline__ void wgrad_scatter(const WgradScatter& sc, long long 
       const int j = r >> 3, c = r & 7;
       if (j < sc.W && c < 4) sc.o0[(j * 4 + c) * sc.Fw + n] = tot;
     }
+  } else if (sc.mode == 3) {
+    // transposed heads job: rows = im2col index kk = j'*Cp + ch of d8, cols = tower channel c
+    if (is_b || n >= sc.Fw) return;
+    const int jp = r / sc.Cp, ch = r % sc.Cp;
+    if (jp >= sc.W) return;
+    if (ch < sc.T) sc.o0[(static_cast<long long>(sc.W - 1 - jp) * sc.Fw + n) * sc.T + ch] = tot;
+    else if (ch < sc.T + sc.H && jp == 0) sc.o2[n * sc.H + (ch - sc.T)] = tot;
   } else {
     // rows = tower channel c, cols = im2col index kk = j'*Cp + ch of the packed loss gradient
     const int jp = n / sc.Cp, ch = n % sc.Cp;
@@ -502,6 +509,14 @@ static int launch_wgrad(const WgradMaps& maps, const WgradKParams& kp, size_t sm
   return 0;
 }
 
+static bool wgrad_strip_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("BPB_STRIP");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // All descs share Ncols, batch and passes; the unit structure (taps x chunks, STRIP staging) and the
 // scatter of the result may differ per job; d[0].ws is the workspace.
 static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
@@ -518,10 +533,7 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
     halo_rows[j] = (d[j].allow_halo && d[j].NC == 1 && d[j].n_taps > 1)
                        ? 128 + (d[j].n_taps - 1) * d[j].dil : 0;
   }
-  static const bool strip_enabled = [] {
-    const char* e = getenv("BPB_STRIP");
-    return !(e && e[0] == '0');
-  }();
+  const bool strip_enabled = wgrad_strip_enabled();
   bool want_strip[kWgMaxJobs];
   int units[kWgMaxJobs];
   for (int j = 0; j < n_jobs; ++j) {
@@ -611,11 +623,13 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
 
 static int wgrad_run(const WgradDesc& d, cudaStream_t stream) { return wgrad_run(&d, 1, stream); }
 
+// (strip_j must say which jobs the launch will STRIP-stage: the split-K shares, and with them the
+// workspace layout, depend on it)
 static long long wgrad_ws_bytes(const char* who, int n_jobs, int B, const int* rows,
-                                const int* n_units_j, int Ncols) {
+                                const int* n_units_j, int Ncols, const bool* strip_j = nullptr) {
   WgradPlan pl;
   if (Ncols <= 0 || Ncols % 64 != 0 || n_jobs < 1 || n_jobs > kWgMaxJobs ||
-      !plan_wgrad(n_jobs, B, rows, nullptr, n_units_j, Ncols, &pl)) {
+      !plan_wgrad(n_jobs, B, rows, nullptr, n_units_j, Ncols, &pl, strip_j)) {
     set_error("%s: unsupported geometry or no CUDA device", who);
     return -1;
   }
@@ -769,29 +783,49 @@ extern "C" int bpb_input_conv_wgrad(int B, int L_in, int L_out, int W, int Fw, i
 // The tower layers of a step AND the input convolution in one launch (bf16 path; the jobs differ
 // in their unit structure: 3 tap units HALO/SLAB-staged vs ceil(8W/64) window units STRIP-staged).
 extern "C" long long bpb_wgrad_tower_input_ws_bytes(int n_layers, int B, const int* L_out, int F,
-                                                    int L_out0, int W) {
+                                                    int L_out0, int W, int L_last, int W_out) {
   using namespace bp;
-  if (n_layers < 1 || n_layers + 1 > kWgMaxJobs || L_out == nullptr || F <= 0 || F % 64 != 0) {
-    set_error("bpb_wgrad_tower_input_ws_bytes: 1..%d layers, F a multiple of 64", kWgMaxJobs - 1);
+  const int extra = 1 + (W_out > 0 ? 1 : 0);
+  if (n_layers < 1 || n_layers + extra > kWgMaxJobs || L_out == nullptr || F <= 0 || F % 64 != 0) {
+    set_error("bpb_wgrad_tower_input_ws_bytes: 1..%d layers, F a multiple of 64",
+              kWgMaxJobs - extra);
     return -1;
   }
   int rows[kWgMaxJobs], units[kWgMaxJobs];
+  bool strip[kWgMaxJobs];
   for (int j = 0; j < n_layers; ++j) {
     rows[j] = L_out[j];
     units[j] = 3 * (F / 64);
+    strip[j] = false;
   }
   rows[n_layers] = L_out0;
   units[n_layers] = window_kc(W, 8);
-  return wgrad_ws_bytes("bpb_wgrad_tower_input_ws_bytes", n_layers + 1, B, rows, units, F);
+  strip[n_layers] = wgrad_strip_enabled() && units[n_layers] <= 4;
+  if (W_out > 0) {
+    rows[n_layers + 1] = L_last;
+    units[n_layers + 1] = window_kc(W_out, 8);
+    strip[n_layers + 1] = wgrad_strip_enabled() && units[n_layers + 1] <= 4;
+  }
+  // the window jobs must be STRIP-staged to share a launch with the tower's tap structure
+  if (!strip[n_layers] || (W_out > 0 && !strip[n_layers + 1])) {
+    set_error("bpb_wgrad_tower_input_ws_bytes: window too wide for STRIP staging");
+    return -1;
+  }
+  return wgrad_ws_bytes("bpb_wgrad_tower_input_ws_bytes", n_layers + extra, B, rows, units, F,
+                        strip);
 }
 
 extern "C" int bpb_wgrad_tower_input(const bpb_wgrad3_args* layers, int n_layers, int L_in0,
                                      int L_out0, int W, int Fw, const bpb_bf16* x8,
-                                     const bpb_bf16* gz0_hi, float* dw1, float* db1, float* ws,
+                                     const bpb_bf16* gz0_hi, float* dw1, float* db1, int L_last,
+                                     int W_out, int T, int H, const bpb_bf16* act_last,
+                                     const bpb_bf16* d8, float* dpw, float* dcw, float* ws,
                                      long long ws_bytes, void* stream_) {
   using namespace bp;
-  BP_REQUIRE(layers != nullptr && ws != nullptr && n_layers >= 1 && n_layers + 1 <= kWgMaxJobs,
-             "bpb_wgrad_tower_input: 1..%d layers and a workspace are required", kWgMaxJobs - 1);
+  const bool with_heads = d8 != nullptr;
+  BP_REQUIRE(layers != nullptr && ws != nullptr && n_layers >= 1 &&
+                 n_layers + 1 + (with_heads ? 1 : 0) <= kWgMaxJobs,
+             "bpb_wgrad_tower_input: 1..%d layers and a workspace are required", kWgMaxJobs - 2);
   BP_REQUIRE(x8 && gz0_hi && dw1, "bpb_wgrad_tower_input: NULL argument");
   WgradDesc d[kWgMaxJobs];
   for (int i = 0; i < n_layers; ++i) {
@@ -806,9 +840,49 @@ extern "C" int bpb_wgrad_tower_input(const bpb_wgrad3_args* layers, int n_layers
   d[n_layers].pa_bits = d[0].pa_bits;
   d[n_layers].pg_bits = d[0].pg_bits;
   d[n_layers].db_mask = d[0].db_mask;
+  int n_jobs = n_layers + 1;
+  if (with_heads) {
+    // The heads' weight gradients, transposed so that they have the tower's column count: the A
+    // operand is the STRIP of the packed loss gradient d8 (8 channels = 16 bytes per position),
+    // the G operand the last tower activations:
+    //   out[j'*8 + ch][c] = sum_s d8[s + j'][ch] act[s][c]   (= dpw[W-1-j'][c][ch], dcw on j' = 0)
+    BP_REQUIRE(act_last && dpw && dcw && W_out >= 1 && T >= 1 && H >= 1 && T + H <= 8,
+               "bpb_wgrad_tower_input: the heads job needs T + H <= 8 (one 16-byte d8 row)");
+    WgradDesc h{};
+    h.who = "bpb_wgrad_tower_input";
+    h.B = B;
+    h.rows = L_last;
+    h.n_taps = 1;
+    h.NC = window_kc(W_out, 8);
+    h.Ncols = F;
+    h.a_ptr[0] = d8;
+    h.a_inner = static_cast<unsigned long long>(W_out) * 8;
+    h.a_rows = L_last;
+    h.a_row_stride_bytes = 16;
+    h.a_batch_stride_bytes = static_cast<unsigned long long>(L_last + W_out - 1) * 16;
+    h.g_ptr[0] = act_last;
+    h.g_inner = F;
+    h.g_rows = L_last;
+    h.g_row_stride_bytes = static_cast<unsigned long long>(F) * 2;
+    h.g_batch_stride_bytes = h.g_row_stride_bytes * L_last;
+    h.n_passes = 1;
+    h.pa_bits = d[0].pa_bits;
+    h.pg_bits = d[0].pg_bits;
+    h.db_mask = d[0].db_mask;
+    h.allow_strip = true;  // d8 carries the spare tail (bpb_heads_d8_elems)
+    h.sc.mode = 3;
+    h.sc.W = W_out;
+    h.sc.Fw = Fw;
+    h.sc.T = T;
+    h.sc.H = H;
+    h.sc.Cp = 8;
+    h.sc.o0 = dpw;
+    h.sc.o2 = dcw;
+    d[n_jobs++] = h;
+  }
   d[0].ws = ws;
   d[0].ws_bytes = ws_bytes;
-  return wgrad_run(d, n_layers + 1, static_cast<cudaStream_t>(stream_));
+  return wgrad_run(d, n_jobs, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" long long bpb_heads_wgrad_ws_bytes(int B, int L_in, int W, int F, int Cp) {

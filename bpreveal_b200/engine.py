@@ -245,10 +245,18 @@ class SoloNet:
             # one gz buffer per layer (no ping-pong): the tower weight gradients are computed
             # together after the data-gradient chain
             ws["gzl"] = [ops.new_planes(B, L, Fp, prec, dev) for L in Ls]
-            joint = -1
-            if not prec and 0 < len(Ls) - 1 <= 11:
-                joint = ops.wgrad_tower_input_ws_bytes(B, Ls[1:], Fp, Ls[0], cfg.inputFilterWidth)
+            joint, joint_heads = -1, False
+            if not prec and 0 < len(Ls) - 1 <= 10:
+                if self.cp == 8:  # the heads' d8 rows are 16 bytes: they can join as well
+                    joint = ops.wgrad_tower_input_ws_bytes(B, Ls[1:], Fp, Ls[0],
+                                                           cfg.inputFilterWidth, Ls[-1],
+                                                           cfg.outputFilterWidth)
+                    joint_heads = joint > 0
+                if joint <= 0:
+                    joint = ops.wgrad_tower_input_ws_bytes(B, Ls[1:], Fp, Ls[0],
+                                                           cfg.inputFilterWidth)
             ws["wg_joint"] = joint > 0
+            ws["wg_joint_heads"] = joint_heads
             nb = max([max(joint, 0)] + [ops.wgrad3_ws_bytes(B, L, Fp, prec) for L in Ls[1:]] +
                      ([ops.wgrad3_multi_ws_bytes(B, Ls[1:], Fp)] if 0 < len(Ls) - 1 <= 12 else []) +
                      [ops.input_conv_wgrad_ws_bytes(B, Ls[0], cfg.inputFilterWidth, Fp),
@@ -392,8 +400,9 @@ class SoloNet:
         if not fused:
             ops.heads_pack_grad(ws["dlogits"], ws["dlogcounts"], Ls[nL], cfg.outputFilterWidth,
                                 self.cp, planes, ws["d8"], dpb=g["prof_b"], dcb=g["cnt_b"])
-        ops.heads_wgrad(aL, ws["d8"], cfg.outputFilterWidth, cfg.numFilters, cfg.T, cfg.H,
-                        self.cp, planes, g["prof_w"], g["cnt_w"], ws["scratch"])
+        if not ws.get("wg_joint_heads"):
+            ops.heads_wgrad(aL, ws["d8"], cfg.outputFilterWidth, cfg.numFilters, cfg.T, cfg.H,
+                            self.cp, planes, g["prof_w"], g["cnt_w"], ws["scratch"])
         ops.heads_dgrad(ws["d8"], self.w_hd_op, ws["B"], Ls[nL], cfg.outputFilterWidth, cfg.Fp,
                         self.cp, planes, g=gcur, gz=gzcur, mask_in=ws["masks"][nL])
         for i in range(nL - 1, -1, -1):
@@ -408,7 +417,10 @@ class SoloNet:
             ops.wgrad_tower_input([(ws["acts"][i], ws["gzl"][i + 1], 2 ** (i + 1), g["dil_w"][i],
                                     g["dil_b"][i]) for i in range(nL)], ws["x8"], ws["gzl"][0],
                                   cfg.inputFilterWidth, cfg.numFilters, g["conv1_w"],
-                                  g["conv1_b"], ws["scratch"])
+                                  g["conv1_b"], ws["scratch"],
+                                  heads=(aL, ws["d8"], cfg.outputFilterWidth, cfg.T, cfg.H,
+                                         g["prof_w"], g["cnt_w"]) if ws.get("wg_joint_heads")
+                                  else None)
             return
         if 0 < nL <= 12:
             ops.wgrad3_multi([(ws["acts"][i], ws["gzl"][i + 1], 2 ** (i + 1), g["dil_w"][i],

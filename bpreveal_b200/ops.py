@@ -174,15 +174,18 @@ def wgrad3_multi(layers, ws):
                                _stream()), "bpb_wgrad3_multi")
 
 
-def wgrad_tower_input_ws_bytes(B, L_outs, F, L_out0, W):
-    """Workspace of ``wgrad_tower_input``; -1 when tower and input conv cannot share a launch."""
+def wgrad_tower_input_ws_bytes(B, L_outs, F, L_out0, W, L_last=0, W_out=0):
+    """Workspace of ``wgrad_tower_input`` (W_out > 0: with the heads job); -1 when the jobs cannot
+    share a launch."""
     arr = (C.c_int * len(L_outs))(*L_outs)
-    return _lib.load().bpb_wgrad_tower_input_ws_bytes(len(L_outs), B, arr, F, L_out0, W)
+    return _lib.load().bpb_wgrad_tower_input_ws_bytes(len(L_outs), B, arr, F, L_out0, W, L_last,
+                                                      W_out)
 
 
-def wgrad_tower_input(layers, x8, gz0, W, Fw, dw1, db1, ws):
-    """Every tower weight gradient of a step and the input convolution's in one launch (bf16
-    path).  layers as in ``wgrad3_multi``; gz0 = gradient planes at the input conv's output."""
+def wgrad_tower_input(layers, x8, gz0, W, Fw, dw1, db1, ws, heads=None):
+    """Every tower weight gradient of a step, the input convolution's and (``heads`` =
+    (act_last planes, d8, W_out, T, H, dpw, dcw)) the heads' in one launch (bf16 path).  layers as
+    in ``wgrad3_multi``; gz0 = gradient planes at the input conv's output."""
     lib = _lib.load()
     arr = (Wgrad3Args * len(layers))()
     for a, (act, gz, dil, dw, db) in zip(arr, layers):
@@ -193,8 +196,14 @@ def wgrad_tower_input(layers, x8, gz0, W, Fw, dw1, db1, ws):
         a.act_hi, a.act_lo, a.gz_hi, a.gz_lo = _p(a_hi), _p(a_lo), _p(g_hi), _p(g_lo)
         a.dw, a.db = _p(dw), _p(db)
     g0_hi, _ = _planes(gz0)
+    if heads is not None:
+        act_last, d8, W_out, T, H, dpw, dcw = heads
+        al_hi, _ = _planes(act_last)
+        hargs = (al_hi.shape[1], W_out, T, H, _p(al_hi), _p(d8), _p(dpw), _p(dcw))
+    else:
+        hargs = (0, 0, 0, 0, None, None, None, None)
     check(lib.bpb_wgrad_tower_input(arr, len(layers), x8.shape[1], g0_hi.shape[1], W, Fw, _p(x8),
-                                    _p(g0_hi), _p(dw1), _p(db1), _p(ws),
+                                    _p(g0_hi), _p(dw1), _p(db1), *hargs, _p(ws),
                                     ws.numel() * ws.element_size(), _stream()),
           "bpb_wgrad_tower_input")
 

@@ -139,13 +139,18 @@ typedef struct {
 int bpb_input_conv_fwd(const bpb_input_conv_args* a, void* stream);
 /* bpb_wgrad3_multi and bpb_input_conv_wgrad in ONE launch (bf16 path): the tower layers plus the
  * input convolution as one more job of the same split-K kernel (its window units are STRIP-staged
- * from x8).  _ws_bytes returns -1 when the geometry cannot share a launch (e.g. F > 64, where the
- * tower needs several accumulator groups); callers then use the two separate entry points. */
+ * from x8) and, with d8 != NULL, the heads' weight gradients of bpb_heads_wgrad_tc as a further
+ * job (transposed: its window units are STRIP-staged from d8 [B][L_last+W_out-1][8], so T + H <= 8;
+ * act_last [B][L_last][F]).  _ws_bytes (W_out = 0: no heads job) returns -1 when the geometry
+ * cannot share a launch (e.g. F > 64, where the tower needs several accumulator groups); callers
+ * then use the separate entry points. */
 long long bpb_wgrad_tower_input_ws_bytes(int n_layers, int B, const int* L_out, int F, int L_out0,
-                                         int W);
+                                         int W, int L_last, int W_out);
 int bpb_wgrad_tower_input(const bpb_wgrad3_args* layers, int n_layers, int L_in0, int L_out0, int W,
                           int Fw, const bpb_bf16* x8, const bpb_bf16* gz0_hi, float* dw1,
-                          float* db1, float* ws, long long ws_bytes, void* stream);
+                          float* db1, int L_last, int W_out, int T, int H,
+                          const bpb_bf16* act_last, const bpb_bf16* d8, float* dpw, float* dcw,
+                          float* ws, long long ws_bytes, void* stream);
 
 /* dw[j][c][f] = sum_{b,t} x[b,t+j,c] gz[b,t,f]; db[f] = sum gz  (dw is [W][4][Fw], overwritten).
  * Runs on the K7 tensor-core kernel: the A operand is the implicit im2col view of x8. */
