@@ -430,12 +430,17 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
   // split-K factors: the SMs are shared between the jobs in proportion to their position tiles
   // (a STRIP-staged job is bound by its MMAs -- units + 1 groups of 8 per position tile -- where a
   // tower job is bound by HBM: measured ~1.7k against ~1.4k cycles per tile, hence the weight)
+  static const double strip_cost = [] {
+    const char* e = getenv("BPB_WG_STRIP_COST");
+    const double v = e ? atof(e) : 0.0;
+    return v > 0.1 ? v : 1.25;
+  }();
   double total_kb = 0;
   int kb[kWgMaxJobs];
   double cost[kWgMaxJobs];
   for (int j = 0; j < n_jobs; ++j) {
     kb[j] = B * ((rows[j] + 127) / 128);
-    cost[j] = kb[j] * ((strip_j && strip_j[j] && n_jobs > 1) ? 1.25 : 1.0);
+    cost[j] = kb[j] * ((strip_j && strip_j[j] && n_jobs > 1) ? strip_cost : 1.0);
     total_kb += cost[j];
   }
   int budget = sms / pl->n_items;  // splits available in total
