@@ -191,6 +191,10 @@ def gpu_extras(net_cfg, dev, rank):
     return out
 
 
+WORKLOAD = ("C1 trainSoloModel step (configs[0]): 1 head x 2 tasks, F=64, 9 dilated layers, "
+            "3090->1000 bp, batch 64 per GPU, Adam lr 0.004")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -200,11 +204,11 @@ def run_reference(args):
     rate, sec, cores = cpu_train_rate(C1, steps, warm, BATCH)
     line = {
         "impl": "reference", "metric": "BPNet train seq/s", "value": rate, "unit": "seq/s",
-        "n_gpus": 0, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
+        "n_gpus": args.gpus, "device": "cpu", "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "C1 trainSoloModel step: 1 head x 2 tasks, F=64, 9 dilated layers, "
-                               "3090->1000 bp, batch 64", "global_batch": BATCH},
+        "config": {"workload": WORKLOAD, "global_batch": BATCH,
+                   "note": "CPU host cores, one process (rank 0); batch 64 per step"},
         "cpu_baseline": {"value": rate, "unit": "seq/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} full C1 train steps of batch {BATCH} after {warm} "
                                    "warm-up, fp32 torch-CPU restatement of the Keras graph "
@@ -470,8 +474,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 planes x2 (hi/lo), fp32 accumulate" if args.precise else "bf16 (fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": "C1 trainSoloModel step (configs[0]): 1 head x 2 tasks, F=64, "
-                                   "9 dilated layers, 3090->1000 bp, batch 64 per GPU, Adam lr 0.004",
+            "config": {"workload": WORKLOAD,
                        "global_batch": BATCH * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (~0.5 GB of activations) exceeds the 126 MB L2; "
                              f"{N_BATCHES} distinct batches cycled"},
