@@ -41,6 +41,8 @@ constexpr int kTileBytes = kTileM * 128;  // [128 x 64] bf16
 constexpr int kMaxStages = 12;
 constexpr int kMaxRStages = 4;
 constexpr int kMaxAcc = 6;
+constexpr int kBiasTileBytes = 64 * 128;
+constexpr int kBiasMmaBytes = kBiasTileBytes + 128 * 128;  // bias tile + tile of ones
 constexpr int kEpiThreads = 256;
 
 enum { EPI_FWD = 0, EPI_FWD_Z = 1, EPI_FWD_R = 2, EPI_BWD_MASK = 3, EPI_BWD_MULT = 4 };
@@ -75,6 +77,10 @@ struct ConvKParams {
   int zx_div;
   int has_out, has_out2;
   int epi_groups, ring_resid;
+  // 1: the bias enters the accumulator through one extra K = 16 MMA per tile (a tile of ones
+  // times a tile holding the bias as three bf16 remainders in its first K columns) instead of 32
+  // FADDs and 8 shared-memory reads per epilogue thread
+  int bias_mma;
   const float* bias;
   int bias_n;  // valid entries of bias (the rest of the F channels get 0)
   const __nv_bfloat16 *mult_hi, *mult_lo;
@@ -193,8 +199,12 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   const int n_out = p.has_out + p.has_out2;
   const int stg_bytes = n_out * PLANES * kTileBytes;
   const int rstage_bytes = PLANES * kTileBytes;
+  constexpr bool CAN_BIAS_MMA = IS_FWD && RESIDENT && NT == 64;
+  const bool bias_mma = CAN_BIAS_MMA && p.bias_mma != 0;
   uint8_t* w_smem = smem;
-  uint8_t* ring = w_smem + static_cast<size_t>(w_tiles) * B_TILE_BYTES;
+  uint8_t* bias_tile = w_smem + static_cast<size_t>(w_tiles) * B_TILE_BYTES;  // [64 n][64 k]
+  uint8_t* ones_tile = bias_tile + kBiasTileBytes;                            // [128 m][64 k]
+  uint8_t* ring = bias_tile + (bias_mma ? kBiasMmaBytes : 0);
   uint8_t* stg = ring + static_cast<size_t>(p.stages) * stage_bytes;
   uint8_t* rring = stg + static_cast<size_t>(p.nstg) * stg_bytes;
   float* s_bias = reinterpret_cast<float*>(
@@ -207,7 +217,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   uint64_t* rfull = acc_empty + kMaxAcc;
   uint64_t* rempty = rfull + kMaxRStages;
   uint64_t* w_full = rempty + kMaxRStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint64_t* b_full = w_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,6 +248,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         mbar_init(b1, c1);
       }
     }
+    if (lane == 30) mbar_init(b_full, 1);
     if (lane == 31) {
       tma_prefetch_desc(&tm.A[0]);
       tma_prefetch_desc(&tm.W);
@@ -366,6 +378,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     // ------------------------------------------------------------- MMA issuer
     if (elect_one()) {
       if (RESIDENT) mbar_wait_wd(w_full, 0, p.dbg, 0x300);
+      if (bias_mma) mbar_wait_wd(b_full, 0, p.dbg, 0x310);
       BPB_STAMP(28);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, ntile = 0;
       // Fast path (the bf16 tower layer: 3 taps, one 64-channel chunk, one pass, resident
@@ -389,6 +402,14 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         mbar_wait_wd(&acc_empty[as], aphase ^ 1, p.dbg, 0x400 + as, ntile);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * NT;
+        // bias: D = ones[128 x 16] * bias_tile[16 x 64] opens the accumulation of the tile
+        uint32_t accum0 = 0;
+        if (bias_mma) {
+          tc_fence_after();
+          umma_bf16_lohi(d_tmem, umma_desc_lo(smem_u32(ones_tile), 0), umma_desc_hi(1024),
+                         umma_desc_lo(smem_u32(bias_tile), 0), umma_desc_hi(1024), IDESC, 0u);
+          accum0 = 1;
+        }
         if (fast && HALO) {
           mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
 #ifdef BPB_ROLE_PROFILE
@@ -401,7 +422,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16_lohi(d_tmem, (a0 + a_row[j] + 2u * k) & 0x3FFFu, DHI, b_lo[j][k], DHI, IDESC,
-                             (j | k) != 0 ? 1u : 0u);
+                             (j | k) != 0 ? 1u : accum0);
           umma_commit(&empty[stage]);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         } else if (fast) {
@@ -413,7 +434,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16_lohi(d_tmem, (a0 + 2u * k) & 0x3FFFu, DHI, b_lo[j][k], DHI, IDESC,
-                             (j | k) != 0 ? 1u : 0u);
+                             (j | k) != 0 ? 1u : accum0);
             umma_commit(&empty[stage]);
             if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
           }
@@ -424,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           // no-swizzle K-major: LBO = 16 B (next core matrix along K), SBO = 128 B (along M)
           constexpr uint32_t A_HI = (128u >> 4) | (1u << 14);
           constexpr uint32_t A_LBO = (16u >> 4) << 16;
-          uint32_t accum = 0;
+          uint32_t accum = accum0;
           for (int ps = 0; ps < p.npass; ++ps) {
             const uint32_t ap = (p.pa_bits >> ps) & 1;
             const uint32_t wp = (p.pw_bits >> (2 * ps)) & 3;
@@ -454,7 +475,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
           tc_fence_after();
           const uint32_t base = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
-          uint32_t accum = 0;
+          uint32_t accum = accum0;
           for (int pass = 0; pass < p.npass; ++pass)
             for (int c = 0; c < p.KC; ++c)
               for (int j = 0; j < p.n_taps; ++j) {
@@ -476,7 +497,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         } else {
           const int inner = RESIDENT ? p.n_aplanes : p.npass;
           const int nsteps = p.n_taps * p.KC * inner;
-          uint32_t accum = 0;
+          uint32_t accum = accum0;
           for (int step = 0; step < nsteps; ++step) {
             const int pass = step % inner;  // RESIDENT: the A plane held by this stage
             const int c = (step / inner) % p.KC;
@@ -526,7 +547,34 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     // producer's and the MMA issuer's start-up path.
     for (int i = static_cast<int>(threadIdx.x) - 64; i < p.F; i += EG * kEpiThreads)
       s_bias[i] = (p.bias && i < p.bias_n) ? p.bias[i] : 0.f;
+    if (bias_mma) {
+      const int te = static_cast<int>(threadIdx.x) - 64;
+      uint4 one4;
+      one4.x = one4.y = one4.z = one4.w = 0x3F803F80u;
+      for (int i = te; i < 128 * 128 / 16; i += EG * kEpiThreads)
+        reinterpret_cast<uint4*>(ones_tile)[i] = one4;
+      if (te < 64) {
+        // row n of the K-major bias tile: k = 0..2 hold bias[n] as successive bf16 remainders
+        // (exact to fp32), every other k is zero; 16-byte chunks XOR-ed with the row (SW128)
+        const float bv = (p.bias && te < p.bias_n) ? p.bias[te] : 0.f;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(bv);
+        const float r1 = bv - __bfloat162float(h0);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+        uint4 c0;
+        c0.x = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+               (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        c0.y = static_cast<uint32_t>(__bfloat16_as_ushort(h2));
+        c0.z = c0.w = 0u;
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(bias_tile + te * 128 + ((c ^ (te & 7)) << 4)) = (c == 0) ? c0 : z4;
+      }
+      fence_proxy_async();
+    }
     named_bar_sync(7, EG * kEpiThreads);
+    if (bias_mma && threadIdx.x == 64) mbar_arrive(b_full);
     pdl_wait();  // global reads (masks, multipliers) and TMA stores below
     const int grp = (warp - 2) >> 3;
     const int q = warp & 3;
@@ -655,10 +703,12 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           }
           float o[8], o2[8];
           if (IS_FWD) {
-            const float4 b0 = lds_f4(s_bias + n0 + half * 32 + g * 8);
-            const float4 b1 = lds_f4(s_bias + n0 + half * 32 + g * 8 + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            if (!bias_mma) {
+              const float4 b0 = lds_f4(s_bias + n0 + half * 32 + g * 8);
+              const float4 b1 = lds_f4(s_bias + n0 + half * 32 + g * 8 + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
             if (EPI == EPI_FWD_R) {
               // DeepSHAP rescale multiplier of this reference against the query's pre-activation
               // (shap.py:623-638); only the query-half gradient is used downstream (shap.py:374).
@@ -851,6 +901,12 @@ static int g_epi_groups = [] {
   return (e && e[0] == '1') ? 1 : 2;
 }();
 
+// Tuning knob (BPB_BIAS_MMA=0|1, default 1): forward bias through the tensor core.
+static bool g_bias_mma = [] {
+  const char* e = getenv("BPB_BIAS_MMA");
+  return !(e && e[0] == '0');
+}();
+
 template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID>
 static int launch_conv_eg(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
                           cudaStream_t stream) {
@@ -956,7 +1012,7 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   const size_t b_tile = static_cast<size_t>(NT) * 128;
   const size_t w_res = static_cast<size_t>(d.n_wplanes) * d.n_taps * d.KC * b_tile;
   const size_t fixed = 1024 /*align slack*/ + static_cast<size_t>(F) * 4 +
-                       (2 * kMaxStages + 2 * kMaxAcc + 2 * kMaxRStages + 1) * 8 + 16;
+                       (2 * kMaxStages + 2 * kMaxAcc + 2 * kMaxRStages + 2) * 8 + 16;
   const bool can_reside = (kp.n_ntiles == 1) && (NT <= 128);
   // With two epilogue groups (bf16 path, two staging buffers) the residual ring must have an EVEN
   // number of slots: a slot is then always consumed by the same group.  With an odd ring a group
@@ -979,7 +1035,11 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   int box_rows = 0;
   auto try_plan = [&](bool want_halo, bool want_res, int want_nstg, int want_rst, int min_stages) {
     const bool ring_resid = RESID && !(want_halo && is_fwd);
-    size_t used = fixed + (want_res ? w_res : 0) +
+    // (not for STRIP staging: that kernel is bound by its MMA issue, the extra MMA costs more
+    // than the adds it saves -- measured)
+    const bool want_bias_mma = want_res && is_fwd && NT == 64 && d.bias != nullptr && g_bias_mma &&
+                               !(strip_ok && !want_halo);
+    size_t used = fixed + (want_res ? w_res : 0) + (want_bias_mma ? kBiasMmaBytes : 0) +
                   static_cast<size_t>(want_nstg) * n_out * n_planes * kTileBytes +
                   (ring_resid ? static_cast<size_t>(want_rst) * n_planes * kTileBytes : 0);
     if (used >= static_cast<size_t>(max_smem)) return false;
@@ -1022,6 +1082,8 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
               try_plan(false, false, 1, 2, 2);
   BP_REQUIRE(planned, "%s: not enough shared memory for F=%d planes=%d", d.who, F, n_planes);
   kp.stages = stages;
+  kp.bias_mma = (resident && is_fwd && NT == 64 && d.bias != nullptr && g_bias_mma &&
+                 !(strip_ok && !halo)) ? 1 : 0;
   if (resident && !halo && strip_ok) {
     kp.strip = 1;
     kp.strip_bytes = strip_bytes;
@@ -1049,7 +1111,8 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   } else {
     for (int j = 0; j < d.n_taps; ++j) kp.tap_row[j] = d.tap_off[j];
   }
-  const size_t smem_bytes = fixed + (resident ? w_res : 0) + stages * stage_bytes +
+  const size_t smem_bytes = fixed + (resident ? w_res : 0) + (kp.bias_mma ? kBiasMmaBytes : 0) +
+                            stages * stage_bytes +
                             static_cast<size_t>(nstg) * n_out * n_planes * kTileBytes +
                             static_cast<size_t>(rstages) * n_planes * kTileBytes;
 
