@@ -258,7 +258,23 @@ def main():
     cfg = NetConfig(precise=args.precise, **C1)
     net = SoloNet(cfg, dev)
     net.init_random(seed=1234)
-    net.enable_training()
+    # N > 1: the gradient all-reduce is fused into the optimiser kernel over NVLink peer memory
+    # (BPB_DP_PEER=0 selects the NCCL all-reduce between two CUDA graphs instead); the choice is
+    # made collectively so that every rank takes the same path
+    peers = None
+    if world > 1 and os.environ.get("BPB_DP_PEER", "0") == "1":
+        from bpreveal_b200 import parallel
+        ok = 1
+        try:
+            peers = parallel.PeerGradExchange(net.params.flat.numel(), dev)
+        except Exception as e:  # noqa: BLE001
+            say(f"peer exchange unavailable on rank {rank}: {e}")
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peers = None
+    net.enable_training(grads_flat=peers.grads if peers is not None else None)
     lr = 0.004
     # synthetic batches: resident on the device (for `value`) and in pinned host memory (`e2e`)
     xs, cs = synth(BATCH * N_BATCHES, C1, 20261019 + rank)
@@ -269,9 +285,11 @@ def main():
     loss_host = torch.zeros((2 * cfg.H,), dtype=torch.float32).pin_memory()
 
     allreduce = None
-    if world > 1:
+    if world > 1 and peers is None:
         def allreduce(flat):
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+
+    dp = dict(peers=peers) if peers is not None else dict(allreduce=allreduce, world=world)
 
     def batch_slice(t, i):
         j = i % N_BATCHES
@@ -290,11 +308,11 @@ def main():
         for i in range(nsteps):
             if host_io:
                 losses = net.train_step(batch_slice(x_host, i), batch_slice(c_host, i), lr,
-                                        allreduce=allreduce, world=world)
+                                        **dp)
                 loss_host.copy_(losses, non_blocking=True)
             else:
                 net.train_step(batch_slice(x_dev, i), batch_slice(c_dev, i), lr,
-                               allreduce=allreduce, world=world)
+                               **dp)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -309,7 +327,7 @@ def main():
     lib = __import__("bpreveal_b200._lib", fromlist=["_lib"])
     orig_check = ops.check
 
-    kernels_per_call = {"bpb_wgrad3_tc": 2, "bpb_wgrad3_multi": 2, "bpb_wgrad_tower_input": 2, "bpb_input_conv_wgrad": 2, "bpb_heads_fwd": 2,
+    kernels_per_call = {"bpb_wgrad3_tc": 2, "bpb_wgrad3_multi": 2, "bpb_wgrad_tower_input": 2, "bpb_peer_wait": 1, "bpb_adam_prep_step_peer": 1, "bpb_input_conv_wgrad": 2, "bpb_heads_fwd": 2,
                         "bpb_heads_wgrad_tc": 2, "bpb_heads_pack_grad": 2, "bpb_heads_fwd_tc": 2}
 
     def counting_check(rc, what):
@@ -317,8 +335,7 @@ def main():
         return orig_check(rc, what)
 
     for i in range(warmup):
-        net.train_step(batch_slice(x_dev, 0), batch_slice(c_dev, 0), lr, allreduce=allreduce,
-                       world=world)
+        net.train_step(batch_slice(x_dev, 0), batch_slice(c_dev, 0), lr, **dp)
         if i == 0:
             torch.cuda.synchronize()
             say("first step done")
@@ -327,7 +344,7 @@ def main():
     # launches per step: replay the step body un-graphed once with the counter armed
     ops.check = counting_check
     net.train_step(batch_slice(x_dev, 1), batch_slice(c_dev, 1), lr, use_graph=False,
-                   allreduce=allreduce, world=world)
+                   **dp)
     ops.check = orig_check
     torch.cuda.synchronize()
     calls_per_step = counter["n"]
@@ -359,8 +376,8 @@ def main():
         names = ["conv3", "wgrad3", "wgrad3_multi", "wgrad_tower_input", "onehot_expand", "input_conv_fwd", "input_conv_wgrad",
                  "heads_fwd", "heads_fwd_tc", "heads_wgrad", "heads_dgrad", "heads_pack_grad",
                  "loss_fwd_bwd", "loss_fwd_bwd_pack", "prep_heads_fwd_weights",
-                 "adam_step", "adam_prep_step", "prep_conv3_weights", "prep_input_conv_weights",
-                 "prep_heads_dgrad_weights"]
+                 "adam_step", "adam_prep_step", "adam_prep_step_peer", "peer_wait",
+                 "prep_conv3_weights", "prep_input_conv_weights", "prep_heads_dgrad_weights"]
 
         def wrap(name):
             fn = getattr(ops, name)
@@ -404,7 +421,8 @@ def main():
         agg = {}
         counts = {}
         for key in dict.fromkeys(c[0] for c in calls):
-            if key in ("adam_step", "adam_prep_step", "prep_conv3_weights", "prep_input_conv_weights",
+            if key in ("adam_step", "adam_prep_step", "adam_prep_step_peer", "peer_wait",
+                       "prep_conv3_weights", "prep_input_conv_weights",
                        "prep_heads_dgrad_weights", "prep_heads_fwd_weights"):
                 continue  # replaying the optimiser would train; they are ~10 us together
             agg[key], counts[key] = time_family(key)
@@ -476,6 +494,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                       "grad_exchange": ("none" if world == 1 else
+                                         "fused into the optimiser kernel over NVLink peer memory"
+                                         if peers is not None else "NCCL all-reduce"),
                        "l2": "per-step working set (~0.5 GB of activations) exceeds the 126 MB L2; "
                              f"{N_BATCHES} distinct batches cycled"},
             "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": h2d,
@@ -491,6 +512,10 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        if peers is not None:
+            peers.close()
         dist.destroy_process_group()
 
 

@@ -80,6 +80,10 @@ class PrepTable(C.Structure):
     ]
 
 
+class PeerArgs(C.Structure):
+    _fields_ = [("world", c_int), ("rank", c_int), ("grads", c_void_p * 8), ("flags", c_void_p * 8)]
+
+
 # name -> (restype, argtypes); mirrors include/bpreveal_b200.h one to one.
 SIGNATURES = {
     "bpb_version": (c_int, []),
@@ -126,6 +130,13 @@ SIGNATURES = {
     "bpb_loss_fwd_bwd_pack": (c_int, [c_int] * 4 + [c_void_p] * 10 + [c_int] * 4 + [c_void_p] * 6),
     "bpb_ushuffle_ohe": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, C.c_uint]),
     "bpb_adam_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 + [c_void_p]),
+    "bpb_peer_alloc": (c_int, [c_ll, C.POINTER(c_void_p), c_void_p]),
+    "bpb_peer_open": (c_int, [c_void_p, C.POINTER(c_void_p)]),
+    "bpb_peer_close": (c_int, [c_void_p]),
+    "bpb_peer_free": (c_int, [c_void_p]),
+    "bpb_peer_wait": (c_int, [C.POINTER(PeerArgs), c_void_p]),
+    "bpb_adam_prep_step_peer": (c_int, [c_ll] + [c_void_p] * 4 + [c_float] * 3 +
+                                [C.POINTER(PrepTable), C.POINTER(PeerArgs), c_void_p]),
     "bpb_adam_prep_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 +
                            [C.POINTER(PrepTable), c_void_p]),
     "bpb_prep_conv3_weights": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,

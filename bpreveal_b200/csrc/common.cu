@@ -178,6 +178,7 @@ int bpb_abi_struct_size(int which) {
     case 2: return static_cast<int>(sizeof(bpb_input_conv_args));
     case 3: return static_cast<int>(sizeof(bpb_heads_dgrad_args));
     case 4: return static_cast<int>(sizeof(bpb_prep_table));
+    case 5: return static_cast<int>(sizeof(bpb_peer_args));
     default: return -1;
   }
 }

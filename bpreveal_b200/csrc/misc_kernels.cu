@@ -2,6 +2,7 @@
 // weight re-layout for the tcgen05 kernels, the epoch jitter gather that replaces libslide, and
 // the scalar regressions of the transformation / combined models.
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -416,10 +417,54 @@ __device__ __forceinline__ void scatter_planes(__nv_bfloat16* dst, long long pla
   }
 }
 
+// Data-parallel variant (PEER): the gradient all-reduce is part of this kernel.  Every rank's
+// gradient bucket and a small flag block live in memory its peers map over NVLink (CUDA IPC);
+// the kernel announces "my gradients are complete" in every peer's flag block, waits until all
+// peers have announced theirs, then each thread adds the world's values of its element straight
+// out of peer memory in rank order (a one-shot all-reduce: identical sums, hence identical
+// parameters, on every rank) and applies the update; the last block to finish tells every peer
+// that this rank no longer reads its bucket.  Flag block of a rank: words 0..7 ready[r],
+// 8..15 done[r], 16 sequence number of the last completed exchange.  Waits are bounded: a peer
+// that never arrives traps this kernel after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_spin_until(const unsigned* flag, unsigned want) {
+  const long long t0 = clock64();
+  while (static_cast<int>(ld_acquire_sys(flag) - want) < 0) {
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a peer is missing
+  }
+}
+
+__global__ void peer_wait_kernel(const bpb_peer_args pa) {
+  // the previous exchange must be over on every peer before this rank's gradients change again
+  const unsigned* mine = pa.flags[pa.rank];
+  if (threadIdx.x < static_cast<unsigned>(pa.world)) peer_spin_until(mine + 8 + threadIdx.x, mine[16]);
+}
+
+template <bool PEER>
 __global__ void __launch_bounds__(256)
 adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                  float* __restrict__ m, float* __restrict__ v, float* __restrict__ state, float b1,
-                 float b2, float eps, float gscale, const bpb_prep_table tb) {
+                 float b2, float eps, float gscale, const bpb_prep_table tb,
+                 const bpb_peer_args pa) {
+  unsigned seq = 0;
+  if (PEER) {
+    unsigned* mine = pa.flags[pa.rank];
+    seq = mine[16] + 1u;
+    if (blockIdx.x == 0 && threadIdx.x < static_cast<unsigned>(pa.world)) {
+      __threadfence_system();
+      st_release_sys(pa.flags[threadIdx.x] + pa.rank, seq);  // ready[rank] on peer threadIdx.x
+    }
+    if (threadIdx.x < static_cast<unsigned>(pa.world)) peer_spin_until(mine + threadIdx.x, seq);
+    __syncthreads();
+  }
   // bias-corrected step size: double-precision pow is long and slow, one thread per block does it
   __shared__ float s_alpha;
   const float step_f = state[0] + 1.f;
@@ -446,7 +491,14 @@ adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g
   __nv_bfloat16* w_hf_op = reinterpret_cast<__nv_bfloat16*>(tb.w_hf_op);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * gscale;
+    float gsum;
+    if (PEER) {
+      gsum = 0.f;
+      for (int rk = 0; rk < pa.world; ++rk) gsum += __ldcv(pa.grads[rk] + i);  // uncached peer reads
+    } else {
+      gsum = g[i];
+    }
+    const float gi = gsum * gscale;
     const float mi = m[i] + (gi - m[i]) * (1.f - b1);
     const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
     m[i] = mi;
@@ -507,6 +559,13 @@ adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g
     if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
       *ticket = 0u;
       state[0] = step_f;
+      if (PEER) {
+        // every block of this rank has read the peers' buckets: release them
+        unsigned* mine = pa.flags[pa.rank];
+        mine[16] = seq;
+        __threadfence_system();
+        for (int rk = 0; rk < pa.world; ++rk) st_release_sys(pa.flags[rk] + 8 + pa.rank, seq);
+      }
     }
   }
 }
@@ -818,9 +877,72 @@ extern "C" int bpb_adam_prep_step(long long n, float* param, const float* grad, 
                  (t.w_hf_op == nullptr || t.N_heads >= t.T + t.H),
              "bpb_adam_prep_step: missing operand buffers");
   if (n <= 0) return 0;
-  adam_prep_kernel<<<ew_blocks(n), 256, 0, stream>>>(n, param, grad, m, v, state, beta1, beta2, eps,
-                                                     grad_scale, t);
+  adam_prep_kernel<false><<<ew_blocks(n), 256, 0, stream>>>(n, param, grad, m, v, state, beta1, beta2,
+                                                            eps, grad_scale, t, bpb_peer_args{});
   BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int check_peer_args(const char* who, const bpb_peer_args* pa) {
+  BP_REQUIRE(pa != nullptr && pa->world >= 1 && pa->world <= 8 && pa->rank >= 0 && pa->rank < pa->world,
+             "%s: bad peer arguments (world 1..8)", who);
+  for (int r = 0; r < pa->world; ++r)
+    BP_REQUIRE(pa->grads[r] != nullptr && pa->flags[r] != nullptr, "%s: peer %d is not mapped", who, r);
+  return 0;
+}
+
+extern "C" int bpb_adam_prep_step_peer(long long n, float* param, float* m, float* v, float* state,
+                                       float beta1, float beta2, float eps,
+                                       const bpb_prep_table* table, const bpb_peer_args* peers,
+                                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(param && m && v && state && table, "bpb_adam_prep_step_peer: NULL argument");
+  if (int rc = check_peer_args("bpb_adam_prep_step_peer", peers)) return rc;
+  if (n <= 0) return 0;
+  // every block waits for the peers at its start: the whole grid must be resident
+  int blocks = ew_blocks(n);
+  adam_prep_kernel<true><<<blocks, 256, 0, stream>>>(n, param, nullptr, m, v, state, beta1, beta2, eps,
+                                                     1.f / static_cast<float>(peers->world), *table,
+                                                     *peers);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bpb_peer_wait(const bpb_peer_args* peers, void* stream_) {
+  if (int rc = check_peer_args("bpb_peer_wait", peers)) return rc;
+  peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(*peers);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Memory a peer process can map (CUDA IPC): the gradient bucket and flag block of the exchange.
+extern "C" int bpb_peer_alloc(long long bytes, void** ptr, unsigned char* handle64) {
+  BP_REQUIRE(ptr && handle64 && bytes > 0, "bpb_peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  BP_CHECK_CUDA(cudaMalloc(ptr, static_cast<size_t>(bytes)));
+  BP_CHECK_CUDA(cudaMemset(*ptr, 0, static_cast<size_t>(bytes)));
+  cudaIpcMemHandle_t h;
+  BP_CHECK_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle64, &h, 64);
+  BP_CHECK_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" int bpb_peer_open(const unsigned char* handle64, void** ptr) {
+  BP_REQUIRE(ptr && handle64, "bpb_peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  BP_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int bpb_peer_close(void* ptr) {
+  if (ptr) BP_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+extern "C" int bpb_peer_free(void* ptr) {
+  if (ptr) BP_CHECK_CUDA(cudaFree(ptr));
   return 0;
 }
 

@@ -349,9 +349,16 @@ class SoloNet:
         return out_l, out_c
 
     # ------------------------------------------------------------------ training
-    def enable_training(self):
+    def enable_training(self, grads_flat=None):
+        """Allocates gradients and Adam moments.  ``grads_flat``: an external bucket of the right
+        size (``parallel.PeerGradExchange.grads``: peer-mapped memory for the fused all-reduce)."""
         if self.grads_flat is None:
-            self.grads_flat = torch.zeros_like(self.params.flat)
+            if grads_flat is not None:
+                assert grads_flat.numel() == self.params.flat.numel() and \
+                    grads_flat.dtype == torch.float32
+                grads_flat.zero_()
+            self.grads_flat = grads_flat if grads_flat is not None else \
+                torch.zeros_like(self.params.flat)
             self.adam_m = torch.zeros_like(self.params.flat)
             self.adam_v = torch.zeros_like(self.params.flat)
             self.g = self.params.views(self.grads_flat)
@@ -487,7 +494,7 @@ class SoloNet:
         return ws["losses"]
 
     def train_step(self, x_u8, counts, lr, use_graph=True, allreduce=None, world=1,
-                   bias_logits=None, bias_logcounts=None, use_bias=None):
+                   bias_logits=None, bias_logcounts=None, use_bias=None, peers=None):
         """One optimisation step.  ``x_u8`` / ``counts`` may live on the device or in (pinned)
         host memory.  With ``allreduce`` (a callable taking the flat gradient bucket, e.g. an NCCL
         all-reduce) the step is data parallel: local forward/backward, one all-reduce of the
@@ -501,6 +508,22 @@ class SoloNet:
             self.step_and_lr[1:2].fill_(float(lr))  # stream-ordered scalar fill, only on change
             self._lr_on_device = lr
 
+        if peers is not None:
+            # data parallel over NVLink peer memory: the optimiser kernel sums the ranks' buckets
+            # itself -- one graph per step, no collective call, no host involvement
+            assert bias_logits is None and self.grads_flat.data_ptr() == peers.grads.data_ptr()
+
+            def body_peer():
+                ops.peer_wait(peers.args)
+                self.forward_backward_into(ws)
+                self._rf_twin = None
+                ops.adam_prep_step_peer(self.params.flat, self.adam_m, self.adam_v,
+                                        self.step_and_lr, self._prep_table(), peers.args)
+            if use_graph:
+                self._run_graph(("train_peer", B, peers.world), body_peer)
+            else:
+                body_peer()
+            return ws["losses"]
         if bias_logits is not None:
             # combined model: the frozen bias outputs change every batch -> no graph replay
             self.forward_backward_into(ws, bias_logits, bias_logcounts, use_bias)

@@ -421,6 +421,19 @@ def adam_prep_step(param, grad, m, v, state, table, beta1=0.9, beta2=0.999, eps=
           "bpb_adam_prep_step")
 
 
+def adam_prep_step_peer(param, m, v, state, table, peers, beta1=0.9, beta2=0.999, eps=1e-7):
+    """``adam_prep_step`` with the gradient all-reduce fused in: the gradient is the sum over the
+    ranks' buckets read from NVLink peer memory (``peers`` = ``_lib.PeerArgs``), scaled 1/world."""
+    check(_lib.load().bpb_adam_prep_step_peer(param.numel(), _p(param), _p(m), _p(v), _p(state),
+                                              beta1, beta2, eps, C.byref(table), C.byref(peers),
+                                              _stream()), "bpb_adam_prep_step_peer")
+
+
+def peer_wait(peers):
+    """Enqueue the wait for every peer to have finished reading this rank's gradient bucket."""
+    check(_lib.load().bpb_peer_wait(C.byref(peers), _stream()), "bpb_peer_wait")
+
+
 def prep_conv3_weights(w, F, fwd, bwd, precise):
     """w: [3, Fw, Fw] or [layers, 3, Fw, Fw] fp32 -> fwd/bwd [layers, planes, 3, F, F] bf16."""
     lib = _lib.load()

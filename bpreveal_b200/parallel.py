@@ -100,3 +100,72 @@ def broadcast_object(obj, src=0):
         dist.broadcast_object_list(box, src=src)
         return box[0]
     return obj
+
+
+class PeerGradExchange:
+    """Gradient buckets and flag blocks of all ranks of one node, mapped into every process over
+    CUDA IPC, for the optimiser kernel that does the all-reduce itself
+    (``bpb_adam_prep_step_peer``).  ``grads`` is this rank's bucket as a torch tensor: the engine
+    writes its gradients there (``SoloNet.enable_training(grads_flat=exchange.grads)``).
+
+    Needs an initialised ``torch.distributed`` group (the 64-byte IPC handles travel through
+    ``all_gather_object``), all ranks on one node with peer access."""
+
+    FLAG_BYTES = 128
+
+    def __init__(self, numel, device, rank=None, world=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        lib = _lib.load()
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        if not 1 <= self.world <= 8:
+            raise ValueError("PeerGradExchange supports 1..8 ranks on one node")
+        self.numel = int(numel)
+        nbytes = self.FLAG_BYTES + 4 * self.numel
+        base = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _lib.check(lib.bpb_peer_alloc(nbytes, C.byref(base), handle), "bpb_peer_alloc")
+        self._base = base.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        self._opened = []
+        bases = []
+        for r in range(self.world):
+            if r == self.rank:
+                bases.append(self._base)
+                continue
+            ptr = C.c_void_p()
+            hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+            _lib.check(lib.bpb_peer_open(hb, C.byref(ptr)), "bpb_peer_open")
+            self._opened.append(ptr.value)
+            bases.append(ptr.value)
+        self.args = _lib.PeerArgs()
+        self.args.world, self.args.rank = self.world, self.rank
+        for r in range(self.world):
+            self.args.flags[r] = bases[r]
+            self.args.grads[r] = bases[r] + self.FLAG_BYTES
+
+        class _Raw:  # zero-copy view of the bucket for torch (CUDA array interface)
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.numel,), "typestr": "<f4",
+                                        "data": (self._base + self.FLAG_BYTES, False),
+                                        "version": 2, "strides": None}
+        self._raw = raw
+        self.grads = torch.as_tensor(raw, device=device)
+        dist.barrier()  # every rank has mapped every bucket before anyone uses them
+
+    def close(self):
+        from . import _lib
+        lib = _lib.load()
+        for ptr in self._opened:
+            lib.bpb_peer_close(ptr)
+        self._opened = []
+        if self._base:
+            lib.bpb_peer_free(self._base)
+            self._base = None

@@ -33,8 +33,8 @@ const char* bpb_last_error(void);
 /* Fills SM count and compute capability of the current device. */
 int bpb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* sizeof() of the argument structs as compiled: 0 bpb_conv3_args, 1 bpb_wgrad3_args,
- * 2 bpb_input_conv_args, 3 bpb_heads_dgrad_args, 4 bpb_prep_table (-1 otherwise); lets a binding
- * check its layout. */
+ * 2 bpb_input_conv_args, 3 bpb_heads_dgrad_args, 4 bpb_prep_table, 5 bpb_peer_args (-1 otherwise);
+ * lets a binding check its layout. */
 int bpb_abi_struct_size(int which);
 /* Pipeline watchdog: kernels whose mbarrier waits time out record
  * records in a host-mapped buffer and trap.  Copies up to n (<= 2048) words: word 0 = number of
@@ -307,6 +307,30 @@ typedef struct {
 int bpb_adam_prep_step(long long n, float* param, const float* grad, float* m, float* v,
                        float* state, float beta1, float beta2, float eps, float grad_scale,
                        const bpb_prep_table* table, void* stream);
+
+/* Data-parallel training over NVLink peer memory (one process per GPU, one node): the gradient
+ * all-reduce is fused into the optimiser kernel.  Each rank allocates its gradient bucket and a
+ * 128-byte flag block with bpb_peer_alloc (cudaMalloc + CUDA IPC handle, zero-filled), the ranks
+ * exchange the 64-byte handles by any means and map each other's memory with bpb_peer_open.
+ * bpb_adam_prep_step_peer = bpb_adam_prep_step with grad = the SUM over ranks of grads[r], read
+ * straight out of peer memory in rank order (bit-identical on every rank), scaled by 1/world;
+ * it waits (bounded, ~2 s, then traps) until every peer has reached the same call.  bpb_peer_wait
+ * must be enqueued before anything writes this rank's bucket again (start of the next step): it
+ * waits until every peer has finished reading it.  grads[r] / flags[r] are THIS process's
+ * mappings of rank r's bucket / flag block (r == rank: its own allocation). */
+typedef struct {
+  int world, rank;
+  const float* grads[8];
+  unsigned* flags[8];
+} bpb_peer_args;
+int bpb_peer_alloc(long long bytes, void** ptr, unsigned char* handle64);
+int bpb_peer_open(const unsigned char* handle64, void** ptr);
+int bpb_peer_close(void* ptr);
+int bpb_peer_free(void* ptr);
+int bpb_peer_wait(const bpb_peer_args* peers, void* stream);
+int bpb_adam_prep_step_peer(long long n, float* param, float* m, float* v, float* state, float beta1,
+                            float beta2, float eps, const bpb_prep_table* table,
+                            const bpb_peer_args* peers, void* stream);
 
 /* fp32 Keras conv kernels [layers][3][Fw][Fw] -> padded bf16 operand layouts of bpb_conv3_tc:
  *   fwd[l][p][j][n][c] = w[l][j][c][n]   and   bwd[l][p][j][n][c] = w[l][j][n][c]   (each

@@ -50,7 +50,7 @@ def test_binding_mirrors_header():
 def test_struct_layouts_match_compiled_sizes():
     lib = _lib.load()
     for which, cls in enumerate((_lib.Conv3Args, _lib.Wgrad3Args, _lib.InputConvArgs,
-                                 _lib.HeadsDgradArgs, _lib.PrepTable)):
+                                 _lib.HeadsDgradArgs, _lib.PrepTable, _lib.PeerArgs)):
         assert lib.bpb_abi_struct_size(which) == ctypes.sizeof(cls), cls.__name__
     assert lib.bpb_abi_struct_size(99) == -1
 
