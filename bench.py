@@ -262,7 +262,7 @@ def main():
     # (BPB_DP_PEER=0 selects the NCCL all-reduce between two CUDA graphs instead); the choice is
     # made collectively so that every rank takes the same path
     peers = None
-    if world > 1 and os.environ.get("BPB_DP_PEER", "0") == "1":
+    if world > 1 and os.environ.get("BPB_DP_PEER", "1") == "1":
         from bpreveal_b200 import parallel
         ok = 1
         try:

@@ -121,8 +121,8 @@ class PeerGradExchange:
 
         from . import _lib
         lib = _lib.load()
-        self.rank = dist.get_rank() if rank is None else rank
-        self.world = dist.get_world_size() if world is None else world
+        self.rank = rank if rank is not None else dist.get_rank()
+        self.world = world if world is not None else dist.get_world_size()
         if not 1 <= self.world <= 8:
             raise ValueError("PeerGradExchange supports 1..8 ranks on one node")
         self.numel = int(numel)
@@ -131,8 +131,10 @@ class PeerGradExchange:
         handle = (C.c_ubyte * 64)()
         _lib.check(lib.bpb_peer_alloc(nbytes, C.byref(base), handle), "bpb_peer_alloc")
         self._base = base.value
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle))
+        handles = [bytes(handle)]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle))
         self._opened = []
         bases = []
         for r in range(self.world):
@@ -158,7 +160,8 @@ class PeerGradExchange:
                                         "version": 2, "strides": None}
         self._raw = raw
         self.grads = torch.as_tensor(raw, device=device)
-        dist.barrier()  # every rank has mapped every bucket before anyone uses them
+        if self.world > 1:
+            dist.barrier()  # every rank has mapped every bucket before anyone uses them
 
     def close(self):
         from . import _lib

@@ -299,3 +299,29 @@ def test_fused_adam_refresh_matches_separate_kernels(dev, precise):
     assert torch.equal(net.adam_m, ref["m"]) and torch.equal(net.adam_v, ref["v"])
     for k in names:
         assert torch.equal(getattr(net, k).view(torch.int16), ref[k].view(torch.int16)), k
+
+
+def test_peer_exchange_kernel_with_one_rank_equals_plain_step(dev):
+    """The fused all-reduce + Adam kernel (bpb_adam_prep_step_peer) on a world of one rank --
+    bucket and flags in CUDA-IPC-capable memory, both flag barriers exercised over three steps --
+    gives bit for bit the parameters of the plain step.  (Several ranks: tests/diag_peer.py under
+    torchrun, which also checks that every rank ends with identical parameters.)"""
+    from bpreveal_b200 import parallel
+    cfg = dict(CASES[0][1])
+    B = 4
+    x = torch.tensor(O.synthetic_sequences(B, cfg["inputLength"], seed=3), device=dev)
+    c = torch.tensor(O.synthetic_profiles(B, cfg["outputLength"], 2, seed=3, meanReads=30.0), device=dev)
+    net_a, _ = build(cfg, False, dev)
+    net_b, _ = build(cfg, False, dev)
+    ex = parallel.PeerGradExchange(net_b.params.flat.numel(), dev, rank=0, world=1)
+    try:
+        net_b.enable_training(grads_flat=ex.grads)
+        for _ in range(3):
+            la = net_a.train_step(x, c, 0.004).clone()
+            lb = net_b.train_step(x, c, 0.004, peers=ex).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(la, lb)
+        assert torch.equal(net_a.params.flat, net_b.params.flat)
+        assert float(net_b.step_and_lr[0]) == 3.0
+    finally:
+        ex.close()
