@@ -48,6 +48,7 @@ struct WgradKParams {
   // STRIP staging of the A operand (window gradients over a 16-byte-per-position tensor): the raw
   // strip of 128 + 8*n_units positions is copied once per position tile and read through
   // NON-swizzled MN-major descriptors (LBO 128 B along K, SBO 16 B along MN), unit u at +128*u B.
+  int pair_units;  // 1: two units per M = 128 MMA
   int strip[kWgMaxJobs], strip_bytes[kWgMaxJobs];
   long long a_batch_bytes[kWgMaxJobs];
   const uint8_t* a_base[kWgMaxJobs];
@@ -65,15 +66,22 @@ __global__ void __launch_bounds__(192, 1)
 wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   constexpr int NSUB = NT / 64;
   constexpr uint32_t IDESC = umma_idesc_bf16(64, NT, 1, 1);
+  // Two units per MMA (M = 128): the second 64-row block of the MN-major A operand lies one
+  // "leading byte offset" after the first -- the next tile (SLAB), dil rows further into the box
+  // (HALO), contiguous (STRIP) or, for the last unit of an odd count, the constant tile of ones
+  // whose product is the bias gradient.  Halves the tensor-pipe time of this kernel, which the
+  // M = 64 form kept 69 % busy re-reading operands (profiles/other_kernels_full_r1_final_summary).
+  constexpr uint32_t IDESC2 = umma_idesc_bf16(128, NT, 1, 1);
   constexpr uint32_t TMEM_COLS = 512;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const size_t stage_bytes = static_cast<size_t>(p.stage_bytes);
-  uint8_t* ones = smem;
-  uint8_t* ring = smem + kWgTile;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.stages * stage_bytes);
+  // the ones tile sits ABOVE the ring: a pair (unit, ones) reaches it with a positive offset
+  uint8_t* ring = smem;
+  uint8_t* ones = ring + p.stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + kWgTile);
   uint64_t* full = bars;
   uint64_t* empty = bars + kWgMaxStages;
   uint64_t* acc_full = bars + 2 * kWgMaxStages;
@@ -108,6 +116,14 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   const int u0 = grp * p.UG;
   const int nu = min(p.UG, n_units - u0);
   const bool do_db = (grp == 0);
+  // accumulator slots of NT columns: real pairs, then the odd unit (paired with the ones tile on
+  // the single-pass path), then -- if it is not paired -- the bias-gradient unit
+  const int n_pairs = p.pair_units ? (nu >> 1) : 0;
+  const int n_single = nu - 2 * n_pairs;  // M = 64 units when pairing is off, else 0 | 1
+  // (not for STRIP jobs: in the non-swizzled MN-major form the rows of an operand are contiguous,
+  // there is no second-block offset to point at the ones tile)
+  const bool pair_ones = p.pair_units && n_single == 1 && do_db && p.n_passes == 1 && !strip;
+  const int db_slot = n_pairs + n_single;  // used when !pair_ones
   const int kblocks = p.B * tiles_per_seq;
   const int my_kb = (kblocks - split + ksplit - 1) / ksplit;  // split < ksplit <= kblocks
   const int visits = my_kb * p.n_passes;
@@ -200,6 +216,10 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
       const uint32_t a_lbo = strip ? ((128u >> 4) << 16) : lbo_bits;
       const uint32_t a_hi = strip ? ((16u >> 4) | (1u << 14)) : DHI;
       const uint32_t a_kstep = strip ? (256u >> 4) : 128u;
+      // distance between the two units of a pair, as the descriptor's leading byte offset
+      const uint32_t pair_lbo = strip ? a_lbo
+                                : halo ? ((static_cast<uint32_t>(dil) * 128u) >> 4) << 16
+                                       : lbo_bits;
       for (int v = 0; v < visits; ++v) {
         const int pass = v % p.n_passes;
         mbar_wait_wd(&full[stage], phase, p.dbg, 0x1500 + stage, v);
@@ -208,24 +228,46 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
 #endif
         tc_fence_after();
         const uint32_t g_lo = ((ring_lo + stage * stage_lo) & 0x3FFFu) | lbo_bits;
+        const uint32_t st_lo = (ring_lo + stage * stage_lo) & 0x3FFFu;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i < nu) {
+        for (int pr = 0; pr < 2; ++pr) {
+          if (pr < n_pairs) {
             // HALO: tap i starts i*dil rows into the box (the 128-byte swizzle is a function of
             // the absolute shared-memory address, so an MN-major operand may start on any row)
-            const uint32_t a_lo = (((ring_lo + stage * stage_lo) & 0x3FFFu) + a_off[i]) | a_lbo;
+            const uint32_t a_lo = (st_lo + a_off[2 * pr]) | pair_lbo;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_bf16_lohi(tmem_base + i * NT, a_lo + k * a_kstep, a_hi, g_lo + k * 128u, DHI,
-                             IDESC, (v | k) != 0 ? 1u : 0u);
+              umma_bf16_lohi(tmem_base + pr * NT, a_lo + k * a_kstep, a_hi, g_lo + k * 128u, DHI,
+                             IDESC2, (v | k) != 0 ? 1u : 0u);
           }
         }
-        if (do_db && ((p.db_mask >> pass) & 1)) {
+        if (pair_ones) {
+          // (last unit, ones): the second block starts at the ones tile, wherever this stage is
+          const uint32_t a_addr = st_lo + a_off[nu - 1];
+          const uint32_t lbo = ((smem_u32(ones) >> 4) - a_addr) & 0x3FFFu;
+          const uint32_t a_lo = a_addr | (lbo << 16);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16_lohi(tmem_base + p.UG * NT, ones_lo + k * 128u, DHI, g_lo + k * 128u, DHI,
-                           IDESC, (db_started | k) != 0 ? 1u : 0u);
-          db_started = 1;
+            umma_bf16_lohi(tmem_base + n_pairs * NT, a_lo + k * a_kstep, a_hi, g_lo + k * 128u, DHI,
+                           IDESC2, (v | k) != 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < n_single) {
+              const uint32_t a_lo = (st_lo + a_off[2 * n_pairs + i]) | a_lbo;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_bf16_lohi(tmem_base + (n_pairs + i) * NT, a_lo + k * a_kstep, a_hi,
+                               g_lo + k * 128u, DHI, IDESC, (v | k) != 0 ? 1u : 0u);
+            }
+          }
+          if (do_db && ((p.db_mask >> pass) & 1)) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16_lohi(tmem_base + db_slot * NT, ones_lo + k * 128u, DHI, g_lo + k * 128u, DHI,
+                             IDESC, (db_started | k) != 0 ? 1u : 0u);
+            db_started = 1;
+          }
         }
         umma_commit(&empty[stage]);
         if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
@@ -241,13 +283,34 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
     if (threadIdx.x == 64) WG_STAMP(24);
     const size_t rows = static_cast<size_t>(n_units) * 64;
     float* wsp = p.ws + p.ws_off[job] + static_cast<size_t>(split) * (rows + 1) * p.Ncols;
-    for (int i = 0; i < nu; ++i) {
-      const int u = u0 + i;
+    // M = 128 slots: accumulator row = TMEM lane, rows 0-63 the first unit of the pair, 64-127
+    // the second (or the ones tile: every one of its rows is the bias gradient)
+    for (int pr = 0; pr < n_pairs + (pair_ones ? 1 : 0); ++pr) {
+      const bool ones_half = pr == n_pairs && q >= 2;
+      const int u = u0 + 2 * pr + (q >> 1);
+      const int m = (q & 1) * 32 + lane;
+      for (int col = 0; col < NT; col += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + pr * NT + col + (static_cast<uint32_t>(q * 32) << 16), r);
+        tmem_ld_wait();
+        if (!ones_half || (q == 2 && lane == 0)) {
+          float4* dst = reinterpret_cast<float4*>(
+              ones_half ? wsp + rows * p.Ncols + nt * NT + col
+                        : wsp + (static_cast<size_t>(u) * 64 + m) * p.Ncols + nt * NT + col);
+#pragma unroll
+          for (int x = 0; x < 8; ++x)
+            dst[x] = make_float4(__uint_as_float(r[4 * x]), __uint_as_float(r[4 * x + 1]),
+                                 __uint_as_float(r[4 * x + 2]), __uint_as_float(r[4 * x + 3]));
+        }
+      }
+    }
+    for (int i = 0; i < (pair_ones ? 0 : n_single); ++i) {
+      const int u = u0 + 2 * n_pairs + i;
       // M=64 accumulators occupy lanes 0-15 of each TMEM quadrant: row = 16*q + lane.
       const int m = 16 * q + lane;
       for (int col = 0; col < NT; col += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + i * NT + col + (static_cast<uint32_t>(q * 32) << 16), r);
+        tmem_ld32(tmem_base + (n_pairs + i) * NT + col + (static_cast<uint32_t>(q * 32) << 16), r);
         tmem_ld_wait();
         if (lane < 16) {
           float4* dst = reinterpret_cast<float4*>(
@@ -259,10 +322,10 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
         }
       }
     }
-    if (do_db && q == 0) {
+    if (do_db && q == 0 && !pair_ones) {
       for (int col = 0; col < NT; col += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + p.UG * NT + col, r);
+        tmem_ld32(tmem_base + db_slot * NT + col, r);
         tmem_ld_wait();
         if (lane == 0) {
           float* dst = wsp + rows * p.Ncols + nt * NT + col;
@@ -570,6 +633,11 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
   kp.stage_bytes = static_cast<int>(pl.stage_bytes);
   kp.Ncols = d0.Ncols;
   kp.n_jobs = n_jobs;
+  static const bool pair_enabled = [] {
+    const char* e = getenv("BPB_WG_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  kp.pair_units = pair_enabled ? 1 : 0;
   kp.ws = d0.ws;
   kp.dbg = debug_buffer();
 
