@@ -491,12 +491,12 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
   const int sms = sm_count();
   if (sms <= 0) return false;
   // split-K factors: the SMs are shared between the jobs in proportion to their position tiles
-  // (a STRIP-staged job is bound by its MMAs -- units + 1 groups of 8 per position tile -- where a
-  // tower job is bound by HBM: measured ~1.7k against ~1.4k cycles per tile, hence the weight)
+  // (BPB_WG_STRIP_COST weights the STRIP-staged jobs: they were MMA-bound at ~1.7k against ~1.4k
+  // cycles per tile with M = 64 MMAs (best weight 1.25); with paired M = 128 MMAs 1.0 measures best)
   static const double strip_cost = [] {
     const char* e = getenv("BPB_WG_STRIP_COST");
     const double v = e ? atof(e) : 0.0;
-    return v > 0.1 ? v : 1.25;
+    return v > 0.1 ? v : 1.0;
   }();
   double total_kb = 0;
   int kb[kWgMaxJobs];
