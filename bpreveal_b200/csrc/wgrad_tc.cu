@@ -470,7 +470,16 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
                        const int* n_units_j, int Ncols, WgradPlan* pl,
                        const bool* strip_j = nullptr) {
   if (n_jobs < 1 || n_jobs > kWgMaxJobs) return false;
-  const int NT = (Ncols % 256 == 0) ? 256 : (Ncols % 128 == 0 ? 128 : 64);
+  // BPB_WG_NT caps the column tile (256 | 128 | 64; default 128): a 128-column tile leaves TMEM
+  // room for three units per CTA, which the paired M = 128 MMAs need (F = 512 weight gradients:
+  // 520 TFLOP/s with 256-column tiles and one unit per CTA, 685 with 128)
+  static const int nt_cap = [] {
+    const char* e = getenv("BPB_WG_NT");
+    const int v = e ? atoi(e) : 128;
+    return (v == 64 || v == 256) ? v : 128;
+  }();
+  int NT = (Ncols % 256 == 0) ? 256 : (Ncols % 128 == 0 ? 128 : 64);
+  if (NT > nt_cap) NT = nt_cap;
   pl->NT = NT;
   int n_units = 0;
   bool uniform = true;
