@@ -742,10 +742,17 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float flag = gt0_flag(v[i]);
-              if (g < 2) obits_lo = fmaf(flag, static_cast<float>(1u << (g * 8 + i)), obits_lo);
-              else obits_hi = fmaf(flag, static_cast<float>(1u << (g * 8 + i - 16)), obits_hi);
-              o[i] = fmaf(v[i], flag, r[i]);
+              if (EPI != EPI_FWD_R) {
+                const float flag = gt0_flag(v[i]);
+                if (g < 2) obits_lo = fmaf(flag, static_cast<float>(1u << (g * 8 + i)), obits_lo);
+                else obits_hi = fmaf(flag, static_cast<float>(1u << (g * 8 + i - 16)), obits_hi);
+                o[i] = fmaf(v[i], flag, r[i]);
+              } else {
+                // the reference pass of DeepSHAP keeps multipliers, not ReLU masks (the ABI rejects
+                // mask_out together with out2): no mask bits, and max(v, 0) is shared with the
+                // rescale rule above
+                o[i] = fmaxf(v[i], 0.f) + r[i];
+              }
             }
           } else {
 #pragma unroll
@@ -816,7 +823,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         // The mask goes out AFTER the proxy fence above: fence.proxy.async compiles to a
         // MEMBAR that drains this warp's outstanding stores, and a global store issued before
         // it would put a round trip to L2 on the critical path of every chunk.
-        if (IS_FWD && p.mask_out != nullptr && valid)
+        if (EPI != EPI_FWD_R && p.mask_out != nullptr && valid)
           p.mask_out[(orow * chunks_per_row + (n0 >> 6)) * 2 + half] =
               static_cast<uint32_t>(obits_lo) | (static_cast<uint32_t>(obits_hi) << 16);
       }
