@@ -145,6 +145,15 @@ def gpu_extras(net_cfg, dev, rank):
     e1.record()
     torch.cuda.synchronize()
     out["predict_windows_per_s"] = 3 * 1024 / (e0.elapsed_time(e1) / 1e3)
+    # the same end to end: pinned host windows in, pinned host logits / log-counts out
+    xh = torch.tensor(xs).pin_memory()
+    net.predict_host(xh, batchSize=128)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        net.predict_host(xh, batchSize=128)
+    torch.cuda.synchronize()
+    out["predict_e2e_windows_per_s"] = 3 * 1024 / (time.perf_counter() - t0)
     for label, precise in (("pisa_bases_per_s", False), ("pisa_bases_per_s_precise", True)):
         pn = SoloNet(NetConfig(precise=precise, **net_cfg), dev)
         pn.load_state(net.state())

@@ -348,6 +348,65 @@ class SoloNet:
             out_c[s:e].copy_(ws["logcounts"])
         return out_l, out_c
 
+    def predict_host(self, x_host, batchSize=128, out_logits=None, out_logcounts=None):
+        """Streaming prediction for host data (utils.BatchPredictor.runBatch, utils.py:986-1051, at
+        makePredictions scale): ``x_host`` (N, Lin, 4) uint8 in (ideally pinned) host memory ->
+        pinned host tensors (logits (N, Lout, T), logcounts (N, H)).  Three streams: the H2D copy
+        of batch i+1 and the D2H copy of batch i-1 overlap the forward pass of batch i (two
+        staging slots each way)."""
+        cfg, dev = self.cfg, self.device
+        x_host = torch.as_tensor(x_host)
+        N, B = x_host.shape[0], int(batchSize)
+        if out_logits is None:
+            out_logits = torch.empty((N, cfg.outputLength, cfg.T), dtype=torch.float32,
+                                     pin_memory=True)
+        if out_logcounts is None:
+            out_logcounts = torch.empty((N, cfg.H), dtype=torch.float32, pin_memory=True)
+        n_full = N // B
+        if n_full > 0:
+            ws = self._workspace(B, "predict")
+            st = ws.get("stream_io")
+            if st is None:
+                st = {"xin": [torch.empty_like(ws["x"]) for _ in range(2)],
+                      "lo": [torch.empty_like(ws["logits"]) for _ in range(2)],
+                      "co": [torch.empty_like(ws["logcounts"]) for _ in range(2)],
+                      "in_ready": [torch.cuda.Event() for _ in range(2)],
+                      "in_free": [torch.cuda.Event() for _ in range(2)],
+                      "out_ready": [torch.cuda.Event() for _ in range(2)],
+                      "out_free": [torch.cuda.Event() for _ in range(2)],
+                      "h2d": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev)}
+                ws["stream_io"] = st
+            cur = torch.cuda.current_stream(dev)
+            for ev in st["in_free"] + st["out_free"]:
+                ev.record(cur)
+            body = lambda ws=ws: self.predict_into(ws)  # noqa: E731
+            for i in range(n_full):
+                k, s, e = i & 1, i * B, (i + 1) * B
+                st["h2d"].wait_event(st["in_free"][k])
+                with torch.cuda.stream(st["h2d"]):
+                    st["xin"][k].copy_(x_host[s:e], non_blocking=True)
+                    st["in_ready"][k].record(st["h2d"])
+                cur.wait_event(st["in_ready"][k])
+                ws["x"].copy_(st["xin"][k], non_blocking=True)
+                st["in_free"][k].record(cur)
+                self._run_graph(("predict", B), body)
+                cur.wait_event(st["out_free"][k])
+                st["lo"][k].copy_(ws["logits"], non_blocking=True)
+                st["co"][k].copy_(ws["logcounts"], non_blocking=True)
+                st["out_ready"][k].record(cur)
+                st["d2h"].wait_event(st["out_ready"][k])
+                with torch.cuda.stream(st["d2h"]):
+                    out_logits[s:e].copy_(st["lo"][k], non_blocking=True)
+                    out_logcounts[s:e].copy_(st["co"][k], non_blocking=True)
+                    st["out_free"][k].record(st["d2h"])
+            st["d2h"].synchronize()
+        if n_full * B < N:  # ragged tail through the plain path
+            s = n_full * B
+            tl, tc = self.predict(x_host[s:].to(dev), batchSize=B)
+            out_logits[s:].copy_(tl)
+            out_logcounts[s:].copy_(tc)
+        return out_logits, out_logcounts
+
     # ------------------------------------------------------------------ training
     def enable_training(self, grads_flat=None):
         """Allocates gradients and Adam moments.  ``grads_flat``: an external bucket of the right

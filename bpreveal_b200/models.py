@@ -143,6 +143,14 @@ class Model:
         as numpy float32 (Keras ``predict`` contract used at utils.py:1021-1023)."""
         del verbose
         dev = self._device
+        host = getattr(self, "_predict_host", None)
+        if host is not None and not (isinstance(x, torch.Tensor) and x.is_cuda):
+            # streaming path: copies overlap the forward passes
+            xh = torch.as_tensor(np.ascontiguousarray(x))
+            if xh.dtype != torch.uint8:
+                xh = xh.to(torch.uint8)
+            logits, lc = host(xh, batch_size)
+            return self._split_outputs(logits.numpy(), lc.numpy())
         xt = torch.as_tensor(np.ascontiguousarray(x)).to(device=dev, dtype=torch.uint8)
         logits, lc = self._predict_device(xt, batch_size)
         return self._split_outputs(logits.cpu().numpy(), lc.cpu().numpy())
@@ -338,6 +346,9 @@ class SoloModel(Model):
 
     def _predict_device(self, xt, batch_size):
         return self.net.predict(xt, batchSize=batch_size)
+
+    def _predict_host(self, xh, batch_size):
+        return self.net.predict_host(xh, batchSize=batch_size)
 
     def _step(self, xb, counts, train):
         net = self.net

@@ -355,3 +355,22 @@ def test_prediction_side_kernels(dev):
             ref = e / e.sum() * np.exp(lcn[bi, h])
             assert np.allclose(prof[bi, :, k0:k1], ref, rtol=2e-5, atol=1e-9)
             assert np.isclose(prof[bi, :, k0:k1].sum(), np.exp(lcn[bi, h]), rtol=1e-5)
+
+
+def test_streaming_host_prediction_equals_device_prediction(dev):
+    """SoloNet.predict_host (H2D / forward / D2H on three streams, two staging slots each way, ragged
+    tail) returns exactly what the device-resident path returns, also when called twice."""
+    from bpreveal_b200 import models
+    m = models.soloModel(52, 20, 16, 3, 3, 3, HEADS, "solo", device=dev, seed=7)
+    x = O.synthetic_sequences(8 * 5 + 3, 52, seed=4)
+    want_l, want_c = m.net.predict(torch.tensor(x, device=dev), batchSize=8)
+    torch.cuda.synchronize()
+    for pinned in (True, False):
+        xh = torch.tensor(x).pin_memory() if pinned else torch.tensor(x)
+        for _ in range(2):
+            got_l, got_c = m.net.predict_host(xh, batchSize=8)
+            assert got_l.is_pinned() and torch.equal(got_l, want_l.cpu()) and \
+                torch.equal(got_c, want_c.cpu())
+    outs = m.predict(x, batch_size=8)  # the Keras-style call takes the streaming path for numpy
+    assert np.array_equal(outs[0], want_l.cpu().numpy()[:, :, :2])
+    assert np.array_equal(outs[3], want_c.cpu().numpy()[:, 1:2])
