@@ -337,7 +337,7 @@ def main():
     orig_check = ops.check
 
     kernels_per_call = {"bpb_wgrad3_tc": 2, "bpb_wgrad3_multi": 2, "bpb_wgrad_tower_input": 2, "bpb_peer_wait": 1, "bpb_adam_prep_step_peer": 1, "bpb_input_conv_wgrad": 2, "bpb_heads_fwd": 2,
-                        "bpb_heads_wgrad_tc": 2, "bpb_heads_pack_grad": 2, "bpb_heads_fwd_tc": 2}
+                        "bpb_heads_wgrad_tc": 2, "bpb_heads_pack_grad": 2, "bpb_heads_fwd_tc": 1}
 
     def counting_check(rc, what):
         counter["n"] += kernels_per_call.get(what, 1)

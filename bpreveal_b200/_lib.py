@@ -127,7 +127,8 @@ SIGNATURES = {
     "bpb_heads_fwd_tc": (c_int, [c_int] * 6 + [c_void_p] * 8 + [c_ll, c_void_p]),
     "bpb_loss_fwd_bwd": (c_int, [c_int] * 4 + [c_void_p] * 11),
     "bpb_loss_pack_ws_elems": (c_ll, [c_int] * 3),
-    "bpb_loss_fwd_bwd_pack": (c_int, [c_int] * 4 + [c_void_p] * 10 + [c_int] * 4 + [c_void_p] * 6),
+    "bpb_loss_fwd_bwd_pack": (c_int, [c_int] * 4 + [c_void_p] * 10 + [c_int] * 4 + [c_void_p] * 6 +
+                              [c_int, c_void_p, c_void_p]),  # ..., hto, counts_partials | tiles, cb, stream
     "bpb_ushuffle_ohe": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, C.c_uint]),
     "bpb_adam_step": (c_int, [c_ll] + [c_void_p] * 5 + [c_float] * 4 + [c_void_p]),
     "bpb_peer_alloc": (c_int, [c_ll, C.POINTER(c_void_p), c_void_p]),

@@ -436,7 +436,7 @@ static int heads_fwd_run(const char* who, int full, int B, int L_in, int W, int 
   else LAUNCH_HD(512);
 #undef LAUNCH_HD
   BP_CHECK_CUDA(cudaGetLastError());
-  if (H > 0) {
+  if (H > 0 && logcounts != nullptr) {
     heads_counts_finish_kernel<<<(B * H + 127) / 128, 128, 0, stream>>>(B, kp.tiles_per_seq, H, L_in,
                                                                         ws, cb, logcounts);
     BP_CHECK_CUDA(cudaGetLastError());
@@ -449,7 +449,8 @@ extern "C" int bpb_heads_fwd_tc(int B, int L_in, int W, int F, int T, int H,
                                 const bpb_bf16* w_op, const float* pb, const float* cb,
                                 float* logits, float* logcounts, float* ws, long long ws_bytes,
                                 void* stream_) {
-  BP_REQUIRE(act_hi && w_op && pb && cb && logits && logcounts && ws, "bpb_heads_fwd_tc: NULL argument");
+  // logcounts == NULL: leave the per-tile partial sums in ws for bpb_loss_fwd_bwd_pack to finish
+  BP_REQUIRE(act_hi && w_op && pb && cb && logits && ws, "bpb_heads_fwd_tc: NULL argument");
   BP_REQUIRE(F > 0 && F % 64 == 0 && H >= 1 && H <= 16 && T >= 1 && T <= 240 && L_in >= W,
              "bpb_heads_fwd_tc: bad geometry F=%d T=%d H=%d", F, T, H);
   return heads_fwd_run("bpb_heads_fwd_tc", 0, B, L_in, W, F, T, H, act_hi, act_lo, w_op, pb, cb, logits,

@@ -188,6 +188,12 @@ struct LossPack {
   __nv_bfloat16* d8;
   float *dpb, *dcb;
   float* ws;  // [B][2H] loss terms | [B][T] profile-bias terms | [B][H] dlogcounts | counter
+  // optional: the heads' forward left per-tile partial sums of the counts columns (bpb_heads_fwd_tc
+  // with logcounts == NULL); this kernel then finishes log-counts itself (and stores them)
+  const float* cpart;  // [B][tiles][H]
+  const float* cb;     // [H]
+  int tiles;
+  float* logcounts_out;
   unsigned* dbg;
 };
 
@@ -207,7 +213,18 @@ loss_pack_kernel(int B, int L, int T, int H, const int* __restrict__ task_off,
   const int k0 = task_off[h];
   const int Th = task_off[h + 1] - k0;
   // scalars of this (sequence, head): fetched now so that their latency hides behind pass 1
-  const float w_prof = profile_weight[h], lam_h = lambda[h], lc_pred = logcounts[b * H + h];
+  const float w_prof = profile_weight[h], lam_h = lambda[h];
+  float lc_pred;
+  if (pk.cpart != nullptr) {
+    // the same sum, in the same order, as heads_counts_finish_kernel
+    float cs = 0.f;
+    for (int tIdx = 0; tIdx < pk.tiles; ++tIdx)
+      cs += pk.cpart[(static_cast<size_t>(b) * pk.tiles + tIdx) * H + h];
+    lc_pred = pk.cb[h] + cs / static_cast<float>(pk.L_in);
+    if (threadIdx.x == 0) pk.logcounts_out[b * H + h] = lc_pred;
+  } else {
+    lc_pred = logcounts[b * H + h];
+  }
   const float lc_true = logcounts_true ? logcounts_true[b * H + h] : 0.f;
   const float* lg = logits + static_cast<size_t>(b) * L * T + k0;
   const float* ct = counts + static_cast<size_t>(b) * L * T + k0;
@@ -810,11 +827,14 @@ extern "C" int bpb_loss_fwd_bwd_pack(int B, int L, int T, int H, const int* task
                                      float* losses, float* dlogits, float* dlogcounts, int L_in,
                                      int W, int Cp, int planes, bpb_bf16* d8, float* dpb,
                                      float* dcb, float* ws, const int* host_task_off,
+                                     const float* counts_partials, int tiles, const float* cb,
                                      void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BP_REQUIRE(task_off && logits && logcounts && counts && profile_weight && lambda && losses &&
                  d8 && ws && host_task_off,
              "bpb_loss_fwd_bwd_pack: NULL argument");
+  BP_REQUIRE(counts_partials == nullptr || (cb != nullptr && tiles == (L_in + 127) / 128),
+             "bpb_loss_fwd_bwd_pack: counts_partials needs cb and tiles = ceil(L_in / 128)");
   BP_REQUIRE(B > 0 && L > 0 && T > 0 && H > 0, "bpb_loss_fwd_bwd_pack: bad sizes");
   BP_REQUIRE(Cp % 8 == 0 && Cp >= T + H && L == L_in - W + 1 && (planes == 1 || planes == 2),
              "bpb_loss_fwd_bwd_pack: bad geometry (Cp=%d must be a multiple of 8 >= T+H=%d)", Cp,
@@ -836,6 +856,10 @@ extern "C" int bpb_loss_fwd_bwd_pack(int B, int L, int T, int H, const int* task
   pk.dpb = dpb;
   pk.dcb = dcb;
   pk.ws = ws;
+  pk.cpart = counts_partials;
+  pk.cb = cb;
+  pk.tiles = tiles;
+  pk.logcounts_out = const_cast<float*>(logcounts);
   pk.dbg = debug_buffer();
   dim3 grid(B, H);
   static const int n_threads = [] {

@@ -294,7 +294,7 @@ class SoloNet:
 
     # ------------------------------------------------------------------ forward
     def _forward(self, ws, x, save_masks=False, z_list=None, zx_list=None, zx_div=1,
-                 mult_list=None):
+                 mult_list=None, defer_counts=False):
         cfg = self.cfg
         p = self.p
         Ls = cfg.lengths()
@@ -322,8 +322,10 @@ class SoloNet:
                       out2=mult_list[i + 1] if mult_list else None)
             a = nxt
         if self.heads_tc:
+            # defer_counts: the fused loss kernel finishes the log-counts from the per-tile sums
             ops.heads_fwd_tc(a, self.w_hf_op, cfg.outputFilterWidth, cfg.T, cfg.H, p["prof_b"],
-                             p["cnt_b"], ws["logits"], ws["logcounts"], ws["hf_ws"])
+                             p["cnt_b"], ws["logits"], None if defer_counts else ws["logcounts"],
+                             ws["hf_ws"])
         else:
             ops.heads_fwd(a, p["prof_w"], p["prof_b"], p["cnt_w"], p["cnt_b"], ws["logits"],
                           ws["gap"], ws["logcounts"])
@@ -432,7 +434,10 @@ class SoloNet:
         loss: logits by addition, logcounts by CountsLogSumExp where ``use_bias[h]``."""
         cfg, p, g = self.cfg, self.p, self.g
         Ls = cfg.lengths()
-        aL = self._forward(ws, ws["x"], save_masks=True)
+        # solo model: losses, packed loss gradient and the heads' bias gradients in ONE launch
+        fused = bias_logits is None and max(cfg.headTasks) <= 8
+        defer = fused and self.heads_tc
+        aL = self._forward(ws, ws["x"], save_masks=True, defer_counts=defer)
         logits, lc = ws["logits"], ws["logcounts"]
         if bias_logits is not None:
             if "logits_c" not in ws:
@@ -444,14 +449,14 @@ class SoloNet:
             logits, lc = ws["logits_c"], ws["lc_c"]
         nL = cfg.numLayers
         planes = 2 if cfg.precise else 1
-        # solo model: losses, packed loss gradient and the heads' bias gradients in ONE launch
-        fused = bias_logits is None and max(cfg.headTasks) <= 8
         if fused:
             ops.loss_fwd_bwd_pack(self.task_off, self.host_task_off, logits, lc, ws["counts"],
                                   self.profile_weight, self.lam, ws["losses"], Ls[nL],
                                   cfg.outputFilterWidth, self.cp, planes, ws["d8"], ws["loss_ws"],
                                   dlogits=ws["dlogits"], dlogcounts=ws["dlogcounts"],
-                                  dpb=g["prof_b"], dcb=g["cnt_b"])
+                                  dpb=g["prof_b"], dcb=g["cnt_b"],
+                                  counts_partials=ws["hf_ws"] if defer else None,
+                                  cb=p["cnt_b"] if defer else None)
         else:
             ops.loss_fwd_bwd(self.task_off, logits, lc, ws["counts"], self.profile_weight,
                              self.lam, ws["losses"], ws["dlogits"], ws["dlogcounts"])

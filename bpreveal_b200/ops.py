@@ -378,7 +378,7 @@ def loss_pack_ws(B, T, H, device):
 
 def loss_fwd_bwd_pack(task_off, host_task_off, logits, logcounts, counts, profile_weight, lam, losses,
                       L_in, W, Cp, planes, d8, ws, dlogits=None, dlogcounts=None, dpb=None, dcb=None,
-                      logcounts_true=None):
+                      logcounts_true=None, counts_partials=None, cb=None):
     """K5 + bpb_heads_pack_grad in one launch; ``d8`` must have been zero-filled once
     (``heads_d8``), ``host_task_off`` is a sequence of ints."""
     lib = _lib.load()
@@ -388,7 +388,8 @@ def loss_fwd_bwd_pack(task_off, host_task_off, logits, logcounts, counts, profil
     check(lib.bpb_loss_fwd_bwd_pack(B, L, T, H, _p(task_off), _p(logits), _p(logcounts), _p(counts),
                                     _p(logcounts_true), _p(profile_weight), _p(lam), _p(losses),
                                     _p(dlogits), _p(dlogcounts), L_in, W, Cp, planes, _p(d8),
-                                    _p(dpb), _p(dcb), _p(ws), hto, _stream()),
+                                    _p(dpb), _p(dcb), _p(ws), hto, _p(counts_partials),
+                                    (L_in + 127) // 128, _p(cb), _stream()),
           "bpb_loss_fwd_bwd_pack")
 
 

@@ -190,8 +190,9 @@ int bpb_input_conv_dgrad_tc(int B, int L_in, int L_out, int W, int F, const bpb_
  * columns with weights on tap 0 only; gap is not materialised).  w_op comes from
  * bpb_prep_heads_fwd_weights (an opaque bf16 image of the kernel's shared-memory operand:
  * [planes][W][F/64] tiles of N x 64, 128-byte swizzled); ws holds per-tile partial sums of the counts
- * columns.  bpb_heads_fwd_tc_supported returns 0 when the geometry fits shared memory; otherwise
- * use bpb_heads_fwd (CUDA cores). */
+ * columns (logcounts may be NULL: the sums are then left in ws for bpb_loss_fwd_bwd_pack).
+ * bpb_heads_fwd_tc_supported returns 0 when the geometry fits shared memory; otherwise use
+ * bpb_heads_fwd (CUDA cores). */
 long long bpb_heads_fwd_wop_elems(int W, int F, int T, int H, int planes);
 int bpb_prep_heads_fwd_weights(int W, int Fw, int F, int T, int H, const float* pw,
                                const float* cw, bpb_bf16* w_op, int planes, void* stream);
@@ -268,14 +269,17 @@ int bpb_loss_fwd_bwd(int B, int L, int T, int H, const int* task_off, const floa
  * over the batch in sequence order by the last block to finish (deterministic; no atomics on
  * floats).  dlogits may be NULL.  ws: bpb_loss_pack_ws_elems() floats, zero-filled once by the
  * caller and then owned by these calls (one buffer per stream).  host_task_off is the HOST copy of
- * task_off (heads of 1..8 tasks). */
+ * task_off (heads of 1..8 tasks).  counts_partials (nullable): the workspace bpb_heads_fwd_tc was
+ * given when it was called with logcounts == NULL ([B][tiles][H], tiles = ceil(L_in / 128)); the
+ * kernel then finishes logcounts[b,h] = cb[h] + sum / L_in itself -- in the order of the finishing
+ * kernel it replaces -- and stores them into `logcounts`, which is an OUTPUT in that mode. */
 long long bpb_loss_pack_ws_elems(int B, int T, int H);
 int bpb_loss_fwd_bwd_pack(int B, int L, int T, int H, const int* task_off, const float* logits,
                           const float* logcounts, const float* counts, const float* logcounts_true,
                           const float* profile_weight, const float* lambda, float* losses,
                           float* dlogits, float* dlogcounts, int L_in, int W, int Cp, int planes,
                           bpb_bf16* d8, float* dpb, float* dcb, float* ws, const int* host_task_off,
-                          void* stream);
+                          const float* counts_partials, int tiles, const float* cb, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K9: Keras-semantics Adam over one flat fp32 bucket:
