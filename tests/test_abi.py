@@ -86,3 +86,16 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), \
                     f"{f} imports the oracle"
                 assert "import_module(\"oracle" not in text and "__import__(\"oracle" not in text
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 (no C++ constructs, no torch types),
+    so that a cgo / JNI / ctypes / f2py-style binding can include it as is."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc on this box")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
