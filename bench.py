@@ -524,6 +524,7 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         if peers is not None:
+            peers.check()  # raises if any in-kernel wait for a peer expired
             peers.close()
         dist.destroy_process_group()
 

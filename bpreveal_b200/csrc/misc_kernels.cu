@@ -441,8 +441,13 @@ __device__ __forceinline__ void scatter_planes(__nv_bfloat16* dst, long long pla
 // out of peer memory in rank order (a one-shot all-reduce: identical sums, hence identical
 // parameters, on every rank) and applies the update; the last block to finish tells every peer
 // that this rank no longer reads its bucket.  Flag block of a rank: words 0..7 ready[r],
-// 8..15 done[r], 16 sequence number of the last completed exchange.  Waits are bounded: a peer
-// that never arrives traps this kernel after ~2 s instead of hanging the GPU.
+// 8..15 done[r], 16 sequence number of the last completed exchange, 17 wait bound in seconds
+// (0 = 30 s, set by the host), 18 error word.  Waits are bounded in WALL time (%globaltimer, so
+// the bound does not move with the SM clock): a peer that has not arrived when the bound expires
+// -- ranks legitimately diverge by seconds around checkpoints, validation or a first-step graph
+// capture -- makes the waiting thread record 1 + the missing rank in the error word and go on
+// (with that peer's stale bucket), instead of trapping and leaving a sticky fault in the CUDA
+// context; the host reads the error word (parallel.PeerGradExchange.check) and raises.
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -451,18 +456,32 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void peer_spin_until(const unsigned* flag, unsigned want) {
-  const long long t0 = clock64();
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void peer_spin_until(const unsigned* flag, unsigned want, unsigned* mine,
+                                                unsigned who) {
+  if (static_cast<int>(ld_acquire_sys(flag) - want) >= 0) return;
+  const unsigned long long t0 = globaltimer_ns();
+  const unsigned secs = mine[17] ? mine[17] : 30u;
+  const unsigned long long bound = static_cast<unsigned long long>(secs) * 1000000000ULL;
+  unsigned spins = 0;
   while (static_cast<int>(ld_acquire_sys(flag) - want) < 0) {
     __nanosleep(40);
-    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a peer is missing
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > bound) {
+      atomicMax(mine + 18, 1u + who);  // a peer is missing: tell the host, do not trap
+      return;
+    }
   }
 }
 
 __global__ void peer_wait_kernel(const bpb_peer_args pa) {
   // the previous exchange must be over on every peer before this rank's gradients change again
-  const unsigned* mine = pa.flags[pa.rank];
-  if (threadIdx.x < static_cast<unsigned>(pa.world)) peer_spin_until(mine + 8 + threadIdx.x, mine[16]);
+  unsigned* mine = pa.flags[pa.rank];
+  if (threadIdx.x < static_cast<unsigned>(pa.world))
+    peer_spin_until(mine + 8 + threadIdx.x, mine[16], mine, threadIdx.x);
 }
 
 template <bool PEER>
@@ -479,7 +498,8 @@ adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g
       __threadfence_system();
       st_release_sys(pa.flags[threadIdx.x] + pa.rank, seq);  // ready[rank] on peer threadIdx.x
     }
-    if (threadIdx.x < static_cast<unsigned>(pa.world)) peer_spin_until(mine + threadIdx.x, seq);
+    if (threadIdx.x < static_cast<unsigned>(pa.world))
+      peer_spin_until(mine + threadIdx.x, seq, mine, threadIdx.x);
     __syncthreads();
   }
   // bias-corrected step size: double-precision pow is long and slow, one thread per block does it

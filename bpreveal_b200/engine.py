@@ -239,6 +239,9 @@ class SoloNet:
             ws["counts"] = torch.zeros((B, cfg.outputLength, cfg.T), dtype=torch.float32,
                                        device=dev)
             ws["losses"] = torch.zeros((2 * cfg.H,), dtype=torch.float32, device=dev)
+            # log-count targets handed in by the generator (generators.py:139-140); without them
+            # the loss kernels use log(sum of the profile), which is what that generator computes
+            ws["lc_true"] = torch.zeros((B, cfg.H), dtype=torch.float32, device=dev)
             ws["dlogits"] = torch.empty_like(ws["logits"])
             ws["dlogcounts"] = torch.empty_like(ws["logcounts"])
             ws["g"] = [ops.new_planes(B, Ls[0], Fp, prec, dev) for _ in range(2)]
@@ -427,7 +430,8 @@ class SoloNet:
                                              device=self.device)
             self.lam = torch.ones((self.cfg.H,), dtype=torch.float32, device=self.device)
 
-    def forward_backward_into(self, ws, bias_logits=None, bias_logcounts=None, use_bias=None):
+    def forward_backward_into(self, ws, bias_logits=None, bias_logcounts=None, use_bias=None,
+                              lc_true=False):
         """Forward + losses + backward on ws['x'], ws['counts'] -> self.grads_flat, ws['losses'].
 
         For the combined model (models.py:363-380) the frozen bias outputs are added before the
@@ -455,11 +459,13 @@ class SoloNet:
                                   cfg.outputFilterWidth, self.cp, planes, ws["d8"], ws["loss_ws"],
                                   dlogits=ws["dlogits"], dlogcounts=ws["dlogcounts"],
                                   dpb=g["prof_b"], dcb=g["cnt_b"],
+                                  logcounts_true=ws["lc_true"] if lc_true else None,
                                   counts_partials=ws["hf_ws"] if defer else None,
                                   cb=p["cnt_b"] if defer else None)
         else:
             ops.loss_fwd_bwd(self.task_off, logits, lc, ws["counts"], self.profile_weight,
-                             self.lam, ws["losses"], ws["dlogits"], ws["dlogcounts"])
+                             self.lam, ws["losses"], ws["dlogits"], ws["dlogcounts"],
+                             logcounts_true=ws["lc_true"] if lc_true else None)
         if bias_logits is not None:
             ops.mul_f32(ws["dlogcounts"], ws["dscale"], ws["dlogcounts"])
         # Backward.  The data-gradient chain comes first (heads -> tower layers, each needing the
@@ -533,7 +539,8 @@ class SoloNet:
         self.step_and_lr[:2].copy_(torch.tensor([float(step), float(lr)], dtype=torch.float32),
                                    non_blocking=False)
 
-    def eval_losses(self, x_u8, counts, bias_logits=None, bias_logcounts=None, use_bias=None):
+    def eval_losses(self, x_u8, counts, bias_logits=None, bias_logcounts=None, use_bias=None,
+                    logcounts_true=None):
         """Forward + losses only (validation batches): returns the device vector
         [mnll_h ..., lambda_h * mse_h ...]."""
         self.enable_training()
@@ -542,6 +549,8 @@ class SoloNet:
         ws = self._workspace(B, "train")
         ws["x"].copy_(x_u8, non_blocking=True)
         ws["counts"].copy_(counts, non_blocking=True)
+        if logcounts_true is not None:
+            ws["lc_true"].copy_(logcounts_true.reshape(B, cfg.H), non_blocking=True)
         self._forward(ws, ws["x"])
         logits, lc = ws["logits"], ws["logcounts"]
         if bias_logits is not None:
@@ -553,12 +562,14 @@ class SoloNet:
             ops.counts_lse(use_bias, bias_logcounts, lc, ws["lc_c"], ws["dscale"])
             logits, lc = ws["logits_c"], ws["lc_c"]
         ops.loss_fwd_bwd(self.task_off, logits, lc, ws["counts"], self.profile_weight, self.lam,
-                         ws["losses"], None, None)
+                         ws["losses"], None, None,
+                         logcounts_true=ws["lc_true"] if logcounts_true is not None else None)
         del cfg
         return ws["losses"]
 
     def train_step(self, x_u8, counts, lr, use_graph=True, allreduce=None, world=1,
-                   bias_logits=None, bias_logcounts=None, use_bias=None, peers=None):
+                   bias_logits=None, bias_logcounts=None, use_bias=None, peers=None,
+                   logcounts_true=None):
         """One optimisation step.  ``x_u8`` / ``counts`` may live on the device or in (pinned)
         host memory.  With ``allreduce`` (a callable taking the flat gradient bucket, e.g. an NCCL
         all-reduce) the step is data parallel: local forward/backward, one all-reduce of the
@@ -567,6 +578,9 @@ class SoloNet:
         B = x_u8.shape[0]
         ws = self._workspace(B, "train")
         self._stage_inputs(ws, x_u8, counts)
+        lct = logcounts_true is not None
+        if lct:  # (B, H) log-count targets of the generator; [B] / [B, 1] per head stacked
+            ws["lc_true"].copy_(logcounts_true.reshape(B, self.cfg.H), non_blocking=True)
         self.step += 1
         if lr != getattr(self, "_lr_on_device", None):
             self.step_and_lr[1:2].fill_(float(lr))  # stream-ordered scalar fill, only on change
@@ -579,37 +593,37 @@ class SoloNet:
 
             def body_peer():
                 ops.peer_wait(peers.args)
-                self.forward_backward_into(ws)
+                self.forward_backward_into(ws, lc_true=lct)
                 self._rf_twin = None
                 ops.adam_prep_step_peer(self.params.flat, self.adam_m, self.adam_v,
                                         self.step_and_lr, self._prep_table(), peers.args)
             if use_graph:
-                self._run_graph(("train_peer", B, peers.world), body_peer)
+                self._run_graph(("train_peer", B, peers.world, lct), body_peer)
             else:
                 body_peer()
             return ws["losses"]
         if bias_logits is not None:
             # combined model: the frozen bias outputs change every batch -> no graph replay
-            self.forward_backward_into(ws, bias_logits, bias_logcounts, use_bias)
+            self.forward_backward_into(ws, bias_logits, bias_logcounts, use_bias, lc_true=lct)
             if allreduce is not None:
                 allreduce(self.grads_flat)
             self.apply_adam(grad_scale=1.0 / world)
         elif allreduce is None:
             def body():
-                self.forward_backward_into(ws)
+                self.forward_backward_into(ws, lc_true=lct)
                 self.apply_adam()
             if use_graph:
-                self._run_graph(("train", B), body)
+                self._run_graph(("train", B, lct), body)
             else:
                 body()
         else:
             def body_a():
-                self.forward_backward_into(ws)
+                self.forward_backward_into(ws, lc_true=lct)
 
             def body_b():
                 self.apply_adam(grad_scale=1.0 / world)
             if use_graph:
-                self._run_graph(("train_fb", B), body_a)
+                self._run_graph(("train_fb", B, lct), body_a)
                 allreduce(self.grads_flat)
                 self._run_graph(("train_opt", B, world), body_b)
             else:

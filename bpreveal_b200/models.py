@@ -236,12 +236,20 @@ class Model:
         nseq = 0
         for bi in order:
             xb, yb = gen[int(bi)]
+            # log-count targets as the generator supplies them (generators.py:139-140): they are
+            # the MSE targets even when they are not log(sum of the profile)
+            lct = None
             if isinstance(xb, torch.Tensor):  # device-resident generator: stay on the device
                 counts = yb[0] if H == 1 else torch.cat(list(yb[:H]), dim=2)
+                if len(yb) >= 2 * H:
+                    lct = torch.stack([y.reshape(-1).float() for y in yb[H:2 * H]], dim=1)
             else:
                 counts = np.concatenate([np.asarray(y, dtype=np.float32) for y in yb[:H]], axis=2)
                 xb = np.asarray(xb)
-            losses = self._step(xb, counts, train)
+                if len(yb) >= 2 * H:
+                    lct = torch.as_tensor(np.stack(
+                        [np.asarray(y, dtype=np.float32).reshape(-1) for y in yb[H:2 * H]], axis=1))
+            losses = self._step(xb, counts, train, lct)
             n = xb.shape[0]
             # every loss is a mean over the batch (losses.py:36-38)
             if isinstance(losses, torch.Tensor):
@@ -259,11 +267,22 @@ class Model:
             logs[f"{prefix}{self.output_names[H + h]}_loss"] = per[H + h]
             # the metric names Keras derives from metrics=losses, which the reference's callbacks
             # match by regex (callbacks.py:56-59): unweighted MNLL, lambda-weighted MSE
-            logs[f"{prefix}{self.output_names[h]}_multinomial_nll"] = per[h]
-            logs[f"{prefix}{self.output_names[H + h]}_reweightable_mse"] = per[H + h]
+            logs[f"{prefix}{self._metric_base(h, 'profile')}_multinomial_nll"] = per[h]
+            logs[f"{prefix}{self._metric_base(h, 'logcounts')}_reweightable_mse"] = per[H + h]
             tot += self._loss_weights[h] * per[h] + per[H + h]
         logs[f"{prefix}loss"] = tot
         return logs
+
+    def _metric_base(self, h, kind):
+        """Stem of the per-head metric keys.  Keras derives them from the output layer's name;
+        the reference's callbacks find them with ``.*profile_{head}_multinomial_nll`` /
+        ``.*logcounts_{head}_reweightable_mse`` under ``re.fullmatch`` (callbacks.py:56-59,
+        205-208), which a single-term transformation output (``regress_linear_profile_{head}_r2``,
+        layers.py:46) does not satisfy -- the reference raises "The loss didn't match any regex"
+        there.  Here the stem always ends in ``{kind}_{head}``, so every model kind trains."""
+        name = self.output_names[h if kind == "profile" else len(self.headTasks) + h]
+        tail = f"{kind}_{self.headNames[h]}"
+        return name if name.endswith(tail) else name[:name.rfind(tail) + len(tail)]
 
     # ---- weights ------------------------------------------------------------------------
     def save(self, path):
@@ -271,6 +290,10 @@ class Model:
         lacks -- the native format is always available)."""
         arch = self.get_config()
         named = self.named_weights()
+        keys = [k for k, _ in named]
+        if len(set(keys)) != len(keys):
+            dup = sorted({k for k in keys if keys.count(k) > 1})
+            raise RuntimeError(f"weight names are not unique: {dup[:4]}")
         if path.endswith(".npz"):
             np.savez(path, __config__=json.dumps(arch), **{k: v for k, v in named})
             return
@@ -350,15 +373,16 @@ class SoloModel(Model):
     def _predict_host(self, xh, batch_size):
         return self.net.predict_host(xh, batchSize=batch_size)
 
-    def _step(self, xb, counts, train):
+    def _step(self, xb, counts, train, lct=None):
         net = self.net
         net.enable_training()
         self._push_weights(net)
         if train and self.trainable:
             losses = net.train_step(torch.as_tensor(xb), torch.as_tensor(counts),
-                                    self.optimizer.learning_rate)
+                                    self.optimizer.learning_rate, logcounts_true=lct)
         else:
-            losses = net.eval_losses(torch.as_tensor(xb), torch.as_tensor(counts))
+            losses = net.eval_losses(torch.as_tensor(xb), torch.as_tensor(counts),
+                                     logcounts_true=lct)
         return losses.double()  # a copy: the engine reuses its loss buffer next step
 
 
@@ -494,7 +518,7 @@ class TransformationModel(Model):
         logits, lc = self.solo.net.predict(xt, batchSize=batch_size)
         return self.transform_device(logits, lc)
 
-    def _step(self, xb, counts, train):
+    def _step(self, xb, counts, train, lct=None):
         """One batch of trainTransformationModel: solo forward (frozen), transformations, losses,
         gradients of the 4-vectors, Keras-Adam on them."""
         net = self.solo.net
@@ -502,16 +526,19 @@ class TransformationModel(Model):
         dev = self._device
         xt = torch.as_tensor(xb).to(device=dev, dtype=torch.uint8)
         ct = torch.as_tensor(counts).to(device=dev, dtype=torch.float32).contiguous()
-        logits, lc = net.predict(xt, batchSize=xt.shape[0])
-        tl, tc = self.transform_device(logits, lc)
         B = xt.shape[0]
         H = len(self.headTasks)
+        logits, lc = net.predict(xt, batchSize=xt.shape[0])
+        tl, tc = self.transform_device(logits, lc)
         losses = torch.zeros((2 * H,), dtype=torch.float32, device=dev)
         dl = torch.empty_like(tl)
         dc = torch.empty_like(tc)
         pw = torch.tensor(self._loss_weights, dtype=torch.float32, device=dev)
         lam = torch.tensor(self._lambdas, dtype=torch.float32, device=dev)
-        ops.loss_fwd_bwd(net.task_off, tl.contiguous(), tc.contiguous(), ct, pw, lam, losses, dl, dc)
+        if lct is not None:
+            lct = torch.as_tensor(lct).to(device=dev, dtype=torch.float32).reshape(B, H).contiguous()
+        ops.loss_fwd_bwd(net.task_off, tl.contiguous(), tc.contiguous(), ct, pw, lam, losses, dl, dc,
+                         logcounts_true=lct)
         if train:
             grads = torch.zeros_like(self.coeffs)
             k = 0
@@ -544,7 +571,6 @@ class TransformationModel(Model):
             a["sl"][1] = float(self.optimizer.learning_rate)
             flat = self.coeffs.view(-1)
             ops.adam_step(flat, grads.view(-1).contiguous(), a["m"].view(-1), a["v"].view(-1), a["sl"])
-        del B
         return losses.double().cpu().numpy()
 
 
@@ -582,7 +608,12 @@ class CombinedModel(Model):
                 "use-bias-counts": [bool(v) for v in self.useBias.cpu().tolist()]}
 
     def named_weights(self):
-        return list(self.residual.named_weights()) + list(self.bias.named_weights())
+        """Residual variables under their own layer names, the frozen bias model's under the
+        nested model's name (in the reference graph it IS a nested ``transformation_model``,
+        models.py:349-352): both towers own layers called ``solo_profile_{head}`` /
+        ``solo_logcounts_{head}`` (models.py:41-48), so a flat list would collide."""
+        return list(self.residual.named_weights()) + \
+            [(f"{self.bias.name}/{k}", v) for k, v in self.bias.named_weights()]
 
     def set_weights(self, weights):
         n = len(self.residual.named_weights())
@@ -606,7 +637,7 @@ class CombinedModel(Model):
         ops.counts_lse(self.useBias, bc.contiguous(), rc, out_c)
         return out_l, out_c
 
-    def _step(self, xb, counts, train):
+    def _step(self, xb, counts, train, lct=None):
         net = self.residual.net
         net.enable_training()
         dev = self._device
@@ -614,13 +645,16 @@ class CombinedModel(Model):
         xt = torch.as_tensor(xb).to(device=dev, dtype=torch.uint8)
         ct = torch.as_tensor(counts).to(device=dev, dtype=torch.float32)
         bl, bc = self._bias_device(xt, xt.shape[0])
+        if lct is not None:
+            lct = torch.as_tensor(lct).to(device=dev, dtype=torch.float32)
         if train:
             losses = net.train_step(xt, ct, self.optimizer.learning_rate, use_graph=False,
                                     bias_logits=bl.contiguous(), bias_logcounts=bc.contiguous(),
-                                    use_bias=self.useBias)
+                                    use_bias=self.useBias, logcounts_true=lct)
         else:
             losses = net.eval_losses(xt, ct, bias_logits=bl.contiguous(),
-                                     bias_logcounts=bc.contiguous(), use_bias=self.useBias)
+                                     bias_logcounts=bc.contiguous(), use_bias=self.useBias,
+                                     logcounts_true=lct)
         return losses.double()
 
 

@@ -160,8 +160,30 @@ class PeerGradExchange:
                                         "version": 2, "strides": None}
         self._raw = raw
         self.grads = torch.as_tensor(raw, device=device)
+        fraw = _Raw()
+        fraw.__cuda_array_interface__ = {"shape": (self.FLAG_BYTES // 4,), "typestr": "<i4",
+                                         "data": (self._base, False), "version": 2,
+                                         "strides": None}
+        self._fraw = fraw
+        self.flags = torch.as_tensor(fraw, device=device)  # words 17: wait bound (s), 18: error
+        self.set_timeout(float(os.environ.get("BPB_PEER_TIMEOUT_S", "30")))
         if self.world > 1:
             dist.barrier()  # every rank has mapped every bucket before anyone uses them
+
+    def set_timeout(self, seconds):
+        """Wall-clock bound of the in-kernel waits for a peer (default 30 s, ``BPB_PEER_TIMEOUT_S``)."""
+        self.flags[17] = max(1, int(round(seconds)))
+
+    def check(self):
+        """Raises if a kernel of this rank gave up waiting for a peer (the kernels record it in
+        the flag block instead of trapping, so the CUDA context stays usable and the caller can
+        fall back to ``GradAllReducer``).  Synchronises: call it at epoch boundaries."""
+        err = int(self.flags[18].item())
+        if err:
+            self.flags[18] = 0
+            raise RuntimeError(
+                f"rank {self.rank}: peer rank {err - 1} did not reach the gradient exchange within "
+                f"{int(self.flags[17].item())} s (parameters of the ranks may have diverged)")
 
     def close(self):
         from . import _lib

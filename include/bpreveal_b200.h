@@ -318,7 +318,10 @@ int bpb_adam_prep_step(long long n, float* param, const float* grad, float* m, f
  * exchange the 64-byte handles by any means and map each other's memory with bpb_peer_open.
  * bpb_adam_prep_step_peer = bpb_adam_prep_step with grad = the SUM over ranks of grads[r], read
  * straight out of peer memory in rank order (bit-identical on every rank), scaled by 1/world;
- * it waits (bounded, ~2 s, then traps) until every peer has reached the same call.  bpb_peer_wait
+ * it waits until every peer has reached the same call -- bounded in wall time by flag word 17
+ * (seconds, 0 = 30): a thread whose wait expires stores 1 + the missing rank into flag word 18 of
+ * this rank's block and carries on, so the host can detect it and recover (no trap, no sticky
+ * fault).  Flag block words: 0..7 ready[r], 8..15 done[r], 16 sequence, 17 bound, 18 error.  bpb_peer_wait
  * must be enqueued before anything writes this rank's bucket again (start of the next step): it
  * waits until every peer has finished reading it.  grads[r] / flags[r] are THIS process's
  * mappings of rank r's bucket / flag block (r == rank: its own allocation). */
