@@ -286,8 +286,8 @@ class Model:
 
     # ---- weights ------------------------------------------------------------------------
     def save(self, path):
-        """``.npz`` (native) or ``.keras`` / ``.h5`` (Keras 3 layout; needs h5py, which this image
-        lacks -- the native format is always available)."""
+        """``.keras`` (Keras 3 zip: config.json + model.weights.h5), ``.h5`` (legacy whole-model
+        HDF5) -- both written without h5py through ``h5lite`` -- or ``.npz`` (native)."""
         arch = self.get_config()
         named = self.named_weights()
         keys = [k for k, _ in named]
@@ -688,7 +688,11 @@ def combinedModel(inputLength, outputLength, numFilters, numLayers, inputFilterW
 
 
 def loadModel(path, device=None, precise=False):
-    """Counterpart of ``utils.loadModel`` (utils.py:60-90) for files written by ``Model.save``."""
+    """Counterpart of ``utils.loadModel`` (utils.py:24-85): ``.keras`` and legacy ``.h5`` files
+    written by Keras for the reference's builders or by ``Model.save`` here (the architecture is
+    derived from the file's own layer configuration), and the native ``.npz``."""
+    if path.endswith(".model") and not os.path.exists(path):
+        path = path[:-5] + "keras"  # utils.py:67-72: old extension in an old configuration file
     if path.endswith(".npz"):
         z = np.load(path, allow_pickle=False)
         arch = json.loads(str(z["__config__"]))

@@ -152,6 +152,32 @@ def solo_forward(x, p, relu=F.relu, keep=False):
     return profiles, counts
 
 
+def round_bf16(t):
+    """Round-to-nearest-even to bfloat16 (8 significand bits), returned in t's dtype."""
+    return t.to(torch.float32).to(torch.bfloat16).to(t.dtype)
+
+
+def solo_forward_bf16_emulation(x, p):
+    """The same graph as ``solo_forward`` under the storage rules of a bf16 tensor-core pipeline
+    with exact (fp64) accumulation: kernels of the dilated layers and of the heads rounded to
+    bf16, every stored activation rounded to bf16, the first layer's kernel kept (its one-hot
+    input makes extra weight planes free).  It is NOT a model of any kernel: it is the error
+    floor of bf16 storage, which the tests use to judge whether a bf16 kernel path loses more
+    than the number format itself does."""
+    q = {k: (round_bf16(v) if k.endswith("_w") and not k.startswith("conv1") else v)
+         for k, v in p.items()}
+    a = round_bf16(F.relu(_conv1d_cl(x, q["conv1_w"], q["conv1_b"])))
+    for i in range(num_layers_of(q)):
+        d = 2 ** (i + 1)
+        z = _conv1d_cl(a, q[f"dil{i}_w"], q[f"dil{i}_b"], dilation=d)
+        a = round_bf16(F.relu(z) + a[:, d:a.shape[1] - d, :])
+    profiles, counts = [], []
+    for h in range(num_heads_of(q)):
+        profiles.append(_conv1d_cl(a, q[f"prof{h}_w"], q[f"prof{h}_b"]))
+        counts.append(a.mean(dim=1) @ q[f"cnt{h}_w"] + q[f"cnt{h}_b"])
+    return profiles, counts
+
+
 # --------------------------------------------------------------------------------------
 # layers.py:10-49 linearRegression, models.py:118-175 simple transformation
 # --------------------------------------------------------------------------------------

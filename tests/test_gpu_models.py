@@ -100,8 +100,17 @@ def test_solo_fit_history_and_save_roundtrip(dev, tmp_path):
     a, b = m.predict(x[:4]), m2.predict(x[:4])
     for u, v in zip(a, b):
         assert np.array_equal(u, v)
-    with pytest.raises(RuntimeError):
-        m.save(str(tmp_path / "m.keras"))  # no h5py in this image: loud, not silent
+    # Keras formats, written and read without h5py (keras_io + h5lite)
+    for ext in (".keras", ".h5"):
+        kp = str(tmp_path / ("m" + ext))
+        m.save(kp)
+        m3 = models.loadModel(kp, device=dev)
+        assert m3.name == "solo_model" and m3.output_names == m.output_names
+        for u, v in zip(a, m3.predict(x[:4])):
+            assert np.array_equal(u, v)
+    # utils.py:67-72: a configuration still naming "<x>.model" finds "<x>.keras"
+    m4 = models.loadModel(str(tmp_path / "m.model"), device=dev)
+    assert np.array_equal(m4.predict(x[:4])[0], a[0])
 
 
 def test_transformation_model_forward_and_training(dev):
