@@ -611,7 +611,16 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           mbits = __ldg(p.mask_in + (orow * chunks_per_row + (n0 >> 6)) * 2 + half);
 
         // ---- residual (already in shared memory: HALO box or residual ring)
+        // The slot is handed back to the TMA producer only AFTER the values read from it have
+        // been consumed (``release`` below, after the staging writes).  Arriving right behind
+        // the ld.shared instructions is not enough: they are asynchronous, the arrive does not
+        // depend on their destination registers, and a refill that lands while some of them are
+        // still outstanding was observed -- about once per hundred launches of C1's d = 64
+        // layer a warp added the residual of the tile four steps ahead
+        // (tests/test_gpu_baseline_cfgs.py::test_every_c1_tower_shape...).  In-order issue puts
+        // every instruction behind the stores that use the loaded registers behind the loads.
         uint4 rr[4], rl[4];
+        uint64_t* release = nullptr;
         if (RESID) {
           if (RING_RESID) {
             mbar_wait_wd(&rfull[rbase + rs], rphase, p.dbg, 0x600 + rbase + rs, ntile);
@@ -621,8 +630,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               rr[g] = lds128(src + sw128(row, cq + g));
               if (PLANES == 2) rl[g] = lds128(src + kTileBytes + sw128(row, cq + g));
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&rempty[rbase + rs]);
+            release = &rempty[rbase + rs];
             ring_advance(rs, rphase, 1, RG);
           } else {
             if (ch == 0) mbar_wait_wd(&full[hs], hphase, p.dbg, 0x700 + hs, ntile);
@@ -636,8 +644,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               if (PLANES == 2) rl[g] = lds128(src + p.sub_bytes + sw128(brow, cq + g));
             }
             if (ch == NCH - 1) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&empty[hs]);
+              release = &empty[hs];
               ring_advance(hs, hphase, EG, p.stages);
             }
           }
@@ -803,6 +810,11 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         }
 
         BPB_PHASE(11);  // math + staging writes
+        if (RESID && release != nullptr) {
+          // every lane's residual values went through the stores above: the slot may be refilled
+          __syncwarp();
+          if (lane == 0) mbar_arrive(release);
+        }
         // ---- publish: generic-proxy writes -> async proxy, one barrier, one thread stores
         fence_proxy_async();
         BPB_PHASE(12);  // proxy fence

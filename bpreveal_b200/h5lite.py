@@ -64,6 +64,10 @@ def _encode_dtype(dt: np.dtype) -> bytes:
     raise H5Unsupported(f"cannot store numpy dtype {dt}")
 
 
+_VLEN_STR_DTYPE = bytes([0x19, 0x01, 0x01, 0x00]) + struct.pack("<I", 16) + \
+    bytes([0x13, 0x10, 0, 0, 1, 0, 0, 0])  # variable-length string, null-terminated, UTF-8
+
+
 class _TypeInfo:
     __slots__ = ("np_dtype", "vlen_str", "size", "consumed", "str_utf8")
 
@@ -669,6 +673,9 @@ def _pad8(b: bytes) -> bytes:
 
 def _msg(mtype: int, body: bytes, flags: int = 0) -> bytes:
     body = _pad8(body)
+    if len(body) > 0xFFF8:
+        raise H5Unsupported("object-header message over 64 KiB (store long text as str, which "
+                            "goes to the global heap, not as bytes)")
     return struct.pack("<HHBBBB", mtype, len(body), flags, 0, 0, 0) + body
 
 
@@ -694,6 +701,7 @@ class _WDataset(_WNode):
         self.shape, self.dtype, self.data = tuple(shape), np.dtype(dtype), data
         self.chunks, self.compression, self.shuffle = chunks, compression, shuffle
         self.addr = None  # raw data address (contiguous), set by Writer
+        self.vlen = None  # list of utf-8 byte strings for a variable-length string dataset
 
 
 class Writer:
@@ -733,6 +741,13 @@ class Writer:
         parent = self._walk_to("/".join(parts[:-1]))
         if parts[-1] in parent.children:
             raise ValueError(f"{path}: name already exists")
+        if data is not None and isinstance(data, (list, tuple)) and \
+                all(isinstance(d, str) for d in data) and (len(data) > 0 or dtype is str):
+            # what h5py stores for dtype=h5py.string_dtype("utf-8"): references into a global heap
+            ds = _WDataset((len(data),), np.dtype("V16"), None, None, None, False)
+            ds.vlen = [d.encode("utf-8") for d in data]
+            parent.children[parts[-1]] = ds
+            return ds
         if data is not None:
             if isinstance(data, (list, tuple)) and data and isinstance(data[0], (str, bytes)):
                 data = np.array([d.encode("utf-8") if isinstance(d, str) else d for d in data])
@@ -776,7 +791,22 @@ class Writer:
                 for name, ds in late}
 
     @staticmethod
-    def _attr_msg(name, value):
+    def _attr_msg(name, value, heap=None):
+        """``heap(list of bytes) -> list of 16-byte references`` stores variable-length strings:
+        Python ``str`` values (and lists of them) become variable-length UTF-8 strings as with
+        h5py, so their size is not bound by the 64 KiB limit of an object-header message;
+        ``bytes`` and numpy "S" arrays stay fixed-length."""
+        vl = None
+        if isinstance(value, str):
+            vl, shape = [value.encode("utf-8")], ()
+        elif isinstance(value, (list, tuple)) and value and all(isinstance(v, str) for v in value):
+            vl, shape = [v.encode("utf-8") for v in value], (len(value),)
+        if vl is not None and heap is not None:
+            nm = name.encode("utf-8") + b"\0"
+            sp = _dataspace(shape)
+            body = struct.pack("<BBHHH", 1, 0, len(nm), len(_VLEN_STR_DTYPE), len(sp)) + \
+                _pad8(nm) + _pad8(_VLEN_STR_DTYPE) + _pad8(sp) + b"".join(heap(vl))
+            return _msg(0x000C, body)
         if isinstance(value, str):
             value = value.encode("utf-8")
         if isinstance(value, bytes):
@@ -823,6 +853,22 @@ class Writer:
 
         def emit(addr, b):
             out.append((addr, b))
+
+        def heap(strings):
+            """One global heap collection holding ``strings``; returns their references."""
+            need = 16 + sum(16 + (len(b) + 7) // 8 * 8 for b in strings)
+            size = max(4096, (need + 16 + 7) // 8 * 8)
+            addr = alloc(size)
+            blob = bytearray(b"GCOL" + struct.pack("<B3xQ", 1, size))
+            refs = []
+            for i, b in enumerate(strings, start=1):
+                if i > 0xFFFF:
+                    raise H5Unsupported("more than 65535 strings in one dataset / attribute")
+                blob += struct.pack("<HHIQ", i, 0, 0, len(b)) + _pad8(b)
+                refs.append(struct.pack("<IQI", len(b), addr, i))
+            blob += struct.pack("<HHIQ", 0, 0, 0, size - len(blob))  # free space object
+            emit(addr, bytes(blob).ljust(size, b"\0"))
+            return refs
 
         def object_header(msgs):
             body = b"".join(msgs)
@@ -871,6 +917,19 @@ class Writer:
         cur_chunks = [None]
 
         def write_dataset(ds, name):
+            if ds.vlen is not None:
+                msgs = [_msg(0x0001, _dataspace(ds.shape)), _msg(0x0003, _VLEN_STR_DTYPE, 1),
+                        _msg(0x0005, struct.pack("<BBBB", 2, 2, 2, 0))]
+                raw = b"".join(heap(ds.vlen)) if ds.vlen else b""
+                if raw:
+                    a_ = alloc(len(raw))
+                    emit(a_, raw)
+                    msgs.append(_msg(0x0008, struct.pack("<BBQQ", 3, 1, a_, len(raw))))
+                else:
+                    msgs.append(_msg(0x0008, struct.pack("<BBQQ", 3, 1, UNDEF, 0)))
+                for k, v in ds.attrs.items():
+                    msgs.append(self._attr_msg(k, v, heap))
+                return object_header(msgs)
             msgs = [_msg(0x0001, _dataspace(ds.shape)), _msg(0x0003, _encode_dtype(ds.dtype), 1),
                     _msg(0x0005, struct.pack("<BBBB", 2, 2, 2, 0))]
             esz = ds.dtype.itemsize
@@ -924,7 +983,7 @@ class Writer:
                     struct.pack(f"<{rank + 1}I", *cd, esz)
                 msgs.append(_msg(0x0008, lay))
             for k, v in ds.attrs.items():
-                msgs.append(self._attr_msg(k, v))
+                msgs.append(self._attr_msg(k, v, heap))
             return object_header(msgs)
 
         def write_group(g, name):
@@ -972,7 +1031,7 @@ class Writer:
             emit(bt_addr, b.ljust(node_size, b"\0"))
             msgs = [_msg(0x0011, struct.pack("<QQ", bt_addr, heap_addr))]
             for k, v in g.attrs.items():
-                msgs.append(self._attr_msg(k, v))
+                msgs.append(self._attr_msg(k, v, heap))
             return object_header(msgs), bt_addr, heap_addr
 
         root_oh, root_bt, root_heap = write_group(self.root, "/")

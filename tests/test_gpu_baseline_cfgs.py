@@ -338,9 +338,12 @@ def test_dilated_layer_weight_gradient(dev, B, L, Fn, d, precise):
 
 
 def test_every_c1_tower_shape_many_launches_in_a_graph(dev):
-    """Each of C1's nine layer shapes at batch 64, forward and both backward forms, 10 replays of
-    a 10-launch CUDA graph -- the mbarrier-phase race fixed in round 1 showed up only this way --
-    and every replay must reproduce the first launch bit for bit."""
+    """Each of C1's nine layer shapes at batch 64, forward and backward, 30 replays of a
+    10-launch CUDA graph; every replay must reproduce the first launch bit for bit.  This test
+    found a real race in round 2: the forward at d = 64 (HALO staging, 4 box slots) released a
+    box slot to the TMA producer right behind the ld.shared instructions that read the residual
+    out of it, and ~1 launch in 100 added the residual of the tile four steps ahead
+    (conv_core.cuh, "release")."""
     from bpreveal_b200 import ops
     B, Fn, L = 64, 64, 3066
     g = torch.Generator().manual_seed(9)
@@ -374,11 +377,11 @@ def test_every_c1_tower_shape_many_launches_in_a_graph(dev):
             with torch.cuda.graph(gr):
                 for _ in range(10):
                     fn()
-            for _ in range(10):
+            for _ in range(30):  # 300 launches: the d = 64 race of round 1 hit ~1 launch in 100
                 gr.replay()
-            torch.cuda.synchronize()
-            for a_, b_ in zip(first, res()):
-                assert torch.equal(a_, b_), f"layer {i} (d={d}): replay differs"
+                torch.cuda.synchronize()
+                for a_, b_ in zip(first, res()):
+                    assert torch.equal(a_, b_), f"layer {i} (d={d}): replay differs"
         L = L_out
 
 

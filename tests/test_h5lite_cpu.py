@@ -22,7 +22,10 @@ def test_round_trip_of_everything_the_writer_can_write(tmp_path):
     ints = np.arange(1000, dtype=np.int64).reshape(10, 100)
     w.create_dataset("ints", data=ints, chunks=(3, 40), shuffle=True, compression=6)
     w.create_dataset("plainchunks", data=ints.astype(np.uint8), chunks=(4, 100))
-    w.create_dataset("names", data=["chr1", "chrX_long"])
+    w.create_dataset("names", data=np.array([b"chr1", b"chrX_long"]))
+    w.create_dataset("descriptions", data=["first window", "second \u00e9", ""])
+    w.attrs("")["big"] = "x" * 200000   # beyond one object-header message: global heap
+    w.attrs("")["tags"] = ["a", "bc"]
     w.create_dataset("scalar", data=np.float64(3.5))
     w.create_dataset("empty", data=np.zeros((0, 4), dtype=np.float32))
     w.attrs("")["keras_version"] = "3.5.0"
@@ -37,8 +40,10 @@ def test_round_trip_of_everything_the_writer_can_write(tmp_path):
     late["/late"][...] = np.arange(35, dtype=np.float32).reshape(5, 7)
     late["/late"].flush()
     with h5lite.File(path) as f:
-        assert sorted(f.keys()) == ["empty", "ints", "late", "layers", "many", "names",
-                                    "plainchunks", "scalar", "shap"]
+        assert sorted(f.keys()) == ["descriptions", "empty", "ints", "late", "layers", "many",
+                                    "names", "plainchunks", "scalar", "shap"]
+        assert list(f["descriptions"][...]) == ["first window", "second \u00e9", ""]
+        assert f.attrs["big"] == "x" * 200000 and list(f.attrs["tags"]) == ["a", "bc"]
         assert np.array_equal(f["layers/conv1d/vars/0"][...], k)
         assert f["layers/conv1d/vars/0"].dtype == np.float32
         assert np.array_equal(f["shap"][...], shap) and f["shap"].dtype == np.float16
@@ -47,7 +52,7 @@ def test_round_trip_of_everything_the_writer_can_write(tmp_path):
         assert list(f["names"][...]) == [b"chr1", b"chrX_long"]
         assert f["scalar"][...] == 3.5 and f["scalar"].shape == ()
         assert f["empty"].shape == (0, 4)
-        assert f.attrs["keras_version"] == b"3.5.0"
+        assert f.attrs["keras_version"] == "3.5.0"  # str -> variable-length UTF-8, like h5py
         assert list(f["layers"].attrs["layer_names"]) == [b"a", b"bcd"]
         assert f["shap"].attrs["scale"] == np.float32(2.5)
         assert list(f["shap"].attrs["dims"]) == [1, 2, 3]
