@@ -88,3 +88,18 @@ class DeviceBatchGenerator:
 
     def on_epoch_end(self):
         self.refreshData()
+
+
+class H5BatchGenerator(DeviceBatchGenerator):
+    """``generators.H5BatchGenerator`` with the reference's constructor (generators.py:32-56):
+    ``dataH5`` is an opened training file (``h5lite.File``, an ``h5py.File`` or any mapping) with
+    ``sequence (N, inputLength + 2 maxJitter, 4)`` u8 and ``head_<i> (N, outputLength + 2
+    maxJitter, numTasks)`` f32 as written by prepareTrainingData (prepareTrainingData.py:209-230).
+    The whole file goes to HBM once (the reference loads it into host RAM, generators.py:43-53)."""
+
+    def __init__(self, headList, dataH5, inputLength, outputLength, maxJitter, batchSize,
+                 device=None, seed=1234):
+        seqs = np.asarray(dataH5["sequence"][...])
+        profiles = [np.asarray(dataH5[f"head_{i}"][...]) for i in range(len(headList))]
+        super().__init__(headList, seqs, profiles, inputLength, outputLength, maxJitter, batchSize,
+                         device=device, seed=seed)

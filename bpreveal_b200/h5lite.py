@@ -940,7 +940,7 @@ class Writer:
                 else:
                     ds.addr = alloc(nbytes)
                     if ds.data is not None:
-                        emit(ds.addr, ds.data.tobytes())
+                        emit(ds.addr, ds.data)  # streamed out below (may be a numpy.memmap)
                     else:
                         late.append((name, ds))
                     msgs.append(_msg(0x0008, struct.pack("<BBQQ", 3, 1, ds.addr, nbytes)))
@@ -1047,8 +1047,16 @@ class Writer:
                 fp.seek(addr - 1)
                 fp.write(b"\0")
             fp.seek(addr)
-            fp.write(b)
-            cur = max(cur, addr + len(b))
+            if isinstance(b, np.ndarray):
+                flat = b.reshape(-1)
+                step = max(1, (64 << 20) // max(b.dtype.itemsize, 1))
+                for i in range(0, flat.shape[0], step):  # bounded pieces: sources may be memmaps
+                    fp.write(flat[i:i + step].tobytes())
+                nb = b.nbytes
+            else:
+                fp.write(b)
+                nb = len(b)
+            cur = max(cur, addr + nb)
         if cur < eof:
             fp.seek(eof - 1)
             fp.write(b"\0")

@@ -56,6 +56,29 @@ def trainModel(model, trainBatchGen, valBatchGen, epochs, earlyStop, outputPrefi
     return history
 
 
+def trainWithGenerators(model, config, inputLength, outputLength, device=None):
+    """training.py:104-141: open ``train-data`` / ``val-data``, build the batch generators,
+    train, write ``<output-prefix>.history.json``.  ``config["heads"]`` must already carry the
+    λ variables of ``buildLosses``."""
+    from . import h5lite, logUtils
+    from .generators import H5BatchGenerator
+    model.summary(print_fn=logUtils.debug)
+    logUtils.info("Loading data into generators.")
+    st = config["settings"]
+    with h5lite.File(config["train-data"]) as trainH5, h5lite.File(config["val-data"]) as valH5:
+        trainGenerator = H5BatchGenerator(config["heads"], trainH5, inputLength, outputLength,
+                                          st["max-jitter"], st["batch-size"], device=device)
+        valGenerator = H5BatchGenerator(config["heads"], valH5, inputLength, outputLength,
+                                        st["max-jitter"], st["batch-size"], device=device)
+    logUtils.info("Generators initialized. Training.")
+    history = trainModel(model, trainGenerator, valGenerator, st["epochs"],
+                         st["early-stopping-patience"], st["output-prefix"],
+                         st["learning-rate-plateau-patience"], config["heads"])
+    logUtils.info("Saving history.")
+    saveHistory(history, config)
+    return history
+
+
 def saveHistory(history, config, historyName=None):
     """``<output-prefix>.history.json`` as trainWithGenerators writes it (training.py:134-140)."""
     historyName = historyName or f"{config['settings']['output-prefix']}.history.json"
