@@ -1,13 +1,17 @@
 #!/usr/bin/env python
-"""Benchmark of the BPNet training hot path (BASELINE.json metric: "BPNet train seq/s").
+"""Benchmark of the BPNet hot path (BASELINE.json metric: "BPNet train seq/s at 1/2/4/8 B200;
+PISA attribution bases/s vs TF CPU host").
 
-  python bench.py --gpus N --steps K --warmup W            # our arm (B200, sm_100a kernels)
+  python bench.py --gpus N --steps K --warmup W            # our arm, headline workload (C1)
   python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+  python bench.py --config c4 [--batch 64]                 # wide model, tensor-bound regime
+  python bench.py --config c3                              # combined model (bias + residual)
+  python bench.py --config c2 | c5                         # makePredictions / interpretPisa
 
-One "step" = forward + losses + backward + Keras-Adam update on one batch of 64 synthetic
-sequences per GPU of configs[0] (C1: 1-task BPNet, 64 filters, 9 dilated layers, 3090 -> 1000 bp,
-2 strands), i.e. the trainSoloModel inner loop (src/training.py:168-170 of the reference).
-Prints ONE JSON line on rank 0.
+Headline (default, --config c1): one "step" = forward + losses + backward + Keras-Adam update on
+one batch of 64 synthetic sequences per GPU of configs[0] (1-task BPNet, 64 filters, 9 dilated
+layers, 3090 -> 1000 bp, 2 strands), i.e. the trainSoloModel inner loop (src/training.py:168-170
+of the reference).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -22,17 +26,57 @@ sys.path.insert(0, ROOT)
 
 C1 = dict(inputLength=3090, outputLength=1000, numFilters=64, numLayers=9, inputFilterWidth=25,
           outputFilterWidth=23, headTasks=[2])
-BATCH = 64
+C3R = dict(inputLength=3056, outputLength=1000, numFilters=64, numLayers=9, inputFilterWidth=7,
+           outputFilterWidth=7, headTasks=[2, 2, 2, 2])
+C3B = dict(inputLength=3056, outputLength=1000, numFilters=16, numLayers=9, inputFilterWidth=7,
+           outputFilterWidth=7, headTasks=[2, 2, 2, 2])
+C4 = dict(inputLength=9286, outputLength=1000, numFilters=512, numLayers=11, inputFilterWidth=25,
+          outputFilterWidth=75, headTasks=[2])
 N_BATCHES = 4  # distinct resident batches cycled through (working set per step >> L2 anyway)
-FWD_FLOP_PER_SEQ = 0.624e9
-TRAIN_FLOP_PER_SEQ = 3 * FWD_FLOP_PER_SEQ
+WORKLOADS = {
+    "c1": "C1 trainSoloModel step (configs[0]): 1 head x 2 tasks, F=64, 9 dilated layers, "
+          "3090->1000 bp, batch 64 per GPU, Adam lr 0.004",
+    "c2": "C2 makePredictions (configs[1]): C1 model, batched inference over synthetic genome "
+          "windows, 3090->1000 bp, windows sharded over the GPUs",
+    "c3": "C3 trainCombinedModel step (configs[2]): frozen solo bias (F=16, 9 layers) + "
+          "transformation (linear+sigmoid profile, linear counts) + residual F=64, 9 layers, "
+          "7/7, 4 heads x 2 tasks (use-bias-counts on one), 3056->1000 bp, batch 64 per GPU",
+    "c4": "C4 wide BPNet train step (configs[3]): F=512, 11 dilated layers, 25/75, "
+          "9286->1000 bp, bf16, Adam lr 0.004",
+    "c5": "C5 interpretPisa (configs[4]): DeepSHAP PISA on the C1 model, 3090-bp windows, 20 "
+          "shuffled references per explained base",
+}
+
+
+def fwd_flop_per_seq(cfg):
+    """MAC = 2 FLOP."""
+    F, W, Wo, T = cfg["numFilters"], cfg["inputFilterWidth"], cfg["outputFilterWidth"], \
+        sum(cfg["headTasks"])
+    L = cfg["inputLength"] - W + 1
+    fl = 2.0 * W * 4 * F * L
+    for i in range(cfg["numLayers"]):
+        L -= 2 * 2 ** (i + 1)
+        fl += 2.0 * 3 * F * F * L
+    return fl + 2.0 * Wo * F * T * cfg["outputLength"] + 2.0 * F * len(cfg["headTasks"])
 
 
 def synth(n, cfg, seed):
-    from oracle import bpnet_oracle as O  # synthetic data generator only
-    x = O.synthetic_sequences(n, cfg["inputLength"], seed=seed)
-    c = O.synthetic_profiles(n, cfg["outputLength"], sum(cfg["headTasks"]), seed=seed)
+    from bpreveal_b200 import synthetic
+    x = synthetic.sequences(n, cfg["inputLength"], seed=seed)
+    c = synthetic.profiles(n, cfg["outputLength"], sum(cfg["headTasks"]), seed=seed)
     return x, c
+
+
+def peaks():
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        p = json.load(open(pk_path, encoding="utf-8"))
+        return {"hbm": p.get("hbm_gbs", 6650.0), "tensor": p.get("bf16_tflops_sustained", 1406.5),
+                "tensor_burst": p.get("bf16_tflops", 1702.8),
+                "source": "MEASURED_PEAKS.json (hbm_gbs: measured copy bandwidth; "
+                          "bf16_tflops_sustained: cuBLAS bf16 back to back)"}
+    return {"hbm": 6650.0, "tensor": 1406.5, "tensor_burst": 1702.8,
+            "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
 
 
 class ClockSampler(threading.Thread):
@@ -73,9 +117,14 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_train_rate(cfg, steps, warmup, batch):
-    """The reference's path on the host cores: fp32 torch-CPU restatement of the Keras graph
-    (oracle port; TensorFlow is not installable here), forward + loss + backward + Keras Adam."""
+# ---------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port): the ONLY place this file touches oracle/
+# ---------------------------------------------------------------------------------------------
+def cpu_train_rate(cfg, steps, warmup, batch, seed=20261019, n_total=None):
+    """fp32 torch-CPU restatement of the Keras graph on all host cores: forward + loss + backward
+    + Keras Adam.  Returns (seq/s, s/step, cores, losses of the first step) -- the first step uses
+    the same initial weights (seed 1234) and the same batch as the device arm's first step, so
+    its losses double as a sanity anchor for the device's."""
     import torch
     from oracle import bpnet_oracle as O
     cores = os.cpu_count() or 1
@@ -85,25 +134,30 @@ def cpu_train_rate(cfg, steps, warmup, batch):
     p = O.to_torch(params, torch.float32, requires_grad=True)
     m = {k: torch.zeros_like(v) for k, v in p.items()}
     v = {k: torch.zeros_like(t) for k, t in p.items()}
-    x, c = synth(batch, cfg, 20261019)
-    xt = torch.tensor(x, dtype=torch.float32)
-    ct = torch.tensor(c, dtype=torch.float32)
-    y = torch.log(ct.sum(dim=(1, 2)))
-    times = []
+    x, c = synth(n_total or batch, cfg, seed)  # the device arm's first batch: same draw, same rows
+    xt = torch.tensor(x[:batch], dtype=torch.float32)
+    ct = torch.tensor(c[:batch], dtype=torch.float32)
+    tasks = cfg["headTasks"]
+    offs = [sum(tasks[:h]) for h in range(len(tasks) + 1)]
+    trueP = [ct[:, :, offs[h]:offs[h + 1]] for h in range(len(tasks))]
+    trueC = [torch.log(t.sum(dim=(1, 2))) for t in trueP]
+    times, first = [], None
     for step in range(1, warmup + steps + 1):
         t0 = time.perf_counter()
         profs, cnts = O.solo_forward(xt, p)
-        tot, _, _ = O.total_loss(profs, cnts, [ct], [y], [1.0], [1.0])
+        tot, pl, cl = O.total_loss(profs, cnts, trueP, trueC, [1.0] * len(tasks), [1.0] * len(tasks))
         for t in p.values():
             t.grad = None
         tot.backward()
         with torch.no_grad():
             for k in p:
                 O.adam_step(p[k], p[k].grad, m[k], v[k], step, 0.004)
+        if first is None:
+            first = [float(a.detach()) for a in pl] + [float(a.detach()) for a in cl]
         if step > warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return batch / sec, sec, cores
+    return batch / sec, sec, cores, first
 
 
 def cpu_pisa_rate(cfg, n_bases, numShuffles):
@@ -125,106 +179,613 @@ def cpu_pisa_rate(cfg, n_bases, numShuffles):
     return n_bases / (time.perf_counter() - t0)
 
 
-def gpu_extras(net_cfg, dev, rank):
-    """Secondary measurements on one GPU: makePredictions windows/s (C2 shape, per GPU) and
-    interpretPisa bases/s (C5: 20 shuffled references per base, whole 3090-bp window)."""
-    import torch
-    from bpreveal_b200 import interpret
-    from bpreveal_b200.engine import NetConfig, SoloNet
-    out = {}
-    net = SoloNet(NetConfig(**net_cfg), dev)
-    net.init_random(seed=1234)
-    xs, _ = synth(1024, net_cfg, 777 + rank)
-    x_dev = torch.tensor(xs, device=dev)
-    net.predict(x_dev[:256], batchSize=128)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        net.predict(x_dev, batchSize=128)
-    e1.record()
-    torch.cuda.synchronize()
-    out["predict_windows_per_s"] = 3 * 1024 / (e0.elapsed_time(e1) / 1e3)
-    # the same end to end: pinned host windows in, pinned host logits / log-counts out
-    xh = torch.tensor(xs).pin_memory()
-    net.predict_host(xh, batchSize=128)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        net.predict_host(xh, batchSize=128)
-    torch.cuda.synchronize()
-    out["predict_e2e_windows_per_s"] = 3 * 1024 / (time.perf_counter() - t0)
-    for label, precise in (("pisa_bases_per_s", False), ("pisa_bases_per_s_precise", True)):
-        pn = SoloNet(NetConfig(precise=precise, **net_cfg), dev)
-        pn.load_state(net.state())
-        Q, n = 24, 20
-        interpret.pisa_batch(pn, x_dev[:Q], headID=0, taskID=0, numShuffles=n)
-        torch.cuda.synchronize()
-        e0.record()
-        reps = 6
-        nq = x_dev.shape[0] // Q
-        for r in range(reps):
-            o = (r % nq) * Q
-            interpret.pisa_batch(pn, x_dev[o:o + Q], headID=0, taskID=0, numShuffles=n)
-        e1.record()
-        torch.cuda.synchronize()
-        out[label] = reps * Q / (e0.elapsed_time(e1) / 1e3)
-        del pn
-        torch.cuda.empty_cache()
-    # C4: the wide model (512 filters, 11 dilated layers, 25/75 filters, 9286 -> 1000 bp), the
-    # tensor-bound regime of the same kernels; 407 GFLOP per sequence and training step
-    c4 = dict(inputLength=9286, outputLength=1000, numFilters=512, numLayers=11,
-              inputFilterWidth=25, outputFilterWidth=75, headTasks=[2])
-    wide = SoloNet(NetConfig(**c4), dev)
-    wide.init_random(seed=1234)
-    Bw = 16
-    xw, cw_ = synth(Bw, c4, 99 + rank)
-    xw_d, cw_d = torch.tensor(xw, device=dev), torch.tensor(cw_, device=dev)
-    for _ in range(3):
-        wide.train_step(xw_d, cw_d, 0.004)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(10):
-        wide.train_step(xw_d, cw_d, 0.004)
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) / 1e3 / 10
-    flop_fwd = 2.0 * (25 * 4 * 512 * 9262 + 3 * 512 * 512 * sum(
-        9262 - sum(2 * 2 ** (k + 1) for k in range(i + 1)) for i in range(11)) + 75 * 512 * 2 * 1000)
-    out["c4_wide_train_seq_per_s"] = Bw / sec
-    out["c4_wide_train_tflops"] = 3 * flop_fwd * Bw / sec / 1e12
-    out["c4_config"] = "C4: F=512, 11 dilated layers, 25/75, 9286->1000 bp, batch 16, bf16"
-    del wide
-    torch.cuda.empty_cache()
-    out["pisa_config"] = "C5: C1 model, 20 row-shuffled references per base, 24 bases per CUDA-graph replay"
-    return out
-
-
-WORKLOAD = ("C1 trainSoloModel step (configs[0]): 1 head x 2 tasks, F=64, 9 dilated layers, "
-            "3090->1000 bp, batch 64 per GPU, Adam lr 0.004")
-
-
 def run_reference(args):
+    """``--impl reference``: the reference's own CPU implementation of the path.  The real one
+    (TensorFlow / Keras) cannot run here -- TensorFlow is not in the image and the reference has
+    no setup.py / pyproject.toml to install -- so this is the fp32 torch-CPU oracle port of the
+    same step (kind "port") on all host cores, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
+    steps = max(1, min(args.steps, 20))
     warm = max(1, min(args.warmup, 2))
-    rate, sec, cores = cpu_train_rate(C1, steps, warm, BATCH)
+    if args.config == "c5":
+        n = max(4, min(args.steps, 32))
+        rate = cpu_pisa_rate(C1, n, 20)
+        metric, unit, sec = "PISA attribution bases/s", "bases/s", 1.0 / rate
+        sample = (f"{n} bases, 20 shuffled references each, reference algorithm (40-sequence "
+                  "forward + input gradient per base), fp32 torch-CPU port")
+        steps, warm = n, 0
+    else:
+        cfg = {"c1": C1, "c4": C4, "c3": C3R}.get(args.config, C1)
+        batch = args.batch or (64 if args.config != "c4" else 4)
+        if args.config == "c4":
+            steps, warm = min(steps, 2), 1
+        rate, sec, cores, _ = cpu_train_rate(cfg, steps, warm, batch)
+        metric, unit = "BPNet train seq/s", "seq/s"
+        sample = (f"{steps} full {args.config.upper()} train steps of batch {batch} after {warm} "
+                  "warm-up, fp32 torch-CPU restatement of the Keras graph (TensorFlow unavailable "
+                  "offline)" + ("; residual tower only" if args.config == "c3" else ""))
+    cores = os.cpu_count() or 1
     line = {
-        "impl": "reference", "metric": "BPNet train seq/s", "value": rate, "unit": "seq/s",
-        "n_gpus": args.gpus, "device": "cpu", "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": BATCH,
-                   "note": "CPU host cores, one process (rank 0); batch 64 per step"},
-        "cpu_baseline": {"value": rate, "unit": "seq/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} full C1 train steps of batch {BATCH} after {warm} "
-                                   "warm-up, fp32 torch-CPU restatement of the Keras graph "
-                                   "(TensorFlow unavailable offline)"},
-        "e2e": {"value": rate, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": metric, "value": rate, "unit": unit,
+        "n_gpus": args.gpus, "device": "cpu", "steps": steps, "warmup": warm,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config],
+                   "note": "CPU host cores, one process (rank 0)"},
+        "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-family device time and roofline of a training step
+# ---------------------------------------------------------------------------------------------
+TRACED = ["conv3", "wgrad3", "wgrad3_multi", "wgrad_tower_input", "onehot_expand", "input_conv_fwd",
+          "input_conv_wgrad", "heads_fwd", "heads_fwd_tc", "heads_wgrad", "heads_dgrad",
+          "heads_pack_grad", "loss_fwd_bwd", "loss_fwd_bwd_pack", "prep_heads_fwd_weights",
+          "adam_step", "adam_prep_step", "adam_prep_step_peer", "peer_wait", "prep_conv3_weights",
+          "prep_input_conv_weights", "prep_heads_dgrad_weights", "combine_bias", "mul_f32"]
+NOT_REPLAYED = ("adam_step", "adam_prep_step", "adam_prep_step_peer", "peer_wait",
+                "prep_conv3_weights", "prep_input_conv_weights", "prep_heads_dgrad_weights",
+                "prep_heads_fwd_weights")
+
+
+def trace_step(run_step):
+    """Runs one eager step with the launchers of ``bpreveal_b200.ops`` recording their calls."""
+    import torch
+    from bpreveal_b200 import ops
+    calls, real = [], {}
+
+    def wrap(name):
+        fn = getattr(ops, name)
+        real[name] = fn
+
+        def inner(*a, **k):
+            key = name
+            if name == "conv3":
+                key = "conv3_fwd" if a[3] == 0 else "conv3_dgrad"
+            calls.append((key, fn, a, k))
+            return fn(*a, **k)
+        setattr(ops, name, inner)
+
+    for nm in TRACED:
+        wrap(nm)
+    try:
+        run_step()
+        torch.cuda.synchronize()
+    finally:
+        for nm in TRACED:
+            setattr(ops, nm, real[nm])
+    return calls
+
+
+def time_family(calls, key, reps=20):
+    """Average device time (ms) of the launches of one family inside a step: the family is
+    replayed as its own CUDA graph between two CUDA events on the launching stream (events around
+    eager launches would time the Python launch path, which is slower than these kernels)."""
+    import torch
+    fam = [c for c in calls if c[0] == key]
+    if not fam:
+        return 0.0, 0
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _, fn, a, k in fam:
+            fn(*a, **k)
+    g.replay()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, len(fam)
+
+
+def _shape(t):
+    t = t[0] if isinstance(t, tuple) else t
+    return t.shape
+
+
+def family_work(calls, planes):
+    """ALGORITHMIC bytes and FLOPs per family of one step: every operand
+    that the operation must read once and every result it must write once, at the storage types
+    of this path -- independent of how many times the implementation actually moves them.
+      conv3_fwd    read a_i, write a_{i+1} (bf16 planes), write the 1-bit ReLU mask
+      conv3_dgrad  read g_{i+1} and the mask that turns it into gz_{i+1}, write g_i
+      wgrad        read a_i and gz_{i+1} of every layer (+ x8 / gz_0 and a_L / d8 for the input
+                   convolution and the heads)"""
+    work = {}
+
+    def add(key, b, f):
+        w = work.setdefault(key, {"bytes": 0.0, "flop": 0.0})
+        w["bytes"] += b
+        w["flop"] += f
+
+    for key, fn, a, k in calls:
+        if key == "conv3_fwd":
+            B, Lin, F = _shape(a[0])
+            Lout = a[4]
+            add(key, planes * 2.0 * B * (Lin + Lout) * F + B * Lout * F / 8.0,
+                2.0 * 3 * F * F * B * Lout)
+        elif key == "conv3_dgrad":
+            B, Lg, F = _shape(a[0])
+            Lout = a[4]
+            add(key, planes * 2.0 * B * (Lg + Lout) * F + B * Lg * F / 8.0,
+                2.0 * 3 * F * F * B * Lg)
+        elif key in ("wgrad_tower_input", "wgrad3_multi"):
+            for (act, gz, d, dw, db) in a[0]:
+                B, Li, F = _shape(act)
+                Lo = _shape(gz)[1]
+                add(key, planes * 2.0 * B * (Li + Lo) * F, 2.0 * 3 * F * F * B * Lo)
+            if key == "wgrad_tower_input":
+                x8, gz0, W, Fw = a[1], a[2], a[3], a[4]
+                B, L0, F = _shape(gz0)
+                add(key, x8.numel() * 2.0 + planes * 2.0 * B * L0 * F, 2.0 * W * 4 * Fw * B * L0)
+                heads = k.get("heads")
+                if heads is not None:
+                    aL, d8, Wo, T = heads[0], heads[1], heads[2], heads[3]
+                    B, LL, F = _shape(aL)
+                    add(key, 2.0 * B * LL * F + d8.numel() * 2.0,
+                        2.0 * Wo * F * T * B * (LL - Wo + 1))
+        elif key == "wgrad3":
+            B, Li, F = _shape(a[0])
+            Lo = _shape(a[1])[1]
+            add(key, planes * 2.0 * B * (Li + Lo) * F, 2.0 * 3 * F * F * B * Lo)
+        elif key == "input_conv_fwd":
+            x8, out = a[0], a[7]
+            B, L0, F = _shape(out)
+            add(key, x8.numel() * 2.0 + planes * 2.0 * B * L0 * F + B * L0 * F / 8.0,
+                2.0 * a[3] * 4 * a[4] * B * L0)
+    return work
+
+
+def family_report(calls, planes, pk, traffic):
+    agg, counts = {}, {}
+    for key in dict.fromkeys(c[0] for c in calls):
+        if key in NOT_REPLAYED:
+            continue  # replaying the optimiser would train; they are ~10 us together
+        agg[key], counts[key] = time_family(calls, key)
+    work = family_work(calls, planes)
+    fams = {}
+    for key, ms in sorted(agg.items(), key=lambda kv: -kv[1]):
+        e = {"launches": counts[key], "us": round(ms * 1e3, 2)}
+        w = work.get(key)
+        if w and ms > 0:
+            e["bytes"] = w["bytes"]
+            e["gbs"] = w["bytes"] / (ms / 1e3) / 1e9
+            e["hbm_frac"] = e["gbs"] / pk["hbm"]
+            e["tflops"] = w["flop"] / (ms / 1e3) / 1e12
+            e["tensor_frac"] = e["tflops"] / pk["tensor"]
+        if traffic and key in traffic:
+            e["dram_bytes_measured"] = traffic[key]
+        fams[key] = e
+    return fams, sum(agg.values())
+
+
+def load_traffic(config):
+    """Measured DRAM bytes per family and step (ncu over one whole step, caches NOT flushed
+    between kernels), committed under profiles/ -- bench.py cannot run under ncu."""
+    path = os.path.join(ROOT, "profiles", f"step_traffic_r2_{config}.json")
+    if os.path.exists(path):
+        return json.load(open(path, encoding="utf-8"))["dram_bytes_per_step"], \
+            f"profiles/step_traffic_r2_{config}.json"
+    return None, None
+
+
+def roofline_of(fams, total_ms, bound, pk, traffic_src):
+    """``roofline`` = the LARGEST family of the step."""
+    name = next(iter(fams))
+    f = fams[name]
+    if "bytes" not in f:
+        return None
+    hbm = bound == "hbm"
+    ach = f["gbs"] if hbm else f["tflops"]
+    peak = pk["hbm"] if hbm else pk["tensor"]
+    per_step = f.get("dram_bytes_measured")
+    return {"bound": bound, "kernel": f"{name}: the {f['launches']} launches of one step replayed "
+                                      "as a CUDA graph 20x between CUDA events",
+            "achieved": ach, "peak": peak, "unit": "GB/s" if hbm else "TFLOP/s",
+            "frac": ach / peak, "peak_source": pk["source"],
+            "traffic": per_step / f["launches"] if per_step else None,
+            "traffic_source": traffic_src if per_step else None,
+            "launches": f["launches"], "avg_launch_us": f["us"] / f["launches"],
+            "algorithmic_bytes_per_launch": f["bytes"] / f["launches"],
+            "share_of_step": f["us"] / 1e3 / total_ms if total_ms else None,
+            "tensor_tflops": f["tflops"], "hbm_gbs": f["gbs"]}
+
+
+# ---------------------------------------------------------------------------------------------
+# training benchmarks (c1, c4, c3)
+# ---------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.verbose = os.environ.get("BENCH_VERBOSE", "0") != "0"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.warmup = max(3, args.warmup)
+        self.steps = max(1, args.steps)
+        self.args = args
+
+    def say(self, msg):
+        if self.verbose:
+            print(f"[bench rank {self.rank}] {msg}", file=sys.stderr, flush=True)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, nsteps, body):
+        """barrier + synchronize, CUDA events around ``nsteps`` calls of ``body(i)``, max over
+        ranks (ms)."""
+        torch = self.torch
+        self.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nsteps):
+            body(i)
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def peer_exchange(self, numel):
+        """N > 1: the gradient all-reduce is fused into the optimiser kernel over NVLink peer
+        memory (BPB_DP_PEER=0 selects NCCL between two CUDA graphs); decided collectively."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1 or os.environ.get("BPB_DP_PEER", "1") != "1":
+            return None
+        from bpreveal_b200 import parallel
+        ok, peers = 1, None
+        try:
+            peers = parallel.PeerGradExchange(numel, self.dev)
+        except Exception as e:  # noqa: BLE001
+            self.say(f"peer exchange unavailable on rank {self.rank}: {e}")
+            ok = 0
+        flag = torch.tensor([ok], device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return peers if int(flag.item()) == 1 else None
+
+    def finish(self, peers=None):
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+            if peers is not None:
+                peers.check()  # raises if any in-kernel wait for a peer expired
+                peers.close()
+            self.dist.destroy_process_group()
+
+
+def count_launches(step_eager):
+    """Native kernel launches of one step (our claim for ``gpu_launches``): the step body runs
+    un-graphed once with the C-ABI status check counting calls."""
+    from bpreveal_b200 import ops
+    counter = {"n": 0}
+    orig_check = ops.check
+    kernels_per_call = {"bpb_wgrad3_tc": 2, "bpb_wgrad3_multi": 2, "bpb_wgrad_tower_input": 2,
+                        "bpb_input_conv_wgrad": 2, "bpb_heads_fwd": 2, "bpb_heads_wgrad_tc": 2,
+                        "bpb_heads_pack_grad": 2}
+
+    def counting_check(rc, what):
+        counter["n"] += kernels_per_call.get(what, 1)
+        return orig_check(rc, what)
+
+    ops.check = counting_check
+    try:
+        step_eager()
+    finally:
+        ops.check = orig_check
+    return counter["n"]
+
+
+def c3_bias_hook(net, batch, dev):
+    """The frozen bias model of C3 (solo F=16 + transformation) wired to the residual network:
+    returns the closure the combined training step calls after the residual forward."""
+    from bpreveal_b200 import models
+    heads = [{"head-name": n, "num-tasks": 2, "profile-loss-weight": 1.0,
+              "counts-loss-weight": 10.0, "use-bias-counts": i == 0}
+             for i, n in enumerate(["oct4", "sox2", "klf4", "nanog"])]
+    bias_solo = models.soloModel(C3B["inputLength"], 1000, 16, 9, 7, 7, heads, "solo",
+                                 device=dev, seed=77)
+    tm = models.transformationModel(bias_solo, {"name": "simple", "types": ["linear", "sigmoid"]},
+                                    {"name": "simple", "types": ["linear"]}, heads)
+    resid = models.SoloModel.__new__(models.SoloModel)
+    models.Model.__init__(resid, "residual_model", C3R["inputLength"], 1000, heads)
+    resid.modelName, resid._device, resid.net = "residual", dev, net
+    resid._set_outputs([f"solo_profile_{h['head-name']}" for h in heads],
+                       [f"solo_logcounts_{h['head-name']}" for h in heads])
+    comb = models.CombinedModel(resid, tm, heads)
+    return comb._bias_hook(batch, "train"), comb
+
+
+def bench_train(ctx, name):
+    """c1 / c4 (solo) and c3 (combined): value with device-resident batches, e2e with pinned
+    host batches through the public training call, per-family device times, roofline."""
+    torch, args = ctx.torch, ctx.args
+    from bpreveal_b200.engine import NetConfig, SoloNet
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    cfgd = {"c1": C1, "c4": C4, "c3": C3R}[name]
+    batch = args.batch or (64 if name != "c4" else 32)
+    cfg = NetConfig(precise=args.precise, **cfgd)
+    net = SoloNet(cfg, dev)
+    net.init_random(seed=1234)
+    peers = ctx.peer_exchange(net.params.flat.numel())
+    net.enable_training(grads_flat=peers.grads if peers is not None else None)
+    lr = 0.004
+    hook = keep = None
+    if name == "c3":
+        hook, keep = c3_bias_hook(net, batch, dev)
+    n_b = N_BATCHES if name != "c4" else 2
+    xs, cs = synth(batch * n_b, cfgd, 20261019 + rank)
+    x_host = torch.tensor(xs).pin_memory()
+    c_host = torch.tensor(cs).pin_memory()
+    x_dev, c_dev = x_host.to(dev), c_host.to(dev)
+    loss_host = torch.zeros((2 * cfg.H,), dtype=torch.float32).pin_memory()
+    allreduce = None
+    if world > 1 and peers is None:
+        def allreduce(flat):
+            ctx.dist.all_reduce(flat, op=ctx.dist.ReduceOp.SUM)
+    dp = dict(peers=peers) if peers is not None else dict(allreduce=allreduce, world=world)
+    if hook is not None:
+        dp["bias_logits"] = hook
+
+    def sl(t, i):
+        j = i % n_b
+        return t[j * batch:(j + 1) * batch]
+
+    first_losses = None
+    for i in range(ctx.warmup):
+        out = net.train_step(sl(x_dev, 0), sl(c_dev, 0), lr, **dp)
+        if i == 0:
+            torch.cuda.synchronize()
+            first_losses = [float(v) for v in out.cpu()]
+            ctx.say("first step done")
+    torch.cuda.synchronize()
+    calls_per_step = count_launches(
+        lambda: net.train_step(sl(x_dev, 1), sl(c_dev, 1), lr, use_graph=False, **dp))
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = ctx.timed(ctx.steps, lambda i: net.train_step(sl(x_dev, i), sl(c_dev, i), lr, **dp))
+    ctx.say(f"timed region done: {ms / ctx.steps:.3f} ms/step")
+
+    def host_step(i):
+        losses = net.train_step(sl(x_host, i), sl(c_host, i), lr, **dp)
+        loss_host.copy_(losses, non_blocking=True)
+    ctx.timed(max(ctx.warmup, 3), host_step)  # warm-up of the host-input path (staging slots)
+    ms_e2e = ctx.timed(ctx.steps, host_step)
+    clocks = sampler.stop() if sampler else None
+    final_losses = [float(v) for v in loss_host]
+
+    steps = ctx.steps
+    value = world * batch * steps / (ms / 1e3)
+    e2e = world * batch * steps / (ms_e2e / 1e3)
+    pk = peaks()
+    planes = 2 if args.precise else 1
+    fams = roof = None
+    if rank == 0:
+        local_dp = {"bias_logits": hook} if hook is not None else {}
+        calls = trace_step(lambda: net.train_step(sl(x_dev, 0), sl(c_dev, 0), lr, use_graph=False,
+                                                  **local_dp))
+        traffic, tsrc = load_traffic(name) if not args.precise else (None, None)
+        fams, tot = family_report(calls, planes, pk, traffic)
+        roof = roofline_of(fams, tot, "tensor" if cfgd["numFilters"] >= 256 else "hbm", pk, tsrc)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and name in ("c1", "c3"):
+        nst = 3
+        rate, sec, cores, cpu_first = cpu_train_rate(cfgd, nst, 1, batch, seed=20261019 + rank,
+                                                     n_total=batch * n_b)
+        cpu = {"value": rate, "unit": "seq/s", "cores": cores, "kind": "port",
+               "sample": f"{nst} full {name.upper()} train steps of batch {batch} after 1 warm-up "
+                         f"({sec:.2f} s/step), fp32 torch-CPU restatement of the Keras graph"
+                         + ("; residual tower only (the frozen bias forward is not counted)"
+                            if name == "c3" else ""),
+               "first_step_losses": cpu_first if name == "c1" else None}
+    train_flop = 3 * fwd_flop_per_seq(cfgd) + (fwd_flop_per_seq(C3B) if name == "c3" else 0.0)
+    h2d = batch * (cfgd["inputLength"] * 4 + cfgd["outputLength"] * cfg.T * 4)
+    line = {
+        "metric": "BPNet train seq/s", "value": value, "unit": "seq/s", "n_gpus": world,
+        "steps": steps, "warmup": ctx.warmup, "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 planes x2 (hi/lo), fp32 accumulate" if args.precise
+        else "bf16 (fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": WORKLOADS[name] + (f" [batch {batch} per GPU]" if name == "c4" else ""),
+                   "global_batch": batch * world, "parallelism": f"dp{world}",
+                   "grad_exchange": ("none" if world == 1 else
+                                     "fused into the optimiser kernel over NVLink peer memory"
+                                     if peers is not None else "NCCL all-reduce"),
+                   "l2": "per-step working set (>= 0.5 GB of activations) exceeds the 126 MB L2; "
+                         f"{n_b} distinct batches cycled"},
+        "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": ms_e2e / steps},
+        "gpu_launches": calls_per_step * steps * 2, "native_calls_per_step": calls_per_step,
+        "tflops": value * train_flop / 1e12,
+        "roofline": roof, "families": fams, "cpu_baseline": cpu, "clocks": clocks,
+        "first_step_losses": first_losses, "final_losses": final_losses,
+    }
+    del net, keep
+    torch.cuda.empty_cache()
+    return line, peers
+
+
+# ---------------------------------------------------------------------------------------------
+# prediction (c2) and PISA (c5)
+# ---------------------------------------------------------------------------------------------
+def bench_predict(ctx):
+    torch = ctx.torch
+    from bpreveal_b200.engine import NetConfig, SoloNet
+    net = SoloNet(NetConfig(**C1), ctx.dev)
+    net.init_random(seed=1234)
+    n, B = 4096, 128
+    xs, _ = synth(n, C1, 777 + ctx.rank)
+    xh = torch.tensor(xs).pin_memory()
+    x_dev = xh.to(ctx.dev)
+    net.predict(x_dev[:256], batchSize=B)
+    # pinned result buffers are the caller's (allocating 33 MB of pinned memory per call costs
+    # more than the pass itself)
+    out_l = torch.empty((n, 1000, 2), dtype=torch.float32).pin_memory()
+    out_c = torch.empty((n, 1), dtype=torch.float32).pin_memory()
+    net.predict_host(xh, batchSize=B, out_logits=out_l, out_logcounts=out_c)
+    reps = max(1, ctx.steps // 10)
+    ms = ctx.timed(reps, lambda i: net.predict(x_dev, batchSize=B))
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        net.predict_host(xh, batchSize=B, out_logits=out_l, out_logcounts=out_c)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    if ctx.world > 1:
+        t = torch.tensor([sec], device=ctx.dev)
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+        sec = float(t.item())
+    pk = peaks()
+    value = ctx.world * reps * n / (ms / 1e3)
+    fl = fwd_flop_per_seq(C1)
+    out_b = 1000 * 2 * 4 + 4
+    gbs = value / ctx.world * 6.8e6 / 1e9
+    return {
+        "metric": "makePredictions windows/s", "value": value, "unit": "windows/s",
+        "n_gpus": ctx.world, "steps": reps, "warmup": 1, "ms_per_step": ms / reps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": WORKLOADS["c2"], "windows_per_step": n, "batch": B,
+                   "l2": "4096 windows of activations per pass exceed L2"},
+        "e2e": {"value": ctx.world * reps * n / sec, "unit": "windows/s",
+                "h2d_bytes_per_step": n * 3090 * 4, "d2h_bytes_per_step": n * out_b},
+        "tflops": value * fl / 1e12,
+        "roofline": {"bound": "hbm", "kernel": "whole forward pass (layer-by-layer)",
+                     "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                     "traffic": None, "peak_source": pk["source"],
+                     "note": "6.8 MB of algorithmic activation traffic per window (SURVEY 8d)"},
+    }
+
+
+def bench_pisa(ctx):
+    torch = ctx.torch
+    from bpreveal_b200 import interpret
+    from bpreveal_b200.engine import NetConfig, SoloNet
+    args = ctx.args
+    net = SoloNet(NetConfig(precise=args.precise, **C1), ctx.dev)
+    net.init_random(seed=1234)
+    Q, n = 24, 20
+    xs, _ = synth(Q * 8, C1, 555 + ctx.rank)
+    xh = torch.tensor(xs).pin_memory()
+    x_dev = xh.to(ctx.dev)
+    interpret.pisa_batch(net, x_dev[:Q], headID=0, taskID=0, numShuffles=n)
+    reps = max(2, ctx.steps // 5)
+    nq = x_dev.shape[0] // Q
+    launches = count_launches(lambda: interpret.pisa_batch(net, x_dev[:Q], 0, 0, n,
+                                                           use_graph=False))
+    ms = ctx.timed(reps, lambda i: interpret.pisa_batch(net, x_dev[(i % nq) * Q:(i % nq + 1) * Q],
+                                                        headID=0, taskID=0, numShuffles=n))
+    out_h = torch.empty((Q, 3090, 4), dtype=torch.float32).pin_memory()
+
+    def host_step(i):
+        o = (i % nq) * Q
+        phi, vx, vr = interpret.pisa_batch(net, xh[o:o + Q].to(ctx.dev, non_blocking=True), 0, 0, n)
+        out_h.copy_(phi, non_blocking=True)
+        vx.cpu()
+    ms_e2e = ctx.timed(reps, host_step)
+    pk = peaks()
+    value = ctx.world * reps * Q / (ms / 1e3)
+    flop_base = 25.6e9  # BASELINE.md section 2: 1 query + 20 reference fwd + 20 input-gradient passes
+    cpu = None
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+        nb = 32
+        r = cpu_pisa_rate(C1, nb, n)
+        cpu = {"value": r, "unit": "bases/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{nb} bases x {n} shuffled references, the reference's algorithm "
+                         "(joint batch of 40 sequences forward + input gradient per base, "
+                         "shap.py:362-377), fp32 torch-CPU port"}
+    tf = value / ctx.world * flop_base / 1e12
+    return {
+        "metric": "PISA attribution bases/s", "value": value, "unit": "bases/s",
+        "n_gpus": ctx.world, "steps": reps, "warmup": 1, "ms_per_step": ms / reps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 planes x2 (hi/lo), fp32 accumulate" if args.precise
+        else "bf16 (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": WORKLOADS["c5"], "bases_per_step": Q,
+                   "l2": "one replay touches ~0.6 GB of activations / multipliers (> L2)"},
+        "e2e": {"value": ctx.world * reps * Q / (ms_e2e / 1e3), "unit": "bases/s",
+                "h2d_bytes_per_step": Q * 3090 * 4, "d2h_bytes_per_step": Q * 3090 * 16 + 4 * Q},
+        "gpu_launches": launches * reps * 2, "native_calls_per_step": launches,
+        "tflops": tf,
+        "roofline": {"bound": "hbm", "kernel": "one CUDA-graph replay: reference generation, query "
+                     "+ reference forward passes, rescale backward, combiner (whole attribution)",
+                     "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s",
+                     "frac": tf / pk["tensor"], "traffic": None, "peak_source": pk["source"],
+                     "note": "25.6 GFLOP per base = 1 query + 20 reference forward passes + 20 "
+                             "input-gradient passes over the whole window (BASELINE.md section 2); "
+                             "the F=64 layers are HBM-bound, so the tensor fraction is quoted for "
+                             "comparison with the reference's 63 GFLOP per base, not as a target"},
+        "cpu_baseline": cpu,
+    }
+
+
+def extras_c1(ctx):
+    """Secondary numbers attached to the headline line (one GPU, short runs)."""
+    class A:
+        pass
+    saved = (ctx.steps, ctx.warmup, ctx.args)
+    out = {}
+    try:
+        a = A()
+        a.__dict__.update(vars(saved[2]))
+        a.no_cpu_baseline, a.batch = True, 0
+        ctx.args = a
+        ctx.steps = 20
+        p = bench_predict(ctx)
+        out["predict_windows_per_s"] = p["value"]
+        out["predict_e2e_windows_per_s"] = p["e2e"]["value"]
+        ctx.steps = 30
+        a.precise = False
+        q = bench_pisa(ctx)
+        out["pisa_bases_per_s"], out["pisa_e2e_bases_per_s"] = q["value"], q["e2e"]["value"]
+        a.precise = True
+        out["pisa_bases_per_s_precise"] = bench_pisa(ctx)["value"]
+        line, _ = bench_train(ctx, "c1")
+        out["c1_precise_train_seq_per_s"] = line["value"]
+        out["c1_precise_e2e_seq_per_s"] = line["e2e"]["value"]
+        a.precise = False
+        ctx.steps = 20
+        line, _ = bench_train(ctx, "c3")
+        out["c3_combined_train_seq_per_s"] = line["value"]
+        out["c3_combined_e2e_seq_per_s"] = line["e2e"]["value"]
+        ctx.steps = 6
+        a.batch = 32
+        line, _ = bench_train(ctx, "c4")
+        out["c4_wide_train_seq_per_s"] = line["value"]
+        out["c4_wide_train_tflops"] = line["tflops"]
+        out["c4_config"] = line["config"]["workload"]
+        if not saved[2].no_cpu_baseline:
+            out["pisa_cpu_bases_per_s"] = cpu_pisa_rate(C1, 32, 20)
+            out["pisa_cpu_note"] = ("oracle port of the reference's algorithm (40-sequence joint "
+                                    "batch per base), fp32 torch-CPU, all host cores, 32 bases")
+    finally:
+        ctx.steps, ctx.warmup, ctx.args = saved
+    return out
 
 
 def main():
@@ -233,300 +794,30 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c1", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU and step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
-                    help="skip the secondary predict / PISA measurements")
-    ap.add_argument("--precise", action="store_true")
+                    help="skip the secondary measurements attached to the C1 line")
+    ap.add_argument("--precise", action="store_true", help="fp32-accumulate (hi/lo plane) path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
-
-    import torch
-    import torch.distributed as dist
-    from bpreveal_b200 import ops
-    from bpreveal_b200.engine import NetConfig, SoloNet
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    verbose = os.environ.get("BENCH_VERBOSE", "0") != "0"
-
-    def say(msg):
-        if verbose:
-            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
-
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        say("process group up")
-    warmup = max(3, args.warmup)
-    steps = max(1, args.steps)
-
-    cfg = NetConfig(precise=args.precise, **C1)
-    net = SoloNet(cfg, dev)
-    net.init_random(seed=1234)
-    # N > 1: the gradient all-reduce is fused into the optimiser kernel over NVLink peer memory
-    # (BPB_DP_PEER=0 selects the NCCL all-reduce between two CUDA graphs instead); the choice is
-    # made collectively so that every rank takes the same path
+    ctx = Ctx(args)
     peers = None
-    if world > 1 and os.environ.get("BPB_DP_PEER", "1") == "1":
-        from bpreveal_b200 import parallel
-        ok = 1
-        try:
-            peers = parallel.PeerGradExchange(net.params.flat.numel(), dev)
-        except Exception as e:  # noqa: BLE001
-            say(f"peer exchange unavailable on rank {rank}: {e}")
-            ok = 0
-        flag = torch.tensor([ok], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            peers = None
-    net.enable_training(grads_flat=peers.grads if peers is not None else None)
-    lr = 0.004
-    # synthetic batches: resident on the device (for `value`) and in pinned host memory (`e2e`)
-    xs, cs = synth(BATCH * N_BATCHES, C1, 20261019 + rank)
-    x_host = torch.tensor(xs).pin_memory()
-    c_host = torch.tensor(cs).pin_memory()
-    x_dev = x_host.to(dev)
-    c_dev = c_host.to(dev)
-    loss_host = torch.zeros((2 * cfg.H,), dtype=torch.float32).pin_memory()
-
-    allreduce = None
-    if world > 1 and peers is None:
-        def allreduce(flat):
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-
-    dp = dict(peers=peers) if peers is not None else dict(allreduce=allreduce, world=world)
-
-    def batch_slice(t, i):
-        j = i % N_BATCHES
-        return t[j * BATCH:(j + 1) * BATCH]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(nsteps, host_io):
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(nsteps):
-            if host_io:
-                losses = net.train_step(batch_slice(x_host, i), batch_slice(c_host, i), lr,
-                                        **dp)
-                loss_host.copy_(losses, non_blocking=True)
-            else:
-                net.train_step(batch_slice(x_dev, i), batch_slice(c_dev, i), lr,
-                               **dp)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    # count native launches per step (our claim for gpu_launches)
-    counter = {"n": 0}
-    lib = __import__("bpreveal_b200._lib", fromlist=["_lib"])
-    orig_check = ops.check
-
-    kernels_per_call = {"bpb_wgrad3_tc": 2, "bpb_wgrad3_multi": 2, "bpb_wgrad_tower_input": 2, "bpb_peer_wait": 1, "bpb_adam_prep_step_peer": 1, "bpb_input_conv_wgrad": 2, "bpb_heads_fwd": 2,
-                        "bpb_heads_wgrad_tc": 2, "bpb_heads_pack_grad": 2, "bpb_heads_fwd_tc": 1}
-
-    def counting_check(rc, what):
-        counter["n"] += kernels_per_call.get(what, 1)
-        return orig_check(rc, what)
-
-    for i in range(warmup):
-        net.train_step(batch_slice(x_dev, 0), batch_slice(c_dev, 0), lr, **dp)
-        if i == 0:
-            torch.cuda.synchronize()
-            say("first step done")
-    torch.cuda.synchronize()
-    say("warm-up done")
-    # launches per step: replay the step body un-graphed once with the counter armed
-    ops.check = counting_check
-    net.train_step(batch_slice(x_dev, 1), batch_slice(c_dev, 1), lr, use_graph=False,
-                   **dp)
-    ops.check = orig_check
-    torch.cuda.synchronize()
-    calls_per_step = counter["n"]
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms = timed(steps, host_io=False)
-    say(f"timed region done: {ms / steps:.3f} ms/step")
-    timed(max(warmup, 3), host_io=True)  # warm-up of the host-input path (staging slots, copy stream)
-    ms_e2e = timed(steps, host_io=True)
-    say("e2e region done")
-    clocks = sampler.stop() if sampler else None
-    final_losses = loss_host.clone()
-
-    value = world * BATCH * steps / (ms / 1e3)
-    e2e = world * BATCH * steps / (ms_e2e / 1e3)
-
-    # ------------------------------------------------------------------ roofline of the dominant kernel
-    # Device time per kernel family: one eager step is recorded as a list of native calls (same
-    # buffers as the real step), then every family is replayed as its own CUDA graph between two
-    # CUDA events on the launching stream.  (Events around eager launches would measure the Python
-    # launch path, which is slower than these kernels.)
-    roof = None
-    breakdown = None
-    if rank == 0:
-        calls = []
-        real = {}
-        names = ["conv3", "wgrad3", "wgrad3_multi", "wgrad_tower_input", "onehot_expand", "input_conv_fwd", "input_conv_wgrad",
-                 "heads_fwd", "heads_fwd_tc", "heads_wgrad", "heads_dgrad", "heads_pack_grad",
-                 "loss_fwd_bwd", "loss_fwd_bwd_pack", "prep_heads_fwd_weights",
-                 "adam_step", "adam_prep_step", "adam_prep_step_peer", "peer_wait",
-                 "prep_conv3_weights", "prep_input_conv_weights", "prep_heads_dgrad_weights"]
-
-        def wrap(name):
-            fn = getattr(ops, name)
-            real[name] = fn
-
-            def inner(*a, **k):
-                key = name
-                if name == "conv3":
-                    key = "conv3_fwd" if a[3] == 0 else "conv3_dgrad"
-                calls.append((key, fn, a, k))
-                return fn(*a, **k)
-            setattr(ops, name, inner)
-
-        for nm in names:
-            wrap(nm)
-        # local step (no collective: only rank 0 is here, a collective would wait forever)
-        net.train_step(batch_slice(x_dev, 0), batch_slice(c_dev, 0), lr, use_graph=False)
-        torch.cuda.synchronize()
-        for nm in names:
-            setattr(ops, nm, real[nm])
-
-        def time_family(key, reps=20):
-            fam = [c for c in calls if c[0] == key]
-            if not fam:
-                return 0.0, 0
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for _, fn, a, k in fam:
-                    fn(*a, **k)
-            g.replay()
-            torch.cuda.synchronize()
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                g.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / reps, len(fam)
-
-        agg = {}
-        counts = {}
-        for key in dict.fromkeys(c[0] for c in calls):
-            if key in ("adam_step", "adam_prep_step", "adam_prep_step_peer", "peer_wait",
-                       "prep_conv3_weights", "prep_input_conv_weights",
-                       "prep_heads_dgrad_weights", "prep_heads_fwd_weights"):
-                continue  # replaying the optimiser would train; they are ~10 us together
-            agg[key], counts[key] = time_family(key)
-        tot = sum(agg.values())
-        breakdown = {k: round(v, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
-        # algorithmic bytes of the dilated-conv forward launches of one step (bf16
-        # activations read once + written once per layer, plus the 1-bit ReLU masks)
-        conv_fwd_bytes = 0.0
-        for key, fn, a, k in calls:
-            if key == "conv3_fwd":
-                inp = a[0][0] if isinstance(a[0], tuple) else a[0]
-                Bq, Lin, Fq = inp.shape
-                Lout = a[4]
-                planes = 2 if args.precise else 1
-                conv_fwd_bytes += planes * 2.0 * Bq * (Lin + Lout) * Fq + Bq * Lout * Fq / 8.0
-        conv_fwd_t = agg.get("conv3_fwd", 0.0)
-        conv_fwd_n = counts.get("conv3_fwd", 0)
-        peaks = {}
-        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk_path):
-            peaks = json.load(open(pk_path))
-        peak = peaks.get("hbm_gbs", 6650.0)
-        achieved = conv_fwd_bytes / (conv_fwd_t / 1e3) / 1e9 if conv_fwd_t > 0 else 0.0
-        # DRAM bytes per launch of this kernel from the committed ncu capture (bench.py cannot run
-        # under ncu); only quoted for the workload the capture was taken on
-        traffic, traffic_src = None, None
-        tr_path = os.path.join(ROOT, "profiles", "conv_fwd_traffic_r1.json")
-        if os.path.exists(tr_path) and not args.precise:
-            tr = json.load(open(tr_path))
-            traffic, traffic_src = tr["dram_bytes_per_launch"], "profiles/conv_fwd_traffic_r1.json (ncu --set full)"
-        roof = {"bound": "hbm",
-                "kernel": "conv_tc_kernel, forward of the 9 dilated residual layers of one step "
-                          "(CUDA graph of the 9 launches replayed 20x between CUDA events)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks
-                else "fallback 6650 GB/s",
-                "traffic": traffic, "traffic_source": traffic_src, "launches": conv_fwd_n,
-                "avg_launch_us": conv_fwd_t / max(conv_fwd_n, 1) * 1e3,
-                "algorithmic_bytes_per_launch": conv_fwd_bytes / max(conv_fwd_n, 1),
-                "share_of_step": conv_fwd_t / tot if tot else None,
-                "tensor_tflops": (2.0 * 3 * 64 * 64 * sum(
-                    (a[0][0] if isinstance(a[0], tuple) else a[0]).shape[0] * a[4]
-                    for key, fn, a, k in calls if key == "conv3_fwd")) / (conv_fwd_t / 1e3) / 1e12
-                if conv_fwd_t > 0 and not args.precise else None}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_train_rate(C1, 3, 1, BATCH)
-        cpu = {"value": rate, "unit": "seq/s", "cores": cores, "kind": "port",
-               "sample": f"3 full C1 train steps of batch {BATCH} after 1 warm-up "
-                         f"({sec:.2f} s/step), fp32 torch-CPU restatement of the Keras graph"}
-
-    extras = None
-    if rank == 0 and not args.no_extras and not args.precise:
-        del net
-        torch.cuda.empty_cache()
-        extras = gpu_extras(C1, dev, rank)
-        if world == 1 and not args.no_cpu_baseline:
-            extras["pisa_cpu_bases_per_s"] = cpu_pisa_rate(C1, 2, 20)
-            extras["pisa_cpu_note"] = "oracle port of the reference algorithm, fp32 torch-CPU, 2 bases"
-
-    if rank == 0:
-        h2d = BATCH * (C1["inputLength"] * 4 + C1["outputLength"] * cfg.T * 4)
-        line = {
-            "metric": "BPNet train seq/s", "value": value, "unit": "seq/s", "n_gpus": world,
-            "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 planes x2 (hi/lo), fp32 accumulate" if args.precise else "bf16 (fp32 accumulate)",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                       "grad_exchange": ("none" if world == 1 else
-                                         "fused into the optimiser kernel over NVLink peer memory"
-                                         if peers is not None else "NCCL all-reduce"),
-                       "l2": "per-step working set (~0.5 GB of activations) exceeds the 126 MB L2; "
-                             f"{N_BATCHES} distinct batches cycled"},
-            "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": int(loss_host.numel() * 4),
-                    "ms_per_step": ms_e2e / steps},
-            "gpu_launches": calls_per_step * steps * 2,
-            "native_calls_per_step": calls_per_step,
-            "tflops": value * TRAIN_FLOP_PER_SEQ / 1e12,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-            "kernel_ms_per_step": breakdown,
-            "extra": extras,
-            "final_losses": [float(v) for v in final_losses],
-        }
+    if args.config in ("c1", "c3", "c4"):
+        line, peers = bench_train(ctx, args.config)
+        if (ctx.rank == 0 and args.config == "c1" and not args.no_extras and not args.precise
+                and ctx.world == 1):
+            line["extra"] = extras_c1(ctx)
+    elif args.config == "c2":
+        line = bench_predict(ctx)
+    else:
+        line = bench_pisa(ctx)
+    if ctx.rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.cuda.synchronize()
-        dist.barrier()
-        if peers is not None:
-            peers.check()  # raises if any in-kernel wait for a peer expired
-            peers.close()
-        dist.destroy_process_group()
+    ctx.finish(peers)
 
 
 if __name__ == "__main__":

@@ -798,6 +798,70 @@ __global__ void counts_lse_kernel(int B, int H, const int* __restrict__ use,
   }
 }
 
+// models.py:349-380 in one launch: the frozen bias model's raw outputs go through the per-head
+// transformation (models.py:118-175; coefficient table [H][n_p + n_c][4], profile terms first),
+// profile logits are added to the residual's, log-counts are combined by CountsLogSumExp (fp64)
+// where use[h], else the residual's pass through.  Thread i < B*L*T handles one logit, the next
+// B*H threads one log-count.
+__global__ void combine_bias_kernel(int B, int L, int T, int H, const int* __restrict__ task_off,
+                                    const float* __restrict__ bias_logits,
+                                    const float* __restrict__ bias_lc, int n_p,
+                                    const int* __restrict__ p_act, int n_c,
+                                    const int* __restrict__ c_act,
+                                    const float* __restrict__ coeffs, const int* __restrict__ use,
+                                    const float* __restrict__ resid_logits,
+                                    const float* __restrict__ resid_lc,
+                                    float* __restrict__ out_logits, float* __restrict__ out_lc,
+                                    float* __restrict__ dresid_scale,
+                                    float* __restrict__ bias_logits_t,
+                                    float* __restrict__ bias_lc_t) {
+  const long long nl = static_cast<long long>(B) * L * T;
+  const long long total = nl + static_cast<long long>(B) * H;
+  const int per = n_p + n_c;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (i < nl) {
+      const int col = static_cast<int>(i % T);
+      int h = 0;
+      while (h + 1 < H && task_off[h + 1] <= col) ++h;
+      const float x = bias_logits[i];
+      float s = x;
+      if (n_p > 0) {
+        s = 0.f;
+        const float* c = coeffs + static_cast<long long>(h) * per * 4;
+        for (int t = 0; t < n_p; ++t) {
+          const float m1 = c[4 * t], b1 = c[4 * t + 1], m2 = c[4 * t + 2], b2 = c[4 * t + 3];
+          s += (p_act[t] == 0) ? m1 * x + b1 : m1 * act_fn(p_act[t], m2 * x + b2) + b1;
+        }
+      }
+      if (bias_logits_t) bias_logits_t[i] = s;
+      out_logits[i] = s + resid_logits[i];
+    } else {
+      const long long j = i - nl;
+      const int h = static_cast<int>(j % H);
+      const float x = bias_lc[j];
+      float s = x;
+      if (n_c > 0) {
+        s = 0.f;
+        const float* c = coeffs + (static_cast<long long>(h) * per + n_p) * 4;
+        for (int t = 0; t < n_c; ++t) {
+          const float m1 = c[4 * t], b1 = c[4 * t + 1], m2 = c[4 * t + 2], b2 = c[4 * t + 3];
+          s += (c_act[t] == 0) ? m1 * x + b1 : m1 * act_fn(c_act[t], m2 * x + b2) + b1;
+        }
+      }
+      if (bias_lc_t) bias_lc_t[j] = s;
+      if (use[h]) {
+        const double ea = exp(static_cast<double>(s)), eb = exp(static_cast<double>(resid_lc[j]));
+        out_lc[j] = static_cast<float>(log(ea + eb));
+        if (dresid_scale) dresid_scale[j] = static_cast<float>(eb / (ea + eb));
+      } else {
+        out_lc[j] = resid_lc[j];
+        if (dresid_scale) dresid_scale[j] = 1.f;
+      }
+    }
+  }
+}
+
 __global__ void mul_kernel(long long n, const float* __restrict__ a, const float* __restrict__ b,
                            float* __restrict__ out) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -1098,6 +1162,28 @@ extern "C" int bpb_mul_f32(long long n, const float* a, const float* b, float* o
   BP_REQUIRE(a && b && out, "bpb_mul_f32: NULL argument");
   if (n <= 0) return 0;
   mul_kernel<<<ew_blocks(n), 256, 0, stream>>>(n, a, b, out);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bpb_combine_bias(int B, int L, int T, int H, const int* task_off,
+                                const float* bias_logits, const float* bias_lc, int n_pterms,
+                                const int* p_act, int n_cterms, const int* c_act,
+                                const float* coeffs, const int* use_bias,
+                                const float* resid_logits, const float* resid_lc,
+                                float* out_logits, float* out_lc, float* dresid_scale,
+                                float* bias_logits_t, float* bias_lc_t, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(task_off && bias_logits && bias_lc && use_bias && resid_logits && resid_lc &&
+                 out_logits && out_lc, "bpb_combine_bias: NULL argument");
+  BP_REQUIRE(n_pterms >= 0 && n_cterms >= 0 && (n_pterms + n_cterms == 0 || coeffs) &&
+                 (n_pterms == 0 || p_act) && (n_cterms == 0 || c_act),
+             "bpb_combine_bias: transformation terms without their tables");
+  const long long total = static_cast<long long>(B) * L * T + static_cast<long long>(B) * H;
+  if (total <= 0) return 0;
+  combine_bias_kernel<<<ew_blocks(total), 256, 0, stream>>>(
+      B, L, T, H, task_off, bias_logits, bias_lc, n_pterms, p_act, n_cterms, c_act, coeffs,
+      use_bias, resid_logits, resid_lc, out_logits, out_lc, dresid_scale, bias_logits_t, bias_lc_t);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

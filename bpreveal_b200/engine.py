@@ -448,8 +448,13 @@ class SoloNet:
                 ws["logits_c"] = torch.empty_like(logits)
                 ws["lc_c"] = torch.empty_like(lc)
                 ws["dscale"] = torch.empty_like(lc)
-            ops.add_f32(logits, bias_logits, ws["logits_c"])
-            ops.counts_lse(use_bias, bias_logcounts, lc, ws["lc_c"], ws["dscale"])
+            if callable(bias_logits):
+                # combined model: ``bias_logits(ws)`` runs the frozen bias model and the fused
+                # transformation + add + log-sum-exp launch into ws['logits_c' / 'lc_c' / 'dscale']
+                bias_logits(ws)
+            else:
+                ops.add_f32(logits, bias_logits, ws["logits_c"])
+                ops.counts_lse(use_bias, bias_logcounts, lc, ws["lc_c"], ws["dscale"])
             logits, lc = ws["logits_c"], ws["lc_c"]
         nL = cfg.numLayers
         planes = 2 if cfg.precise else 1
@@ -558,8 +563,13 @@ class SoloNet:
                 ws["logits_c"] = torch.empty_like(logits)
                 ws["lc_c"] = torch.empty_like(lc)
                 ws["dscale"] = torch.empty_like(lc)
-            ops.add_f32(logits, bias_logits, ws["logits_c"])
-            ops.counts_lse(use_bias, bias_logcounts, lc, ws["lc_c"], ws["dscale"])
+            if callable(bias_logits):
+                # combined model: ``bias_logits(ws)`` runs the frozen bias model and the fused
+                # transformation + add + log-sum-exp launch into ws['logits_c' / 'lc_c' / 'dscale']
+                bias_logits(ws)
+            else:
+                ops.add_f32(logits, bias_logits, ws["logits_c"])
+                ops.counts_lse(use_bias, bias_logcounts, lc, ws["lc_c"], ws["dscale"])
             logits, lc = ws["logits_c"], ws["lc_c"]
         ops.loss_fwd_bwd(self.task_off, logits, lc, ws["counts"], self.profile_weight, self.lam,
                          ws["losses"], None, None,
@@ -586,44 +596,46 @@ class SoloNet:
             self.step_and_lr[1:2].fill_(float(lr))  # stream-ordered scalar fill, only on change
             self._lr_on_device = lr
 
+        hook = bias_logits if callable(bias_logits) else None
         if peers is not None:
             # data parallel over NVLink peer memory: the optimiser kernel sums the ranks' buckets
             # itself -- one graph per step, no collective call, no host involvement
-            assert bias_logits is None and self.grads_flat.data_ptr() == peers.grads.data_ptr()
+            assert (bias_logits is None or hook is not None) and \
+                self.grads_flat.data_ptr() == peers.grads.data_ptr()
 
             def body_peer():
                 ops.peer_wait(peers.args)
-                self.forward_backward_into(ws, lc_true=lct)
+                self.forward_backward_into(ws, hook, lc_true=lct)
                 self._rf_twin = None
                 ops.adam_prep_step_peer(self.params.flat, self.adam_m, self.adam_v,
                                         self.step_and_lr, self._prep_table(), peers.args)
             if use_graph:
-                self._run_graph(("train_peer", B, peers.world, lct), body_peer)
+                self._run_graph(("train_peer", B, peers.world, lct, id(hook)), body_peer)
             else:
                 body_peer()
             return ws["losses"]
-        if bias_logits is not None:
-            # combined model: the frozen bias outputs change every batch -> no graph replay
+        if bias_logits is not None and hook is None:
+            # bias outputs handed in as tensors (they change every batch): eager
             self.forward_backward_into(ws, bias_logits, bias_logcounts, use_bias, lc_true=lct)
             if allreduce is not None:
                 allreduce(self.grads_flat)
             self.apply_adam(grad_scale=1.0 / world)
         elif allreduce is None:
             def body():
-                self.forward_backward_into(ws, lc_true=lct)
+                self.forward_backward_into(ws, hook, lc_true=lct)
                 self.apply_adam()
             if use_graph:
-                self._run_graph(("train", B, lct), body)
+                self._run_graph(("train", B, lct, id(hook)), body)
             else:
                 body()
         else:
             def body_a():
-                self.forward_backward_into(ws, lc_true=lct)
+                self.forward_backward_into(ws, hook, lc_true=lct)
 
             def body_b():
                 self.apply_adam(grad_scale=1.0 / world)
             if use_graph:
-                self._run_graph(("train_fb", B, lct), body_a)
+                self._run_graph(("train_fb", B, lct, id(hook)), body_a)
                 allreduce(self.grads_flat)
                 self._run_graph(("train_opt", B, world), body_b)
             else:

@@ -623,38 +623,67 @@ class CombinedModel(Model):
     def _layer_table(self):
         return [(k, np.shape(v), int(np.size(v))) for k, v in self.named_weights()]
 
-    def _bias_device(self, xt, batch_size):
-        f = self.cropFlank
-        xc = xt[:, f:xt.shape[1] - f, :].contiguous() if f > 0 else xt
-        return self.bias._predict_device(xc, batch_size)
+    def _bias_parts(self):
+        """(solo network of the bias model, profile act table, counts act table, coefficient
+        table, n profile terms, n counts terms) -- a plain solo bias model has no terms."""
+        if isinstance(self.bias, TransformationModel):
+            tm = self.bias
+            return (tm.solo.net, tm.pAct, tm.cAct, tm.coeffs, len(tm.pTypes), len(tm.cTypes))
+        return (self.bias.net, None, None, None, 0, 0)
+
+    def _bias_hook(self, B, kind):
+        """The closure ``SoloNet.forward_backward_into`` / ``eval_losses`` call after the residual
+        forward: crop the input (models.py:339-347), run the frozen bias network, then ONE launch
+        for transformation + logit add + CountsLogSumExp (``bpb_combine_bias``) into the
+        residual workspace.  Every buffer is fixed, so the whole combined step -- bias forward
+        included -- replays as one CUDA graph, and shards over GPUs like the solo step."""
+        key = (B, kind)
+        hooks = self.__dict__.setdefault("_hooks", {})
+        if key not in hooks:
+            bnet, pAct, cAct, coeffs, n_p, n_c = self._bias_parts()
+            wb = bnet._workspace(B, "predict")
+            f = self.cropFlank
+            useBias = self.useBias
+
+            def hook(ws):
+                x = ws["x"]
+                wb["x"].copy_(x[:, f:x.shape[1] - f, :] if f > 0 else x)
+                bnet.predict_into(wb)
+                ops.combine_bias(bnet.task_off, wb["logits"], wb["logcounts"], pAct, cAct, coeffs,
+                                 n_p, n_c, useBias, ws["logits"], ws["logcounts"],
+                                 ws["logits_c"], ws["lc_c"], ws["dscale"])
+            hooks[key] = hook
+        return hooks[key]
 
     def _predict_device(self, xt, batch_size):
-        bl, bc = self._bias_device(xt, batch_size)
+        bnet, pAct, cAct, coeffs, n_p, n_c = self._bias_parts()
+        f = self.cropFlank
+        xc = xt[:, f:xt.shape[1] - f, :].contiguous() if f > 0 else xt
+        bl, bc = bnet.predict(xc, batchSize=batch_size)
         rl, rc = self.residual.net.predict(xt, batchSize=batch_size)
-        out_l = torch.empty_like(rl)
-        ops.add_f32(rl, bl.contiguous(), out_l)
-        out_c = torch.empty_like(rc)
-        ops.counts_lse(self.useBias, bc.contiguous(), rc, out_c)
+        out_l, out_c = torch.empty_like(rl), torch.empty_like(rc)
+        if rl.shape[0] > 0:
+            ops.combine_bias(bnet.task_off, bl, bc, pAct, cAct, coeffs, n_p, n_c, self.useBias,
+                             rl, rc, out_l, out_c)
         return out_l, out_c
 
-    def _step(self, xb, counts, train, lct=None):
+    def _step(self, xb, counts, train, lct=None, peers=None, allreduce=None, world=1):
         net = self.residual.net
         net.enable_training()
-        dev = self._device
         self._push_weights(net)
-        xt = torch.as_tensor(xb).to(device=dev, dtype=torch.uint8)
-        ct = torch.as_tensor(counts).to(device=dev, dtype=torch.float32)
-        bl, bc = self._bias_device(xt, xt.shape[0])
+        xt, ct = torch.as_tensor(xb), torch.as_tensor(counts)
+        if xt.dtype != torch.uint8:
+            xt = xt.to(torch.uint8)
         if lct is not None:
-            lct = torch.as_tensor(lct).to(device=dev, dtype=torch.float32)
+            lct = torch.as_tensor(lct).to(device=self._device, dtype=torch.float32)
+        B = xt.shape[0]
         if train:
-            losses = net.train_step(xt, ct, self.optimizer.learning_rate, use_graph=False,
-                                    bias_logits=bl.contiguous(), bias_logcounts=bc.contiguous(),
-                                    use_bias=self.useBias, logcounts_true=lct)
+            losses = net.train_step(xt, ct.float(), self.optimizer.learning_rate,
+                                    bias_logits=self._bias_hook(B, "train"), logcounts_true=lct,
+                                    peers=peers, allreduce=allreduce, world=world)
         else:
-            losses = net.eval_losses(xt, ct, bias_logits=bl.contiguous(),
-                                     bias_logcounts=bc.contiguous(), use_bias=self.useBias,
-                                     logcounts_true=lct)
+            losses = net.eval_losses(xt.to(self._device), ct.to(self._device, torch.float32),
+                                     bias_logits=self._bias_hook(B, "eval"), logcounts_true=lct)
         return losses.double()
 
 

@@ -518,6 +518,19 @@ def counts_lse(use_bias, bias_lc, resid_lc, out, dscale=None):
                                      _p(dscale), _stream()), "bpb_counts_lse")
 
 
+def combine_bias(task_off, bias_logits, bias_lc, p_act, c_act, coeffs, n_p, n_c, use_bias,
+                 resid_logits, resid_lc, out_logits, out_lc, dscale=None, bias_logits_t=None,
+                 bias_lc_t=None):
+    """bpb_combine_bias: transformation of the bias outputs + logit add + CountsLogSumExp."""
+    B, L, T = resid_logits.shape
+    H = resid_lc.shape[1]
+    check(_lib.load().bpb_combine_bias(B, L, T, H, _p(task_off), _p(bias_logits), _p(bias_lc),
+                                       n_p, _p(p_act), n_c, _p(c_act), _p(coeffs), _p(use_bias),
+                                       _p(resid_logits), _p(resid_lc), _p(out_logits), _p(out_lc),
+                                       _p(dscale), _p(bias_logits_t), _p(bias_lc_t), _stream()),
+          "bpb_combine_bias")
+
+
 def shuffle_rows(x, perm, refs):
     Q, L, _ = x.shape
     n = perm.shape[0]

@@ -382,6 +382,20 @@ int bpb_mul_f32(long long n, const float* a, const float* b, float* out, void* s
 int bpb_counts_lse(int B, int H, const int* use_bias, const float* bias_lc, const float* resid_lc,
                    float* out, float* dresid_scale, void* stream);
 
+/* The combined model's output stage in one launch (models.py:349-380): the frozen bias model's
+ * raw outputs [B][L][T] / [B][H] go through the per-head transformation of models.py:118-175
+ * (coeffs [H][n_pterms + n_cterms][4], a head's profile terms first; 0 terms = a plain solo bias
+ * model), out_logits = transformed bias logits + resid_logits, out_lc = CountsLogSumExp (fp64)
+ * of the transformed bias log-counts and resid_lc where use_bias[h], else resid_lc;
+ * dresid_scale (optional) = d out_lc / d resid_lc; bias_logits_t / bias_lc_t (optional) receive
+ * the transformed bias outputs.  Replaces 2 H bpb_transform_fwd + bpb_add_f32 + bpb_counts_lse. */
+int bpb_combine_bias(int B, int L, int T, int H, const int* task_off, const float* bias_logits,
+                     const float* bias_lc, int n_pterms, const int* p_act, int n_cterms,
+                     const int* c_act, const float* coeffs, const int* use_bias,
+                     const float* resid_logits, const float* resid_lc, float* out_logits,
+                     float* out_lc, float* dresid_scale, float* bias_logits_t, float* bias_lc_t,
+                     void* stream);
+
 /* k-let preserving shuffles of a one-hot sequence (HOST pointers, host code -- the reference's
  * internal/libushuffle.c:59-344 runs on the host too): the DeepSHAP references for kmer-size > 1
  * (ushuffle.shuffleOHE, interpretUtils.py:1223-1225).  host_in [length][alphabet] (alphabet <= 8,

@@ -6,40 +6,21 @@ import argparse
 import os
 import sys
 
-import numpy as np
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bpreveal_b200 import h5lite  # noqa: E402
-
-
-def sequences(n, length, rng):
-    idx = rng.integers(0, 4, size=(n, length))
-    out = np.zeros((n, length, 4), dtype=np.uint8)
-    np.put_along_axis(out, idx[..., None], 1, axis=2)
-    return out
-
-
-def profiles(n, length, tasks, rng, meanReads=200.0):
-    pos = np.arange(length)[None, :, None]
-    centers = rng.uniform(0, length, size=(n, 1, tasks))
-    widths = rng.uniform(length / 40, length / 6, size=(n, 1, tasks))
-    rate = np.exp(-0.5 * ((pos - centers) / widths) ** 2) + 0.05
-    rate = rate / rate.sum(axis=1, keepdims=True) * meanReads
-    out = rng.poisson(rate).astype(np.float32)
-    out[:, length // 2, :] += 1.0  # never an empty region: log(0) in generators.py:139-140
-    return out
+from bpreveal_b200 import h5lite, synthetic  # noqa: E402
 
 
 def write(fname, numRegions, inputLength, outputLength, maxJitter, headTasks, seed=20261019,
           meanReads=200.0, compress=True):
-    rng = np.random.default_rng(seed)
     w = h5lite.Writer()
     kw = dict(chunks=True, compression="gzip") if compress else {}
-    w.create_dataset("sequence", data=sequences(numRegions, inputLength + 2 * maxJitter, rng), **kw)
+    w.create_dataset("sequence",
+                     data=synthetic.sequences(numRegions, inputLength + 2 * maxJitter, seed), **kw)
     for i, t in enumerate(headTasks):
-        w.create_dataset(f"head_{i}", data=profiles(numRegions, outputLength + 2 * maxJitter, t,
-                                                    rng, meanReads), **kw)
+        w.create_dataset(f"head_{i}",
+                         data=synthetic.profiles(numRegions, outputLength + 2 * maxJitter, t,
+                                                 seed + 17 * (i + 1), meanReads), **kw)
     w.save(fname)
 
 
