@@ -1,14 +1,31 @@
 #!/bin/bash
-# Round profile on one B200 (run under gpurun): plain bench, per-launch device times of the same
-# command under ncu, and one full-metric capture of the dominant kernel family.  Outputs land in
-# gpurun_out/; tools/ncu_summary.py turns the .ncu-rep into the CSV summaries kept in profiles/.
-TAG=${1:-r1}
+# Round profile on one B200 (run under gpurun after the same commands exited 0 without ncu):
+#   1. plain bench (never a number from a profiled run),
+#   2. per-launch device times of the profiled command (launch list),
+#   3. DRAM bytes per kernel of ONE step with the caches left alone (tools/step_traffic.py),
+#   4. one --set full capture of the conv kernel families (C1) and of the F = 512 kernels (C4).
+# Outputs land in gpurun_out/; tools/ncu_summary.py and tools/step_traffic.py turn them into the
+# summaries kept in profiles/.
+TAG=${1:-r2}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_${TAG}.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch_${TAG}.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel" -s 20 -c 12 \
-    -o gpurun_out/conv_full_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
-echo "full capture rc=$?"
+for CFG in c1 c4; do
+  python tools/step_traffic.py run $CFG > /dev/null 2>&1 || { echo "step_traffic $CFG failed"; continue; }
+  ncu --profile-from-start off --cache-control none --clock-control none \
+      --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
+      --csv --log-file gpurun_out/step_traffic_${CFG}.csv python tools/step_traffic.py run $CFG \
+      > gpurun_out/ncu_traffic_${CFG}.log 2>&1
+  echo "step traffic $CFG rc=$?"
+done
+ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel|wgrad3_tc_kernel" \
+    --profile-from-start off -c 24 -o gpurun_out/conv_full_${TAG} python tools/step_traffic.py run c1 \
+    > gpurun_out/ncu_full_${TAG}.log 2>&1
+echo "full capture c1 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel|wgrad3_tc_kernel" \
+    --profile-from-start off -c 40 -o gpurun_out/c4_full_${TAG} python tools/step_traffic.py run c4 \
+    > gpurun_out/ncu_c4_full_${TAG}.log 2>&1
+echo "full capture c4 rc=$?"
