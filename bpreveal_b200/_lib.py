@@ -160,6 +160,8 @@ SIGNATURES = {
                                  c_void_p]),
     "bpb_counts_lse": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
+    "bpb_combined_shap_seed": (c_int, [c_int] * 5 + [c_void_p] * 7 + [c_int, c_void_p, c_int] +
+                               [c_void_p] * 10),
     "bpb_combine_bias": (c_int, [c_int] * 4 + [c_void_p] * 3 + [c_int, c_void_p, c_int] +
                          [c_void_p] * 11),
 }

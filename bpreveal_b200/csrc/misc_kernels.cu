@@ -862,6 +862,114 @@ __global__ void combine_bias_kernel(int B, int L, int T, int H, const int* __res
   }
 }
 
+// DeepSHAP through the output stage of a transformation / combined model (shap.py:612-639 applied
+// to models.py:118-175 and 349-380): the rescale rule replaces the local derivative of every
+// Sigmoid / Relu / Exp / Log by (out_x - out_r) / (in_x - in_r) of the (query, reference) pair --
+// the ordinary derivative at the query where |in_x - in_r| < 1e-6 (shap.py:634-638) -- while
+// linear regressions, adds and casts keep their ordinary gradients (shap.py:737-779).  Given the
+// gradient of the metric wrt the COMBINED outputs of every pair, this writes the gradients wrt
+// the residual network's outputs and wrt the bias network's RAW outputs, i.e. the seeds of the two
+// rescale-rule backward passes.  Pair i uses query i / n.
+__device__ __forceinline__ double rescale_term(int a, double m1, double m2, double b2, double ux,
+                                               double ur) {
+  if (a == 0) return m1;  // linear regression: ordinary gradient
+  const double zx = m2 * ux + b2, zr = m2 * ur + b2;
+  double fx, fr, dfx;
+  if (a == 1) {
+    fx = 1.0 / (1.0 + exp(-zx));
+    fr = 1.0 / (1.0 + exp(-zr));
+    dfx = fx * (1.0 - fx);
+  } else {
+    fx = zx > 0.0 ? zx : 0.0;
+    fr = zr > 0.0 ? zr : 0.0;
+    dfx = zx > 0.0 ? 1.0 : 0.0;
+  }
+  const double din = zx - zr;
+  return m1 * (fabs(din) < 1e-6 ? dfx : (fx - fr) / din) * m2;
+}
+
+__device__ __forceinline__ double transform_value(int n_t, const int* act, const float* c, double u) {
+  if (n_t == 0) return u;
+  double s = 0.0;
+  for (int t = 0; t < n_t; ++t) {
+    const double m1 = c[4 * t], b1 = c[4 * t + 1], m2 = c[4 * t + 2], b2 = c[4 * t + 3];
+    const double z = m2 * u + b2;
+    s += b1 + m1 * (act[t] == 0 ? u : (act[t] == 1 ? 1.0 / (1.0 + exp(-z)) : (z > 0.0 ? z : 0.0)));
+  }
+  return s;
+}
+
+__global__ void combined_shap_seed_kernel(
+    int R, int n, int L, int T, int H, const int* __restrict__ task_off,
+    const float* __restrict__ bl_x, const float* __restrict__ bl_r,   // bias raw logits
+    const float* __restrict__ bc_x, const float* __restrict__ bc_r,   // bias raw log-counts
+    const float* __restrict__ rc_x, const float* __restrict__ rc_r,   // residual log-counts
+    int n_p, const int* __restrict__ p_act, int n_c, const int* __restrict__ c_act,
+    const float* __restrict__ coeffs, const int* __restrict__ use,
+    const float* __restrict__ dl_c, const float* __restrict__ dc_c,   // wrt combined outputs
+    float* __restrict__ dl_r, float* __restrict__ dc_r, float* __restrict__ dl_b,
+    float* __restrict__ dc_b) {
+  const long long nl = static_cast<long long>(R) * L * T;
+  const long long total = nl + static_cast<long long>(R) * H;
+  const int per = n_p + n_c;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (i < nl) {
+      const long long pair = i / (static_cast<long long>(L) * T);
+      const long long within = i - pair * L * T;
+      const int col = static_cast<int>(within % T);
+      int h = 0;
+      while (h + 1 < H && task_off[h + 1] <= col) ++h;
+      const float g = dl_c[i];
+      if (dl_r) dl_r[i] = g;  // Add: ordinary gradient
+      if (dl_b) {
+        double m = 1.0;
+        if (n_p > 0) {
+          m = 0.0;
+          const float* c = coeffs + static_cast<long long>(h) * per * 4;
+          const double ux = bl_x[(pair / n) * L * T + within], ur = bl_r[i];
+          for (int t = 0; t < n_p; ++t)
+            m += rescale_term(p_act[t], c[4 * t], c[4 * t + 2], c[4 * t + 3], ux, ur);
+        }
+        dl_b[i] = static_cast<float>(g * m);
+      }
+    } else {
+      const long long j = i - nl;
+      const long long pair = j / H;
+      const int h = static_cast<int>(j % H);
+      const long long jx = (pair / n) * H + h;
+      const double g = dc_c[j];
+      const float* c = coeffs + (static_cast<long long>(h) * per + n_p) * 4;
+      double mt = 1.0;  // transformation multiplier of the bias log-counts
+      if (n_c > 0) {
+        mt = 0.0;
+        for (int t = 0; t < n_c; ++t)
+          mt += rescale_term(c_act[t], c[4 * t], c[4 * t + 2], c[4 * t + 3], bc_x[jx], bc_r[j]);
+      }
+      if (rc_x == nullptr) {  // transformation model alone: no residual branch
+        if (dc_b) dc_b[j] = static_cast<float>(g * mt);
+        continue;
+      }
+      if (!use[h]) {  // Identity on the residual's log-counts (models.py:376-380)
+        if (dc_r) dc_r[j] = static_cast<float>(g);
+        if (dc_b) dc_b[j] = 0.f;
+        continue;
+      }
+      // CountsLogSumExp (layers.py:66-75, fp64): Exp on each branch, Add, Log
+      const double ax = transform_value(n_c, c_act, c, bc_x[jx]);
+      const double ar = transform_value(n_c, c_act, c, bc_r[j]);
+      const double bx = rc_x[jx], br = rc_r[j];
+      const double eax = exp(ax), ear = exp(ar), ebx = exp(bx), ebr = exp(br);
+      const double sx = eax + ebx, sr = ear + ebr;
+      const double m_log = fabs(sx - sr) < 1e-6 ? 1.0 / sx : (log(sx) - log(sr)) / (sx - sr);
+      const double m_ea = fabs(ax - ar) < 1e-6 ? eax : (eax - ear) / (ax - ar);
+      const double m_eb = fabs(bx - br) < 1e-6 ? ebx : (ebx - ebr) / (bx - br);
+      if (dc_r) dc_r[j] = static_cast<float>(g * m_log * m_eb);
+      if (dc_b) dc_b[j] = static_cast<float>(g * m_log * m_ea * mt);
+    }
+  }
+}
+
 __global__ void mul_kernel(long long n, const float* __restrict__ a, const float* __restrict__ b,
                            float* __restrict__ out) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -1184,6 +1292,34 @@ extern "C" int bpb_combine_bias(int B, int L, int T, int H, const int* task_off,
   combine_bias_kernel<<<ew_blocks(total), 256, 0, stream>>>(
       B, L, T, H, task_off, bias_logits, bias_lc, n_pterms, p_act, n_cterms, c_act, coeffs,
       use_bias, resid_logits, resid_lc, out_logits, out_lc, dresid_scale, bias_logits_t, bias_lc_t);
+  BP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bpb_combined_shap_seed(int R, int n, int L, int T, int H, const int* task_off,
+                                      const float* bias_logits_x, const float* bias_logits_r,
+                                      const float* bias_lc_x, const float* bias_lc_r,
+                                      const float* resid_lc_x, const float* resid_lc_r,
+                                      int n_pterms, const int* p_act, int n_cterms,
+                                      const int* c_act, const float* coeffs, const int* use_bias,
+                                      const float* dlogits_c, const float* dlc_c,
+                                      float* dlogits_resid, float* dlc_resid, float* dlogits_bias,
+                                      float* dlc_bias, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BP_REQUIRE(task_off && bias_logits_x && bias_logits_r && bias_lc_x && bias_lc_r && dlogits_c &&
+                 dlc_c && n > 0 && R % n == 0,
+             "bpb_combined_shap_seed: bad argument");
+  BP_REQUIRE((resid_lc_x == nullptr) == (resid_lc_r == nullptr) && (resid_lc_x == nullptr || use_bias),
+             "bpb_combined_shap_seed: residual log-counts need both halves and use_bias");
+  BP_REQUIRE((n_pterms + n_cterms == 0 || coeffs) && (n_pterms == 0 || p_act) &&
+                 (n_cterms == 0 || c_act),
+             "bpb_combined_shap_seed: transformation terms without their tables");
+  const long long total = static_cast<long long>(R) * L * T + static_cast<long long>(R) * H;
+  if (total <= 0) return 0;
+  combined_shap_seed_kernel<<<ew_blocks(total), 256, 0, stream>>>(
+      R, n, L, T, H, task_off, bias_logits_x, bias_logits_r, bias_lc_x, bias_lc_r, resid_lc_x,
+      resid_lc_r, n_pterms, p_act, n_cterms, c_act, coeffs, use_bias, dlogits_c, dlc_c,
+      dlogits_resid, dlc_resid, dlogits_bias, dlc_bias);
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -702,8 +702,15 @@ class SoloNet:
         with the gradient of the metric wrt the outputs of every (query, reference) pair.
         Returns (dx (Q*n, Lin, 4) fp32 multipliers, ws_x, ws_r).  shap.py:347-394, 612-639.
         """
-        cfg, p = self.cfg, self.p
-        Ls = cfg.lengths()
+        wx, wr = self.shap_forward(x_u8, refs_u8)
+        dlogits_fn(wx, wr)
+        return self.shap_backward(wx, wr), wx, wr
+
+    def shap_forward(self, x_u8, refs_u8):
+        """The two forward passes of ``shap_batch``: the queries (fp32 pre-activations kept) and
+        the references (rescale multipliers against the queries' pre-activations kept).  Separate
+        so that a combined model can look at both networks' outputs before seeding the backward
+        passes."""
         Q = x_u8.shape[0]
         R = refs_u8.shape[0]
         n = R // Q
@@ -713,7 +720,14 @@ class SoloNet:
         wr["x"].copy_(refs_u8)
         self._forward(wx, wx["x"], z_list=wx["z"])
         self._forward(wr, wr["x"], zx_list=wx["z"], zx_div=n, mult_list=wr["mult"])
-        dlogits_fn(wx, wr)
+        return wx, wr
+
+    def shap_backward(self, wx, wr):
+        """The multiplier-weighted backward pass from wr['dlogits'] / wr['dlogcounts'] to the
+        one-hot input: returns dx (R, Lin, 4) fp32."""
+        cfg, p = self.cfg, self.p
+        Ls = cfg.lengths()
+        R = wr["B"]
         nL = cfg.numLayers
         gcur = self._sub(wr["g"][nL % 2], Ls[nL])
         gzcur = self._sub(wr["gz"][nL % 2], Ls[nL])
@@ -737,4 +751,4 @@ class SoloNet:
             ops.input_conv_dgrad_tc(gzcur, self.w_id_op, cfg.inputFilterWidth, wr["dx"])
         else:
             ops.input_conv_dgrad(gzcur, p["conv1_w"], cfg.inputLength, wr["dx"])
-        return wr["dx"], wx, wr
+        return wr["dx"]

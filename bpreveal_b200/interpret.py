@@ -196,3 +196,151 @@ def flat_batch(net, x_u8, headID, numShuffles, kind="profile", taskIDs=None, ref
     hyp = torch.empty((Q, cfg.inputLength, 4), dtype=torch.float32, device=dev)
     ops.shap_combine(x_u8, refs_u8, dx, hyp, True)
     return hyp, vals["x"], vals["r"]
+
+
+# ---------------------------------------------------------------------------------------------
+# transformation / combined models (shap.py:782-793: Exp, Log, Sigmoid under the rescale rule)
+# ---------------------------------------------------------------------------------------------
+def _model_parts(model):
+    """(residual network | None, bias network, transformation tables, crop flank, use-bias flags)
+    of a SoloModel / TransformationModel / CombinedModel."""
+    from .models import CombinedModel, SoloModel, TransformationModel
+    if isinstance(model, SoloModel):
+        return None
+    if isinstance(model, TransformationModel):
+        tm = model
+        return (None, tm.solo.net, (tm.pAct, tm.cAct, tm.coeffs, len(tm.pTypes), len(tm.cTypes)),
+                0, None)
+    if isinstance(model, CombinedModel):
+        bnet, pAct, cAct, coeffs, n_p, n_c = model._bias_parts()
+        return (model.residual.net, bnet, (pAct, cAct, coeffs, n_p, n_c), model.cropFlank,
+                model.useBias)
+    raise TypeError(f"cannot interpret {type(model).__name__}")
+
+
+def model_shap_batch(model, x_u8, refs_u8, seed_fn, hypothetical):
+    """DeepSHAP of Q queries against their n references each on ANY of the three model kinds.
+
+    ``seed_fn(logits_x (Q,L,T), lc_x (Q,H), logits_r (R,L,T), lc_r (R,H), dlogits (R,L,T),
+    dlc (R,H))`` sees the MODEL's outputs (transformed / combined) on the queries and on the
+    references and fills the metric's gradient wrt the outputs of every pair; it returns
+    ``(metric on queries (Q,), metric on references (Q, n))``.
+
+    For a combined model the attribution is the sum of two rescale-rule backward passes -- through
+    the residual network, and through the frozen bias network on the cropped window (models.py:
+    339-347) seeded with the gradient propagated through transformation, add and
+    CountsLogSumExp by ``bpb_combined_shap_seed``.  Returns (phi (Q, Lin, 4), vx, vr)."""
+    parts = _model_parts(model)
+    Q, Lin, _ = x_u8.shape
+    R = refs_u8.shape[0]
+    n = R // Q
+    dev = x_u8.device
+    x_u8, refs_u8 = x_u8.contiguous(), refs_u8.contiguous()
+    phi = torch.empty((Q, Lin, 4), dtype=torch.float32, device=dev)
+    if parts is None:
+        net = model.net
+
+        def dlogits_fn(wx, wr):
+            wr["dlogits"].zero_()
+            wr["dlogcounts"].zero_()
+            model_shap_batch.vals = seed_fn(wx["logits"], wx["logcounts"], wr["logits"],
+                                            wr["logcounts"], wr["dlogits"], wr["dlogcounts"])
+        dx, _, _ = net.shap_batch(x_u8, refs_u8, dlogits_fn)
+        ops.shap_combine(x_u8, refs_u8, dx, phi, hypothetical)
+        return (phi,) + tuple(model_shap_batch.vals)
+    rnet, bnet, (pAct, cAct, coeffs, n_p, n_c), f, useBias = parts
+    xb = x_u8[:, f:Lin - f, :].contiguous() if f > 0 else x_u8
+    rb = refs_u8[:, f:Lin - f, :].contiguous() if f > 0 else refs_u8
+    bx, br = bnet.shap_forward(xb, rb)
+    T, H = bnet.cfg.T, bnet.cfg.H
+    zeros_l = zeros_c = None
+    if rnet is not None:
+        rx, rr = rnet.shap_forward(x_u8, refs_u8)
+        rl_x, rc_x, rl_r, rc_r = rx["logits"], rx["logcounts"], rr["logits"], rr["logcounts"]
+        use = useBias
+    else:
+        # transformation model alone: "residual" outputs of zero, log-counts not combined
+        rl_x = torch.zeros_like(bx["logits"])
+        rl_r = torch.zeros_like(br["logits"])
+        rc_x = torch.zeros_like(bx["logcounts"])
+        rc_r = torch.zeros_like(br["logcounts"])
+        use = torch.zeros((H,), dtype=torch.int32, device=dev)
+        zeros_l, zeros_c = rl_x, rc_x
+    # the model's outputs on queries and references
+    ox_l, ox_c = torch.empty_like(bx["logits"]), torch.empty_like(bx["logcounts"])
+    or_l, or_c = torch.empty_like(br["logits"]), torch.empty_like(br["logcounts"])
+    bt_x, bt_r = torch.empty_like(ox_c), torch.empty_like(or_c)
+    ops.combine_bias(bnet.task_off, bx["logits"], bx["logcounts"], pAct, cAct, coeffs, n_p, n_c,
+                     use, rl_x, rc_x, ox_l, ox_c, bias_lc_t=bt_x)
+    ops.combine_bias(bnet.task_off, br["logits"], br["logcounts"], pAct, cAct, coeffs, n_p, n_c,
+                     use, rl_r, rc_r, or_l, or_c, bias_lc_t=bt_r)
+    if rnet is None:  # the transformation model's log-counts ARE the transformed bias ones
+        ox_c, or_c = bt_x, bt_r
+    dl_c = torch.zeros_like(or_l)
+    dc_c = torch.zeros_like(or_c)
+    vx, vr = seed_fn(ox_l, ox_c, or_l, or_c, dl_c, dc_c)
+    ops.combined_shap_seed(n, bnet.task_off, bx["logits"], br["logits"], bx["logcounts"],
+                           br["logcounts"], rc_x if rnet is not None else None,
+                           rc_r if rnet is not None else None, pAct, cAct, coeffs, n_p, n_c,
+                           use, dl_c, dc_c,
+                           dl_r=rr["dlogits"] if rnet is not None else None,
+                           dc_r=rr["dlogcounts"] if rnet is not None else None,
+                           dl_b=br["dlogits"], dc_b=br["dlogcounts"])
+    dxb = bnet.shap_backward(bx, br)
+    phib = torch.empty((Q, xb.shape[1], 4), dtype=torch.float32, device=dev)
+    ops.shap_combine(xb, rb, dxb, phib, hypothetical)
+    if rnet is not None:
+        dxr = rnet.shap_backward(rx, rr)
+        ops.shap_combine(x_u8, refs_u8, dxr, phi, hypothetical)
+    else:
+        phi.zero_()
+    phi[:, f:Lin - f, :] += phib
+    del zeros_l, zeros_c
+    return phi, vx, vr
+
+
+def pisa_model(model, x_u8, headID, taskID, numShuffles, refs_u8=None, kmerSize=1):
+    """PISA on any model kind (solo models: prefer ``pisa_batch``, which adds the receptive-field
+    crop and the CUDA graph).  Returns (phi, input_predictions, shuffle_predictions)."""
+    from .models import SoloModel
+    if isinstance(model, SoloModel):
+        return pisa_batch(model.net, x_u8, headID, taskID, numShuffles, refs_u8=refs_u8,
+                          kmerSize=kmerSize)
+    Q = x_u8.shape[0]
+    if refs_u8 is None:
+        refs_u8 = make_references(x_u8.contiguous(), numShuffles, kmerSize=kmerSize)
+    col = int(sum(model.headTasks[:headID])) + taskID
+
+    def seed(lx, cx, lr, cr, dl, dc):
+        dl[:, 0, col] = 1.0
+        return lx[:, 0, col].clone(), lr[:, 0, col].reshape(Q, numShuffles).clone()
+    return model_shap_batch(model, x_u8, refs_u8, seed, hypothetical=False)
+
+
+def flat_model(model, x_u8, headID, numShuffles, kind="profile", taskIDs=None, refs_u8=None,
+               kmerSize=1):
+    """interpretFlat hypothetical contribution scores on any model kind."""
+    from .models import SoloModel
+    if isinstance(model, SoloModel):
+        return flat_batch(model.net, x_u8, headID, numShuffles, kind=kind, taskIDs=taskIDs,
+                          refs_u8=refs_u8, kmerSize=kmerSize)
+    Q = x_u8.shape[0]
+    dev = x_u8.device
+    if refs_u8 is None:
+        refs_u8 = make_references(x_u8.contiguous(), numShuffles, kmerSize=kmerSize)
+    k0 = int(sum(model.headTasks[:headID]))
+    tasks = list(range(model.headTasks[headID])) if taskIDs is None else list(taskIDs)
+    T = int(sum(model.headTasks))
+    sel = torch.zeros((T,), dtype=torch.int32, device=dev)
+    for t in tasks:
+        sel[k0 + t] = 1
+
+    def seed(lx, cx, lr, cr, dl, dc):
+        if kind == "counts":
+            dc[:, headID] = 1.0
+            return cx[:, headID].clone(), cr[:, headID].reshape(Q, numShuffles).clone()
+        vx = torch.empty((Q,), dtype=torch.float32, device=dev)
+        vr = torch.empty((Q * numShuffles,), dtype=torch.float32, device=dev)
+        ops.flat_profile_seed(sel, lx.contiguous(), lr.contiguous(), dl, vx, vr)
+        return vx, vr.reshape(Q, numShuffles)
+    return model_shap_batch(model, x_u8, refs_u8, seed, hypothetical=True)

@@ -414,12 +414,12 @@ class InterpRunner:
         from .models import SoloModel, loadModel
         model = loadModel(modelFname, device=device, precise=precise) \
             if isinstance(modelFname, str) else modelFname
-        if not isinstance(model, SoloModel):
-            raise NotImplementedError(
-                "DeepSHAP on transformation / combined graphs (Exp / Log / Sigmoid under the "
-                "rescale rule, shap.py:782-793) is not built; interpret the residual model "
-                "(<prefix>_residual.keras), which is what the reference's tutorials do")
-        self.net = model.net
+        self.model = model
+        self.solo = isinstance(model, SoloModel)
+        # transformation / combined models go through interpret.model_shap_batch (rescale rule
+        # on Sigmoid / Relu / Exp / Log, shap.py:782-793), solo models through the graph-captured
+        # receptive-field path
+        self.net = model.net if self.solo else None
         self.metrics, self.savers, self.generator = list(metrics), list(savers), generator
         self.batchSize, self.numShuffles, self.kmerSize = batchSize, numShuffles, kmerSize
         self.hypothetical = useHypotheticalContribs
@@ -428,21 +428,24 @@ class InterpRunner:
     def _explain(self, metric, x):
         from . import interpret
         if isinstance(metric, PisaMetric):
-            return interpret.pisa_batch(self.net, x, metric.headID, metric.taskID,
-                                        self.numShuffles, hypothetical=self.hypothetical,
-                                        kmerSize=self.kmerSize)
+            if self.solo:
+                return interpret.pisa_batch(self.net, x, metric.headID, metric.taskID,
+                                            self.numShuffles, hypothetical=self.hypothetical,
+                                            kmerSize=self.kmerSize)
+            return interpret.pisa_model(self.model, x, metric.headID, metric.taskID,
+                                        self.numShuffles, kmerSize=self.kmerSize)
         if isinstance(metric, ProfileMetric):
-            return interpret.flat_batch(self.net, x, metric.headID, self.numShuffles,
+            return interpret.flat_model(self.model, x, metric.headID, self.numShuffles,
                                         kind="profile", taskIDs=list(metric.taskIDs),
                                         kmerSize=self.kmerSize)
         if isinstance(metric, CountsMetric):
-            return interpret.flat_batch(self.net, x, metric.headID, self.numShuffles,
+            return interpret.flat_model(self.model, x, metric.headID, self.numShuffles,
                                         kind="counts", kmerSize=self.kmerSize)
         raise TypeError(f"unknown metric {metric!r}")
 
     def run(self):
         import torch
-        dev = self.net.device
+        dev = self.model._device
         for s in self.savers:
             s.construct()
         self.generator.construct()

@@ -531,6 +531,17 @@ def combine_bias(task_off, bias_logits, bias_lc, p_act, c_act, coeffs, n_p, n_c,
           "bpb_combine_bias")
 
 
+def combined_shap_seed(n, task_off, bl_x, bl_r, bc_x, bc_r, rc_x, rc_r, p_act, c_act, coeffs, n_p,
+                       n_c, use_bias, dl_c, dc_c, dl_r=None, dc_r=None, dl_b=None, dc_b=None):
+    """bpb_combined_shap_seed: rescale-rule gradients through transformation + add + LSE."""
+    R, L, T = bl_r.shape
+    H = bc_r.shape[1]
+    check(_lib.load().bpb_combined_shap_seed(
+        R, n, L, T, H, _p(task_off), _p(bl_x), _p(bl_r), _p(bc_x), _p(bc_r), _p(rc_x), _p(rc_r),
+        n_p, _p(p_act), n_c, _p(c_act), _p(coeffs), _p(use_bias), _p(dl_c), _p(dc_c), _p(dl_r),
+        _p(dc_r), _p(dl_b), _p(dc_b), _stream()), "bpb_combined_shap_seed")
+
+
 def shuffle_rows(x, perm, refs):
     Q, L, _ = x.shape
     n = perm.shape[0]

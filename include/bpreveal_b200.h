@@ -396,6 +396,23 @@ int bpb_combine_bias(int B, int L, int T, int H, const int* task_off, const floa
                      float* out_lc, float* dresid_scale, float* bias_logits_t, float* bias_lc_t,
                      void* stream);
 
+/* DeepSHAP through the output stage of a transformation / combined model (shap.py:612-639,
+ * 782-793 applied to models.py:118-175, 349-380): rescale rule on Sigmoid / Relu / Exp / Log,
+ * ordinary gradients on the linear pieces.  R = Q * n (query, reference) pairs, pair i belongs to
+ * query i / n.  *_x are the QUERY outputs ([Q][L][T] / [Q][H]), *_r the reference outputs
+ * ([R][L][T] / [R][H]) of the bias network (raw, before the transformation) and of the residual
+ * network; dlogits_c / dlc_c the metric's gradient wrt the COMBINED outputs of every pair.
+ * Outputs (any may be NULL): the seeds of the two rescale-rule backward passes.  resid_lc_* NULL =
+ * a transformation model alone. */
+int bpb_combined_shap_seed(int R, int n, int L, int T, int H, const int* task_off,
+                           const float* bias_logits_x, const float* bias_logits_r,
+                           const float* bias_lc_x, const float* bias_lc_r,
+                           const float* resid_lc_x, const float* resid_lc_r, int n_pterms,
+                           const int* p_act, int n_cterms, const int* c_act, const float* coeffs,
+                           const int* use_bias, const float* dlogits_c, const float* dlc_c,
+                           float* dlogits_resid, float* dlc_resid, float* dlogits_bias,
+                           float* dlc_bias, void* stream);
+
 /* k-let preserving shuffles of a one-hot sequence (HOST pointers, host code -- the reference's
  * internal/libushuffle.c:59-344 runs on the host too): the DeepSHAP references for kmer-size > 1
  * (ushuffle.shuffleOHE, interpretUtils.py:1223-1225).  host_in [length][alphabet] (alphabet <= 8,

@@ -212,10 +212,23 @@ def test_interpret_pisa_and_flat(chain, dev):
     hyp, vx, _ = interpret.flat_batch(m.net, torch.as_tensor(xs2[:10]).to(dev), 0, 5, kind="counts")
     assert np.array_equal(fc_["hyp_scores"][...][:10], hyp.cpu().numpy().astype(np.float16))
     assert np.allclose(fc_["input_predictions"][...][:10], vx.cpu().numpy(), rtol=1e-6)
-    # a combined model is refused with an explanation, not silently mis-attributed
-    cfg2 = dict(cfg, **{"model-file": str(d / "joint_combined.keras")})
-    with pytest.raises(NotImplementedError, match="residual"):
-        interpretPisa.main(cfg2)
+    # a combined model goes through the rescale rule on Sigmoid / Exp / Log as well
+    # (shap.py:782-793); its window is the residual model's, 32 bp longer
+    chain_dir, LIN_R = chain
+    pad_r = (LIN_R - LOUT) // 2
+    cfg2 = dict(cfg, **{"model-file": str(d / "joint_combined.keras"), "input-length": LIN_R,
+                        "output-h5": str(d / "pisa_comb.h5")})
+    (d / "pisa.bed").write_text("chrZ\t180\t185\n")
+    interpretPisa.main(cfg2)
+    fcomb = h5lite.File(str(d / "pisa_comb.h5"))
+    assert fcomb["shap"].shape == (5, LIN_R - LOUT + 1, 4)
+    got = fcomb["shap"][...].astype(np.float64).sum(axis=(1, 2))
+    want = fcomb["input_predictions"][...] - fcomb["shuffle_predictions"][...].mean(axis=1)
+    assert np.allclose(got, want, atol=3e-2 * max(1.0, np.abs(want).max()))
+    comb = models.loadModel(str(d / "joint_combined.keras"))
+    xc = np.stack([utils.oneHotEncode(chrom[p - pad_r:p - pad_r + LIN_R]) for p in range(180, 185)])
+    pred = comb.predict(xc)
+    assert np.allclose(fcomb["input_predictions"][...], pred[0][:, 0, 1], rtol=2e-2, atol=2e-2)
 
 
 def test_batch_predictor_on_a_real_model_with_long_inputs(chain):

@@ -383,3 +383,85 @@ def test_streaming_host_prediction_equals_device_prediction(dev):
     outs = m.predict(x, batch_size=8)  # the Keras-style call takes the streaming path for numpy
     assert np.array_equal(outs[0], want_l.cpu().numpy()[:, :, :2])
     assert np.array_equal(outs[3], want_c.cpu().numpy()[:, 1:2])
+
+
+def test_deepshap_on_transformation_and_combined_models(dev):
+    """shap.py:782-793: on transformation / combined graphs the rescale rule also covers Sigmoid,
+    Exp and Log (CountsLogSumExp), linear regressions keep ordinary gradients.  PISA, the flat
+    counts metric (through the fp64 log-sum-exp on the head with use-bias-counts, identity on the
+    other) and the flat profile metric against the oracle's autograd restatement."""
+    import os
+    from bpreveal_b200 import interpret, models
+    vec = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.npz"))
+    spec_p = {"name": "simple", "types": ["linear", "sigmoid"]}
+    spec_c = {"name": "simple", "types": ["linear", "relu"]}
+    heads = [dict(HEADS[0], **{"use-bias-counts": True}), dict(HEADS[1], **{"use-bias-counts": False})]
+    bias_p = {k[2:]: vec[k] for k in vec.files if k.startswith("p_")}
+    resid_p = {k[2:]: vec[k] for k in vec.files if k.startswith("r_")}
+    solo = models.soloModel(52, 20, 8, 3, 3, 3, heads, "solo", precise=True, device=dev)
+    load_solo(solo, bias_p)
+    tm = models.transformationModel(solo, spec_p, spec_c, heads)
+    rng = np.random.default_rng(11)
+    tp = O.init_transform_params(2, spec_p, spec_c)
+    for k in tp:
+        tp[k] = (tp[k] + rng.standard_normal(2) * 0.3).astype(np.float32)
+    named = dict(tm.named_weights())
+    for h, n in enumerate(["a", "b"]):
+        for key, base in ((f"profile{h}_linear", f"regress_linear_profile_{n}_conv"),
+                          (f"profile{h}_sigmoid_in", f"sigmoid_in_linear_profile_{n}_conv"),
+                          (f"profile{h}_sigmoid_out", f"sigmoid_out_linear_profile_{n}_conv"),
+                          (f"logcounts{h}_linear", f"regress_linear_logcounts_{n}_conv"),
+                          (f"logcounts{h}_relu_in", f"relu_in_linear_logcounts_{n}_conv"),
+                          (f"logcounts{h}_relu_out", f"relu_out_linear_logcounts_{n}_conv")):
+            named[base + "/kernel"] = tp[key][0].reshape(1, 1, 1)
+            named[base + "/bias"] = tp[key][1].reshape(1)
+    tm.set_weights(named)
+    xr = vec["xr"]
+    Lr = xr.shape[1]
+    comb, resid, _ = models.combinedModel(Lr, 20, 8, 4, 3, 3, heads, tm, precise=True)
+    resid.net.load_state(resid_p)
+    Q, n = 2, 6
+    xs = xr[:Q]
+    xt = torch.tensor(xs, device=dev)
+    p64b, p64r = O.to_torch(bias_p, torch.float64), O.to_torch(resid_p, torch.float64)
+    tpt = {k: torch.tensor(v, dtype=torch.float64) for k, v in tp.items()}
+    fwd_c = O.combined_shap_forward(p64r, p64b, tpt, spec_p, spec_c, [True, False], 52)
+
+    def fwd_t(joint):
+        return O.transformation_forward(joint, p64b, tpt, spec_p, spec_c, relu=O.rescale_relu,
+                                        sigmoid=O.rescale_sigmoid)
+
+    f = (Lr - 52) // 2
+    cases = [
+        ("combined pisa", comb, xs, fwd_c, lambda: interpret.pisa_model(comb, xt, 0, 1, n),
+         lambda pr, cn: O.pisa_metric(pr, cn, 0, 1), False),
+        ("combined counts (LSE head)", comb, xs, fwd_c,
+         lambda: interpret.flat_model(comb, xt, 0, n, kind="counts"),
+         lambda pr, cn: O.counts_metric(pr, cn, 0), True),
+        ("combined counts (identity head)", comb, xs, fwd_c,
+         lambda: interpret.flat_model(comb, xt, 1, n, kind="counts"),
+         lambda pr, cn: O.counts_metric(pr, cn, 1), True),
+        ("combined profile", comb, xs, fwd_c,
+         lambda: interpret.flat_model(comb, xt, 0, n, kind="profile", taskIDs=[0, 1]),
+         lambda pr, cn: O.profile_metric(pr, cn, 0, [0, 1], shap=True), True),
+        ("transformation pisa", tm, xs[:, f:Lr - f], fwd_t,
+         lambda: interpret.pisa_model(tm, xt[:, f:Lr - f].contiguous(), 1, 0, n),
+         lambda pr, cn: O.pisa_metric(pr, cn, 1, 0), False),
+        ("transformation counts", tm, xs[:, f:Lr - f], fwd_t,
+         lambda: interpret.flat_model(tm, xt[:, f:Lr - f].contiguous(), 0, n, kind="counts"),
+         lambda pr, cn: O.counts_metric(pr, cn, 0), True),
+    ]
+    for name, model, xq, fwd, run, metric, hyp in cases:
+        phi, vx, vr = run()
+        phi, vx, vr = phi.cpu().numpy(), vx.cpu().numpy(), vr.cpu().numpy()
+        for q in range(Q):
+            refs = O.generate_shuffles(xq[q], n)
+            ref_phi, val, rvals = O.deepshap(xq[q], refs, fwd, metric, hypothetical=hyp)
+            scale = np.abs(ref_phi).max()
+            err = np.abs(phi[q] - ref_phi).max() / scale
+            assert err < 3e-3, f"{name}: attribution rel err {err}"
+            assert abs(vx[q] - val) <= 1e-4 * max(1.0, abs(val)), name
+            assert np.abs(vr[q] - rvals).max() <= 1e-4 * max(1.0, np.abs(rvals).max()), name
+            if not hyp:  # efficiency of the standard combiner
+                rhs = vx[q] - vr[q].mean()
+                assert abs(phi[q].sum() - rhs) <= 3e-3 * max(abs(rhs), scale), name

@@ -29,3 +29,12 @@ ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel|
     --profile-from-start off -c 40 -o gpurun_out/c4_full_${TAG} python tools/step_traffic.py run c4 \
     > gpurun_out/ncu_c4_full_${TAG}.log 2>&1
 echo "full capture c4 rc=$?"
+# the reports are 2-3 MB per kernel: summarise on the box, bring back the CSVs (gpurun_out/ is
+# capped at 64 MiB) and only a small report for the source-level view
+python tools/ncu_summary.py full gpurun_out/conv_full_${TAG}.ncu-rep gpurun_out/conv_full_${TAG}_summary.csv > /dev/null
+python tools/ncu_summary.py full gpurun_out/c4_full_${TAG}.ncu-rep gpurun_out/c4_full_${TAG}_summary.csv > /dev/null
+rm -f gpurun_out/c4_full_${TAG}.ncu-rep gpurun_out/conv_full_${TAG}.ncu-rep
+ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel" \
+    --profile-from-start off -s 8 -c 6 -o gpurun_out/conv_src_${TAG} python tools/step_traffic.py run c1 \
+    > /dev/null 2>&1
+echo "source capture rc=$?"
