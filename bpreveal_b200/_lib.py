@@ -77,6 +77,7 @@ class PrepTable(C.Structure):
         ("N_heads", c_int),
         ("w_fwd", c_void_p), ("w_bwd", c_void_p), ("w_in_op", c_void_p), ("w_hd_op", c_void_p),
         ("w_hf_op", c_void_p),
+        ("hf_kcg", c_int),
     ]
 
 
@@ -123,6 +124,7 @@ SIGNATURES = {
     "bpb_heads_fwd_wop_elems": (c_ll, [c_int] * 5),
     "bpb_prep_heads_fwd_weights": (c_int, [c_int] * 5 + [c_void_p] * 3 + [c_int, c_void_p]),
     "bpb_heads_fwd_ws_bytes": (c_ll, [c_int] * 3),
+    "bpb_heads_fwd_groups": (c_int, [c_int] * 5),
     "bpb_heads_fwd_tc_supported": (c_int, [c_int] * 5),
     "bpb_heads_fwd_tc": (c_int, [c_int] * 6 + [c_void_p] * 8 + [c_ll, c_void_p]),
     "bpb_loss_fwd_bwd": (c_int, [c_int] * 4 + [c_void_p] * 11),

@@ -31,10 +31,14 @@ struct HeadsKParams {
   int sub_bytes, box_bytes, stages;
   int row_shift;  // the box of tile t0 starts at row t0 + row_shift (negative rows read as zero)
   uint32_t idesc;
+  // 1: this launch handles one GROUP of input channels of a model whose weights do not fit shared
+  // memory at once (F = 512 with 75-wide heads: 1.2 MB); logits are added to what the previous
+  // group's launch left (the bias comes with group 0)
+  int accumulate;
   const float* pb;
   const uint8_t* w_image;  // the prepared weights: the shared-memory image, copied in one piece
   float* logits;
-  float* cpart;  // [B][tiles_per_seq][H]
+  float* cpart;  // [B][tiles_per_seq][H] (of this channel group)
   unsigned* dbg;
 };
 
@@ -196,7 +200,8 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           float* dst = p.logits + (static_cast<size_t>(b) * p.L_out + t) * p.T;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (n0 + i < p.T) dst[n0 + i] = __uint_as_float(acc[i]) + s_bias[n0 + i];
+            if (n0 + i < p.T)
+              dst[n0 + i] = __uint_as_float(acc[i]) + (p.accumulate ? dst[n0 + i] : s_bias[n0 + i]);
         }
         // counts columns T .. T+H-1: deterministic sum over the 128 rows of the tile (rows beyond
         // L_in were zero-filled by TMA and add nothing); the column test is warp-uniform
@@ -236,8 +241,8 @@ heads_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #endif
 }
 
-// logcounts[b][h] = cb[h] + (sum over tiles of cpart[b][tile][h]) / L_in
-__global__ void heads_counts_finish_kernel(int B, int tiles, int H, int L_in,
+// logcounts[b][h] = cb[h] + (sum over channel groups and tiles of cpart[g][b][tile][h]) / L_in
+__global__ void heads_counts_finish_kernel(int B, int tiles, int H, int L_in, int groups,
                                            const float* __restrict__ cpart,
                                            const float* __restrict__ cb,
                                            float* __restrict__ logcounts) {
@@ -245,15 +250,19 @@ __global__ void heads_counts_finish_kernel(int B, int tiles, int H, int L_in,
   if (i >= B * H) return;
   const int b = i / H, h = i % H;
   float s = 0.f;
-  for (int tIdx = 0; tIdx < tiles; ++tIdx) s += cpart[(static_cast<size_t>(b) * tiles + tIdx) * H + h];
+  for (int g = 0; g < groups; ++g)
+    for (int tIdx = 0; tIdx < tiles; ++tIdx)
+      s += cpart[((static_cast<size_t>(g) * B + b) * tiles + tIdx) * H + h];
   logcounts[i] = cb[h] + s / static_cast<float>(L_in);
 }
 
 // pw [W][Fw][T], cw [Fw][H] fp32 -> op: bf16 image of the kernel's shared-memory operand,
 // [planes][W][KC] tiles of N rows x 64 channels
+// (planes, taps, KCg chunks) per channel GROUP, groups back to back: one group's image is what one
+// launch keeps resident (KCg = K / 64 when everything fits, i.e. a single group)
 __global__ void __launch_bounds__(256)
 prep_heads_fwd_kernel(int W, int Fw, int K, int N, int T, int H, int planes, int flip_input_conv,
-                      const float* __restrict__ pw, const float* __restrict__ cw,
+                      int KCg, const float* __restrict__ pw, const float* __restrict__ cw,
                       __nv_bfloat16* __restrict__ op) {
   const long long n_el = static_cast<long long>(W) * N * K;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -275,13 +284,13 @@ prep_heads_fwd_kernel(int W, int Fw, int K, int N, int T, int H, int planes, int
   }
   // destination: tile (plane, tap, 64-channel chunk) of N rows x 128 B, 16-byte chunks XOR-ed
   // with the row (the 128-byte swizzle of a tile whose base is 1024-aligned in shared memory)
-  const int KC = K >> 6;
   const int cc = c & 63;
   const long long in_tile = static_cast<long long>(n) * 64 + (((cc >> 3) ^ (n & 7)) << 3) + (cc & 7);
+  const int grp = (c >> 6) / KCg, cg = (c >> 6) % KCg;
   float r = v;
   for (int pl = 0; pl < planes; ++pl) {
     const __nv_bfloat16 hbits = __float2bfloat16_rn(r);
-    const long long tile = (static_cast<long long>(pl) * W + j) * KC + (c >> 6);
+    const long long tile = ((static_cast<long long>(grp) * planes + pl) * W + j) * KCg + cg;
     op[tile * (static_cast<long long>(N) * 64) + in_tile] = hbits;
     r -= __bfloat162float(hbits);
   }
@@ -290,26 +299,39 @@ prep_heads_fwd_kernel(int W, int Fw, int K, int N, int T, int H, int planes, int
 static int heads_n(int T, int H) { return (T + H + 15) / 16 * 16; }
 
 struct HeadsPlan {
-  int N, KC, box_rows, sub_bytes, stages;
+  int N, KC, groups, box_rows, sub_bytes, stages;  // KC: chunks of ONE channel group
   size_t w_bytes, smem_bytes;
 };
 
+// The largest channel group (a divisor of F / 64 chunks) whose weights stay resident next to at
+// least two operand stages; groups > 1 means one launch per group, accumulating into the logits.
 static bool plan_heads(int W, int F, int T, int H, int planes, HeadsPlan* pl) {
   pl->N = heads_n(T, H);
-  pl->KC = F / 64;
   pl->box_rows = 128 + W - 1;
-  if (pl->N > 256 || pl->box_rows > 256) return false;
+  if (pl->N > 256 || pl->box_rows > 256 || F <= 0 || F % 64 != 0) return false;
   pl->sub_bytes = (pl->box_rows * 128 + 1023) / 1024 * 1024;
-  pl->w_bytes = (static_cast<size_t>(planes) * W * pl->KC * pl->N * 128 + 1023) / 1024 * 1024;
   const size_t fixed = 1024 + 256 * 4 + 64 * 4 + (2 * kHdStages + 5) * 8 + 16;
-  const size_t stage = static_cast<size_t>(pl->KC) * planes * pl->sub_bytes;
   const int max_smem = max_smem_optin();
-  if (max_smem <= 0 || fixed + pl->w_bytes + stage > static_cast<size_t>(max_smem)) return false;
-  int st = static_cast<int>((static_cast<size_t>(max_smem) - fixed - pl->w_bytes) / stage);
-  if (st > kHdStages) st = kHdStages;
-  pl->stages = st;
-  pl->smem_bytes = fixed + pl->w_bytes + st * stage;
-  return true;
+  if (max_smem <= 0) return false;
+  const int KCall = F / 64;
+  for (int groups = 1; groups <= KCall; ++groups) {
+    if (KCall % groups != 0) continue;
+    const int KC = KCall / groups;
+    const size_t w_bytes = (static_cast<size_t>(planes) * W * KC * pl->N * 128 + 1023) / 1024 * 1024;
+    const size_t stage = static_cast<size_t>(KC) * planes * pl->sub_bytes;
+    if (fixed + w_bytes + 2 * stage > static_cast<size_t>(max_smem) &&
+        !(groups == 1 && fixed + w_bytes + stage <= static_cast<size_t>(max_smem)))
+      continue;
+    int st = static_cast<int>((static_cast<size_t>(max_smem) - fixed - w_bytes) / stage);
+    if (st > kHdStages) st = kHdStages;
+    pl->KC = KC;
+    pl->groups = groups;
+    pl->w_bytes = w_bytes;
+    pl->stages = st;
+    pl->smem_bytes = fixed + w_bytes + st * stage;
+    return true;
+  }
+  return false;
 }
 
 }  // namespace bp
@@ -327,9 +349,12 @@ extern "C" int bpb_prep_heads_fwd_weights(int W, int Fw, int F, int T, int H, co
              "bpb_prep_heads_fwd_weights: bad arguments");
   const int N = heads_n(T, H);
   const long long n = static_cast<long long>(W) * N * F;
+  HeadsPlan pl;
+  BP_REQUIRE(plan_heads(W, F, T, H, planes, &pl),
+             "bpb_prep_heads_fwd_weights: W=%d F=%d planes=%d does not fit shared memory", W, F, planes);
   prep_heads_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
                           static_cast<cudaStream_t>(stream_)>>>(
-      W, Fw, F, N, T, H, planes, 0, pw, cw, reinterpret_cast<__nv_bfloat16*>(w_op));
+      W, Fw, F, N, T, H, planes, 0, pl.KC, pw, cw, reinterpret_cast<__nv_bfloat16*>(w_op));
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -340,7 +365,7 @@ extern "C" long long bpb_input_dgrad_wop_elems(int W, int F, int planes) {
 
 extern "C" int bpb_input_conv_dgrad_tc_supported(int W, int F, int planes) {
   bp::HeadsPlan pl;
-  return (F > 0 && F % 64 == 0 && bp::plan_heads(W, F, 4, 0, planes, &pl)) ? 0 : 1;
+  return (F > 0 && F % 64 == 0 && bp::plan_heads(W, F, 4, 0, planes, &pl) && pl.groups == 1) ? 0 : 1;
 }
 
 extern "C" int bpb_prep_input_dgrad_weights(int W, int Fw, int F, const float* w, bpb_bf16* w_op,
@@ -352,20 +377,32 @@ extern "C" int bpb_prep_input_dgrad_weights(int W, int Fw, int F, const float* w
   const long long n = static_cast<long long>(W) * N * F;
   prep_heads_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
                           static_cast<cudaStream_t>(stream_)>>>(
-      W, Fw, F, N, 4, 0, planes, 1, w, nullptr, reinterpret_cast<__nv_bfloat16*>(w_op));
+      W, Fw, F, N, 4, 0, planes, 1, F / 64, w, nullptr, reinterpret_cast<__nv_bfloat16*>(w_op));
   BP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+// one [B][tiles][H] block of partial sums per channel group, for up to 16 groups (F <= 1024)
 extern "C" long long bpb_heads_fwd_ws_bytes(int B, int L_in, int H) {
-  return static_cast<long long>(B) * ((L_in + 127) / 128) * H * 4;
+  return static_cast<long long>(B) * ((L_in + 127) / 128) * H * 4 * 16;
 }
 
-// Returns 0 if the tensor-core kernel can run this geometry (weights + one box fit in shared
-// memory, T + H <= 256, H <= 16, W <= 129); callers fall back to bpb_heads_fwd otherwise.
+// Returns 0 if the tensor-core kernel can run this geometry (the weights of at least one
+// 64-channel group + two boxes fit in shared memory, T + H <= 256, H <= 16, W <= 129); callers
+// fall back to bpb_heads_fwd otherwise.
 extern "C" int bpb_heads_fwd_tc_supported(int W, int F, int T, int H, int planes) {
   bp::HeadsPlan pl;
-  return (F > 0 && F % 64 == 0 && H <= 16 && T <= 240 && bp::plan_heads(W, F, T, H, planes, &pl)) ? 0 : 1;
+  return (F > 0 && F % 64 == 0 && F <= 1024 && H <= 16 && T <= 240 &&
+          bp::plan_heads(W, F, T, H, planes, &pl)) ? 0 : 1;
+}
+
+// Channel groups bpb_heads_fwd_tc runs this geometry in (1 = everything resident; > 1 = one
+// launch per group, and the per-tile counts partials are [groups][B][tiles][H]); 0 = unsupported.
+extern "C" int bpb_heads_fwd_groups(int W, int F, int T, int H, int planes) {
+  bp::HeadsPlan pl;
+  if (bpb_heads_fwd_tc_supported(W, F, T, H, planes) != 0) return 0;
+  bp::plan_heads(W, F, T, H, planes, &pl);
+  return pl.groups;
 }
 
 // One launch of the window GEMM.  full = 0: the heads ('valid' correlation, L_out = L_in - W + 1,
@@ -383,6 +420,7 @@ static int heads_fwd_run(const char* who, int full, int B, int L_in, int W, int 
   BP_REQUIRE(plan_heads(W, F, T, H, planes, &pl),
              "%s: W=%d F=%d planes=%d does not fit shared memory", who, W, F, planes);
   BP_REQUIRE(H == 0 || ws_bytes >= bpb_heads_fwd_ws_bytes(B, L_in, H), "%s: workspace too small", who);
+  BP_REQUIRE(pl.groups == 1 || (!full && pl.groups <= 16), "%s: channel groups only for the heads", who);
   HeadsKParams kp{};
   kp.B = B;
   kp.L_in = L_in;
@@ -404,19 +442,29 @@ static int heads_fwd_run(const char* who, int full, int B, int L_in, int W, int 
   kp.stages = pl.stages;
   kp.idesc = umma_idesc_bf16(128, pl.N, 0, 0);
   kp.pb = pb;
-  kp.w_image = reinterpret_cast<const uint8_t*>(w_op);
   kp.logits = logits;
-  kp.cpart = ws;
   kp.dbg = debug_buffer();
-  CUtensorMap maps[3];
-  memset(maps, 0, sizeof(maps));
-  if (!make_tmap_3d(&maps[0], act_hi, F, L_in, B, 64, pl.box_rows)) return 3;
-  if (planes == 2 && !make_tmap_3d(&maps[1], act_lo, F, L_in, B, 64, pl.box_rows)) return 3;
-  if (!make_tmap_2d(&maps[2], w_op, F, static_cast<uint64_t>(planes) * W * pl.N, 64, pl.N)) return 3;
   const int total = B * kp.tiles_per_seq;
   int grid = sm_count();
   if (grid > total) grid = total;
   const uint32_t cols = 2u * pl.N;
+  const int Fg = pl.KC * 64;  // channels of one group
+  for (int g = 0; g < pl.groups; ++g) {
+    kp.accumulate = g > 0 ? 1 : 0;
+    kp.w_image = reinterpret_cast<const uint8_t*>(w_op) +
+                 static_cast<size_t>(g) * planes * W * pl.KC * pl.N * 128;
+    kp.cpart = ws ? ws + static_cast<size_t>(g) * B * kp.tiles_per_seq * H : nullptr;
+    CUtensorMap maps[3];
+    memset(maps, 0, sizeof(maps));
+    // the group's channels of the activation: same rows and strides, inner extent Fg
+    const unsigned long long row_b = static_cast<unsigned long long>(F) * 2, bat_b = row_b * L_in;
+    if (!make_tmap_3d_strided(&maps[0], act_hi + static_cast<size_t>(g) * Fg, Fg, L_in, B, row_b, bat_b,
+                              64, pl.box_rows))
+      return 3;
+    if (planes == 2 && !make_tmap_3d_strided(&maps[1], act_lo + static_cast<size_t>(g) * Fg, Fg, L_in, B,
+                                             row_b, bat_b, 64, pl.box_rows))
+      return 3;
+    maps[2] = maps[0];  // (the weights arrive by one bulk copy of their prepared image)
 #define LAUNCH_HD(C)                                                                            \
   do {                                                                                          \
     static bool configured = false;                                                             \
@@ -429,16 +477,17 @@ static int heads_fwd_run(const char* who, int full, int B, int L_in, int W, int 
     BP_CHECK_CUDA(launch_pdl(heads_fwd_tc_kernel<C>, dim3(grid), dim3(192), pl.smem_bytes,    \
                              stream, maps[0], maps[1], maps[2], kp));                           \
   } while (0)
-  if (cols <= 32) LAUNCH_HD(32);
-  else if (cols <= 64) LAUNCH_HD(64);
-  else if (cols <= 128) LAUNCH_HD(128);
-  else if (cols <= 256) LAUNCH_HD(256);
-  else LAUNCH_HD(512);
+    if (cols <= 32) LAUNCH_HD(32);
+    else if (cols <= 64) LAUNCH_HD(64);
+    else if (cols <= 128) LAUNCH_HD(128);
+    else if (cols <= 256) LAUNCH_HD(256);
+    else LAUNCH_HD(512);
 #undef LAUNCH_HD
-  BP_CHECK_CUDA(cudaGetLastError());
+    BP_CHECK_CUDA(cudaGetLastError());
+  }
   if (H > 0 && logcounts != nullptr) {
-    heads_counts_finish_kernel<<<(B * H + 127) / 128, 128, 0, stream>>>(B, kp.tiles_per_seq, H, L_in,
-                                                                        ws, cb, logcounts);
+    heads_counts_finish_kernel<<<(B * H + 127) / 128, 128, 0, stream>>>(
+        B, kp.tiles_per_seq, H, L_in, pl.groups, ws, cb, logcounts);
     BP_CHECK_CUDA(cudaGetLastError());
   }
   return 0;

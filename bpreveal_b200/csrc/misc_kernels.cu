@@ -582,7 +582,11 @@ adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g
         float rem = w;
         for (int pl = 0; pl < tb.planes; ++pl) {
           const __nv_bfloat16 hb = __float2bfloat16_rn(rem);
-          const long long tile = (static_cast<long long>(pl) * tb.W_out + j) * KC + (c >> 6);
+          // grouped image of bpb_prep_heads_fwd_weights: (group, plane, tap, chunk in group)
+          const int KCg = tb.hf_kcg > 0 ? tb.hf_kcg : KC;
+          const long long tile =
+              ((static_cast<long long>((c >> 6) / KCg) * tb.planes + pl) * tb.W_out + j) * KCg +
+              ((c >> 6) % KCg);
           w_hf_op[tile * (static_cast<long long>(tb.N_heads) * 64) + in_tile] = hb;
           rem -= __bfloat162float(hb);
         }

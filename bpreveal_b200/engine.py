@@ -120,9 +120,13 @@ class SoloNet:
         self.w_id_op = ops.input_dgrad_wop(cfg.inputFilterWidth, Fp, planes, self.device)
         # heads forward as one tcgen05 GEMM when its weights fit shared memory (else CUDA cores)
         self.heads_tc = ops.heads_fwd_tc_supported(cfg.outputFilterWidth, Fp, cfg.T, cfg.H, planes)
+        self.heads_groups = 1
         if self.heads_tc:
             self.w_hf_op = ops.heads_fwd_wop(cfg.outputFilterWidth, Fp, cfg.T, cfg.H, planes,
                                              self.device)
+            # > 1: wide models whose head weights do not fit shared memory at once run one launch
+            # per channel group (the per-tile counts partials are then per group as well)
+            self.heads_groups = ops.heads_fwd_groups(cfg.outputFilterWidth, Fp, cfg.T, cfg.H, planes)
         self.host_task_off = [int(v) for v in np.concatenate([[0], np.cumsum(cfg.headTasks)])]
         self.task_off = torch.tensor(self.host_task_off, dtype=torch.int32, device=self.device)
         self._ws = {}
@@ -440,7 +444,7 @@ class SoloNet:
         Ls = cfg.lengths()
         # solo model: losses, packed loss gradient and the heads' bias gradients in ONE launch
         fused = bias_logits is None and max(cfg.headTasks) <= 8
-        defer = fused and self.heads_tc
+        defer = fused and self.heads_tc and self.heads_groups == 1
         aL = self._forward(ws, ws["x"], save_masks=True, defer_counts=defer)
         logits, lc = ws["logits"], ws["logcounts"]
         if bias_logits is not None:
@@ -536,6 +540,7 @@ class SoloNet:
             t.w_fwd, t.w_bwd = self.w_fwd.data_ptr(), self.w_bwd.data_ptr()
             t.w_in_op, t.w_hd_op = self.w_in_op.data_ptr(), self.w_hd_op.data_ptr()
             t.w_hf_op = self.w_hf_op.data_ptr() if self.heads_tc else None
+            t.hf_kcg = (cfg.Fp // 64) // max(self.heads_groups, 1)
             self._ptab = t
         return self._ptab
 

@@ -272,6 +272,11 @@ def heads_fwd_tc_supported(W, F, T, H, planes):
     return _lib.load().bpb_heads_fwd_tc_supported(W, F, T, H, planes) == 0
 
 
+def heads_fwd_groups(W, F, T, H, planes):
+    """Channel groups bpb_heads_fwd_tc needs (1: weights resident; 0: unsupported)."""
+    return _lib.load().bpb_heads_fwd_groups(W, F, T, H, planes)
+
+
 def heads_fwd_wop(W, F, T, H, planes, device):
     n = _lib.load().bpb_heads_fwd_wop_elems(W, F, T, H, planes)
     return torch.zeros((n,), dtype=torch.bfloat16, device=device)

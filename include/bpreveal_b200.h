@@ -198,6 +198,10 @@ int bpb_prep_heads_fwd_weights(int W, int Fw, int F, int T, int H, const float* 
                                const float* cw, bpb_bf16* w_op, int planes, void* stream);
 long long bpb_heads_fwd_ws_bytes(int B, int L_in, int H);
 int bpb_heads_fwd_tc_supported(int W, int F, int T, int H, int planes);
+/* Channel groups the geometry runs in: 1 = all weights resident; g > 1 = one launch per group of
+ * F / g channels accumulating into the logits (wide models: F = 512 with 75-wide heads is 1.2 MB
+ * of weights), the workspace then holds [g][B][tiles][H] partial sums; 0 = unsupported. */
+int bpb_heads_fwd_groups(int W, int F, int T, int H, int planes);
 int bpb_heads_fwd_tc(int B, int L_in, int W, int F, int T, int H, const bpb_bf16* act_hi,
                      const bpb_bf16* act_lo, const bpb_bf16* w_op, const float* pb,
                      const float* cb, float* logits, float* logcounts, float* ws,
@@ -307,6 +311,8 @@ typedef struct {
   bpb_bf16* w_in_op;       /* bpb_prep_input_conv_weights output */
   bpb_bf16* w_hd_op;       /* bpb_prep_heads_dgrad_weights output */
   bpb_bf16* w_hf_op;       /* bpb_prep_heads_fwd_weights output, or NULL */
+  int hf_kcg;              /* 64-channel chunks per channel group of that image:
+                              (F / 64) / bpb_heads_fwd_groups(...) (0 = F / 64, one group) */
 } bpb_prep_table;
 int bpb_adam_prep_step(long long n, float* param, const float* grad, float* m, float* v,
                        float* state, float beta1, float beta2, float eps, float grad_scale,

@@ -256,11 +256,13 @@ def test_fused_loss_pack_matches_separate_kernels(dev, planes):
 
 
 @pytest.mark.parametrize("precise", [False, True])
-def test_fused_adam_refresh_matches_separate_kernels(dev, precise):
+@pytest.mark.parametrize("case", [1, 4])
+def test_fused_adam_refresh_matches_separate_kernels(dev, precise, case):
     """bpb_adam_prep_step == bpb_adam_step + the four bpb_prep_* kernels, bit for bit (parameters,
-    moments and every bf16 operand layout), and it advances the device step counter."""
+    moments and every bf16 operand layout), and it advances the device step counter.  Case 4
+    (F = 256, 75-wide heads) keeps its heads' weights in per-channel-group images."""
     from bpreveal_b200 import ops
-    cfg = dict(CASES[1][1])  # two heads
+    cfg = dict(CASES[case][1])  # two heads | wide
     net, _ = build(cfg, precise, dev, scale=1.0)
     net.enable_training()
     g = torch.Generator().manual_seed(9)
