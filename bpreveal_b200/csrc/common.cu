@@ -116,6 +116,28 @@ bool make_tmap_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uin
   return true;
 }
 
+// [32 channels x 32 rows] boxes, 64-byte swizzle: the per-warp output tiles of the conv epilogue
+bool make_tmap_3d_sw64(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return false;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
+                  box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d sw64 %llu x %llu x %llu) failed with %d",
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (int)r);
+    return false;
+  }
+  return true;
+}
+
 bool make_tmap_3d_strided(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
                           uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
                           uint32_t box1) {

@@ -24,6 +24,7 @@ bool make_tmap_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uin
 // 3-D bf16 tensor with explicit byte strides (multiples of 16) for dims 1 and 2; rows may overlap
 // (stride smaller than the row extent), which turns a channels-last [L][C] tensor into the
 // implicit im2col matrix of a width-W window: row t = elements [t*C, t*C + W*C).
+bool make_tmap_3d_sw64(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2);
 bool make_tmap_3d_strided(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
                           uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
                           uint32_t box1);

@@ -680,14 +680,15 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         }
         BPB_PHASE(9);   // acc wait + TMEM load
 
-        const bool one_buf = (EG >= 2) || p.nstg == 1;  // one staging buffer per writer group
-        uint8_t* sb = stg + static_cast<size_t>(EG >= 2 ? grp : (p.nstg == 2 ? (kc & 1) : 0)) * stg_bytes;
-        uint8_t* sb2 = sb + static_cast<size_t>(p.has_out * PLANES) * kTileBytes;
-        if (one_buf) {
-          // single staging buffer: the previous chunk's stores must have read it
-          if (et == 0) tma_store_wait_read<0>();
-          named_bar_sync(bar_id, kEpiThreads);
-        }
+        // Every warp owns the [32 rows x 32 channels] corner of the tile it computes: its own
+        // 2 KB staging tiles (64-byte swizzle) and its own TMA stores.  No CTA-wide barrier in
+        // the epilogue: `barrier` was the top stall of the HALO-staged launches when one thread
+        // stored the whole [128 x 64] tile for eight warps (two named barriers per tile).
+        const int wepi = warp - 2;  // 0 .. 8 EG - 1
+        uint8_t* sb = stg + static_cast<size_t>(wepi) * (n_out * PLANES * 2048);
+        uint8_t* sb2 = sb + static_cast<size_t>(p.has_out * PLANES) * 2048;
+        if (lane == 0) tma_store_wait_read<0>();  // this warp's previous stores have read sb
+        __syncwarp();
 
         BPB_PHASE(10);  // staging buffer free (wait_read + barrier)
         float obits_lo = 0.f, obits_hi = 0.f;
@@ -786,13 +787,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               for (int i = 0; i < 8; ++i) o2[i] = ((mbits >> (g * 8 + i)) & 1u) ? o[i] : 0.f;
             }
           }
-          const uint32_t off = sw128(row, cq + g);
+          const uint32_t off = sw64(static_cast<uint32_t>(lane), static_cast<uint32_t>(g));
           if (p.has_out) {
             if (PLANES == 2) {
               uint4 h, l;
               split8(o, h, l);
               sts128(sb + off, h);
-              sts128(sb + kTileBytes + off, l);
+              sts128(sb + 2048 + off, l);
             } else {
               sts128(sb + off, pack8(o));
             }
@@ -802,7 +803,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               uint4 h, l;
               split8(o2, h, l);
               sts128(sb2 + off, h);
-              sts128(sb2 + kTileBytes + off, l);
+              sts128(sb2 + 2048 + off, l);
             } else {
               sts128(sb2 + off, pack8(o2));
             }
@@ -815,19 +816,19 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(release);
         }
-        // ---- publish: generic-proxy writes -> async proxy, one barrier, one thread stores
+        // ---- publish: generic-proxy writes -> async proxy, then this warp's own stores
         fence_proxy_async();
         BPB_PHASE(12);  // proxy fence
-        if (!one_buf && et == 0) tma_store_wait_read<0>();  // buffer of chunk kc-1 is free again
-        named_bar_sync(bar_id, kEpiThreads);
-        if (et == 0) {
+        __syncwarp();
+        if (lane == 0) {
+          const int c0 = n0 + half * 32, r0 = t0 + q * 32;
           if (p.has_out) {
-            tma_store_3d(&tm.O[0], sb, n0, t0, b);
-            if (PLANES == 2) tma_store_3d(&tm.O[1], sb + kTileBytes, n0, t0, b);
+            tma_store_3d(&tm.O[0], sb, c0, r0, b);
+            if (PLANES == 2) tma_store_3d(&tm.O[1], sb + 2048, c0, r0, b);
           }
           if (p.has_out2) {
-            tma_store_3d(&tm.P[0], sb2, n0, t0, b);
-            if (PLANES == 2) tma_store_3d(&tm.P[1], sb2 + kTileBytes, n0, t0, b);
+            tma_store_3d(&tm.P[0], sb2, c0, r0, b);
+            if (PLANES == 2) tma_store_3d(&tm.P[1], sb2 + 2048, c0, r0, b);
           }
           tma_store_commit();
         }
@@ -846,7 +847,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
 #ifdef BPB_ROLE_PROFILE
     if (et == 0 && grp == 0) BPB_STAMP(23);
 #endif
-    if (et == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
 #ifdef BPB_ROLE_PROFILE
     if (et == 0 && grp == 0) BPB_STAMP(24);
 #endif
@@ -1145,8 +1146,8 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   const uint64_t wrows = static_cast<uint64_t>(d.n_wplanes) * d.n_taps * F;
   if (!make_tmap_2d(&maps.W, d.w_ptr, static_cast<uint64_t>(d.KC) * 64, wrows, 64, NT)) return 3;
   for (int pl = 0; pl < n_planes; ++pl) {
-    if (has_out && !make_tmap_3d(&maps.O[pl], d.out[pl], F, d.L_out, d.B, 64, kTileM)) return 3;
-    if (has_out2 && !make_tmap_3d(&maps.P[pl], d.out2[pl], F, d.L_out, d.B, 64, kTileM)) return 3;
+    if (has_out && !make_tmap_3d_sw64(&maps.O[pl], d.out[pl], F, d.L_out, d.B)) return 3;
+    if (has_out2 && !make_tmap_3d_sw64(&maps.P[pl], d.out2[pl], F, d.L_out, d.B)) return 3;
     if (rstages > 0 && !make_tmap_3d(&maps.R[pl], d.resid[pl], F, d.L_res, d.B, 64, kTileM))
       return 3;
   }

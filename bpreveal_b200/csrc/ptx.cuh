@@ -297,4 +297,9 @@ __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) {
   return r * 128u + ((c ^ (r & 7u)) << 4);
 }
 
+// The same for a [rows x 64 B] SWIZZLE_64B tile (chunks 0..3): address bits 4-5 ^= bits 7-8.
+__device__ __forceinline__ uint32_t sw64(uint32_t r, uint32_t c) {
+  return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4);
+}
+
 }  // namespace bp
