@@ -319,10 +319,12 @@ def family_work(calls, planes):
             add(key, planes * 2.0 * B * (Lg + Lout) * F + B * Lg * F / 8.0,
                 2.0 * 3 * F * F * B * Lg)
         elif key in ("wgrad_tower_input", "wgrad3_multi"):
-            for (act, gz, d, dw, db) in a[0]:
+            for layer in a[0]:  # (act, gz | g, d, dw, db[, the mask that turns g into gz])
+                act, gz = layer[0], layer[1]
                 B, Li, F = _shape(act)
                 Lo = _shape(gz)[1]
-                add(key, planes * 2.0 * B * (Li + Lo) * F, 2.0 * 3 * F * F * B * Lo)
+                add(key, planes * 2.0 * B * (Li + Lo) * F +
+                    (B * Lo * F / 8.0 if len(layer) > 5 else 0.0), 2.0 * 3 * F * F * B * Lo)
             if key == "wgrad_tower_input":
                 x8, gz0, W, Fw = a[1], a[2], a[3], a[4]
                 B, L0, F = _shape(gz0)

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpreveal_b200.so")
+# BPB_LIB_PATH: another build of the SAME library (the role-profile build of csrc/Makefile)
+LIB_PATH = os.environ.get("BPB_LIB_PATH") or os.path.join(_HERE, "libbpreveal_b200.so")
 
 c_void_p = C.c_void_p
 c_int = C.c_int
@@ -36,6 +37,7 @@ class Conv3Args(C.Structure):
         ("zx_in", c_void_p),
         ("zx_div", c_int),
         ("z_out", c_void_p),
+        ("mask_a", c_void_p),
     ]
 
 
@@ -46,6 +48,7 @@ class Wgrad3Args(C.Structure):
         ("gz_hi", c_void_p), ("gz_lo", c_void_p),
         ("dw", c_void_p), ("db", c_void_p),
         ("ws", c_void_p), ("ws_bytes", c_ll),
+        ("gz_mask", c_void_p),
     ]
 
 
@@ -110,7 +113,7 @@ SIGNATURES = {
     "bpb_heads_dgrad_tc": (c_int, [C.POINTER(HeadsDgradArgs), c_void_p]),
     "bpb_wgrad_tower_input_ws_bytes": (c_ll, [c_int, c_int, c_void_p] + [c_int] * 5),
     "bpb_wgrad_tower_input": (c_int, [C.POINTER(Wgrad3Args), c_int, c_int, c_int, c_int, c_int] +
-                              [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 5 + [c_ll, c_void_p]),
+                              [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 5 + [c_ll, c_void_p]),
     "bpb_input_conv_wgrad_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "bpb_input_conv_wgrad": (c_int, [c_int] * 6 + [c_void_p] * 6 + [c_ll, c_void_p]),
     "bpb_heads_wgrad_ws_bytes": (c_ll, [c_int] * 5),

@@ -39,7 +39,7 @@ namespace bp {
 constexpr int kTileM = 128;
 constexpr int kTileBytes = kTileM * 128;  // [128 x 64] bf16
 constexpr int kMaxStages = 12;
-constexpr int kMaxRStages = 4;
+constexpr int kMaxRStages = 6;
 constexpr int kMaxAcc = 6;
 constexpr int kBiasTileBytes = 64 * 128;
 constexpr int kBiasMmaBytes = kBiasTileBytes + 128 * 128;  // bias tile + tile of ones
@@ -88,8 +88,23 @@ struct ConvKParams {
   uint32_t* mask_out;
   const float* zx_in;
   float* z_out;
+  // XF (backward, bf16 path, F = 64): the A operand is `in (.) mask_a`.  The tiles TMA delivers
+  // are ANDed with the 1-bit ReLU mask of their rows IN SHARED MEMORY by six extra warps before
+  // the MMA reads them, so the caller passes the unmasked gradient g of the layer above and that
+  // layer's mask instead of a materialised gz = g (.) mask plane (one write and one read of a
+  // whole activation plane per layer).  mask_a: [B][L_a] uint64 (F = 64: one word per row); the
+  // words of a tile's rows arrive by a 1-D bulk copy on the same mbarrier as the tile itself.
+  const uint8_t* mask_a;
+  int L_a;                     // rows per sequence of the A operand
+  long long mask_rows_total;   // B * L_a (even)
+  int xf_rows;                 // rows of one staged A tile (HALO: the box, SLAB: 128)
+  int mstage;                  // bytes of one stage's mask words (multiple of 16)
+  int dbg_flags;               // PROFILE builds only (BPB_DBG_FLAGS): 1 no stores, 2 no residual
+                               // loads, 4 no masking work -- ablations for the role profile
   unsigned* dbg;
 };
+
+constexpr int kXfThreads = 192;  // the six masker warps of an XF launch
 
 struct ConvMaps {
   CUtensorMap A[2], W, O[2], P[2], R[2];
@@ -171,9 +186,34 @@ __device__ __forceinline__ void ring_advance(uint32_t& idx, uint32_t& phase, uin
   while (idx >= size) { idx -= size; phase ^= 1; }
 }
 
-template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID>
-__global__ void __launch_bounds__(64 + kEpiThreads * EG, 1)
+// XF: the mask words of the A rows [row0, row0 + xf_rows) of sequence b as one 16-byte aligned
+// 1-D bulk copy.  Row g of the flattened [B * L_a] mask lands at byte (g - (g0 & ~1)) * 8 of the
+// stage's buffer, so shared and global addresses agree modulo 16; rows outside the tensor are
+// not copied (their data rows are zero-filled by TMA, whatever bits the buffer holds).
+struct XfCopy {
+  long long src_row;
+  uint32_t dst_off, bytes;
+};
+__device__ __forceinline__ XfCopy xf_copy(const ConvKParams& p, int b, int row0) {
+  const long long g0 = static_cast<long long>(b) * p.L_a + row0;
+  const long long g0e = g0 & ~1LL;
+  const long long cs = (g0 > 0 ? g0 : 0) & ~1LL;
+  long long ce = g0 + p.xf_rows;
+  if (ce > p.mask_rows_total) ce = p.mask_rows_total;
+  ce = (ce + 1) & ~1LL;
+  XfCopy c;
+  c.src_row = cs;
+  c.dst_off = static_cast<uint32_t>((cs - g0e) * 8);
+  c.bytes = ce > cs ? static_cast<uint32_t>((ce - cs) * 8) : 0u;
+  return c;
+}
+
+template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID, bool XF = false>
+__global__ void __launch_bounds__(64 + kEpiThreads * EG + (XF ? kXfThreads : 0) +
+                                  (RESIDENT ? 0 : 32), 1)
 conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
+  static_assert(!XF || (EPI == EPI_BWD_MASK && NT == 64 && RESIDENT && PLANES == 1 && RESID),
+                "XF: bf16 backward of an F = 64 layer with resident weights");
   // accumulator stages: a multiple of the group count, so a stage (and its mbarriers) always
   // belongs to the same epilogue group
   constexpr int ACC = (EG == 3) ? ((NT <= 64) ? 6 : 3) : ((NT <= 128) ? 4 : 2);
@@ -218,7 +258,11 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   uint64_t* rempty = rfull + kMaxRStages;
   uint64_t* w_full = rempty + kMaxRStages;
   uint64_t* b_full = w_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* xfull = b_full + 1;  // XF: "stage masked, the MMA may read it"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull + kMaxStages);
+  // XF: per-stage mask words, 16-byte aligned (bulk-copy destination)
+  uint8_t* mring = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~static_cast<uintptr_t>(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -247,6 +291,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         mbar_init(b0, 1);
         mbar_init(b1, c1);
       }
+      if (XF && is_ring) mbar_init(&xfull[lane], kXfThreads / 32);
     }
     if (lane == 30) mbar_init(b_full, 1);
     if (lane == 31) {
@@ -316,13 +361,19 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         if (HALO) {
           if (ntile == 0) BPB_STAMP(29);
           mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
-          mbar_expect_tx(&full[stage], static_cast<uint32_t>(p.KC * p.n_aplanes * p.box_bytes));
+          XfCopy xc{0, 0u, 0u};
+          if (XF) xc = xf_copy(p, b, t0 + p.box_off);
+          mbar_expect_tx(&full[stage],
+                         static_cast<uint32_t>(p.KC * p.n_aplanes * p.box_bytes) + xc.bytes);
           if (ntile == 0) BPB_STAMP(30);
           uint8_t* dst = ring + static_cast<size_t>(stage) * stage_bytes;
           for (int c = 0; c < p.KC; ++c)
             for (int pl = 0; pl < p.n_aplanes; ++pl)
               tma_load_3d(&tm.A[pl], dst + static_cast<size_t>(c * p.n_aplanes + pl) * p.sub_bytes,
                           &full[stage], c * 64, t0 + p.box_off, b);
+          if (XF && xc.bytes)
+            bulk_load_1d(mring + static_cast<size_t>(stage) * p.mstage + xc.dst_off,
+                         p.mask_a + xc.src_row * 8, xc.bytes, &full[stage]);
           if (ntile == 0) BPB_STAMP(26);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         } else if (RESIDENT && p.strip) {
@@ -346,19 +397,24 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             const int c = (step / inner) % p.KC;
             const int j = step / (inner * p.KC);
             mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
-            mbar_expect_tx(&full[stage], SLAB_BYTES);
+            XfCopy xc{0, 0u, 0u};
+            if (XF) xc = xf_copy(p, b, t0 + p.tap_row[j]);
+            mbar_expect_tx(&full[stage], SLAB_BYTES + xc.bytes);
             uint8_t* dst = ring + static_cast<size_t>(stage) * SLAB_BYTES;
             tma_load_3d(&tm.A[RESIDENT ? pass : ((p.pa_bits >> pass) & 1)], dst, &full[stage],
                         c * 64, t0 + p.tap_row[j], b);
-            if (!RESIDENT) {
-              const int wp = (p.pw_bits >> (2 * pass)) & 3;
-              tma_load_2d(&tm.W, dst + kTileBytes, &full[stage], c * 64,
-                          (wp * p.n_taps + j) * p.F + nt * NT);
-            }
+            if (XF && xc.bytes)
+              bulk_load_1d(mring + static_cast<size_t>(stage) * p.mstage + xc.dst_off,
+                           p.mask_a + xc.src_row * 8, xc.bytes, &full[stage]);
+            // (!RESIDENT: the weight tile of this stage is fetched by the second producer warp)
             if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
           }
         }
+#ifdef BPB_ROLE_PROFILE
+        if (RING_RESID && !(p.dbg_flags & 2)) {
+#else
         if (RING_RESID) {
+#endif
           const uint32_t g = (EG > 1) ? (ntile % EG) : 0u;
           for (int ch = 0; ch < NCH; ++ch) {
             const uint32_t rs = g * RG + rsg[g];
@@ -381,6 +437,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       if (bias_mma) mbar_wait_wd(b_full, 0, p.dbg, 0x310);
       BPB_STAMP(28);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, ntile = 0;
+      uint64_t* const a_ready = XF ? xfull : full;  // XF: operands are usable once masked
       // Fast path (the bf16 tower layer: 3 taps, one 64-channel chunk, one pass, resident
       // weights): every descriptor word that does not depend on the stage is built once here, so
       // the issue loop is 12 x (one add + one tcgen05.mma) per tile.  The single issuing thread
@@ -411,7 +468,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           accum0 = 1;
         }
         if (fast && HALO) {
-          mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
+          mbar_wait_wd(&a_ready[stage], phase, p.dbg, 0x500 + stage, ntile);
 #ifdef BPB_ROLE_PROFILE
           if (ntile == 0) BPB_STAMP(27);
 #endif
@@ -428,7 +485,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         } else if (fast) {
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            mbar_wait_wd(&full[stage], phase, p.dbg, 0x500 + stage, ntile);
+            mbar_wait_wd(&a_ready[stage], phase, p.dbg, 0x500 + stage, ntile);
             tc_fence_after();
             const uint32_t a0 = ring_lo + stage * stage_lo;
 #pragma unroll
@@ -538,6 +595,135 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         if (++as == ACC) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (!RESIDENT && warp == 2 + 8 * EG) {
+    // ------------------------------------------------------------- second TMA producer
+    // Streamed weights (F >= 256): every K step needs an activation tile AND a weight tile, and
+    // a tensor load costs ~150-280 cycles of issue on the thread that makes it -- two loads per
+    // step on ONE thread took as long as the step's four MMAs (the F = 512 launches sat at 50 %
+    // tensor-pipe activity however many stages the ring had).  This warp issues the weight
+    // tiles; the first producer arms the stage's mbarrier with the bytes of both (a completion
+    // that lands before the expect only drives the pending count negative for a moment: the
+    // phase cannot complete before the first producer's arrive).  Weights are parameters: no
+    // dependency wait.
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0, ntile = 0;
+      TileWalk tw;
+      for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
+        const int nsteps = p.n_taps * p.KC * p.npass;
+        for (int step = 0; step < nsteps; ++step) {
+          const int pass = step % p.npass;
+          const int c = (step / p.npass) % p.KC;
+          const int j = step / (p.npass * p.KC);
+          mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0xF00 + stage, ntile);
+          const int wp = (p.pw_bits >> (2 * pass)) & 3;
+          tma_load_2d(&tm.W, ring + static_cast<size_t>(stage) * SLAB_BYTES + kTileBytes,
+                      &full[stage], c * 64, (wp * p.n_taps + j) * p.F + tw.nt * NT);
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (XF && warp >= 2 + 8 * EG) {
+    // ------------------------------------------------------------- XF masker warps
+    // Every staged A tile is ANDed with the ReLU bits of its rows before the MMA reads it.  A row
+    // of a [rows x 64 ch] SWIZZLE_128B tile is eight 16-byte chunks of eight channels; byte c of
+    // the row's mask word covers chunk c, so chunk i of the tile (row-major) has mask byte i.
+    // A thread takes four consecutive chunks (half a row) per step: one 32-bit load of mask
+    // bytes, four 128-bit loads, the lane masks from PRMT sign replication, four stores.  Lanes
+    // 0-15 of a warp take the first halves of 16 consecutive rows, lanes 16-31 the second halves:
+    // every quarter-warp then touches eight different rows at the same logical chunk, the
+    // conflict-free pattern of a 128-byte-swizzled tile (two lanes per row -- one row's two
+    // halves in neighbouring lanes -- measured 2-way bank conflicts on every access).  The six
+    // warps of a step cover 96 rows.  (The host only selects XF on the fast path: 3 taps, one
+    // chunk, one pass.)
+    const int mw_ = warp - (2 + 8 * EG);    // masker warp 0..5
+    const int xrow = mw_ * 16 + (lane & 15);
+    const uint32_t xhalf = static_cast<uint32_t>(lane) >> 4;
+    const int xrows = p.xf_rows;            // rows per staged tile
+    const int nsub = HALO ? 1 : 3;          // staged tiles per output tile
+    uint32_t xoff[4];                       // byte offsets of this thread's step-0 chunks
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xoff[k] = sw128(static_cast<uint32_t>(xrow), xhalf * 4u + k);
+    uint32_t stage = 0, phase = 0, ntile = 0;
+    TileWalk tw;
+    for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
+      const int t0 = tw.mt * kTileM;
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int row0 = t0 + (HALO ? p.box_off : p.tap_row[sub]);
+        const uint32_t par =
+            static_cast<uint32_t>((static_cast<long long>(tw.b) * p.L_a + row0) & 1);
+        uint8_t* tile = ring + static_cast<size_t>(stage) * stage_bytes;
+        const uint8_t* mb = mring + static_cast<size_t>(stage) * p.mstage + 8u * par;
+        mbar_wait_wd(&full[stage], phase, p.dbg, 0xE00 + stage, ntile);
+#ifdef BPB_ROLE_PROFILE
+        long long tm0 = clock64();
+        const int xre = (p.dbg_flags & 4) ? 0 : xrows;
+#else
+        const int xre = xrows;
+#endif
+        // rows <= 256 = 2.67 x 96: at most three steps per thread.  Step `it` handles row
+        // xrow + 96 it (same swizzle phase, 96 = 0 mod 8), so its byte offsets are the step-0
+        // offsets + 96 * 128 * it.  Inside a step the lane masks are
+        // computed in independent waves (multiplies, PRMTs, ANDs) over the four chunks: written
+        // as one chain per chunk the compiler serialised everything through two temporaries and
+        // a step cost ~600 cycles of pure ALU latency.
+        const uint32_t tile_a = smem_u32(tile), mb_a = smem_u32(mb) + 8u * xrow + 4u * xhalf;
+#pragma unroll 1
+        for (int it = 0; it < 3; ++it) {
+          if (xrow + 96 * it >= xre) break;
+          const uint32_t toff = tile_a + 96u * 128u * it;
+          uint32_t m4;
+          uint4 v[4];
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m4) : "r"(mb_a + 8u * 96u * it));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w)
+                         : "r"(toff + xoff[k]));
+          uint32_t ea[4], eb[4], w[4][4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // bit i of a nibble -> most significant bit of byte i (no two partial products
+            // meet, so no carries); PRMT then replicates those sign bits over the 16-bit lanes
+            ea[k] = ((m4 >> (8 * k)) & 0xFu) * 0x10204080u;
+            eb[k] = ((m4 >> (8 * k + 4)) & 0xFu) * 0x10204080u;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            w[k][0] = prmt(ea[k], 0u, 0x9988u);
+            w[k][1] = prmt(ea[k], 0u, 0xBBAAu);
+            w[k][2] = prmt(eb[k], 0u, 0x9988u);
+            w[k][3] = prmt(eb[k], 0u, 0xBBAAu);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            v[k].x &= w[k][0];
+            v[k].y &= w[k][1];
+            v[k].z &= w[k][2];
+            v[k].w &= w[k][3];
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(toff + xoff[k]),
+                         "r"(v[k].x), "r"(v[k].y), "r"(v[k].z), "r"(v[k].w)
+                         : "memory");
+        }
+        // generic-proxy writes -> visible to the tensor core (async proxy), then hand over
+#ifdef BPB_ROLE_PROFILE
+        {
+          const long long tnow = clock64();
+          if (lane == 0) atomicAdd(prof_smem() + 7, static_cast<unsigned>(tnow - tm0));
+          tm0 = tnow;
+        }
+#endif
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xfull[stage]);
+#ifdef BPB_ROLE_PROFILE
+        if (lane == 0) atomicAdd(prof_smem() + 0, static_cast<unsigned>(clock64() - tm0));
+#endif
+        if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+      }
+    }
   } else {
     // ------------------------------------------------------------- epilogue warps (2..)
     // EG groups of 8 warps; group g owns this CTA's tiles g, g + EG, ... (its own staging buffer
@@ -594,6 +780,12 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       ring_advance(hs, hphase, 1, p.stages);
     }
     uint32_t ntile = grp;
+    uint32_t mbits_nx = ~0u;  // EPI_BWD_MASK: ReLU bits of the next chunk visit (prefetched)
+    if (EPI == EPI_BWD_MASK && !XF && p.mask_in != nullptr && tw.b < p.B &&
+        tw.mt * kTileM + row < p.L_out)
+      mbits_nx = __ldg(p.mask_in +
+                       ((static_cast<size_t>(tw.b) * p.L_out + tw.mt * kTileM + row) *
+                            chunks_per_row + ((tw.nt * NT) >> 6)) * 2 + half);
     for (; tw.b < p.B; tw.next(p), ntile += EG) {
       const int nt = tw.nt, b = tw.b;
       const int t0 = tw.mt * kTileM;
@@ -606,9 +798,28 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       for (int ch = 0; ch < NCH; ++ch, ++kc) {
         const int n0 = nt * NT + ch * 64;
         const int cq = half * 4;  // first 16-byte chunk of this thread's 32 columns
+        // The ReLU bits of this chunk were requested one chunk visit ago (below): a global load
+        // issued here would put an L2 / DRAM round trip inside the math phase of every visit
+        // (`long_scoreboard` was the top stall of the data-gradient launches).
         uint32_t mbits = ~0u;
-        if (EPI == EPI_BWD_MASK && p.mask_in != nullptr && valid)
-          mbits = __ldg(p.mask_in + (orow * chunks_per_row + (n0 >> 6)) * 2 + half);
+        if (EPI == EPI_BWD_MASK && !XF) {
+          mbits = mbits_nx;
+          mbits_nx = ~0u;
+          if (p.mask_in != nullptr) {
+            if (ch + 1 < NCH) {
+              if (valid)
+                mbits_nx = __ldg(p.mask_in + (orow * chunks_per_row + ((n0 + 64) >> 6)) * 2 + half);
+            } else {
+              TileWalk tn = tw;
+              for (int skip = 0; skip < EG && tn.b < p.B; ++skip) tn.next(p);
+              const int tnx = tn.mt * kTileM + row;
+              if (tn.b < p.B && tnx < p.L_out)
+                mbits_nx = __ldg(p.mask_in +
+                                 ((static_cast<size_t>(tn.b) * p.L_out + tnx) * chunks_per_row +
+                                  ((tn.nt * NT) >> 6)) * 2 + half);
+            }
+          }
+        }
 
         // ---- residual (already in shared memory: HALO box or residual ring)
         // The slot is handed back to the TMA producer only AFTER the values read from it have
@@ -623,6 +834,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         uint64_t* release = nullptr;
         if (RESID) {
           if (RING_RESID) {
+#ifdef BPB_ROLE_PROFILE
+            if (!(p.dbg_flags & 2))
+#endif
             mbar_wait_wd(&rfull[rbase + rs], rphase, p.dbg, 0x600 + rbase + rs, ntile);
             const uint8_t* src = rring + static_cast<size_t>(rbase + rs) * rstage_bytes;
 #pragma unroll
@@ -631,6 +845,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               if (PLANES == 2) rl[g] = lds128(src + kTileBytes + sw128(row, cq + g));
             }
             release = &rempty[rbase + rs];
+#ifdef BPB_ROLE_PROFILE
+            if (p.dbg_flags & 2) release = nullptr;
+#endif
             ring_advance(rs, rphase, 1, RG);
           } else {
             if (ch == 0) mbar_wait_wd(&full[hs], hphase, p.dbg, 0x700 + hs, ntile);
@@ -782,7 +999,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) o2[i] = o[i] * m[i];
-            } else {
+            } else if (!XF) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) o2[i] = ((mbits >> (g * 8 + i)) & 1u) ? o[i] : 0.f;
             }
@@ -798,7 +1015,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
               sts128(sb + off, pack8(o));
             }
           }
-          if ((EPI == EPI_FWD_R || !IS_FWD) && p.has_out2) {
+          if ((EPI == EPI_FWD_R || !IS_FWD) && !XF && p.has_out2) {
             if (PLANES == 2) {
               uint4 h, l;
               split8(o2, h, l);
@@ -820,13 +1037,20 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         fence_proxy_async();
         BPB_PHASE(12);  // proxy fence
         __syncwarp();
+#ifdef BPB_ROLE_PROFILE
+        if (lane == 0 && !(p.dbg_flags & 1)) {
+#else
         if (lane == 0) {
+#endif
           const int c0 = n0 + half * 32, r0 = t0 + q * 32;
           if (p.has_out) {
             tma_store_3d(&tm.O[0], sb, c0, r0, b);
             if (PLANES == 2) tma_store_3d(&tm.O[1], sb + 2048, c0, r0, b);
+#ifdef BPB_ROLE_PROFILE
+            if (p.dbg_flags & 8) tma_store_3d(&tm.O[0], sb, c0, r0, b);  // ablation: store twice
+#endif
           }
-          if (p.has_out2) {
+          if (!XF && p.has_out2) {
             tma_store_3d(&tm.P[0], sb2, c0, r0, b);
             if (PLANES == 2) tma_store_3d(&tm.P[1], sb2 + 2048, c0, r0, b);
           }
@@ -894,6 +1118,7 @@ struct ConvDesc {
   void* out2[2];
   const void* mask_in;
   void* mask_out;
+  const void* mask_a;  // XF: 1-bit mask of the A operand's rows [B][a_rows] (F = 64), or NULL
   const void* mult[2];
   const float* zx_in;
   int zx_div;
@@ -927,17 +1152,19 @@ static bool g_bias_mma = [] {
   return !(e && e[0] == '0');
 }();
 
-template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID>
+template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID, bool XF = false>
 static int launch_conv_eg(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
                           cudaStream_t stream) {
-  auto kern = conv_tc_kernel<EPI, NT, RESIDENT, PLANES, HALO, EG, RESID>;
+  auto kern = conv_tc_kernel<EPI, NT, RESIDENT, PLANES, HALO, EG, RESID, XF>;
   static bool configured = false;
   if (!configured) {
     BP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        max_smem_optin()));
     configured = true;
   }
-  BP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + kEpiThreads * EG), smem_bytes, stream, maps, kp));
+  BP_CHECK_CUDA(launch_pdl(kern, dim3(grid),
+                           dim3(64 + kEpiThreads * EG + (XF ? kXfThreads : 0) + (RESIDENT ? 0 : 32)),
+                           smem_bytes, stream, maps, kp));
   return 0;
 }
 
@@ -945,6 +1172,10 @@ static int launch_conv_eg(const ConvMaps& maps, const ConvKParams& kp, size_t sm
 template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, bool RESID>
 static int launch_conv(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
                        cudaStream_t stream) {
+  if constexpr (EPI == EPI_BWD_MASK && NT == 64 && RESIDENT && PLANES == 1 && RESID)
+    if (kp.mask_a != nullptr)  // conv_run planned two staging buffers / group-stable rings for it
+      return launch_conv_eg<EPI, NT, RESIDENT, 1, HALO, 2, RESID, true>(maps, kp, smem_bytes, grid,
+                                                                        stream);
 #ifdef BPB_ENABLE_EG3
   if constexpr (NT == 64 && RESIDENT)
     if (PLANES == 1 && kp.nstg == 3 && kp.epi_groups >= 3 &&
@@ -1018,6 +1249,25 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   kp.zx_in = d.zx_in;
   kp.z_out = d.z_out;
   kp.dbg = debug_buffer();
+  {
+    const char* e = getenv("BPB_DBG_FLAGS");
+    kp.dbg_flags = e ? atoi(e) : 0;
+  }
+  const bool xf = d.mask_a != nullptr;
+  if (xf) {
+    BP_REQUIRE(RESID && d.epi == EPI_BWD_MASK && n_planes == 1 && F == 64 && d.KC == 1 &&
+                   d.n_taps == 3 && d.npass == 1 && d.last_nk == 4 && g_epi_groups >= 2,
+               "%s: mask_a (operand masking in shared memory) needs the bf16 backward of an "
+               "F = 64 layer", d.who);
+    BP_REQUIRE(has_out && !has_out2 && d.mask_in == nullptr,
+               "%s: with mask_a the only output is out (the consumers mask it themselves)", d.who);
+    BP_REQUIRE(((static_cast<unsigned long long>(d.B) * d.a_rows) & 1ull) == 0,
+               "%s: mask_a needs an even B * L_in (16-byte aligned bulk copies of mask words)",
+               d.who);
+    kp.mask_a = static_cast<const uint8_t*>(d.mask_a);
+    kp.L_a = static_cast<int>(d.a_rows);
+    kp.mask_rows_total = static_cast<long long>(d.B) * static_cast<long long>(d.a_rows);
+  }
 
   // ---- shared-memory plan
   const int max_smem = max_smem_optin();
@@ -1032,7 +1282,7 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   const size_t b_tile = static_cast<size_t>(NT) * 128;
   const size_t w_res = static_cast<size_t>(d.n_wplanes) * d.n_taps * d.KC * b_tile;
   const size_t fixed = 1024 /*align slack*/ + static_cast<size_t>(F) * 4 +
-                       (2 * kMaxStages + 2 * kMaxAcc + 2 * kMaxRStages + 2) * 8 + 16;
+                       (3 * kMaxStages + 2 * kMaxAcc + 2 * kMaxRStages + 2) * 8 + 48;
   const bool can_reside = (kp.n_ntiles == 1) && (NT <= 128);
   // With two epilogue groups (bf16 path, two staging buffers) the residual ring must have an EVEN
   // number of slots: a slot is then always consumed by the same group.  With an odd ring a group
@@ -1040,7 +1290,11 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   // skipped is still in flight" from "my phase is complete" (observed as a rare deadlock).
   const bool two_groups = (n_planes == 1) && g_epi_groups >= 2;
   const bool three_groups = (n_planes == 1) && g_epi_groups >= 3 && NT == 64;
-  const int r_hi = two_groups ? 4 : 3;
+  int r_hi = two_groups ? 4 : 3;
+  if (const char* e = getenv("BPB_RSTAGES")) {  // tuning knob: residual ring slots (even: 2..4)
+    const int v = atoi(e);
+    if (v >= 2 && v <= kMaxRStages && (!two_groups || v % 2 == 0)) r_hi = v;
+  }
 
   // STRIP staging: resident weights, one tap, rows one 16-byte position apart
   const int nk16 = (d.KC - 1) * 4 + d.last_nk;
@@ -1051,7 +1305,7 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
                         d.a_row_stride_bytes == 16 && g_strip_enabled;
   bool halo = false, resident = false;
   int stages = 0, rstages = 0, nstg = 0;
-  size_t stage_bytes = 0;
+  size_t stage_bytes = 0, mstage = 0;
   int box_rows = 0;
   auto try_plan = [&](bool want_halo, bool want_res, int want_nstg, int want_rst, int min_stages) {
     const bool ring_resid = RESID && !(want_halo && is_fwd);
@@ -1074,7 +1328,9 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
     } else {
       sb = kTileBytes + (want_res ? 0 : b_tile);
     }
-    int st = static_cast<int>((static_cast<size_t>(max_smem) - used) / sb);
+    // XF: every stage also holds the mask words of its rows (+ 2: 16-byte alignment of the copy)
+    const size_t ms = xf ? static_cast<size_t>((want_halo ? rows : kTileM) + 2) * 8 : 0;
+    int st = static_cast<int>((static_cast<size_t>(max_smem) - used) / (sb + ms));
     if (st > kMaxStages) st = kMaxStages;
     if (want_halo && st > 6) st = 6;
     // same-group ownership of every HALO box slot as well
@@ -1082,7 +1338,7 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
     if (want_halo && is_fwd && want_nstg == 3) st -= st % 3;
     if (st < min_stages) return false;
     halo = want_halo; resident = want_res; nstg = want_nstg; rstages = ring_resid ? want_rst : 0;
-    stages = st; stage_bytes = sb; box_rows = rows;
+    stages = st; stage_bytes = sb; box_rows = rows; mstage = ms;
     return true;
   };
   const bool halo_ok = RESID && d.allow_halo && can_reside && span <= 128 && span > 0 &&
@@ -1116,6 +1372,11 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   kp.rstages = rstages > 0 ? rstages : 1;
   kp.ring_resid = rstages > 0 ? 1 : 0;
   kp.nstg = nstg;
+  if (xf) {
+    BP_REQUIRE(resident && nstg == 2 && (rstages % 2 == 0), "%s: mask_a: unexpected plan", d.who);
+    kp.xf_rows = halo ? box_rows : kTileM;
+    kp.mstage = static_cast<int>(mstage);
+  }
   if (halo) {
     kp.box_off = min_off;
     kp.box_bytes = box_rows * 128;
@@ -1132,7 +1393,7 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
     for (int j = 0; j < d.n_taps; ++j) kp.tap_row[j] = d.tap_off[j];
   }
   const size_t smem_bytes = fixed + (resident ? w_res : 0) + (kp.bias_mma ? kBiasMmaBytes : 0) +
-                            stages * stage_bytes +
+                            stages * (stage_bytes + mstage) +
                             static_cast<size_t>(nstg) * n_out * n_planes * kTileBytes +
                             static_cast<size_t>(rstages) * n_planes * kTileBytes;
 

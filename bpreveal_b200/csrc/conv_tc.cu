@@ -47,6 +47,9 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
     BP_REQUIRE(!(a->mask_in && a->mult_hi), "bpb_conv3_tc: give mask_in or mult, not both");
     epi = a->mult_hi ? EPI_BWD_MULT : EPI_BWD_MASK;
   }
+  if (a->mask_a)
+    BP_REQUIRE(a->mode == 1 && n_planes == 1 && !a->mult_hi && a->F == 64,
+               "bpb_conv3_tc: mask_a needs mode 1, the bf16 path, no multiplier and F = 64");
 
   ConvDesc d{};
   d.who = "bpb_conv3_tc";
@@ -84,6 +87,7 @@ extern "C" int bpb_conv3_tc(const bpb_conv3_args* a, void* stream_) {
   d.out2[1] = a->out2_lo;
   d.mask_in = a->mask_in;
   d.mask_out = a->mask_out;
+  d.mask_a = a->mask_a;
   d.mult[0] = a->mult_hi;
   d.mult[1] = a->mult_lo;
   d.zx_in = a->zx_in;

@@ -292,6 +292,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+// prmt.b32 in its default mode: selector nibble n picks byte (n & 7) of {b, a}; with bit 3 set the
+// byte's SIGN is replicated over the result byte instead (0x00 / 0xFF).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
 // Byte offset of 16-byte chunk `c` (0..7) of row `r` in a [rows x 128 B] SWIZZLE_128B tile.
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) {
   return r * 128u + ((c ^ (r & 7u)) << 4);

@@ -27,6 +27,7 @@ constexpr int kWgTile = 128 * 128;  // bytes of one [128 x 64] bf16 tile
 constexpr int kWgMaxStages = 8;
 
 constexpr int kWgMaxJobs = 12;
+constexpr int kWgMaskStage = (128 + 2) * 8;  // XF: mask words of one G tile (+ alignment slack)
 
 // One launch serves up to kWgMaxJobs independent contractions of the same shape class (all tower
 // layers of a step): job j owns the CTAs [cta_begin[j], cta_begin[j+1]) -- a share of the SMs
@@ -53,6 +54,13 @@ struct WgradKParams {
   long long a_batch_bytes[kWgMaxJobs];
   const uint8_t* a_base[kWgMaxJobs];
   long long ws_off[kWgMaxJobs];  // float offset of the job's [ksplit][(n_units*64+1)*Ncols] partials
+  // XF (bf16 path, 64 columns): job j's G operand is g (.) gmask[j] -- the tile TMA delivers is
+  // ANDed with the 1-bit ReLU mask of its rows in shared memory by the (otherwise idle) epilogue
+  // warps before the MMA reads it, so the backward never materialises gz = g (.) mask.
+  // gmask[j]: [B][g_rows[j]] uint64, or NULL; the words of a tile's rows arrive by a 1-D bulk
+  // copy on the tile's own mbarrier (see XfCopy in conv_core.cuh for the alignment scheme).
+  const uint8_t* gmask[kWgMaxJobs];
+  int g_rows[kWgMaxJobs];
   float* ws;
   unsigned* dbg;
 };
@@ -85,7 +93,10 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   uint64_t* full = bars;
   uint64_t* empty = bars + kWgMaxStages;
   uint64_t* acc_full = bars + 2 * kWgMaxStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* xfull = acc_full + 1;  // XF: "G tile masked, the MMA may read it"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull + kWgMaxStages);
+  uint8_t* mring = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~static_cast<uintptr_t>(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +124,8 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   const int nt = item % p.n_ntiles;
   const int n_units = p.n_units_j[job];
   const bool strip = p.strip[job] != 0;
+  const uint8_t* const gmask = p.gmask[job];
+  const bool xf = gmask != nullptr;
   const int u0 = grp * p.UG;
   const int nu = min(p.UG, n_units - u0);
   const bool do_db = (grp == 0);
@@ -135,6 +148,7 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
+      mbar_init(&xfull[i], 4);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -166,11 +180,25 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
         const int b = kb / tiles_per_seq;
         const int t0 = (kb % tiles_per_seq) * 128;
         mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x1100 + stage, v);
+        // XF: mask words of rows [t0, t0 + 128) of sequence b (16-byte aligned source / target)
+        long long m_src = 0;
+        uint32_t m_dst = 0, m_bytes = 0;
+        if (xf) {
+          const long long total = static_cast<long long>(p.B) * p.g_rows[job];
+          const long long g0 = static_cast<long long>(b) * p.g_rows[job] + t0;
+          m_src = g0 & ~1LL;
+          long long ce = g0 + 128;
+          if (ce > total) ce = total;
+          ce = (ce + 1) & ~1LL;
+          m_bytes = static_cast<uint32_t>((ce - m_src) * 8);
+        }
         mbar_expect_tx(&full[stage],
-                       strip ? static_cast<uint32_t>(NSUB * kWgTile + p.strip_bytes[job])
-                       : halo  ? static_cast<uint32_t>(NSUB * kWgTile + p.halo_bytes[job])
-                               : static_cast<uint32_t>((NSUB + nu) * kWgTile));
+                       (strip ? static_cast<uint32_t>(NSUB * kWgTile + p.strip_bytes[job])
+                        : halo  ? static_cast<uint32_t>(NSUB * kWgTile + p.halo_bytes[job])
+                                : static_cast<uint32_t>((NSUB + nu) * kWgTile)) + m_bytes);
         uint8_t* dst = ring + stage * stage_bytes;
+        if (xf) bulk_load_1d(mring + stage * kWgMaskStage + m_dst, gmask + m_src * 8, m_bytes,
+                             &full[stage]);
         const CUtensorMap* mg = ((p.pg_bits >> pass) & 1) ? tmG1 : tmG0;
         const CUtensorMap* ma = ((p.pa_bits >> pass) & 1) ? tmA1 : tmA0;
         for (int s = 0; s < NSUB; ++s)
@@ -222,7 +250,7 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
                                        : lbo_bits;
       for (int v = 0; v < visits; ++v) {
         const int pass = v % p.n_passes;
-        mbar_wait_wd(&full[stage], phase, p.dbg, 0x1500 + stage, v);
+        mbar_wait_wd(xf ? &xfull[stage] : &full[stage], phase, p.dbg, 0x1500 + stage, v);
 #ifdef BPB_ROLE_PROFILE
         if (v == 0) WG_STAMP(22);
 #endif
@@ -276,6 +304,64 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
       WG_STAMP(23);
     }
   } else {
+    if (xf) {
+      // XF masker: until the accumulators are final these four warps have nothing else to do.
+      // Byte c of a row's mask word covers its 16-byte chunk c.  Lanes 0-15 of a warp take the
+      // first halves (four chunks) of 16 consecutive rows, lanes 16-31 the second halves: every
+      // quarter-warp touches eight different rows at the same logical chunk, which is
+      // conflict-free under the 128-byte swizzle.  Four warps cover 64 rows per step.
+      const int xrow = (warp - 2) * 16 + (lane & 15);
+      const uint32_t xhalf = static_cast<uint32_t>(lane) >> 4;
+      uint32_t xoff[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xoff[k] = sw128(static_cast<uint32_t>(xrow), xhalf * 4u + k);
+      uint32_t stage = 0, phase = 0;
+      for (int v = 0; v < visits; ++v) {
+        const int kb = split + (v / p.n_passes) * ksplit;
+        const int b = kb / tiles_per_seq;
+        const int t0 = (kb % tiles_per_seq) * 128;
+        const uint32_t par =
+            static_cast<uint32_t>((static_cast<long long>(b) * p.g_rows[job] + t0) & 1);
+        const uint32_t tile_a = smem_u32(ring + stage * stage_bytes);
+        const uint32_t mb_a = smem_u32(mring + stage * kWgMaskStage) + 8u * par + 8u * xrow +
+                              4u * xhalf;
+        mbar_wait_wd(&full[stage], phase, p.dbg, 0x1900 + stage, v);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const uint32_t toff = tile_a + 64u * 128u * it;
+          uint32_t m4;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m4) : "r"(mb_a + 8u * 64u * it));
+          uint4 x[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(x[k].x), "=r"(x[k].y), "=r"(x[k].z), "=r"(x[k].w)
+                         : "r"(toff + xoff[k]));
+          uint32_t ea[4], eb[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ea[k] = ((m4 >> (8 * k)) & 0xFu) * 0x10204080u;
+            eb[k] = ((m4 >> (8 * k + 4)) & 0xFu) * 0x10204080u;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            x[k].x &= prmt(ea[k], 0u, 0x9988u);
+            x[k].y &= prmt(ea[k], 0u, 0xBBAAu);
+            x[k].z &= prmt(eb[k], 0u, 0x9988u);
+            x[k].w &= prmt(eb[k], 0u, 0xBBAAu);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(toff + xoff[k]),
+                         "r"(x[k].x), "r"(x[k].y), "r"(x[k].z), "r"(x[k].w)
+                         : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xfull[stage]);
+        if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+      }
+    }
     // epilogue: TMEM partial sums -> workspace slice of this split
     const int q = warp & 3;
     mbar_wait_wd(acc_full, 0, p.dbg, 0x1800, 0);
@@ -446,6 +532,7 @@ struct WgradDesc {
   unsigned long long a_inner, a_rows, a_row_stride_bytes, a_batch_stride_bytes;
   const void* g_ptr[2];
   unsigned long long g_inner, g_rows, g_row_stride_bytes, g_batch_stride_bytes;
+  const void* g_mask;  // XF: the G operand is g (.) g_mask ([B][g_rows] uint64, 64 columns) or NULL
   int n_passes, pa_bits, pg_bits, db_mask;
   bool allow_halo;
   bool allow_strip;  // A rows are one 16-byte position apart (n_taps == 1, single A plane)
@@ -554,7 +641,8 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
     if (sb > stage) stage = sb;
   }
   pl->stage_bytes = stage;
-  const size_t fixed = 1024 + kWgTile + (2 * kWgMaxStages + 2) * 8 + 16;
+  const size_t fixed = 1024 + kWgTile + (3 * kWgMaxStages + 2) * 8 + 48 +
+                       static_cast<size_t>(kWgMaxStages) * kWgMaskStage;
   const int max_smem = max_smem_optin();
   if (max_smem <= 0) return false;
   int stages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / stage);
@@ -665,6 +753,16 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
     kp.halo_bytes[j] = pl.halo_rows[j] * 128;
     kp.ws_off[j] = pl.ws_off[j];
     kp.n_units_j[j] = units[j];
+    if (d[j].g_mask != nullptr) {
+      BP_REQUIRE(pl.NT == 64 && d[j].Ncols == 64 && d[j].n_passes == 1 &&
+                     d[j].g_row_stride_bytes == 128 &&
+                     d[j].g_batch_stride_bytes == 128ull * d[j].g_rows &&
+                     ((static_cast<unsigned long long>(d[j].B) * d[j].g_rows) & 1ull) == 0,
+                 "%s: gz_mask (operand masking in shared memory) needs the bf16 path, F = 64 and "
+                 "an even B * L_out", d0.who);
+      kp.gmask[j] = static_cast<const uint8_t*>(d[j].g_mask);
+      kp.g_rows[j] = static_cast<int>(d[j].g_rows);
+    }
     if (want_strip[j] && pl.n_groups == 1) {
       kp.strip[j] = 1;
       kp.strip_bytes[j] = (128 + 8 * units[j]) * 16;
@@ -762,6 +860,9 @@ static int fill_wgrad3_desc(const char* who, const bpb_wgrad3_args* a, bp::Wgrad
   d.g_rows = a->L_out;
   d.g_row_stride_bytes = static_cast<unsigned long long>(a->F) * 2;
   d.g_batch_stride_bytes = d.g_row_stride_bytes * a->L_out;
+  d.g_mask = a->gz_mask;
+  BP_REQUIRE(!a->gz_mask || (!precise && a->F == 64), "%s: gz_mask needs the bf16 path and F = 64",
+             who);
   // hi*hi, lo*hi, hi*lo; the bias gradient adds the hi and lo planes of gz (passes 0 and 2)
   d.n_passes = precise ? 3 : 1;
   d.pa_bits = 0b010;
@@ -899,7 +1000,8 @@ extern "C" long long bpb_wgrad_tower_input_ws_bytes(int n_layers, int B, const i
 
 extern "C" int bpb_wgrad_tower_input(const bpb_wgrad3_args* layers, int n_layers, int L_in0,
                                      int L_out0, int W, int Fw, const bpb_bf16* x8,
-                                     const bpb_bf16* gz0_hi, float* dw1, float* db1, int L_last,
+                                     const bpb_bf16* gz0_hi, const uint64_t* gz0_mask, float* dw1,
+                                     float* db1, int L_last,
                                      int W_out, int T, int H, const bpb_bf16* act_last,
                                      const bpb_bf16* d8, float* dpw, float* dcw, float* ws,
                                      long long ws_bytes, void* stream_) {
@@ -918,6 +1020,7 @@ extern "C" int bpb_wgrad_tower_input(const bpb_wgrad3_args* layers, int n_layers
   BP_REQUIRE(Fw <= F && L_out0 == L_in0 - W + 1, "bpb_wgrad_tower_input: bad input-conv geometry");
   d[n_layers] = input_conv_wgrad_desc("bpb_wgrad_tower_input", B, L_in0, L_out0, W, Fw, F, x8,
                                       gz0_hi, nullptr, dw1, db1);
+  d[n_layers].g_mask = gz0_mask;
   // single pass: only bit 0 of the plane selectors is read; align them with the tower's
   d[n_layers].pa_bits = d[0].pa_bits;
   d[n_layers].pg_bits = d[0].pg_bits;

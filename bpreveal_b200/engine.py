@@ -481,14 +481,36 @@ class SoloNet:
         # previous one) and leaves one gz buffer per layer; every tower weight gradient is then
         # computed by ONE split-K launch (bpb_wgrad3_multi) instead of one launch + reduction per
         # layer.
-        gcur = self._sub(ws["g"][nL % 2], Ls[nL])
-        gzcur = ws["gzl"][nL]
+        xf = self._xf_backward(ws)
         if not fused:
             ops.heads_pack_grad(ws["dlogits"], ws["dlogcounts"], Ls[nL], cfg.outputFilterWidth,
                                 self.cp, planes, ws["d8"], dpb=g["prof_b"], dcb=g["cnt_b"])
         if not ws.get("wg_joint_heads"):
             ops.heads_wgrad(aL, ws["d8"], cfg.outputFilterWidth, cfg.numFilters, cfg.T, cfg.H,
                             self.cp, planes, g["prof_w"], g["cnt_w"], ws["scratch"])
+        if xf:
+            # XF (bf16 path, F = 64): nothing ever stores gz = g (.) mask.  ws['gzl'][i] holds the
+            # UNMASKED gradient g_i; the data-gradient and weight-gradient kernels AND the staged
+            # operand with the layer's 1-bit ReLU mask in shared memory (bpb_conv3_args.mask_a,
+            # bpb_wgrad3_args.gz_mask).  Per layer the chain reads g and writes g: 2 planes
+            # instead of 4 (gz + g in, g + gz out).
+            gl, mk = ws["gzl"], ws["masks"]
+            ops.heads_dgrad(ws["d8"], self.w_hd_op, ws["B"], Ls[nL], cfg.outputFilterWidth, cfg.Fp,
+                            self.cp, planes, g=gl[nL])
+            for i in range(nL - 1, -1, -1):
+                d = 2 ** (i + 1)
+                ops.conv3(gl[i + 1], self.w_bwd[i], (0, -d, -2 * d), 1, Ls[i], resid=gl[i + 1],
+                          resid_off=-d, out=gl[i], mask_a=mk[i + 1])
+            layers = [(ws["acts"][i], gl[i + 1], 2 ** (i + 1), g["dil_w"][i], g["dil_b"][i],
+                       mk[i + 1]) for i in range(nL)]
+            ops.wgrad_tower_input(layers, ws["x8"], gl[0], cfg.inputFilterWidth, cfg.numFilters,
+                                  g["conv1_w"], g["conv1_b"], ws["scratch"],
+                                  heads=(aL, ws["d8"], cfg.outputFilterWidth, cfg.T, cfg.H,
+                                         g["prof_w"], g["cnt_w"]) if ws.get("wg_joint_heads")
+                                  else None, gz0_mask=mk[0])
+            return
+        gcur = self._sub(ws["g"][nL % 2], Ls[nL])
+        gzcur = ws["gzl"][nL]
         ops.heads_dgrad(ws["d8"], self.w_hd_op, ws["B"], Ls[nL], cfg.outputFilterWidth, cfg.Fp,
                         self.cp, planes, g=gcur, gz=gzcur, mask_in=ws["masks"][nL])
         for i in range(nL - 1, -1, -1):
@@ -517,6 +539,20 @@ class SoloNet:
                            g["dil_b"][i], ws["scratch"])
         ops.input_conv_wgrad(ws["x8"], ws["gzl"][0], cfg.inputFilterWidth, cfg.numFilters,
                              g["conv1_w"], g["conv1_b"], ws["scratch"])
+
+    def _xf_backward(self, ws):
+        """True when the backward masks its operands in shared memory instead of materialising gz
+        planes (BPB_XF=1): bf16 path, F = 64, the joint weight-gradient launch, even row counts
+        (the mask words travel as 16-byte aligned bulk copies).  Opt-in: it removes ~200 MB of
+        DRAM writes per C1 step and is bit-identical, but measured no faster (the
+        data gradient is bound by its per-tile pipeline, not by HBM -- the gz planes it re-reads
+        are L2 hits -- and the masker warps cost the weight-gradient launch 8 us)."""
+        cfg = self.cfg
+        if cfg.precise or cfg.Fp != 64 or not ws.get("wg_joint") or cfg.numLayers < 1:
+            return False
+        if os.environ.get("BPB_XF", "0") != "1":
+            return False
+        return all((ws["B"] * L) % 2 == 0 for L in cfg.lengths())
 
     def apply_adam(self, grad_scale=1.0):
         # the optimiser step counter lives on the device so that the update replays inside a graph

@@ -55,7 +55,7 @@ def device_info():
 
 
 def conv3(inp, w, tap_off, mode, L_out, bias=None, resid=None, resid_off=0, out=None, out2=None,
-          mask_out=None, mask_in=None, mult=None, zx_in=None, zx_div=1, z_out=None):
+          mask_out=None, mask_in=None, mult=None, zx_in=None, zx_div=1, z_out=None, mask_a=None):
     """bpb_conv3_tc.  ``w`` is the prepared operand tensor [planes, 3, F, F] (bf16)."""
     lib = _lib.load()
     in_hi, in_lo = _planes(inp)
@@ -85,6 +85,9 @@ def conv3(inp, w, tap_off, mode, L_out, bias=None, resid=None, resid_off=0, out=
     m_hi, m_lo = _planes(mult)
     a.mult_hi, a.mult_lo = _p(m_hi), _p(m_lo)
     a.zx_in, a.zx_div, a.z_out = _p(zx_in), zx_div, _p(z_out)
+    a.mask_a = _p(mask_a)
+    if mask_a is not None:
+        assert tuple(mask_a.shape) == (B, L_in, F // 64) and mask_a.dtype == torch.int64
     check(lib.bpb_conv3_tc(C.byref(a), _stream()), "bpb_conv3_tc")
 
 
@@ -95,7 +98,7 @@ def wgrad3_ws_bytes(B, L_out, F, precise):
     return n
 
 
-def wgrad3(act, gz, dil, dw, db, ws):
+def wgrad3(act, gz, dil, dw, db, ws, gz_mask=None):
     lib = _lib.load()
     a_hi, a_lo = _planes(act)
     g_hi, g_lo = _planes(gz)
@@ -106,6 +109,9 @@ def wgrad3(act, gz, dil, dw, db, ws):
     assert dw.dtype == torch.float32 and dw.numel() == 3 * F * F
     a.dw, a.db = _p(dw), _p(db)
     a.ws, a.ws_bytes = _p(ws), ws.numel() * ws.element_size()
+    if gz_mask is not None:
+        assert tuple(gz_mask.shape) == (B, g_hi.shape[1], F // 64) and gz_mask.dtype == torch.int64
+    a.gz_mask = _p(gz_mask)
     check(lib.bpb_wgrad3_tc(C.byref(a), _stream()), "bpb_wgrad3_tc")
 
 
@@ -150,6 +156,23 @@ def input_conv_fwd(x8, w_op, w_planes, W, Fw, bias, F, out, mask_out=None, z_out
     check(lib.bpb_input_conv_fwd(C.byref(a), _stream()), "bpb_input_conv_fwd")
 
 
+def _fill_wgrad3(a, layer):
+    """(act planes, gz planes, dilation, dw, db[, gz_mask]) -> bpb_wgrad3_args.  With ``gz_mask``
+    ([B, L_out, 1] int64 ReLU bits) the gz planes hold the UNMASKED gradient and the kernel masks
+    the staged operand in shared memory (bf16 path, F = 64)."""
+    act, gz, dil, dw, db = layer[:5]
+    gz_mask = layer[5] if len(layer) > 5 else None
+    a_hi, a_lo = _planes(act)
+    g_hi, g_lo = _planes(gz)
+    B, L_in, F = a_hi.shape
+    a.B, a.L_in, a.L_out, a.F, a.dil = B, L_in, g_hi.shape[1], F, dil
+    a.act_hi, a.act_lo, a.gz_hi, a.gz_lo = _p(a_hi), _p(a_lo), _p(g_hi), _p(g_lo)
+    a.dw, a.db = _p(dw), _p(db)
+    if gz_mask is not None:
+        assert tuple(gz_mask.shape) == (B, g_hi.shape[1], F // 64) and gz_mask.dtype == torch.int64
+    a.gz_mask = _p(gz_mask)
+
+
 def wgrad3_multi_ws_bytes(B, L_outs, F):
     arr = (C.c_int * len(L_outs))(*L_outs)
     n = _lib.load().bpb_wgrad3_multi_ws_bytes(len(L_outs), B, arr, F)
@@ -163,13 +186,8 @@ def wgrad3_multi(layers, ws):
     one launch (bpb_wgrad3_multi)."""
     lib = _lib.load()
     arr = (Wgrad3Args * len(layers))()
-    for a, (act, gz, dil, dw, db) in zip(arr, layers):
-        a_hi, a_lo = _planes(act)
-        g_hi, g_lo = _planes(gz)
-        B, L_in, F = a_hi.shape
-        a.B, a.L_in, a.L_out, a.F, a.dil = B, L_in, g_hi.shape[1], F, dil
-        a.act_hi, a.act_lo, a.gz_hi, a.gz_lo = _p(a_hi), _p(a_lo), _p(g_hi), _p(g_lo)
-        a.dw, a.db = _p(dw), _p(db)
+    for a, layer in zip(arr, layers):
+        _fill_wgrad3(a, layer)
     check(lib.bpb_wgrad3_multi(arr, len(layers), _p(ws), ws.numel() * ws.element_size(),
                                _stream()), "bpb_wgrad3_multi")
 
@@ -182,19 +200,15 @@ def wgrad_tower_input_ws_bytes(B, L_outs, F, L_out0, W, L_last=0, W_out=0):
                                                       W_out)
 
 
-def wgrad_tower_input(layers, x8, gz0, W, Fw, dw1, db1, ws, heads=None):
+def wgrad_tower_input(layers, x8, gz0, W, Fw, dw1, db1, ws, heads=None, gz0_mask=None):
     """Every tower weight gradient of a step, the input convolution's and (``heads`` =
     (act_last planes, d8, W_out, T, H, dpw, dcw)) the heads' in one launch (bf16 path).  layers as
-    in ``wgrad3_multi``; gz0 = gradient planes at the input conv's output."""
+    in ``wgrad3_multi``; gz0 = gradient planes at the input conv's output (with ``gz0_mask``: the
+    unmasked gradient and the input convolution's ReLU bits)."""
     lib = _lib.load()
     arr = (Wgrad3Args * len(layers))()
-    for a, (act, gz, dil, dw, db) in zip(arr, layers):
-        a_hi, a_lo = _planes(act)
-        g_hi, g_lo = _planes(gz)
-        B, L_in, F = a_hi.shape
-        a.B, a.L_in, a.L_out, a.F, a.dil = B, L_in, g_hi.shape[1], F, dil
-        a.act_hi, a.act_lo, a.gz_hi, a.gz_lo = _p(a_hi), _p(a_lo), _p(g_hi), _p(g_lo)
-        a.dw, a.db = _p(dw), _p(db)
+    for a, layer in zip(arr, layers):
+        _fill_wgrad3(a, layer)
     g0_hi, _ = _planes(gz0)
     if heads is not None:
         act_last, d8, W_out, T, H, dpw, dcw = heads
@@ -203,7 +217,7 @@ def wgrad_tower_input(layers, x8, gz0, W, Fw, dw1, db1, ws, heads=None):
     else:
         hargs = (0, 0, 0, 0, None, None, None, None)
     check(lib.bpb_wgrad_tower_input(arr, len(layers), x8.shape[1], g0_hi.shape[1], W, Fw, _p(x8),
-                                    _p(g0_hi), _p(dw1), _p(db1), *hargs, _p(ws),
+                                    _p(g0_hi), _p(gz0_mask), _p(dw1), _p(db1), *hargs, _p(ws),
                                     ws.numel() * ws.element_size(), _stream()),
           "bpb_wgrad_tower_input")
 

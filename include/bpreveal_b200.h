@@ -57,6 +57,10 @@ int bpb_debug_dump(unsigned* host_out, int n);
  *   mode 1 (backward): v = acc + (0 <= t + resid_off < L_res ? resid[b, t + resid_off, n] : 0)
  *                      out[b,t,n] = v
  *                      out2[b,t,n] = v * (mask_in bit | mult_in[b,t,n] | 1)
+ *                      with mask_a (bf16 path, F = 64, B * L_in even): `in` is read as
+ *                      in[b,s,c] * (bit c of mask_a[b*L_in + s]) -- the ReLU mask of the layer
+ *                      above is applied to the staged operand in shared memory, so the training
+ *                      backward passes the unmasked gradient g and never stores g (.) mask
  * w is [n_wplanes][3][F][F] bf16 with the contraction index innermost.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -76,6 +80,7 @@ typedef struct {
   const float* zx_in;                /* [B/zx_div][L_out][F] fp32 or NULL */
   int zx_div;
   float* z_out;                      /* [B][L_out][F] fp32 or NULL */
+  const uint64_t* mask_a;            /* [B][L_in][F/64] or NULL (mode 1 only, see above) */
 } bpb_conv3_args;
 int bpb_conv3_tc(const bpb_conv3_args* a, void* stream);
 
@@ -94,6 +99,10 @@ typedef struct {
   float* db;                       /* [F] fp32, overwritten, or NULL */
   float* ws;                       /* workspace of bpb_wgrad3_ws_bytes() bytes */
   long long ws_bytes;
+  const uint64_t* gz_mask;         /* [B][L_out] or NULL.  bf16 path, F = 64, B * L_out even: gz_hi
+                                      holds the UNMASKED gradient g and the operand is
+                                      g[b,t,n] * (bit n of gz_mask[b*L_out + t]), masked in shared
+                                      memory (see bpb_conv3_args.mask_a) */
 } bpb_wgrad3_args;
 long long bpb_wgrad3_ws_bytes(int B, int L_out, int F, int precise);
 int bpb_wgrad3_tc(const bpb_wgrad3_args* a, void* stream);
@@ -147,8 +156,9 @@ int bpb_input_conv_fwd(const bpb_input_conv_args* a, void* stream);
 long long bpb_wgrad_tower_input_ws_bytes(int n_layers, int B, const int* L_out, int F, int L_out0,
                                          int W, int L_last, int W_out);
 int bpb_wgrad_tower_input(const bpb_wgrad3_args* layers, int n_layers, int L_in0, int L_out0, int W,
-                          int Fw, const bpb_bf16* x8, const bpb_bf16* gz0_hi, float* dw1,
-                          float* db1, int L_last, int W_out, int T, int H,
+                          int Fw, const bpb_bf16* x8, const bpb_bf16* gz0_hi,
+                          const uint64_t* gz0_mask /* NULL, or as bpb_wgrad3_args.gz_mask */,
+                          float* dw1, float* db1, int L_last, int W_out, int T, int H,
                           const bpb_bf16* act_last, const bpb_bf16* d8, float* dpw, float* dcw,
                           float* ws, long long ws_bytes, void* stream);
 

@@ -337,6 +337,111 @@ def test_dilated_layer_weight_gradient(dev, B, L, Fn, d, precise):
     assert Hh.rel_err(db.cpu().numpy(), gv.sum(dim=(0, 1)).numpy()) < tol
 
 
+XF_CASES = [  # (B, L_in, dilation): F = 64, bf16 -- HALO boxes (d <= 64) and SLAB tiles (d >= 128)
+    (2, 300, 2), (2, 421, 8), (2, 700, 64), (2, 900, 128), (2, 1301, 256), (4, 2047, 512),
+    (64, 3066, 2), (64, 2046, 512),
+]
+
+
+@pytest.mark.parametrize("B,L,d", XF_CASES, ids=["-".join(map(str, c)) for c in XF_CASES])
+def test_dilated_layer_data_gradient_masked_operand(dev, B, L, d):
+    """The training backward without gz planes: the operand of the data gradient is the UNMASKED
+    gradient g' of the layer above, ANDed with that layer's ReLU bits in shared memory
+    (bpb_conv3_args.mask_a):  g_in = g'[. - d] + sum_j (g' (.) bits)[. - j d] W_j^T.
+    Odd row counts exercise the 16-byte alignment of the mask-word bulk copies."""
+    from bpreveal_b200 import ops
+    Fn = 64
+    g = torch.Generator().manual_seed(12)
+    L_g = L - 2 * d
+    gp = torch.randn((B, L_g, Fn), generator=g).to(dev)
+    w = (torch.randn((3, Fn, Fn), generator=g) / (3 * Fn) ** 0.5).to(dev)
+    gpp = split(gp, False)
+    _, bwd = prep_w(w, Fn, False, dev)
+    out = ops.new_planes(B, L, Fn, False, dev)
+    bits = (torch.rand((B, L_g, Fn), generator=g) > 0.4).to(dev)
+    ops.conv3(gpp, bwd, (0, -d, -2 * d), 1, L, resid=gpp, resid_off=-d, out=out,
+              mask_a=pack_mask(bits))
+    torch.cuda.synchronize()
+    a = torch.zeros((B, L, Fn), dtype=torch.float64, requires_grad=True)
+    zf = O._conv1d_cl(a, w_eff(w, False), None, dilation=d)
+    (zf * (val(gpp) * bits.double().cpu())).sum().backward()
+    ref = a.grad.clone()
+    ref[:, d:L - d, :] += val(gpp)
+    e1 = Hh.rel_err(val(out).numpy(), ref.numpy())
+    assert e1 < 6e-3, f"g rel err {e1}"
+    # the materialised path on gz = g' (.) bits gives the same bf16 plane bit for bit
+    gzp = split(gp * bits, False)
+    out_m = ops.new_planes(B, L, Fn, False, dev)
+    ops.conv3(gzp, bwd, (0, -d, -2 * d), 1, L, resid=gpp, resid_off=-d, out=out_m)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], out_m[0]), "masked-operand path differs from the materialised one"
+
+
+@pytest.mark.parametrize("B,L,d", XF_CASES, ids=["-".join(map(str, c)) for c in XF_CASES])
+def test_dilated_layer_weight_gradient_masked_operand(dev, B, L, d):
+    """dW_j = sum a[t + j d]^T (g (.) bits)[t], db = sum g (.) bits with the bits applied to the
+    staged tile in shared memory (bpb_wgrad3_args.gz_mask): bit-identical to the same launch on a
+    materialised gz plane."""
+    from bpreveal_b200 import ops
+    Fn = 64
+    g = torch.Generator().manual_seed(13)
+    L_out = L - 2 * d
+    a = split(torch.randn((B, L, Fn), generator=g).to(dev), False)
+    gfull = torch.randn((B, L_out, Fn), generator=g).to(dev)
+    bits = (torch.rand((B, L_out, Fn), generator=g) > 0.4).to(dev)
+    res = []
+    for masked in (True, False):
+        gz = split(gfull if masked else gfull * bits, False)
+        dw = torch.empty((3, Fn, Fn), dtype=torch.float32, device=dev)
+        db = torch.empty((Fn,), dtype=torch.float32, device=dev)
+        ws = torch.empty((ops.wgrad3_ws_bytes(B, L_out, Fn, False) // 4,), dtype=torch.float32,
+                         device=dev)
+        ops.wgrad3(a, gz, d, dw, db, ws, gz_mask=pack_mask(bits) if masked else None)
+        torch.cuda.synchronize()
+        res.append((dw, db))
+    av, gv = val(a), val(split(gfull * bits, False))
+    ref = torch.stack([torch.einsum("btc,btn->cn", av[:, j * d:j * d + L_out, :], gv)
+                       for j in range(3)])
+    assert Hh.rel_err(res[0][0].cpu().numpy(), ref.numpy()) < 2e-3
+    assert Hh.rel_err(res[0][1].cpu().numpy(), gv.sum(dim=(0, 1)).numpy()) < 2e-3
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+def test_masked_operand_backward_replays_bit_for_bit(dev):
+    """C1's nine layer shapes at batch 64 through the masked-operand data gradient: 20 replays of
+    a 10-launch CUDA graph must reproduce the first launch (the masker warps write the staged
+    tile between the TMA load and the MMA: a missing fence or an early slot release shows here)."""
+    from bpreveal_b200 import ops
+    B, Fn, L = 64, 64, 3066
+    g = torch.Generator().manual_seed(19)
+    for i in range(9):
+        d = 2 ** (i + 1)
+        L_out = L - 2 * d
+        gp = split(torch.randn((B, L_out, Fn), generator=g).to(dev), False)
+        w = (torch.randn((3, Fn, Fn), generator=g) / 14).to(dev)
+        _, bwd = prep_w(w, Fn, False, dev)
+        gin = ops.new_planes(B, L, Fn, False, dev)
+        mask_a = pack_mask((torch.rand((1, L_out, Fn), generator=g) > 0.5).to(dev)).expand(
+            B, L_out, 1).contiguous()
+
+        def f_bwd():
+            ops.conv3(gp, bwd, (0, -d, -2 * d), 1, L, resid=gp, resid_off=-d, out=gin,
+                      mask_a=mask_a)
+
+        f_bwd()
+        torch.cuda.synchronize()
+        first = gin[0].clone()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(10):
+                f_bwd()
+        for _ in range(20):
+            gr.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(first, gin[0]), f"layer {i} (d={d}): replay differs"
+        L = L_out
+
+
 def test_every_c1_tower_shape_many_launches_in_a_graph(dev):
     """Each of C1's nine layer shapes at batch 64, forward and backward, 30 replays of a
     10-launch CUDA graph; every replay must reproduce the first launch bit for bit.  This test

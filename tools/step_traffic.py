@@ -53,7 +53,7 @@ def family(name):
     """Kernel name (demangled, with template arguments) -> the family names of bench.py."""
     if "conv_tc_kernel" in name:
         targs = [a.strip().split(")")[-1] for a in name.split("<", 1)[1].split(">", 1)[0].split(",")]
-        epi, resid = targs[0], targs[-1] == "1"
+        epi, resid = targs[0], targs[6] == "1"  # (EPI, NT, RESIDENT, PLANES, HALO, EG, RESID[, XF])
         if not resid:
             return "input_conv_fwd" if epi in ("0", "1", "2") else "heads_dgrad"
         return "conv3_fwd" if epi in ("0", "1", "2") else "conv3_dgrad"
