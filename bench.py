@@ -179,6 +179,44 @@ def cpu_pisa_rate(cfg, n_bases, numShuffles):
     return n_bases / (time.perf_counter() - t0)
 
 
+def tf_train_rate(cfg, steps, warm, batch):
+    """The REAL reference: bpreveal.models.soloModel under TensorFlow on the host
+    cores, Keras Adam, ``train_on_batch`` on the synthetic batch -- only where tensorflow, keras,
+    tensorflow_probability and the reference package import (tests/test_tf_probe.probe; neither
+    this image nor the GPU box has them).  -> (seq/s, seconds per step) or (None, reason)."""
+    os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
+    try:
+        from tests.test_tf_probe import probe
+        mods, why = probe()
+    except Exception as e:  # noqa: BLE001
+        return None, f"probe failed: {e}"
+    if mods is None:
+        return None, why
+    import numpy as np
+    from bpreveal_b200 import synthetic
+    keras, tf = mods["keras"], mods["tensorflow"]
+    heads = [{"head-name": f"h{i}", "num-tasks": t, "profile-loss-weight": 1.0,
+              "counts-loss-weight": 1.0} for i, t in enumerate(cfg["headTasks"])]
+    model = mods["models"].soloModel(cfg["inputLength"], cfg["outputLength"], cfg["numFilters"],
+                                     cfg["numLayers"], cfg["inputFilterWidth"],
+                                     cfg["outputFilterWidth"], heads, "solo")
+    lams = [tf.Variable(1.0) for _ in heads]
+    model.compile(optimizer=keras.optimizers.Adam(learning_rate=0.004),
+                  loss=[mods["losses"].multinomialNll] * len(heads) +
+                       [mods["losses"].weightedMse(l) for l in lams])
+    x = synthetic.sequences(batch, cfg["inputLength"], seed=20261019).astype(np.float32)
+    ys = [synthetic.profiles(batch, cfg["outputLength"], t, seed=20261019 + i)
+          for i, t in enumerate(cfg["headTasks"])]
+    y = ys + [np.log(v.sum(axis=(1, 2))).astype(np.float32) for v in ys]
+    for _ in range(warm):
+        model.train_on_batch(x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model.train_on_batch(x, y)
+    sec = (time.perf_counter() - t0) / steps
+    return batch / sec, sec
+
+
 def run_reference(args):
     """``--impl reference``: the reference's own CPU implementation of the path.  The real one
     (TensorFlow / Keras) cannot run here -- TensorFlow is not in the image and the reference has
@@ -201,11 +239,25 @@ def run_reference(args):
         batch = args.batch or (64 if args.config != "c4" else 4)
         if args.config == "c4":
             steps, warm = min(steps, 2), 1
-        rate, sec, cores, _ = cpu_train_rate(cfg, steps, warm, batch)
+        kind = "port"
+        tf_rate, tf_info = (None, "not a solo-model config")
+        if args.config in ("c1", "c4"):
+            tf_rate, tf_info = tf_train_rate(cfg if isinstance(cfg, dict) else vars(cfg), steps,
+                                             warm, batch)
         metric, unit = "BPNet train seq/s", "seq/s"
-        sample = (f"{steps} full {args.config.upper()} train steps of batch {batch} after {warm} "
-                  "warm-up, fp32 torch-CPU restatement of the Keras graph (TensorFlow unavailable "
-                  "offline)" + ("; residual tower only" if args.config == "c3" else ""))
+        if tf_rate is not None:
+            rate, sec, kind = tf_rate, tf_info, "tf"
+            sample = (f"{steps} full {args.config.upper()} train steps of batch {batch} after "
+                      f"{warm} warm-up: the reference's own Keras graph (bpreveal.models.soloModel) "
+                      "under TensorFlow on the host cores")
+        else:
+            rate, sec, cores, _ = cpu_train_rate(cfg, steps, warm, batch)
+            sample = (f"{steps} full {args.config.upper()} train steps of batch {batch} after "
+                      f"{warm} warm-up, fp32 torch-CPU restatement of the Keras graph (the real "
+                      f"one is unavailable: {tf_info})" +
+                      ("; residual tower only" if args.config == "c3" else ""))
+    if args.config == "c5":
+        kind = "port"
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": metric, "value": rate, "unit": unit,
@@ -214,7 +266,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config],
                    "note": "CPU host cores, one process (rank 0)"},
-        "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": kind,
                          "sample": sample},
         "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -442,6 +442,37 @@ def test_masked_operand_backward_replays_bit_for_bit(dev):
         L = L_out
 
 
+@pytest.mark.parametrize("name,cfg", [("C1", C1), ("C3R", C3R)])
+def test_masked_operand_step_equals_materialised_step(dev, monkeypatch, name, cfg):
+    """BPB_XF=1 (no gz planes: operands masked in shared memory by the data- and weight-gradient
+    kernels) against the default backward on the full-size network: every gradient and both
+    losses bit for bit, and the same parameters after two optimiser steps."""
+    B = 4
+    x = torch.tensor(O.synthetic_sequences(B, cfg["inputLength"], seed=43), device=dev)
+    counts = [O.synthetic_profiles(B, 1000, t, seed=43 + i, meanReads=150.0)
+              for i, t in enumerate(cfg["headTasks"])]
+    counts = torch.tensor(np.concatenate(counts, axis=2), device=dev)
+    res = {}
+    for xf in ("0", "1"):
+        monkeypatch.setenv("BPB_XF", xf)
+        net, _ = build(cfg, False, dev, scale=1.0)
+        net.enable_training()
+        ws = net._workspace(B, "train")
+        assert net._xf_backward(ws) == (xf == "1")
+        ws["x"].copy_(x)
+        ws["counts"].copy_(counts)
+        net.forward_backward_into(ws)
+        torch.cuda.synchronize()
+        g = net.grads_flat.clone()
+        losses = ws["losses"].clone()
+        for _ in range(2):
+            net.train_step(x, counts, lr=0.004)
+        torch.cuda.synchronize()
+        res[xf] = (g, losses, net.params.flat.clone())
+    for a, b, what in zip(res["0"], res["1"], ("gradients", "losses", "parameters after 2 steps")):
+        assert torch.equal(a, b), f"{name}: {what} differ between the two backward paths"
+
+
 def test_every_c1_tower_shape_many_launches_in_a_graph(dev):
     """Each of C1's nine layer shapes at batch 64, forward and backward, 30 replays of a
     10-launch CUDA graph; every replay must reproduce the first launch bit for bit.  This test
