@@ -52,6 +52,27 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// The same for a kernel of CTA pairs (cluster of two along x).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl_pairs(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                             cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #define BP_CHECK_CUDA(expr)                                                              \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

@@ -99,6 +99,7 @@ struct ConvKParams {
   long long mask_rows_total;   // B * L_a (even)
   int xf_rows;                 // rows of one staged A tile (HALO: the box, SLAB: 128)
   int mstage;                  // bytes of one stage's mask words (multiple of 16)
+  int cg2;                     // 1: CTA pairs (cta_group::2), tiles_per_seq counts 256-row pair tiles
   int dbg_flags;               // PROFILE builds only (BPB_DBG_FLAGS): 1 no stores, 2 no residual
                                // loads, 4 no masking work -- ablations for the role profile
   unsigned* dbg;
@@ -162,8 +163,8 @@ __device__ __forceinline__ float gt0_flag(float v) {
 // advanced by gridDim.x tiles per iteration.
 struct TileWalk {
   int b, mt, nt;
-  __device__ __forceinline__ void init(const ConvKParams& p) {
-    const unsigned tile = blockIdx.x;  // < 2^16, divisors < 2^16: the multiply-high is exact
+  __device__ __forceinline__ void init(const ConvKParams& p, unsigned first = blockIdx.x) {
+    const unsigned tile = first;  // < 2^16, divisors < 2^16: the multiply-high is exact
     const unsigned t1 = p.inv_ntiles ? __umulhi(tile, p.inv_ntiles) : tile;
     nt = static_cast<int>(tile - t1 * static_cast<unsigned>(p.n_ntiles));
     const unsigned bb = p.inv_tiles_per_seq ? __umulhi(t1, p.inv_tiles_per_seq) : t1;
@@ -208,10 +209,24 @@ __device__ __forceinline__ XfCopy xf_copy(const ConvKParams& p, int b, int row0)
   return c;
 }
 
-template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID, bool XF = false>
+template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID, bool XF = false,
+          bool CG2 = false>
 __global__ void __launch_bounds__(64 + kEpiThreads * EG + (XF ? kXfThreads : 0) +
                                   (RESIDENT ? 0 : 32), 1)
 conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
+  // CG2: CTA pairs (cluster of two) issue M = 256 MMAs on streamed weights: each CTA stages its
+  // own 128 rows of A and HALF of the weight tile, so the shared-memory pipe moves 8 KB instead
+  // of 12 KB per MMA (the bound of the F = 512 launches).  The even CTA (the
+  // leader) owns the operand-full and accumulator-empty barriers and issues; both CTAs run
+  // producers and epilogues on their own half of the pair's 256 rows.
+  static_assert(!CG2 || (!RESIDENT && NT == 256 && PLANES == 1 && !HALO && !XF && EG == 2 && RESID),
+                "CG2: streamed-weight bf16 tower layers");
+  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
+  // CG2: the pair walks pair-tiles of 256 rows (p.tiles_per_seq counts those); this CTA's half
+  const unsigned first_tile = CG2 ? (blockIdx.x >> 1) : blockIdx.x;
+  auto tile_row0 = [crank](int mt) -> int {
+    return (CG2 ? 2 * mt + static_cast<int>(crank) : mt) * kTileM;
+  };
   static_assert(!XF || (EPI == EPI_BWD_MASK && NT == 64 && RESIDENT && PLANES == 1 && RESID),
                 "XF: bf16 backward of an F = 64 layer with resident weights");
   // accumulator stages: a multiple of the group count, so a stage (and its mbarriers) always
@@ -220,9 +235,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   static_assert(ACC <= kMaxAcc && ACC * NT <= 512, "TMEM accumulator stages");
   constexpr int NCH = NT / 64;
   constexpr uint32_t TMEM_COLS = (ACC * NT <= 128) ? 128 : (ACC * NT <= 256 ? 256 : 512);
-  constexpr int B_TILE_BYTES = NT * 128;
+  constexpr int B_TILE_BYTES = (CG2 ? NT / 2 : NT) * 128;  // CG2: this CTA's half of the tile
   constexpr int SLAB_BYTES = kTileBytes + (RESIDENT ? 0 : B_TILE_BYTES);
-  constexpr uint32_t IDESC = umma_idesc_bf16(128, NT, 0, 0);
+  constexpr uint32_t IDESC = umma_idesc_bf16(CG2 ? 256 : 128, NT, 0, 0);
   constexpr bool IS_FWD = (EPI <= EPI_FWD_R);
   // the forward residual a[t + d] already sits in the HALO box
   constexpr bool RING_RESID = RESID && !(HALO && IS_FWD);
@@ -286,7 +301,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       uint64_t* b0 = is_ring ? &full[lane] : is_acc ? &acc_full[lane - 16] : &rfull[lane - 24];
       uint64_t* b1 = is_ring ? &empty[lane] : is_acc ? &acc_empty[lane - 16] : &rempty[lane - 24];
       // HALO forward: the box is released by the MMA commit AND by the 8 epilogue warps
-      const uint32_t c1 = is_ring ? ((HALO && IS_FWD && RESID) ? 9u : 1u) : 8u;
+      // (CG2: the leader's accumulator-empty barriers collect the epilogue warps of both CTAs)
+      const uint32_t c1 = is_ring ? ((HALO && IS_FWD && RESID) ? 9u : 1u)
+                                  : ((CG2 && is_acc) ? 16u : 8u);
       if (is_ring || is_acc || is_res) {
         mbar_init(b0, 1);
         mbar_init(b1, c1);
@@ -326,12 +343,15 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         }
       }
       __syncwarp();
-      tmem_alloc<TMEM_COLS>(tmem_slot);
+      if (CG2) tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
+      else tmem_alloc<TMEM_COLS>(tmem_slot);
     }
     tc_fence_before();
     named_bar_sync(8, blockDim.x);
     tc_fence_after();
   }
+  // CG2: no remote arrive / remotely signalled load before both CTAs initialised their barriers
+  if (CG2) cluster_sync_all();
   const uint32_t tmem_base = (warp == 0) ? 0u : *tmem_slot;
 #ifdef BPB_ROLE_PROFILE
 #define BPB_STAMP(slot) prof_smem()[slot] = static_cast<unsigned>(clock64() - t_kernel_start)
@@ -355,9 +375,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       uint32_t stage = 0, phase = 0, ntile = 0;
       uint32_t rsg[3] = {0, 0, 0}, rphg[3] = {0, 0, 0};
       TileWalk tw;
-      for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
+      for (tw.init(p, first_tile); tw.b < p.B; tw.next(p), ++ntile) {
         const int nt = tw.nt, b = tw.b;
-        const int t0 = tw.mt * kTileM;
+        const int t0 = tile_row0(tw.mt);
         if (HALO) {
           if (ntile == 0) BPB_STAMP(29);
           mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
@@ -399,10 +419,18 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0x100 + stage, ntile);
             XfCopy xc{0, 0u, 0u};
             if (XF) xc = xf_copy(p, b, t0 + p.tap_row[j]);
-            mbar_expect_tx(&full[stage], SLAB_BYTES + xc.bytes);
             uint8_t* dst = ring + static_cast<size_t>(stage) * SLAB_BYTES;
-            tma_load_3d(&tm.A[RESIDENT ? pass : ((p.pa_bits >> pass) & 1)], dst, &full[stage],
-                        c * 64, t0 + p.tap_row[j], b);
+            if (CG2) {
+              // the leader arms its barrier with the bytes of both CTAs; a completion of the
+              // peer that lands first only drives the pending count negative for a moment
+              if (crank == 0) mbar_expect_tx(&full[stage], 2 * SLAB_BYTES);
+              tma_load_3d_cg2(&tm.A[(p.pa_bits >> pass) & 1], dst, &full[stage], c * 64,
+                              t0 + p.tap_row[j], b);
+            } else {
+              mbar_expect_tx(&full[stage], SLAB_BYTES + xc.bytes);
+              tma_load_3d(&tm.A[RESIDENT ? pass : ((p.pa_bits >> pass) & 1)], dst, &full[stage],
+                          c * 64, t0 + p.tap_row[j], b);
+            }
             if (XF && xc.bytes)
               bulk_load_1d(mring + static_cast<size_t>(stage) * p.mstage + xc.dst_off,
                            p.mask_a + xc.src_row * 8, xc.bytes, &full[stage]);
@@ -431,8 +459,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------- MMA issuer
-    if (elect_one()) {
+    // ------------------------------------------------------------- MMA issuer (CG2: the leader's)
+    if ((!CG2 || crank == 0) && elect_one()) {
       if (RESIDENT) mbar_wait_wd(w_full, 0, p.dbg, 0x300);
       if (bias_mma) mbar_wait_wd(b_full, 0, p.dbg, 0x310);
       BPB_STAMP(28);
@@ -455,8 +483,16 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       const uint32_t ring_lo = smem_u32(ring) >> 4;
       const uint32_t stage_lo = static_cast<uint32_t>(stage_bytes) >> 4;
       TileWalk tw;
-      for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
-        mbar_wait_wd(&acc_empty[as], aphase ^ 1, p.dbg, 0x400 + as, ntile);
+      for (tw.init(p, first_tile); tw.b < p.B; tw.next(p), ++ntile) {
+        if (CG2) {  // arrivals come from both CTAs: cluster-scope acquire
+          uint32_t spins = 0;
+          while (!mbar_try_wait_cluster(&acc_empty[as], aphase ^ 1)) {
+            if (++spins == (1u << 24)) mbar_timeout(p.dbg, 0x400 + as, aphase ^ 1, ntile);
+            if (spins == (1u << 24) + (1u << 22)) __trap();
+          }
+        } else {
+          mbar_wait_wd(&acc_empty[as], aphase ^ 1, p.dbg, 0x400 + as, ntile);
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * NT;
         // bias: D = ones[128 x 16] * bias_tile[16 x 64] opens the accumulation of the tile
@@ -582,16 +618,22 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 if (k < nk) {
-                  umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
-                            umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, accum);
+                  if (CG2)
+                    umma_bf16_cg2(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
+                                  umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, accum);
+                  else
+                    umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024),
+                              umma_smem_desc(b_addr + k * 32, 0, 1024), IDESC, accum);
                   accum = 1;
                 }
             }
-            umma_commit(&empty[stage]);
+            if (CG2) umma_commit_cg2(&empty[stage]);  // frees the stage in both CTAs
+            else umma_commit(&empty[stage]);
             if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(&acc_full[as]);
+        if (CG2) umma_commit_cg2(&acc_full[as]);
+        else umma_commit(&acc_full[as]);
         if (++as == ACC) { as = 0; aphase ^= 1; }
       }
     }
@@ -608,7 +650,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     if (elect_one()) {
       uint32_t stage = 0, phase = 0, ntile = 0;
       TileWalk tw;
-      for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
+      for (tw.init(p, first_tile); tw.b < p.B; tw.next(p), ++ntile) {
         const int nsteps = p.n_taps * p.KC * p.npass;
         for (int step = 0; step < nsteps; ++step) {
           const int pass = step % p.npass;
@@ -616,8 +658,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           const int j = step / (p.npass * p.KC);
           mbar_wait_wd(&empty[stage], phase ^ 1, p.dbg, 0xF00 + stage, ntile);
           const int wp = (p.pw_bits >> (2 * pass)) & 3;
-          tma_load_2d(&tm.W, ring + static_cast<size_t>(stage) * SLAB_BYTES + kTileBytes,
-                      &full[stage], c * 64, (wp * p.n_taps + j) * p.F + tw.nt * NT);
+          if (CG2)  // this CTA's half of the N = 256 rows, signalled on the leader's barrier
+            tma_load_2d_cg2(&tm.W, ring + static_cast<size_t>(stage) * SLAB_BYTES + kTileBytes,
+                            &full[stage], c * 64,
+                            (wp * p.n_taps + j) * p.F + tw.nt * NT + static_cast<int>(crank) * (NT / 2));
+          else
+            tma_load_2d(&tm.W, ring + static_cast<size_t>(stage) * SLAB_BYTES + kTileBytes,
+                        &full[stage], c * 64, (wp * p.n_taps + j) * p.F + tw.nt * NT);
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         }
       }
@@ -645,8 +692,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     for (int k = 0; k < 4; ++k) xoff[k] = sw128(static_cast<uint32_t>(xrow), xhalf * 4u + k);
     uint32_t stage = 0, phase = 0, ntile = 0;
     TileWalk tw;
-    for (tw.init(p); tw.b < p.B; tw.next(p), ++ntile) {
-      const int t0 = tw.mt * kTileM;
+    for (tw.init(p, first_tile); tw.b < p.B; tw.next(p), ++ntile) {
+      const int t0 = tile_row0(tw.mt);
       for (int sub = 0; sub < nsub; ++sub) {
         const int row0 = t0 + (HALO ? p.box_off : p.tap_row[sub]);
         const uint32_t par =
@@ -773,7 +820,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     const uint32_t rbase = static_cast<uint32_t>(grp) * RG;
     uint32_t as = 0, aphase = 0, rs = 0, rphase = 0, hs = 0, hphase = 0, kc = 0;
     TileWalk tw;
-    tw.init(p);
+    tw.init(p, first_tile);
     for (int skip = 0; skip < grp && tw.b < p.B; ++skip) {  // this group's first tile
       tw.next(p);
       ring_advance(as, aphase, 1, ACC);
@@ -782,13 +829,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
     uint32_t ntile = grp;
     uint32_t mbits_nx = ~0u;  // EPI_BWD_MASK: ReLU bits of the next chunk visit (prefetched)
     if (EPI == EPI_BWD_MASK && !XF && p.mask_in != nullptr && tw.b < p.B &&
-        tw.mt * kTileM + row < p.L_out)
+        tile_row0(tw.mt) + row < p.L_out)
       mbits_nx = __ldg(p.mask_in +
-                       ((static_cast<size_t>(tw.b) * p.L_out + tw.mt * kTileM + row) *
+                       ((static_cast<size_t>(tw.b) * p.L_out + tile_row0(tw.mt) + row) *
                             chunks_per_row + ((tw.nt * NT) >> 6)) * 2 + half);
     for (; tw.b < p.B; tw.next(p), ntile += EG) {
       const int nt = tw.nt, b = tw.b;
-      const int t0 = tw.mt * kTileM;
+      const int t0 = tile_row0(tw.mt);
       const int bz = (EPI == EPI_FWD_R) ? b / p.zx_div : 0;
       const int t = t0 + row;
       const bool valid = t < p.L_out;
@@ -812,7 +859,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
             } else {
               TileWalk tn = tw;
               for (int skip = 0; skip < EG && tn.b < p.B; ++skip) tn.next(p);
-              const int tnx = tn.mt * kTileM + row;
+              const int tnx = tile_row0(tn.mt) + row;
               if (tn.b < p.B && tnx < p.L_out)
                 mbits_nx = __ldg(p.mask_in +
                                  ((static_cast<size_t>(tn.b) * p.L_out + tnx) * chunks_per_row +
@@ -893,7 +940,10 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         if (ch == NCH - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          if (lane == 0) {
+            if (CG2) mbar_arrive_leader(&acc_empty[as]);
+            else mbar_arrive(&acc_empty[as]);
+          }
         }
         BPB_PHASE(9);   // acc wait + TMEM load
 
@@ -1080,7 +1130,14 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (CG2) {
+    // neither CTA may free its TMEM, or exit with barriers the other still signals, before both
+    // are through
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
+  } else if (warp == 1) {
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
 #ifdef BPB_ROLE_PROFILE
   if (threadIdx.x < 32 && p.dbg != nullptr && blockIdx.x < 8) {
     unsigned v = prof_smem()[threadIdx.x];
@@ -1152,19 +1209,20 @@ static bool g_bias_mma = [] {
   return !(e && e[0] == '0');
 }();
 
-template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID, bool XF = false>
+template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, int EG, bool RESID, bool XF = false,
+          bool CG2 = false>
 static int launch_conv_eg(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
                           cudaStream_t stream) {
-  auto kern = conv_tc_kernel<EPI, NT, RESIDENT, PLANES, HALO, EG, RESID, XF>;
+  auto kern = conv_tc_kernel<EPI, NT, RESIDENT, PLANES, HALO, EG, RESID, XF, CG2>;
   static bool configured = false;
   if (!configured) {
     BP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        max_smem_optin()));
     configured = true;
   }
-  BP_CHECK_CUDA(launch_pdl(kern, dim3(grid),
-                           dim3(64 + kEpiThreads * EG + (XF ? kXfThreads : 0) + (RESIDENT ? 0 : 32)),
-                           smem_bytes, stream, maps, kp));
+  const dim3 block(64 + kEpiThreads * EG + (XF ? kXfThreads : 0) + (RESIDENT ? 0 : 32));
+  if (CG2) BP_CHECK_CUDA(launch_pdl_pairs(kern, dim3(grid), block, smem_bytes, stream, maps, kp));
+  else BP_CHECK_CUDA(launch_pdl(kern, dim3(grid), block, smem_bytes, stream, maps, kp));
   return 0;
 }
 
@@ -1172,6 +1230,11 @@ static int launch_conv_eg(const ConvMaps& maps, const ConvKParams& kp, size_t sm
 template <int EPI, int NT, bool RESIDENT, int PLANES, bool HALO, bool RESID>
 static int launch_conv(const ConvMaps& maps, const ConvKParams& kp, size_t smem_bytes, int grid,
                        cudaStream_t stream) {
+  if constexpr ((EPI == EPI_FWD || EPI == EPI_BWD_MASK) && NT == 256 && !RESIDENT && PLANES == 1 &&
+                !HALO && RESID)
+    if (kp.cg2)
+      return launch_conv_eg<EPI, NT, false, 1, false, 2, RESID, false, true>(maps, kp, smem_bytes,
+                                                                             grid, stream);
   if constexpr (EPI == EPI_BWD_MASK && NT == 64 && RESIDENT && PLANES == 1 && RESID)
     if (kp.mask_a != nullptr)  // conv_run planned two staging buffers / group-stable rings for it
       return launch_conv_eg<EPI, NT, RESIDENT, 1, HALO, 2, RESID, true>(maps, kp, smem_bytes, grid,
@@ -1279,7 +1342,14 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   }
   const int span = max_off - min_off;
   const int n_out = has_out + has_out2;
-  const size_t b_tile = static_cast<size_t>(NT) * 128;
+  // CTA pairs (cta_group::2) for the streamed-weight bf16 training launches: BPB_CG2=0 turns it off
+  const bool g_cg2 = [] {  // read per call: the parity tests run both shapes in one process
+    const char* e = getenv("BPB_CG2");
+    return !(e && e[0] == '0');
+  }();
+  bool cg2 = RESID && NT == 256 && n_planes == 1 && g_cg2 && g_epi_groups >= 2 &&
+             (d.epi == EPI_FWD || d.epi == EPI_BWD_MASK) && !xf && sm_count() >= 2;
+  size_t b_tile = static_cast<size_t>(cg2 ? NT / 2 : NT) * 128;
   const size_t w_res = static_cast<size_t>(d.n_wplanes) * d.n_taps * d.KC * b_tile;
   const size_t fixed = 1024 /*align slack*/ + static_cast<size_t>(F) * 4 +
                        (3 * kMaxStages + 2 * kMaxAcc + 2 * kMaxRStages + 2) * 8 + 48;
@@ -1344,6 +1414,13 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   const bool halo_ok = RESID && d.allow_halo && can_reside && span <= 128 && span > 0 &&
                        d.last_nk == 4;
   bool planned = false;
+  if (cg2) {  // needs the two-group plan (two staging buffers, even residual ring)
+    planned = try_plan(false, false, 2, r_hi, 3) || try_plan(false, false, 2, 2, 2);
+    if (!planned) {
+      cg2 = false;
+      b_tile = static_cast<size_t>(NT) * 128;
+    }
+  }
   // Three epilogue groups (3 staging buffers, residual sub-rings of one slot) when shared memory
   // still leaves a useful operand ring; the weights must be resident (F = 64 towers).
   if (three_groups && halo_ok) planned = try_plan(true, true, 3, 3, is_fwd ? 3 : 2);
@@ -1405,7 +1482,9 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
                               d.a_row_stride_bytes, d.a_batch_stride_bytes, 64, a_box))
       return 3;
   const uint64_t wrows = static_cast<uint64_t>(d.n_wplanes) * d.n_taps * F;
-  if (!make_tmap_2d(&maps.W, d.w_ptr, static_cast<uint64_t>(d.KC) * 64, wrows, 64, NT)) return 3;
+  if (!make_tmap_2d(&maps.W, d.w_ptr, static_cast<uint64_t>(d.KC) * 64, wrows, 64,
+                    cg2 ? NT / 2 : NT))
+    return 3;
   for (int pl = 0; pl < n_planes; ++pl) {
     if (has_out && !make_tmap_3d_sw64(&maps.O[pl], d.out[pl], F, d.L_out, d.B)) return 3;
     if (has_out2 && !make_tmap_3d_sw64(&maps.P[pl], d.out2[pl], F, d.L_out, d.B)) return 3;
@@ -1413,12 +1492,15 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
       return 3;
   }
 
+  kp.cg2 = cg2 ? 1 : 0;
+  if (cg2) kp.tiles_per_seq = (kp.tiles_per_seq + 1) / 2;  // pair tiles of 256 rows
   const int total_tiles = kp.B * kp.tiles_per_seq * kp.n_ntiles;
-  int grid = sm_count();
-  if (grid > total_tiles) grid = total_tiles;
-  kp.step_nt = grid % kp.n_ntiles;
-  kp.step_mt = (grid / kp.n_ntiles) % kp.tiles_per_seq;
-  kp.step_b = grid / (kp.n_ntiles * kp.tiles_per_seq);
+  int walkers = cg2 ? sm_count() / 2 : sm_count();  // CTAs, or CTA pairs
+  if (walkers > total_tiles) walkers = total_tiles;
+  const int grid = cg2 ? 2 * walkers : walkers;
+  kp.step_nt = walkers % kp.n_ntiles;
+  kp.step_mt = (walkers / kp.n_ntiles) % kp.tiles_per_seq;
+  kp.step_b = walkers / (kp.n_ntiles * kp.tiles_per_seq);
   auto inv32 = [](int d) -> unsigned {
     return d <= 1 ? 0u : static_cast<unsigned>(((1ull << 32) + static_cast<unsigned>(d) - 1) / static_cast<unsigned>(d));
   };

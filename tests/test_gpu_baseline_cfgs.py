@@ -473,6 +473,50 @@ def test_masked_operand_step_equals_materialised_step(dev, monkeypatch, name, cf
         assert torch.equal(a, b), f"{name}: {what} differ between the two backward paths"
 
 
+CG2_CASES = [  # (B, L_in, dilation): F = 512; odd and even counts of 128-row tiles, one tile
+    (1, 132, 2), (1, 600, 2), (2, 644, 2), (3, 900, 128), (1, 1400, 512), (2, 2308, 64),
+]
+
+
+@pytest.mark.parametrize("B,L,d", CG2_CASES, ids=["-".join(map(str, c)) for c in CG2_CASES])
+def test_cta_pair_launches_equal_single_cta_launches(dev, monkeypatch, B, L, d):
+    """F = 512 training launches run as CTA pairs (cta_group::2: M = 256 MMAs, each CTA stages
+    half of the weight tile); BPB_CG2=0 selects the single-CTA kernel.  Forward (output + ReLU
+    bits) and data gradient (g and gz) must agree bit for bit -- every output element sums the
+    same products in the same order -- including when the second half of the last pair tile lies
+    beyond the sequence."""
+    from bpreveal_b200 import ops
+    Fn = 512
+    g = torch.Generator().manual_seed(21)
+    L_out = L - 2 * d
+    x = split(torch.randn((B, L, Fn), generator=g).to(dev), False)
+    gz = split(torch.randn((B, L_out, Fn), generator=g).to(dev), False)
+    gp = split(torch.randn((B, L_out, Fn), generator=g).to(dev), False)
+    w = (torch.randn((3, Fn, Fn), generator=g) / (3 * Fn) ** 0.5).to(dev)
+    bias = (torch.randn((Fn,), generator=g) * 0.1).to(dev)
+    fwd, bwd = prep_w(w, Fn, False, dev)
+    mask_in = pack_mask((torch.rand((B, L, Fn), generator=g) > 0.5).to(dev))
+    res = {}
+    for cg2 in ("0", "1"):
+        monkeypatch.setenv("BPB_CG2", cg2)
+        out = ops.new_planes(B, L_out, Fn, False, dev)
+        mask = torch.zeros((B, L_out, Fn // 64), dtype=torch.int64, device=dev)
+        ops.conv3(x, fwd, (0, d, 2 * d), 0, L_out, bias=bias, resid=x, resid_off=d, out=out,
+                  mask_out=mask)
+        gin = ops.new_planes(B, L, Fn, False, dev)
+        gz2 = ops.new_planes(B, L, Fn, False, dev)
+        ops.conv3(gz, bwd, (0, -d, -2 * d), 1, L, resid=gp, resid_off=-d, out=gin, out2=gz2,
+                  mask_in=mask_in)
+        torch.cuda.synchronize()
+        res[cg2] = (out[0], mask, gin[0], gz2[0])
+    for a, b, what in zip(res["0"], res["1"], ("forward", "ReLU bits", "g", "gz")):
+        assert torch.equal(a, b), f"{what} differs between CTA-pair and single-CTA launches"
+    xe = val(x)
+    ref = torch.relu(O._conv1d_cl(xe, w_eff(w, False), bias.double().cpu(), dilation=d)) + \
+        xe[:, d:L - d, :]
+    assert Hh.rel_err(val((res["1"][0], None)).numpy(), ref.numpy()) < 6e-3
+
+
 def test_every_c1_tower_shape_many_launches_in_a_graph(dev):
     """Each of C1's nine layer shapes at batch 64, forward and backward, 30 replays of a
     10-launch CUDA graph; every replay must reproduce the first launch bit for bit.  This test
