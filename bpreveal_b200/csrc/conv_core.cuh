@@ -827,12 +827,6 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       ring_advance(hs, hphase, 1, p.stages);
     }
     uint32_t ntile = grp;
-    uint32_t mbits_nx = ~0u;  // EPI_BWD_MASK: ReLU bits of the next chunk visit (prefetched)
-    if (EPI == EPI_BWD_MASK && !XF && p.mask_in != nullptr && tw.b < p.B &&
-        tile_row0(tw.mt) + row < p.L_out)
-      mbits_nx = __ldg(p.mask_in +
-                       ((static_cast<size_t>(tw.b) * p.L_out + tile_row0(tw.mt) + row) *
-                            chunks_per_row + ((tw.nt * NT) >> 6)) * 2 + half);
     for (; tw.b < p.B; tw.next(p), ntile += EG) {
       const int nt = tw.nt, b = tw.b;
       const int t0 = tile_row0(tw.mt);
@@ -845,28 +839,12 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       for (int ch = 0; ch < NCH; ++ch, ++kc) {
         const int n0 = nt * NT + ch * 64;
         const int cq = half * 4;  // first 16-byte chunk of this thread's 32 columns
-        // The ReLU bits of this chunk were requested one chunk visit ago (below): a global load
-        // issued here would put an L2 / DRAM round trip inside the math phase of every visit
-        // (`long_scoreboard` was the top stall of the data-gradient launches).
+        // (Prefetching these bits one chunk visit ahead was measured: -15 % on an L2-hot d = 2
+        // launch, +2 % on the real step -- the extra tile-walk arithmetic costs more than the
+        // load it hides once the masks come out of L2 anyway.)
         uint32_t mbits = ~0u;
-        if (EPI == EPI_BWD_MASK && !XF) {
-          mbits = mbits_nx;
-          mbits_nx = ~0u;
-          if (p.mask_in != nullptr) {
-            if (ch + 1 < NCH) {
-              if (valid)
-                mbits_nx = __ldg(p.mask_in + (orow * chunks_per_row + ((n0 + 64) >> 6)) * 2 + half);
-            } else {
-              TileWalk tn = tw;
-              for (int skip = 0; skip < EG && tn.b < p.B; ++skip) tn.next(p);
-              const int tnx = tile_row0(tn.mt) + row;
-              if (tn.b < p.B && tnx < p.L_out)
-                mbits_nx = __ldg(p.mask_in +
-                                 ((static_cast<size_t>(tn.b) * p.L_out + tnx) * chunks_per_row +
-                                  ((tn.nt * NT) >> 6)) * 2 + half);
-            }
-          }
-        }
+        if (EPI == EPI_BWD_MASK && !XF && p.mask_in != nullptr && valid)
+          mbits = __ldg(p.mask_in + (orow * chunks_per_row + (n0 >> 6)) * 2 + half);
 
         // ---- residual (already in shared memory: HALO box or residual ring)
         // The slot is handed back to the TMA producer only AFTER the values read from it have

@@ -69,7 +69,7 @@ struct WgradMaps {
   CUtensorMap A[2][kWgMaxJobs], G[2][kWgMaxJobs];
 };
 
-template <int NT>
+template <int NT, bool XF = false>
 __global__ void __launch_bounds__(192, 1)
 wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   constexpr int NSUB = NT / 64;
@@ -124,8 +124,8 @@ wgrad3_tc_kernel(const __grid_constant__ WgradMaps tm, const WgradKParams p) {
   const int nt = item % p.n_ntiles;
   const int n_units = p.n_units_j[job];
   const bool strip = p.strip[job] != 0;
-  const uint8_t* const gmask = p.gmask[job];
-  const bool xf = gmask != nullptr;
+  const uint8_t* const gmask = XF ? p.gmask[job] : nullptr;
+  const bool xf = XF && gmask != nullptr;  // (compile-time off: the default launch pays nothing)
   const int u0 = grp * p.UG;
   const int nu = min(p.UG, n_units - u0);
   const bool do_db = (grp == 0);
@@ -660,10 +660,10 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
   return true;
 }
 
-template <int NT>
+template <int NT, bool XF = false>
 static int launch_wgrad(const WgradMaps& maps, const WgradKParams& kp, size_t smem, int grid,
                         cudaStream_t stream) {
-  auto kern = wgrad3_tc_kernel<NT>;
+  auto kern = wgrad3_tc_kernel<NT, XF>;
   static bool configured = false;
   if (!configured) {
     BP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -790,7 +790,10 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
   }
   kp.cta_begin[n_jobs] = cta;
   int rc;
-  if (pl.NT == 64) rc = launch_wgrad<64>(maps, kp, pl.smem_bytes, pl.grid, stream);
+  bool any_xf = false;
+  for (int j = 0; j < n_jobs; ++j) any_xf = any_xf || kp.gmask[j] != nullptr;
+  if (any_xf) rc = launch_wgrad<64, true>(maps, kp, pl.smem_bytes, pl.grid, stream);  // NT == 64
+  else if (pl.NT == 64) rc = launch_wgrad<64>(maps, kp, pl.smem_bytes, pl.grid, stream);
   else if (pl.NT == 128) rc = launch_wgrad<128>(maps, kp, pl.smem_bytes, pl.grid, stream);
   else rc = launch_wgrad<256>(maps, kp, pl.smem_bytes, pl.grid, stream);
   if (rc) return rc;
