@@ -5,12 +5,13 @@ Restates the behaviour of the reference's ``callbacks.py`` -- ``FixLossCallback`
 callbacks it configures (``EarlyStopping(monitor="val_loss", mode="min",
 restore_best_weights=True)``, ``ModelCheckpoint(save_best_only=True)``,
 ``ReduceLROnPlateau(factor=0.5)``; Keras 3 semantics recalled from its source, not in the tree).
-Pure host logic: no kernels here.  ``DisplayCallback`` (the curses log protocol of
-``showTrainingProgress``) is out of scope.
+``DisplayCallback`` (:392-716) emits the log-line protocol that ``showTrainingProgress`` renders.
+Pure host logic: no kernels here.
 """
 from __future__ import annotations
 
 import re
+import time
 
 import numpy as np
 
@@ -59,6 +60,9 @@ class Callback:
 
     def on_train_end(self, logs=None):
         pass
+
+    # per-batch hooks: ``Model.fit`` calls them only on callbacks that define them, with a lazy
+    # ``logs`` mapping (reading a value synchronises with the device)
 
 
 def _head_loss_names(logs, headName):
@@ -282,11 +286,190 @@ class ApplyAdaptiveCountsLoss(Callback):
         self.resetCallbacks()
 
 
+class DisplayCallback(Callback):
+    """The training log in the line protocol of the reference's display program
+    (callbacks.py:392-716; rendered by showTrainingProgress): every line is
+
+        ``∬<row>∬1∬<window>∬<text>``
+
+    with window ``E`` (epoch table, INFO level: name, this epoch's value, the previous epoch's),
+    ``λ`` (counts-loss weights, DEBUG), ``B`` / ``BH`` (running batch losses, DEBUG, at most once a
+    second plus the first and last batch) and ``V`` (validation batch counter, DEBUG); ``<text>``
+    is the row's fields laid out at their columns, each value 11 characters wide.  Row order:
+    Epoch, total and validation loss, per head the profile then the counts losses (train, val),
+    then early-stopping / plateau state, learning rate and the timers."""
+
+    SPACER = "EPOCH_SPACER"
+
+    def __init__(self, plateauCallback, earlyStopCallback, adaptiveLossCallback, trainBatchGen,
+                 valBatchGen):
+        self.plateauCallback = plateauCallback
+        self.earlyStopCallback = earlyStopCallback
+        self.adaptiveLossCallback = adaptiveLossCallback
+        self.numBatches = len(trainBatchGen) if trainBatchGen is not None else 0
+        self.numValBatches = len(valBatchGen) if valBatchGen is not None else 0
+        self.params = {}
+        self.numEpochs = 0
+        self.epochNumber = self.batchNumber = 0
+        self.rowsEpoch, self.rowsBatch = {}, {}
+        self.ignoreMetrics = []
+        self.maxLen = 0
+        self.prevEpochLogs = None
+        self.trainBeginTime = self.lastEpochEndTime = self.curEpochWaitTime = None
+        self.lastBatchEndTime = self.lastValBatchEndTime = 0.0
+        self.firstBatchTime = self.lastBatchTime = 0.0
+        self.firstValBatchTime = self.lastValBatchTime = 0.0
+
+    # -- layout ---------------------------------------------------------------------------
+    def _calcPositions(self, names):
+        """Rows of both tables from the first batch's metric names (callbacks.py:455-530)."""
+        prof, cnt, unknown = [], [], []
+        for name in names:
+            found = False
+            for head in self.adaptiveLossCallback.heads:
+                hn = re.escape(head["head-name"])
+                if re.fullmatch(fr".*profile_{hn}_.*multinomial_nll", name):
+                    prof += [name, "val_" + name, self.SPACER]
+                elif re.fullmatch(fr".*logcounts_{hn}_.*reweightable_mse", name):
+                    cnt += [name, "val_" + name, self.SPACER]
+                elif re.fullmatch(fr".*profile_{hn}_.*loss", name) or \
+                        re.fullmatch(fr".*logcounts_{hn}_.*loss", name):
+                    # the same number under its output's name: shown once, descriptively
+                    self.ignoreMetrics += [name, "val_" + name]
+                else:
+                    continue
+                found = True
+                break
+            if not found and name not in ("lr", "learning_rate", "epoch", "batch", "loss"):
+                unknown.append(name)
+        if unknown:
+            raise ValueError(f"{unknown} includes unknown loss component, not {prof} / {cnt}")
+        epochOrder = ["Epoch", self.SPACER, "loss", "val_loss", self.SPACER] + prof + cnt + [
+            "Best epoch", "Best loss", "Epochs until earlystop", "lr", "Epochs until LR plateau",
+            self.SPACER, "Setup time", "Training time", "Validation time", "Seconds / epoch",
+            "Minutes to earlystop", "Minutes elapsed"]
+        batchOrder = [n for n in ["batch", "loss"] + prof + cnt if n != self.SPACER]
+        self.rowsEpoch = {n: i + 2 for i, n in enumerate(epochOrder)}  # spacers take a row
+        self.rowsBatch = {n: i + 2 for i, n in enumerate(batchOrder)}
+        self.maxLen = max(len(n) for n in epochOrder)
+
+    @staticmethod
+    def formatStr(val):
+        """Eleven characters: right-aligned text, integer, %.3f, or ``a / b`` for a pair."""
+        if isinstance(val, str):
+            return f"{val:>11s}"
+        if isinstance(val, (bool, np.bool_)):
+            return f"{str(val):>11s}"
+        if isinstance(val, (int, np.integer)):
+            return f"{int(val):>11d}"
+        if isinstance(val, (float, np.floating)):
+            return f"{float(val):>11.3f}"
+        if isinstance(val, tuple) and len(val) == 2:
+            if all(isinstance(v, (int, np.integer)) for v in val):
+                return f"{int(val[0]):>4d} / {int(val[1]):>4d}"
+            if val[1] is None:
+                return f"{str(val):>11s}"
+        return "     FMT_ERR"
+
+    def _emit(self, rows, writer, window):
+        """rows: [(row, [(column, text), ...]), ...] -> one protocol line per row."""
+        for row, fields in rows:
+            width = max(col + len(text) for col, text in fields)
+            chars = [" "] * width
+            for col, text in fields:
+                chars[col:col + len(text)] = text
+            writer(f"∬{row}∬1∬{window}∬{''.join(chars)}")
+
+    # -- Keras hooks ----------------------------------------------------------------------
+    def on_train_begin(self, logs=None):
+        self.trainBeginTime = time.perf_counter()
+        total = self.params.get("epochs", self.params.get("nb_epochs"))
+        if total is not None:
+            self.numEpochs = total
+
+    def on_epoch_begin(self, epoch, logs=None):
+        now = time.perf_counter()
+        self.epochNumber, self.batchNumber = epoch, 0
+        self.firstBatchTime = self.firstValBatchTime = now + 1e10
+        if self.lastEpochEndTime is not None:
+            self.curEpochWaitTime = now - self.lastEpochEndTime
+
+    def on_train_batch_end(self, batch, logs=None):
+        logs = logs if logs is not None else {}
+        now = time.perf_counter()
+        self.firstBatchTime = min(now, self.firstBatchTime)
+        self.lastBatchTime = now
+        if not self.rowsEpoch:
+            self._calcPositions(list(logs.keys()))
+        if now - self.lastBatchEndTime > 1.0 or batch in (0, self.numBatches - 1):
+            from . import logUtils
+            self.lastBatchEndTime = now
+            self.batchNumber = batch
+            vals = {k: logs[k] for k in logs.keys()}  # (reads the running means back)
+            vals["batch"] = (batch, self.numBatches - 1)
+            rows = [(self.rowsBatch[k], [(1, k), (self.maxLen + 2, self.formatStr(v))])
+                    for k, v in vals.items() if k not in self.ignoreMetrics and k in self.rowsBatch]
+            self._emit(rows, logUtils.debug, "BH" if batch == 0 else "B")
+
+    def on_test_batch_end(self, batch, logs=None):
+        now = time.perf_counter()
+        self.firstValBatchTime = min(now, self.firstValBatchTime)
+        self.lastValBatchTime = now
+        if now - self.lastValBatchEndTime > 1.0 or batch in (0, self.numValBatches - 1):
+            from . import logUtils
+            self.lastValBatchEndTime = now
+            row = max(self.rowsBatch.values()) if self.rowsBatch else 2
+            self._emit([(row, [(1, "Eval batch"),
+                               (20, self.formatStr((batch, self.numValBatches - 1)))])],
+                       logUtils.debug, "V")
+
+    def on_epoch_end(self, epoch, logs=None):
+        from . import logUtils
+        if logs is None:
+            logUtils.warning("Received empty logs at epoch end.")
+            logs = {}
+        logs = {k: (float(v) if isinstance(v, (np.floating, np.integer)) else v)
+                for k, v in logs.items()}
+        if not self.rowsEpoch:
+            self._calcPositions([k for k in logs if not k.startswith("val_")])
+        es, pl = self.earlyStopCallback, self.plateauCallback
+        now = time.perf_counter()
+        logs["Best epoch"] = int(getattr(es, "best_epoch", 0))
+        logs["Best loss"] = float(es.best)
+        logs["Epochs until earlystop"] = (int(es.wait), int(es.patience))
+        logs["Epochs until LR plateau"] = (int(pl.wait), int(pl.patience))
+        if self.lastEpochEndTime is not None:
+            per = now - self.lastEpochEndTime
+            logs["Seconds / epoch"] = per
+            logs["Minutes to earlystop"] = per * (es.patience - es.wait) / 60
+        if self.curEpochWaitTime is not None:
+            logs["Setup time"] = self.curEpochWaitTime
+        logs["Training time"] = self.lastBatchTime - self.firstBatchTime
+        logs["Validation time"] = self.lastValBatchTime - self.firstValBatchTime
+        self.lastEpochEndTime = now
+        logs["Minutes elapsed"] = (now - (self.trainBeginTime or now)) / 60
+        logs["Epoch"] = (self.epochNumber, self.numEpochs)
+        lr = getattr(getattr(self.model, "optimizer", None), "learning_rate", None)
+        logs["lr"] = f"{float(lr):10.7f}" if lr is not None else "n/a"
+        rows = []
+        for k, v in logs.items():
+            if k in self.ignoreMetrics or k == "learning_rate" or k not in self.rowsEpoch:
+                continue
+            fields = [(1, k), (self.maxLen + 2, self.formatStr(v))]
+            if self.prevEpochLogs is not None:
+                fields.append((self.maxLen + 16, self.formatStr(self.prevEpochLogs.get(k, ""))))
+            rows.append((self.rowsEpoch[k], fields))
+        self._emit(rows, logUtils.info, "E")
+        lam = self.adaptiveLossCallback.λHistory
+        self._emit([(i + 2, [(1, name), (20, f"{lam[name][-1]:8.3f}")])
+                    for i, name in enumerate(lam.keys()) if lam[name]], logUtils.debug, "λ")
+        self.prevEpochLogs = logs
+
+
 def getCallbacks(earlyStop, outputPrefix, plateauPatience, heads, trainBatchGen=None,
                  valBatchGen=None, checkpointSuffix=".checkpoint.keras"):
-    """The reference's callback set in its order, minus the display callback
-    (callbacks.py:718-777)."""
-    del trainBatchGen, valBatchGen
+    """The reference's callback set in its order (callbacks.py:718-777): fix-loss, early stop,
+    checkpoint, LR plateau, adaptive counts loss, display."""
     fixLoss = FixLossCallback(heads)
     earlyStopCb = EarlyStopping(monitor="val_loss", patience=earlyStop, mode="min",
                                 restore_best_weights=True)
@@ -294,4 +477,5 @@ def getCallbacks(earlyStop, outputPrefix, plateauPatience, heads, trainBatchGen=
                                  save_best_only=True, mode="min")
     plateau = ReduceLROnPlateau(monitor="val_loss", factor=0.5, patience=plateauPatience)
     adaptive = ApplyAdaptiveCountsLoss(heads, 0.3, plateau, earlyStopCb, checkpoint)
-    return fixLoss, earlyStopCb, checkpoint, plateau, adaptive
+    display = DisplayCallback(plateau, earlyStopCb, adaptive, trainBatchGen, valBatchGen)
+    return fixLoss, earlyStopCb, checkpoint, plateau, adaptive, display

@@ -48,6 +48,44 @@ def Adam(learning_rate=0.001, **kw):  # noqa: N802  (Keras spelling)
     return _Optimizer(learning_rate, **kw)
 
 
+class _LazyBatchLogs:
+    """The ``logs`` argument of the per-batch callbacks: metric names are known up front, values
+    (running means of the epoch so far) are read back from the device on first access."""
+
+    def __init__(self, model, sums, sums_dev, nseq):
+        self._model, self._sums, self._dev, self._n = model, sums, sums_dev, nseq
+        self._vals = None
+
+    def _materialise(self):
+        if self._vals is None:
+            tot = self._sums.copy()
+            if self._dev is not None:
+                tot = tot + self._dev.cpu().numpy()
+            self._vals = self._model._epoch_logs(tot / max(self._n, 1), "")
+        return self._vals
+
+    def keys(self):
+        if self._vals is None:  # names only: no synchronisation
+            H = len(self._model.headTasks)
+            return list(self._model._epoch_logs(np.zeros(2 * H), "").keys())
+        return list(self._vals.keys())
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __contains__(self, k):
+        return k in self.keys()
+
+    def __getitem__(self, k):
+        return self._materialise()[k]
+
+    def get(self, k, default=None):
+        return self._materialise().get(k, default)
+
+    def items(self):
+        return self._materialise().items()
+
+
 class History:
     """``keras.callbacks.History``: ``.history`` maps metric name -> list over epochs."""
 
@@ -186,8 +224,12 @@ class Model:
         for cb in callbacks:
             if hasattr(cb, "set_model"):
                 cb.set_model(self)
+            if hasattr(cb, "params"):  # Keras' CallbackList.set_params
+                cb.params = {"epochs": epochs, "steps": len(x), "verbose": 0}
             if hasattr(cb, "on_train_begin"):
                 cb.on_train_begin({})
+        batch_cbs = [cb for cb in callbacks if hasattr(cb, "on_train_batch_end")]
+        test_cbs = [cb for cb in callbacks if hasattr(cb, "on_test_batch_end")]
         self.stop_training = False
         rng = np.random.default_rng()
         for epoch in range(initial_epoch, epochs):
@@ -197,10 +239,10 @@ class Model:
             order = np.arange(len(x))
             if shuffle:
                 rng.shuffle(order)  # Keras shuffles the batch order of a Sequence by default
-            logs = self._run_epoch(x, order, train=True, prefix="")
+            logs = self._run_epoch(x, order, train=True, prefix="", batch_cbs=batch_cbs)
             if validation_data is not None:
                 logs.update(self._run_epoch(validation_data, np.arange(len(validation_data)),
-                                            train=False, prefix="val_"))
+                                            train=False, prefix="val_", batch_cbs=test_cbs))
             for gen in (x, validation_data):
                 if gen is not None and hasattr(gen, "on_epoch_end"):
                     gen.on_epoch_end()
@@ -228,13 +270,13 @@ class Model:
             if v is not None:
                 self._lambdas[i] = float(v.read_value() if hasattr(v, "read_value") else v)
 
-    def _run_epoch(self, gen, order, train, prefix):
+    def _run_epoch(self, gen, order, train, prefix, batch_cbs=()):
         H = len(self.headTasks)
         self._refresh_lambdas()
         sums = np.zeros(2 * H, dtype=np.float64)
         sums_dev = None  # losses stay on the device until the epoch ends (one read-back)
         nseq = 0
-        for bi in order:
+        for step, bi in enumerate(order):
             xb, yb = gen[int(bi)]
             # log-count targets as the generator supplies them (generators.py:139-140): they are
             # the MSE targets even when they are not log(sum of the profile)
@@ -257,9 +299,19 @@ class Model:
             else:
                 sums += losses * n
             nseq += n
+            if batch_cbs:
+                # Keras hands the running means to on_train_batch_end / on_test_batch_end; here
+                # they are computed only when a callback reads them (a device read-back)
+                lazy = _LazyBatchLogs(self, sums, sums_dev, nseq)
+                for cb in batch_cbs:
+                    (cb.on_train_batch_end if train else cb.on_test_batch_end)(step, lazy)
         if sums_dev is not None:
             sums += sums_dev.cpu().numpy()
         per = sums / max(nseq, 1)
+        return self._epoch_logs(per, prefix)
+
+    def _epoch_logs(self, per, prefix):
+        H = len(self.headTasks)
         logs = {}
         tot = 0.0
         for h in range(H):

@@ -52,7 +52,7 @@ def trainModel(model, trainBatchGen, valBatchGen, epochs, earlyStop, outputPrefi
                              valBatchGen, checkpointSuffix=checkpointSuffix)
     history = model.fit(trainBatchGen, epochs=epochs, validation_data=valBatchGen,
                         callbacks=callbacks, verbose=0)
-    history.history["counts-loss-weight"] = callbacks[4].λHistory
+    history.history["counts-loss-weight"] = callbacks[4].λHistory  # ApplyAdaptiveCountsLoss
     return history
 
 

@@ -147,3 +147,83 @@ def test_history_json(tmp_path):
     assert data["counts-loss-weight"]["a"][0] == 10.0
     assert data["config"]["heads"][0]["INTERNAL_λ-variable"] == {"λ_a": pytest.approx(22.2222, rel=1e-4)}
     assert len(data["val_loss"]) == 2
+
+
+def test_display_callback_speaks_the_progress_protocol():
+    """callbacks.py:392-716: lines ``∬row∬1∬window∬text`` -- an epoch table at INFO with the
+    reference's row order (Epoch, losses, per-head profile then counts metrics, early-stop /
+    plateau state, timers), value columns 11 wide, the previous epoch beside the current one, the
+    counts-loss weights at DEBUG, batch lines at most once a second plus first and last batch."""
+    import logging
+    from bpreveal_b200 import logUtils
+    heads = heads_cfg()
+    training.buildLosses(heads)
+    fix, es, ck, pl, ad, disp = cb.getCallbacks(3, "/tmp/nowhere", 2, heads, [0] * 5, [0] * 2)
+    assert isinstance(disp, cb.DisplayCallback) and disp.numBatches == 5
+    seen = []
+
+    class Grab(logging.Handler):
+        def emit(self, record):
+            seen.append((record.levelno, record.getMessage()))
+
+    lg = logging.getLogger("BPReveal")
+    h, old = Grab(), lg.level
+    lg.addHandler(h)
+    logUtils.setVerbosity("DEBUG")
+    try:
+        model = ScriptedModel(heads, [[(10.0, 2.0), (5.0, 1.0)], [(9.0, 1.5), (4.5, 0.8)]])
+        ck.on_epoch_end = lambda *a, **k: None  # no files in this test
+        disp.params = {"epochs": 2}
+        for c in (fix, es, pl, ad, disp):
+            c.set_model(model)
+            c.on_train_begin({})
+        names = ["loss", "solo_profile_a_multinomial_nll", "solo_logcounts_a_reweightable_mse",
+                 "solo_profile_b_multinomial_nll", "solo_logcounts_b_reweightable_mse",
+                 "solo_profile_a_loss", "solo_logcounts_a_loss"]
+        for epoch in range(2):
+            disp.on_epoch_begin(epoch)
+            for b in range(5):
+                disp.on_train_batch_end(b, {n: 1.0 + b for n in names})
+            for b in range(2):
+                disp.on_test_batch_end(b, {})
+            logs = {}
+            for head, (p, craw) in zip(heads, model.script[epoch]):
+                lam = float(head["INTERNAL_λ-variable"].read_value())
+                for pre in ("", "val_"):
+                    logs[f"{pre}solo_profile_{head['head-name']}_multinomial_nll"] = p
+                    logs[f"{pre}solo_logcounts_{head['head-name']}_reweightable_mse"] = lam * craw
+            logs["loss"] = logs["val_loss"] = 30.0 - epoch
+            for c in (fix, es, pl, ad, disp):
+                c.on_epoch_end(epoch, logs)
+    finally:
+        lg.removeHandler(h)
+        lg.setLevel(old)
+    lines = [m for _, m in seen if m.startswith("∬")]
+    parsed = [m.split("∬")[1:] for m in lines]            # [row, "1", window, text]
+    assert all(len(p) == 4 and p[1] == "1" for p in parsed)
+    wins = [p[2] for p in parsed]
+    assert {"E", "λ", "B", "BH", "V"} <= set(wins)
+    # batch lines: first (BH) and last batch of each epoch at least, never the ignored *_loss keys
+    btext = [p[3] for p in parsed if p[2] in ("B", "BH")]
+    assert not any("solo_profile_a_loss" in t for t in btext)
+    assert any(t.strip().startswith("batch") and "0 /    4" in t for t in btext)
+    # epoch table: row order and the 11-wide value column
+    e_rows = {p[3].split()[0] if not p[3].strip().startswith(("Best", "Epochs", "Minutes",
+                                                                "Seconds", "Setup", "Training",
+                                                                "Validation"))
+              else " ".join(p[3].split()[:-1]): int(p[0]) for p in parsed if p[2] == "E"}
+    assert e_rows["Epoch"] == 2 and e_rows["loss"] == 4 and e_rows["val_loss"] == 5
+    assert e_rows["solo_profile_a_multinomial_nll"] == 7
+    assert e_rows["val_solo_profile_a_multinomial_nll"] == 8
+    assert e_rows["solo_profile_b_multinomial_nll"] == 10
+    assert e_rows["solo_logcounts_a_reweightable_mse"] == 13
+    epoch_lines = [p[3] for p in parsed if p[2] == "E" and p[3].strip().startswith("Epoch ")]
+    assert epoch_lines[0].endswith("   0 /    2") and "   1 /    2" in epoch_lines[1]
+    assert epoch_lines[1].endswith("   0 /    2")            # previous epoch's column
+    assert any(lv == logging.INFO and "∬E∬" in m for lv, m in seen)
+    assert all(lv == logging.DEBUG for lv, m in seen if "∬λ∬" in m or "∬B∬" in m)
+    lam_lines = [p for p in parsed if p[2] == "λ"]
+    assert lam_lines[0][3].strip().startswith("a") and int(lam_lines[0][0]) == 2
+    assert cb.DisplayCallback.formatStr(3.14159) == "      3.142"
+    assert cb.DisplayCallback.formatStr((3, 17)) == "   3 /   17"
+    assert cb.DisplayCallback.formatStr("x") == "          x"
