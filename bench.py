@@ -578,7 +578,7 @@ def bench_train(ctx, name):
     from bpreveal_b200.engine import NetConfig, SoloNet
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
     cfgd = {"c1": C1, "c4": C4, "c3": C3R}[name]
-    batch = args.batch or (64 if name != "c4" else 32)
+    batch = args.batch or 64
     cfg = NetConfig(precise=args.precise, **cfgd)
     net = SoloNet(cfg, dev)
     net.init_random(seed=1234)

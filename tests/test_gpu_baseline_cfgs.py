@@ -517,6 +517,48 @@ def test_cta_pair_launches_equal_single_cta_launches(dev, monkeypatch, B, L, d):
     assert Hh.rel_err(val((res["1"][0], None)).numpy(), ref.numpy()) < 6e-3
 
 
+def test_cta_pair_launches_replay_bit_for_bit(dev):
+    """F = 512 forward and data gradient as CTA pairs, C4-like lengths at batch 4: 15 replays of
+    an 8-launch CUDA graph must reproduce the first launch (remote mbarrier arrivals, multicast
+    commits and the two producers of a stage: a missing cluster-scope ordering shows here)."""
+    from bpreveal_b200 import ops
+    B, Fn = 4, 512
+    g = torch.Generator().manual_seed(23)
+    for L, d in ((9262, 2), (6000, 256), (5200, 2048)):
+        L_out = L - 2 * d
+        x = split(torch.randn((B, L, Fn), generator=g).to(dev), False)
+        w = (torch.randn((3, Fn, Fn), generator=g) / 40).to(dev)
+        fwd, bwd = prep_w(w, Fn, False, dev)
+        bias = torch.zeros((Fn,), device=dev)
+        out = ops.new_planes(B, L_out, Fn, False, dev)
+        mask = torch.zeros((B, L_out, Fn // 64), dtype=torch.int64, device=dev)
+        gin = ops.new_planes(B, L, Fn, False, dev)
+        gz2 = ops.new_planes(B, L, Fn, False, dev)
+        mask_in = torch.randint(-2 ** 62, 2 ** 62, (B, L, Fn // 64), dtype=torch.int64, device=dev)
+
+        def f_fwd():
+            ops.conv3(x, fwd, (0, d, 2 * d), 0, L_out, bias=bias, resid=x, resid_off=d, out=out,
+                      mask_out=mask)
+
+        def f_bwd():
+            ops.conv3(out, bwd, (0, -d, -2 * d), 1, L, resid=out, resid_off=-d, out=gin,
+                      out2=gz2, mask_in=mask_in)
+
+        for fn, res in ((f_fwd, lambda: (out[0], mask)), (f_bwd, lambda: (gin[0], gz2[0]))):
+            fn()
+            torch.cuda.synchronize()
+            first = [t.clone() for t in res()]
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(8):
+                    fn()
+            for _ in range(15):
+                gr.replay()
+                torch.cuda.synchronize()
+                for a_, b_ in zip(first, res()):
+                    assert torch.equal(a_, b_), f"L={L} d={d}: replay differs"
+
+
 def test_every_c1_tower_shape_many_launches_in_a_graph(dev):
     """Each of C1's nine layer shapes at batch 64, forward and backward, 30 replays of a
     10-launch CUDA graph; every replay must reproduce the first launch bit for bit.  This test

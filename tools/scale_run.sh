@@ -17,7 +17,7 @@ run() {  # N, extra args...
 }
 for N in 1 2 4 8; do run $N --steps 50 --warmup 5; done
 run 8 --config c3 --steps 30 --warmup 5
-run 1 --config c4 --steps 6 --warmup 3 --batch 32
-run 8 --config c4 --steps 6 --warmup 3 --batch 32
+run 1 --config c4 --steps 6 --warmup 3 --batch 64
+run 8 --config c4 --steps 6 --warmup 3 --batch 64
 run 8 --config c2 --steps 20
 run 8 --config c5 --steps 30
