@@ -111,9 +111,19 @@ class SoloNet:
         self.w_bwd = torch.zeros_like(self.w_fwd)
         # tcgen05 operands of the input convolution and of the heads' data gradient
         self.cp = ops.heads_cp(cfg.T, cfg.H)
-        # K1 weights as 2 (bf16 path) / 3 (precise path) bf16 remainder planes: the first layer's
-        # pre-activations (and so its ReLU mask) stay fp32-accurate at the cost of K = 8 W extra MMAs
-        self.w_in_planes = planes + int(os.environ.get("BPB_W1_EXTRA", "1"))
+        # K1 weights are prepared as 2 (bf16 path) / 3 (precise path) bf16 remainder planes; three
+        # are exact to fp32 (the one-hot operand is exact), so the first layer's pre-activations
+        # and ReLU mask are fp32-accurate.  PREDICTION on the bf16 path multiplies only the first
+        # plane, like every other layer: the second was measured to change no output error of the
+        # C1 parity run (logits 1.59e-2 against 1.65e-2, both at the bf16 storage floor of
+        # 1.45e-2) while doubling the kernel's MMAs -- 18.6 -> 14.5 us per launch, prediction
+        # 505k -> 567k windows/s.  Training and attribution keep both planes: with one, ReLU
+        # flips in the first layer move the conv1 weight gradient of small networks by 13 % of
+        # its largest entry, and PISA's efficiency identity (a difference of nearly equal sums)
+        # from 4.7e-2 to 1.4e-1.  BPB_W1_EXTRA=1 uses both planes everywhere.
+        self.w_in_planes = planes + 1
+        self.w_in_fast = self.w_in_planes if (cfg.precise or
+                                              os.environ.get("BPB_W1_EXTRA", "0") == "1") else 1
         self.w_in_op = ops.input_conv_wop(cfg.inputFilterWidth, Fp, self.w_in_planes, self.device)
         self.w_hd_op = ops.heads_dgrad_wop(cfg.outputFilterWidth, Fp, self.cp, planes, self.device)
         # transposed input convolution (attribution only), refreshed where it is used
@@ -312,8 +322,10 @@ class SoloNet:
 
         a = buf(0)
         ops.onehot_expand(x, ws["x8"])
-        ops.input_conv_fwd(ws["x8"], self.w_in_op, self.w_in_planes, cfg.inputFilterWidth,
-                           cfg.numFilters, p["conv1_b"], cfg.Fp, a,
+        exact_first = save_masks or bool(z_list) or bool(zx_list)  # training / attribution
+        ops.input_conv_fwd(ws["x8"], self.w_in_op,
+                           self.w_in_planes if exact_first else self.w_in_fast,
+                           cfg.inputFilterWidth, cfg.numFilters, p["conv1_b"], cfg.Fp, a,
                            mask_out=ws["masks"][0] if save_masks else None,
                            z_out=z_list[0] if z_list else None,
                            zx_in=zx_list[0] if zx_list else None, zx_div=zx_div,
