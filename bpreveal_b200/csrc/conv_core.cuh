@@ -99,6 +99,10 @@ struct ConvKParams {
   long long mask_rows_total;   // B * L_a (even)
   int xf_rows;                 // rows of one staged A tile (HALO: the box, SLAB: 128)
   int mstage;                  // bytes of one stage's mask words (multiple of 16)
+  // Streamed-weight launches (F >= 256) read the residual straight from global memory in the
+  // epilogue instead of through a TMA ring: [B][L_res][F] bf16 planes
+  const uint8_t* resid_ptr[2];
+  int L_res;
   int cg2;                     // 1: CTA pairs (cta_group::2), tiles_per_seq counts 256-row pair tiles
   int dbg_flags;               // PROFILE builds only (BPB_DBG_FLAGS): 1 no stores, 2 no residual
                                // loads, 4 no masking work -- ablations for the role profile
@@ -240,7 +244,20 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   constexpr uint32_t IDESC = umma_idesc_bf16(CG2 ? 256 : 128, NT, 0, 0);
   constexpr bool IS_FWD = (EPI <= EPI_FWD_R);
   // the forward residual a[t + d] already sits in the HALO box
-  constexpr bool RING_RESID = RESID && !(HALO && IS_FWD);
+  // Streamed weights: NO residual ring.  A tile of NT = 256 columns needs four residual chunks;
+  // a two-slot sub-ring per epilogue group made the producer wait for the epilogue of tile i
+  // (which starts when the MMAs of tile i are done) before it could issue the first operand
+  // loads of tile i + 1: a bubble of two chunk visits + one load latency per tile -- the F = 512
+  // data gradient sat at 61 % of the tensor rate because of it.  The epilogue has cycles to
+  // spare there (a tile's MMAs take ~14 k cycles, a chunk visit ~3 k), so it reads its residual
+  // rows with plain global loads issued at the top of the visit; the 64 KB of ring become
+  // operand stages.
+#ifdef BPB_DIRECT_ALL  // experiment: no residual ring anywhere (F = 64 backward, SLAB forward)
+  constexpr bool DIRECT_RESID = RESID && !(HALO && IS_FWD);
+#else
+  constexpr bool DIRECT_RESID = RESID && !RESIDENT;
+#endif
+  constexpr bool RING_RESID = RESID && !(HALO && IS_FWD) && !DIRECT_RESID;
   static_assert(!HALO || RESIDENT, "HALO staging needs resident weights");
   static_assert(!HALO || RESID || !IS_FWD, "HALO forward is the residual layer");
 
@@ -858,7 +875,23 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
         uint4 rr[4], rl[4];
         uint64_t* release = nullptr;
         if (RESID) {
-          if (RING_RESID) {
+          if (DIRECT_RESID) {
+            const int tr = t + p.resid_off;
+            if (tr >= 0 && tr < p.L_res) {  // rows outside the tensor count as zero
+              const size_t roff = ((static_cast<size_t>(b) * p.L_res + tr) * p.F + n0 + half * 32) * 2;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                rr[g] = __ldg(reinterpret_cast<const uint4*>(p.resid_ptr[0] + roff) + g);
+                if (PLANES == 2) rl[g] = __ldg(reinterpret_cast<const uint4*>(p.resid_ptr[1] + roff) + g);
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                rr[g] = make_uint4(0u, 0u, 0u, 0u);
+                if (PLANES == 2) rl[g] = make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+          } else if (RING_RESID) {
 #ifdef BPB_ROLE_PROFILE
             if (!(p.dbg_flags & 2))
 #endif
@@ -1356,7 +1389,11 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   size_t stage_bytes = 0, mstage = 0;
   int box_rows = 0;
   auto try_plan = [&](bool want_halo, bool want_res, int want_nstg, int want_rst, int min_stages) {
-    const bool ring_resid = RESID && !(want_halo && is_fwd);
+#ifdef BPB_DIRECT_ALL
+    const bool ring_resid = false;
+#else
+    const bool ring_resid = RESID && !(want_halo && is_fwd) && want_res;  // streamed: direct loads
+#endif
     // (not for STRIP staging: that kernel is bound by its MMA issue, the extra MMA costs more
     // than the adds it saves -- measured)
     const bool want_bias_mma = want_res && is_fwd && NT == 64 && d.bias != nullptr && g_bias_mma &&
@@ -1424,6 +1461,9 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
     kp.a_base[0] = static_cast<const uint8_t*>(d.a_ptr[0]);
     kp.a_base[1] = static_cast<const uint8_t*>(d.a_ptr[1]);
   }
+  kp.resid_ptr[0] = static_cast<const uint8_t*>(d.resid[0]);
+  kp.resid_ptr[1] = static_cast<const uint8_t*>(d.resid[1]);
+  kp.L_res = d.L_res;
   kp.rstages = rstages > 0 ? rstages : 1;
   kp.ring_resid = rstages > 0 ? 1 : 0;
   kp.nstg = nstg;

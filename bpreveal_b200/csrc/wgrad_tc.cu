@@ -576,9 +576,23 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
     if (n_units_j[j] != n_units_j[0]) uniform = false;
   }
   pl->n_units = n_units;
-  int ug = 512 / NT - 1;  // one accumulator slot is reserved for the bias-gradient unit
+  // Accumulator slots of NT columns: one is reserved for the bias-gradient unit, every other one
+  // holds a PAIR of units (M = 128 MMAs) when pairing is on.  More units per CTA = more FLOPs per
+  // staged G tile: at F = 512 the launch is bound by what one SM can pull out of L2 (80 KB per
+  // 6.3 MFLOP visit with three units), so four units (96 KB per 8.4 MFLOP) are worth ~10 %.
+  // BPB_WG_UG caps the units per CTA (1..4).
+  static const int ug_cap = [] {
+    const char* e = getenv("BPB_WG_UG");
+    const int v = e ? atoi(e) : 4;
+    return (v >= 1 && v <= 4) ? v : 4;
+  }();
+  static const bool pair_on = [] {
+    const char* e = getenv("BPB_WG_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  int ug = (512 / NT - 1) * (pair_on ? 2 : 1);
   if (ug > n_units) ug = n_units;
-  if (ug > 4) ug = 4;
+  if (ug > ug_cap) ug = ug_cap;
   pl->UG = ug;
   pl->n_groups = (n_units + ug - 1) / ug;
   if (!uniform && pl->n_groups != 1) return false;

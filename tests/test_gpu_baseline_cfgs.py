@@ -240,7 +240,7 @@ LAYER_CASES = [  # (B, L_in, F, dilation, precise)
     (2, 700, 64, 64, False), (2, 900, 64, 128, False), (2, 1300, 64, 256, False),
     (3, 2046, 64, 512, False), (2, 900, 64, 128, True), (2, 2046, 64, 512, True),
     (1, 600, 512, 2, False), (1, 700, 512, 64, False), (1, 900, 512, 128, False),
-    (1, 1400, 512, 512, False), (1, 4400, 512, 2048, False), (1, 700, 512, 128, True),  # fwd only
+    (1, 1400, 512, 512, False), (1, 4400, 512, 2048, False), (1, 700, 512, 128, True),
     (2, 700, 256, 128, False), (2, 600, 192, 64, False),
 ]
 
@@ -286,8 +286,6 @@ def test_dilated_layer_data_gradient(dev, B, L, Fn, d, precise, rule):
     from bpreveal_b200 import ops
     if rule == "mult" and Fn == 512 and d < 2048 and d != 128:
         pytest.skip("the multiplier epilogue at F = 512 is covered at d = 128 and 2048")
-    if Fn == 512 and precise:
-        pytest.skip("F = 512 on the fp32-accumulate path is forward-only (C4 trains in bf16)")
     g = torch.Generator().manual_seed(2)
     L_g = L - 2 * d
     gz = torch.randn((B, L_g, Fn), generator=g).to(dev)
@@ -614,23 +612,6 @@ def test_every_c1_tower_shape_many_launches_in_a_graph(dev):
 def test_c4_shaped_forward_loss_gradients(dev, precise):
     cfg = C4S
     net, params = build(cfg, precise, dev, scale=1.0)
-    if precise:
-        # BASELINE's C4 is a bf16 training configuration.  The fp32-accumulate path covers the
-        # F = 512 FORWARD (prediction); its data gradient needs two planes of 3 x 512 x 512
-        # weights streamed per tile and is not built (bpb_conv3_tc reports "not enough shared
-        # memory for F=512 planes=2"): check the forward, and that the backward fails loudly.
-        from bpreveal_b200._lib import BprevealB200Error
-        x = O.synthetic_sequences(1, cfg["inputLength"], seed=51)
-        ref_l, ref_c = Hh.oracle_forward(params, x)
-        got_l, got_c = net.predict(torch.tensor(x, device=dev), batchSize=1)
-        el, ec = Hh.rel_err(got_l.cpu().numpy(), ref_l), Hh.rel_err(got_c.cpu().numpy(), ref_c)
-        record("C4s_fwd_precise", logits=el, logcounts=ec)
-        assert el < 1e-4 and ec < 1e-4, (el, ec)
-        net.enable_training()
-        ws = net._workspace(1, "train")
-        with pytest.raises(BprevealB200Error, match="F=512 planes=2"):
-            net.forward_backward_into(ws)
-        return
     net.enable_training()
     B = 1
     x = O.synthetic_sequences(B, cfg["inputLength"], seed=51)
@@ -652,13 +633,22 @@ def test_c4_shaped_forward_loss_gradients(dev, precise):
     e_mse = abs(losses[1] - cl[0]) / abs(cl[0])
     ge = grad_errors(net.state(net.grads_flat), grads)
     got = dict(logits=el, logcounts=ec, mnll=e_mnll, wmse=e_mse)
-    floor = bf16_floor(params, x, counts, pw, lam)
-    record("C4s_fwd_bwd_bf16", grad_max=max(ge.values()), grad_dil10=ge["dil10_w"],
-           grad_conv1=ge["conv1_w"], **got, **{f"floor_{k}": v for k, v in floor.items()})
-    gate_bf16("C4s", got, floor, dict(logits=6e-2, logcounts=5e-2, mnll=2e-2, wmse=2e-2))
+    floor = {} if precise else bf16_floor(params, x, counts, pw, lam)
+    record(f"C4s_fwd_bwd_{'precise' if precise else 'bf16'}", grad_max=max(ge.values()),
+           grad_dil10=ge["dil10_w"], grad_conv1=ge["conv1_w"], **got,
+           **{f"floor_{k}": v for k, v in floor.items()})
+    if precise:
+        # (Until the streamed-weight launches dropped their residual ring, the two-plane data
+        # gradient at F = 512 did not fit shared memory and this path was forward-only.)
+        assert el < 1e-4 and ec < 1e-4, (el, ec)
+        assert e_mnll < 1e-3 and e_mse < 1e-3, (e_mnll, e_mse)
+    else:
+        gate_bf16("C4s", got, floor, dict(logits=6e-2, logcounts=5e-2, mnll=2e-2, wmse=2e-2))
     # K = 1536 per layer, 13 layers deep: sign flips of near-zero pre-activations are what is
     # left on the precise path; on the bf16 path it is the rounding of every stored plane
-    gtol = 5e-3 if precise else 8e-2
+    # (measured: the last layer's weight gradient 3.5e-5, growing layer by layer down to 1.2e-2
+    # for the input convolution, thirteen ReLU layers below the loss)
+    gtol = 2e-2 if precise else 8e-2
     for k, e in ge.items():
         assert e < gtol, f"grad {k}: rel err {e}"
 
