@@ -252,10 +252,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   // spare there (a tile's MMAs take ~14 k cycles, a chunk visit ~3 k), so it reads its residual
   // rows with plain global loads issued at the top of the visit; the 64 KB of ring become
   // operand stages.
-#ifdef BPB_DIRECT_ALL  // experiment: no residual ring anywhere (F = 64 backward, SLAB forward)
+  // The SLAB-staged forward with resident weights (F = 64, d >= 128) does the same: 100.2 ->
+  // 98.3 us over the nine forward launches of C1.  On the F = 64 data gradient it measured
+  // neutral with more spills (-DBPB_DIRECT_ALL), so that keeps its ring.
+#if defined(BPB_DIRECT_ALL)
   constexpr bool DIRECT_RESID = RESID && !(HALO && IS_FWD);
 #else
-  constexpr bool DIRECT_RESID = RESID && !RESIDENT;
+  constexpr bool DIRECT_RESID = RESID && (!RESIDENT || (IS_FWD && !HALO));
 #endif
   constexpr bool RING_RESID = RESID && !(HALO && IS_FWD) && !DIRECT_RESID;
   static_assert(!HALO || RESIDENT, "HALO staging needs resident weights");
@@ -1389,10 +1392,11 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   size_t stage_bytes = 0, mstage = 0;
   int box_rows = 0;
   auto try_plan = [&](bool want_halo, bool want_res, int want_nstg, int want_rst, int min_stages) {
-#ifdef BPB_DIRECT_ALL
+#if defined(BPB_DIRECT_ALL)
     const bool ring_resid = false;
 #else
-    const bool ring_resid = RESID && !(want_halo && is_fwd) && want_res;  // streamed: direct loads
+    // (forward: from the HALO box or by direct loads; streamed weights: direct loads)
+    const bool ring_resid = RESID && !is_fwd && want_res;
 #endif
     // (not for STRIP staging: that kernel is bound by its MMA issue, the extra MMA costs more
     // than the adds it saves -- measured)
