@@ -485,7 +485,11 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       if (bias_mma) mbar_wait_wd(b_full, 0, p.dbg, 0x310);
       BPB_STAMP(28);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, ntile = 0;
+#ifdef BPB_ROLE_PROFILE  // ablation 16: the MMA does not wait for the masker (timing only)
+      uint64_t* const a_ready = (XF && !(p.dbg_flags & 16)) ? xfull : full;
+#else
       uint64_t* const a_ready = XF ? xfull : full;  // XF: operands are usable once masked
+#endif
       // Fast path (the bf16 tower layer: 3 taps, one 64-channel chunk, one pass, resident
       // weights): every descriptor word that does not depend on the stage is built once here, so
       // the issue loop is 12 x (one add + one tcgen05.mma) per tile.  The single issuing thread
@@ -781,6 +785,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
           if (lane == 0) atomicAdd(prof_smem() + 7, static_cast<unsigned>(tnow - tm0));
           tm0 = tnow;
         }
+#endif
+#ifdef BPB_ROLE_PROFILE
+        if (!(p.dbg_flags & 32))  // ablation 32: no proxy fence (timing only)
 #endif
         fence_proxy_async();
         __syncwarp();
