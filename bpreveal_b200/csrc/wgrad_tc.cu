@@ -617,7 +617,19 @@ static bool plan_wgrad(int n_jobs, int B, const int* rows, const int* halo_rows_
     total_kb += cost[j];
   }
   int budget = sms / pl->n_items;  // splits available in total
-  if (budget < n_jobs) budget = n_jobs;
+  if (budget < 2 * n_jobs) {
+    // Wide models: an (unit group, column tile) item per job already over-subscribes the SMs
+    // (F = 512, 11 layers: 264 CTAs of very different lengths on 148 SMs).  Split the long jobs
+    // further so that the CTAs pack: ~BPB_WG_WAVES (default 4) waves of CTAs in total (measured
+    // at C4, batch 64: 9.5 ms with one split per job, 8.6 at 2.5 waves, 8.0 at 4, 8.2 at 6).
+    static const double waves = [] {
+      const char* e = getenv("BPB_WG_WAVES");
+      const double v = e ? atof(e) : 0.0;
+      return v >= 1.0 ? v : 4.0;
+    }();
+    const int want = static_cast<int>(waves * sms / pl->n_items);
+    budget = want > n_jobs ? want : n_jobs;
+  }
   int used = 0;
   for (int j = 0; j < n_jobs; ++j) {
     int ks = static_cast<int>(budget * cost[j] / total_kb);
