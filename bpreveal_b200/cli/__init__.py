@@ -2,16 +2,15 @@
 ``python -m bpreveal_b200.cli.<program> config.json`` for trainSoloModel,
 trainTransformationModel, trainCombinedModel, makePredictions, interpretPisa, interpretFlat
 (src/<program>.py of the reference).  Each module has ``main(config)`` like its counterpart."""
-import json
 import sys
 
 
 def loadConfig(fname):
     """The reference reads configurations with its expression interpreter
-    (internal/interpreter.py:422-428), of which JSON is a subset; plain JSON is what is read
-    here."""
-    with open(fname, "r", encoding="utf-8") as fp:
-        return json.load(fp)
+    (internal/interpreter.py:419-425; interpretPisa.py:260, interpretFlat.py:317), of which plain
+    JSON is a special case -- ``bpreveal_b200.interpreter`` is that language."""
+    from bpreveal_b200 import interpreter
+    return interpreter.evalFile(fname)
 
 
 def run(program, main):
