@@ -20,13 +20,16 @@
 //   SLAB   (any dilation / width): one [128 x 64] box per (tap, chunk, pass), as a classic
 //          multi-stage K pipeline; weights resident in smem when they fit, else streamed.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9
-// epilogue.  Epilogue warp w reads TMEM lane quadrant w % 4 (rows) and the column half
-// (w - 2) / 4 of each 64-channel chunk, so two warps per scheduler hide each other's latency.
-// The epilogue fuses bias / ReLU / ReLU-mask bits / crop + residual (forward) or residual
-// gradient + mask / rescale multiplier (backward) and writes bf16 planes through double-buffered
-// swizzled staging tiles and TMA stores.  Residual tiles that are not already in the HALO box
-// arrive through their own small TMA ring, so the epilogue never waits on a global load.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, then EG groups of eight
+// epilogue warps (two groups on the bf16 path: 576 threads); streamed-weight launches add a second
+// producer warp for the weight tiles, the masked-operand backward (XF) six masker warps.
+// Epilogue warp w reads TMEM lane quadrant w % 4 (rows) and one 32-column half of each
+// 64-channel chunk, so two warps per scheduler hide each other's latency.  The epilogue fuses
+// bias / ReLU / ReLU-mask bits / crop + residual (forward) or residual gradient + mask / rescale
+// multiplier (backward) and writes bf16 planes through per-warp swizzled staging tiles and TMA
+// stores.  The residual comes from the HALO box (forward), from its own TMA ring (F = 64
+// backward) or straight from global memory (SLAB-staged forward, every streamed-weight launch).
+// F >= 256 training launches run as CTA pairs (cta_group::2, template flag CG2).
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
