@@ -1299,6 +1299,38 @@ static int dispatch_planes(int planes, int NT, bool resident, bool halo, const C
   return dispatch_shape<EPI, 1, RESID>(NT, resident, halo, maps, kp, smem, grid, s);
 }
 
+// CTA pairs that can be resident at once (a pair must sit inside one GPC; with an odd number of
+// usable SMs in a GPC one SM stays empty): asked of the runtime once, for the forward pair kernel at
+// the largest dynamic shared-memory size; sm_count() / 2 if the query fails.
+template <bool RESID>
+static int cg2_max_pairs() {
+  static const int pairs = [] {
+    int n = sm_count() / 2;
+    if constexpr (RESID) {
+      auto kern = conv_tc_kernel<EPI_FWD, 256, false, 1, false, 2, true, false, true>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               max_smem_optin()) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * n);
+        cfg.blockDim = dim3(64 + kEpiThreads * 2 + 32);
+        cfg.dynamicSmemBytes = max_smem_optin();
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int q = 0;
+        if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
+      }
+      (void)cudaGetLastError();
+    }
+    return n > 0 ? n : 1;
+  }();
+  return pairs;
+}
+
 // RESID selects the family a translation unit instantiates: true = residual tower layers (HALO
 // allowed), false = plain position-major GEMMs (input convolution, head data gradient).
 template <bool RESID>
@@ -1527,7 +1559,7 @@ static int conv_run(const ConvDesc& d, cudaStream_t stream) {
   kp.cg2 = cg2 ? 1 : 0;
   if (cg2) kp.tiles_per_seq = (kp.tiles_per_seq + 1) / 2;  // pair tiles of 256 rows
   const int total_tiles = kp.B * kp.tiles_per_seq * kp.n_ntiles;
-  int walkers = cg2 ? sm_count() / 2 : sm_count();  // CTAs, or CTA pairs
+  int walkers = cg2 ? cg2_max_pairs<RESID>() : sm_count();  // CTAs, or resident CTA pairs
   if (walkers > total_tiles) walkers = total_tiles;
   const int grid = cg2 ? 2 * walkers : walkers;
   kp.step_nt = walkers % kp.n_ntiles;
