@@ -486,38 +486,34 @@ struct WgradReduceJobs {
   WgradScatter sc[kWgMaxJobs];  // per-job geometry and outputs
 };
 
-// out[i] = sum_s ws[s][i] in a fixed order (deterministic).  One block owns 32 consecutive outputs
-// of job blockIdx.y; warp w adds the splits s = w, w + 8, ... (each a coalesced 128-byte read, four
-// independent chains), then the eight warp partials are added in warp order.
+// out[i] = sum_s ws[s][i] in a fixed order (deterministic).  One thread per output of job
+// blockIdx.y, four independent chains over the splits (s = 0, 4, ... | 1, 5, ... | ...), every load
+// of a warp one coalesced 128-byte line.  (The first version gave a block 32 outputs and spread
+// the splits over its eight warps: 4 246 blocks of almost no work each for C1, 10.6 us -- a
+// tenth of the weight-gradient family -- for 7 MB of partial sums.)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws_all, const WgradReduceJobs jobs) {
-  __shared__ float part[8][32];
+  pdl_launch_dependents();
   const int job = blockIdx.y;
-  const float* ws = ws_all + jobs.ws_off[job];
   const int ksplit = jobs.ksplit[job];
   const WgradScatter sc = jobs.sc[job];
   const long long n = (static_cast<long long>(sc.rows) + 1) * sc.cols;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long i = static_cast<long long>(blockIdx.x) * 32 + lane;
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  pdl_wait();  // the partial sums are the predecessor's output
+  if (i >= n) return;
+  const float* ws = ws_all + jobs.ws_off[job] + i;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  if (i < n) {
-    int s = warp;
-    for (; s + 24 < ksplit; s += 32) {
-      s0 += ws[(s + 0) * n + i];
-      s1 += ws[(s + 8) * n + i];
-      s2 += ws[(s + 16) * n + i];
-      s3 += ws[(s + 24) * n + i];
-    }
-    for (; s < ksplit; s += 8) s0 += ws[s * n + i];
+  int s = 0;
+  for (; s + 3 < ksplit; s += 4) {
+    s0 += ws[(s + 0) * n];
+    s1 += ws[(s + 1) * n];
+    s2 += ws[(s + 2) * n];
+    s3 += ws[(s + 3) * n];
   }
-  part[warp][lane] = (s0 + s1) + (s2 + s3);
-  __syncthreads();
-  if (warp == 0 && i < n) {
-    float tot = part[0][lane];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) tot += part[w][lane];
-    wgrad_scatter(sc, i, tot);
-  }
+  if (s < ksplit) s0 += ws[s * n];
+  if (s + 1 < ksplit) s1 += ws[(s + 1) * n];
+  if (s + 2 < ksplit) s2 += ws[(s + 2) * n];
+  wgrad_scatter(sc, i, (s0 + s1) + (s2 + s3));
 }
 
 // One contraction: out[u*64 + m][n] = sum over positions of A_u[pos][m] * G[pos][n], u = (tap, chunk).
@@ -824,9 +820,9 @@ static int wgrad_run(const WgradDesc* d, int n_jobs, cudaStream_t stream) {
   else rc = launch_wgrad<256>(maps, kp, pl.smem_bytes, pl.grid, stream);
   if (rc) return rc;
 
-  dim3 rgrid(static_cast<unsigned>((n_max + 31) / 32), static_cast<unsigned>(n_jobs));
-  wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(d0.ws, rj);
-  BP_CHECK_CUDA(cudaGetLastError());
+  dim3 rgrid(static_cast<unsigned>((n_max + 255) / 256), static_cast<unsigned>(n_jobs));
+  BP_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel, rgrid, dim3(256), 0, stream,
+                           static_cast<const float*>(d0.ws), rj));
   return 0;
 }
 
