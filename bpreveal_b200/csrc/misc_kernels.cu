@@ -544,31 +544,42 @@ adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g
     p[i] = w;
     long long r = i - tb.off_dil_w;
     if (r >= 0 && r < n_dil) {
-      const long long l = r / per, rr = r % per;
-      const long long j = rr / (F * F), cin = (rr / F) % F, cout = rr % F;
-      const long long base = l * tb.planes * per;
+      // 32-bit index arithmetic (the host checks n < 2^31): 64-bit divisions were most of this
+      // kernel's instructions
+      const unsigned r32 = static_cast<unsigned>(r), per32 = static_cast<unsigned>(per),
+                     F32 = static_cast<unsigned>(F);
+      const unsigned l = r32 / per32, rr = r32 - l * per32;
+      const unsigned jc = rr / F32, cout = rr - jc * F32;  // jc = j * F + cin
+      const unsigned j = jc / F32, cin = jc - j * F32;
+      const long long base = static_cast<long long>(l) * tb.planes * per;
       scatter_planes(w_fwd, per, tb.planes, base + (j * F + cout) * F + cin, w);
       scatter_planes(w_bwd, per, tb.planes, base + (j * F + cin) * F + cout, w);
       continue;
     }
     r = i - tb.off_conv1_w;
     if (r >= 0 && r < n_c1) {
-      const long long j = r / (4 * tb.Fw), c4 = (r / tb.Fw) % 4, nn = r % tb.Fw;
+      const unsigned r32 = static_cast<unsigned>(r), Fw32 = static_cast<unsigned>(tb.Fw);
+      const unsigned jc = r32 / Fw32, nn = r32 - jc * Fw32;  // jc = j * 4 + c4
+      const unsigned j = jc >> 2, c4 = jc & 3u;
       scatter_planes(w_in_op, F * K_in, tb.in_planes, nn * K_in + j * 8 + c4, w);
       continue;
     }
     r = i - tb.off_prof_w;
     int j = -1, c = 0, col = 0;
     if (r >= 0 && r < n_pw) {
-      j = static_cast<int>(r / (static_cast<long long>(tb.Fw) * tb.T));
-      c = static_cast<int>((r / tb.T) % tb.Fw);
-      col = static_cast<int>(r % tb.T);
+      const unsigned r32 = static_cast<unsigned>(r), T32 = static_cast<unsigned>(tb.T),
+                     Fw32 = static_cast<unsigned>(tb.Fw);
+      const unsigned jc = r32 / T32;  // j * Fw + c
+      col = static_cast<int>(r32 - jc * T32);
+      j = static_cast<int>(jc / Fw32);
+      c = static_cast<int>(jc - static_cast<unsigned>(j) * Fw32);
     } else {
       r = i - tb.off_cnt_w;
       if (r >= 0 && r < n_cw) {
+        const unsigned r32 = static_cast<unsigned>(r), H32 = static_cast<unsigned>(tb.H);
         j = 0;
-        c = static_cast<int>(r / tb.H);
-        col = tb.T + static_cast<int>(r % tb.H);
+        c = static_cast<int>(r32 / H32);
+        col = tb.T + static_cast<int>(r32 - static_cast<unsigned>(c) * H32);
       }
     }
     if (j >= 0) {
@@ -1096,6 +1107,7 @@ extern "C" int bpb_adam_prep_step(long long n, float* param, const float* grad, 
   BP_REQUIRE(t.w_in_op && t.w_hd_op && (t.n_layers == 0 || (t.w_fwd && t.w_bwd)) &&
                  (t.w_hf_op == nullptr || t.N_heads >= t.T + t.H),
              "bpb_adam_prep_step: missing operand buffers");
+  BP_REQUIRE(n < (1ll << 31), "bpb_adam_prep_step: more than 2^31 parameters");
   if (n <= 0) return 0;
   adam_prep_kernel<false><<<ew_blocks(n), 256, 0, stream>>>(n, param, grad, m, v, state, beta1, beta2,
                                                             eps, grad_scale, t, bpb_peer_args{});
@@ -1118,6 +1130,7 @@ extern "C" int bpb_adam_prep_step_peer(long long n, float* param, float* m, floa
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BP_REQUIRE(param && m && v && state && table, "bpb_adam_prep_step_peer: NULL argument");
   if (int rc = check_peer_args("bpb_adam_prep_step_peer", peers)) return rc;
+  BP_REQUIRE(n < (1ll << 31), "bpb_adam_prep_step_peer: more than 2^31 parameters");
   if (n <= 0) return 0;
   // every block waits for the peers at its start: the whole grid must be resident
   int blocks = ew_blocks(n);
