@@ -444,10 +444,12 @@ struct WgradScatter {
 };
 
 __device__ __forceinline__ void wgrad_scatter(const WgradScatter& sc, long long i, float tot) {
-  const long long n_main = static_cast<long long>(sc.rows) * sc.cols;
-  const bool is_b = i >= n_main;
-  const int r = is_b ? 0 : static_cast<int>(i / sc.cols);
-  const int n = static_cast<int>(is_b ? i - n_main : i % sc.cols);
+  // (rows + 1) * cols < 2^31 for every geometry the planner accepts: 32-bit divisions
+  const unsigned n_main = static_cast<unsigned>(sc.rows) * static_cast<unsigned>(sc.cols);
+  const unsigned iu = static_cast<unsigned>(i);
+  const bool is_b = iu >= n_main;
+  const int r = is_b ? 0 : static_cast<int>(iu / static_cast<unsigned>(sc.cols));
+  const int n = static_cast<int>(is_b ? iu - n_main : iu - static_cast<unsigned>(r) * sc.cols);
   if (sc.mode == 0) {
     if (!is_b) sc.o0[i] = tot;
     else if (sc.o1) sc.o1[n] = tot;
