@@ -210,10 +210,12 @@ loss_pack_kernel(int B, int L, int T, int H, const int* __restrict__ task_off,
   __shared__ float s_dlc;
   __shared__ int s_last;
   const int b = blockIdx.x, h = blockIdx.y;
+  pdl_launch_dependents();
   const int k0 = task_off[h];
   const int Th = task_off[h + 1] - k0;
   // scalars of this (sequence, head): fetched now so that their latency hides behind pass 1
   const float w_prof = profile_weight[h], lam_h = lambda[h];
+  pdl_wait();  // logits and per-tile count sums are the predecessor's output
   float lc_pred;
   if (pk.cpart != nullptr) {
     // the same sum, in the same order, as heads_counts_finish_kernel
@@ -503,6 +505,8 @@ adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g
     __syncthreads();
   }
   // bias-corrected step size: double-precision pow is long and slow, one thread per block does it
+  // -- and before the dependency wait: `state` is written only by this kernel's own previous
+  // launch (long complete), so the two pows overlap the tail of the weight-gradient reduction
   __shared__ float s_alpha;
   const float step_f = state[0] + 1.f;
   if (threadIdx.x == 0) {
@@ -510,6 +514,7 @@ adam_prep_kernel(long long n, float* __restrict__ p, const float* __restrict__ g
     s_alpha = static_cast<float>(static_cast<double>(state[1]) * sqrt(1.0 - pow((double)b2, step)) /
                                  (1.0 - pow((double)b1, step)));
   }
+  pdl_wait();  // gradients of the predecessor
   __syncthreads();
   const float alpha = s_alpha;
   const long long F = tb.F;
@@ -1074,10 +1079,11 @@ extern "C" int bpb_loss_fwd_bwd_pack(int B, int L, int T, int H, const int* task
     const int v = e ? atoi(e) : 1024;
     return (v == 256 || v == 512 || v == 1024) ? v : 1024;
   }();
-  loss_pack_kernel<<<grid, n_threads, 0, stream>>>(B, L, T, H, task_off, logits, logcounts, counts,
-                                             logcounts_true, profile_weight, lambda, losses,
-                                             dlogits, dlogcounts, pk);
-  BP_CHECK_CUDA(cudaGetLastError());
+  // programmatic serialization: the successor (the heads' data gradient) may run its prologue
+  // under this kernel's tail, and this kernel's launch latency hides under the heads' forward
+  BP_CHECK_CUDA(launch_pdl(loss_pack_kernel, grid, dim3(n_threads), 0, stream, B, L, T, H, task_off,
+                           logits, logcounts, counts, logcounts_true, profile_weight, lambda, losses,
+                           dlogits, dlogcounts, pk));
   return 0;
 }
 
@@ -1109,9 +1115,9 @@ extern "C" int bpb_adam_prep_step(long long n, float* param, const float* grad, 
              "bpb_adam_prep_step: missing operand buffers");
   BP_REQUIRE(n < (1ll << 31), "bpb_adam_prep_step: more than 2^31 parameters");
   if (n <= 0) return 0;
-  adam_prep_kernel<false><<<ew_blocks(n), 256, 0, stream>>>(n, param, grad, m, v, state, beta1, beta2,
-                                                            eps, grad_scale, t, bpb_peer_args{});
-  BP_CHECK_CUDA(cudaGetLastError());
+  BP_CHECK_CUDA(launch_pdl(adam_prep_kernel<false>, dim3(ew_blocks(n)), dim3(256), 0, stream, n, param,
+                           static_cast<const float*>(grad), m, v, state, beta1, beta2, eps,
+                           grad_scale, t, bpb_peer_args{}));
   return 0;
 }
 
