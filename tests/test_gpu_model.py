@@ -327,3 +327,48 @@ def test_peer_exchange_kernel_with_one_rank_equals_plain_step(dev):
         assert float(net_b.step_and_lr[0]) == 3.0
     finally:
         ex.close()
+
+
+def test_training_from_host_batches_equals_device_batches(dev):
+    """``train_step`` with pinned host tensors (two staging slots filled on a copy stream, one
+    CUDA graph per slot reading the slot itself) against the same batches handed over as device
+    tensors: identical parameters after six steps, with a validation pass and a device-input step
+    interleaved (both must rebind the fixed input buffers while a slot is still bound)."""
+    cfg = Hh.mid_cfg()
+    B, T = 6, sum(cfg["headTasks"])
+    xs = [O.synthetic_sequences(B, cfg["inputLength"], seed=70 + i) for i in range(3)]
+    cs = [O.synthetic_profiles(B, cfg["outputLength"], T, seed=70 + i, meanReads=40.0)
+          for i in range(3)]
+    order = [0, 1, 2, 1, 0, 2]
+    res = []
+    for host in (False, True):
+        net, _ = build(cfg, False, dev)
+        net.enable_training()
+        if host:
+            xb = [torch.tensor(v).pin_memory() for v in xs]
+            cb = [torch.tensor(v).pin_memory() for v in cs]
+        else:
+            xb = [torch.tensor(v, device=dev) for v in xs]
+            cb = [torch.tensor(v, device=dev) for v in cs]
+        losses = []
+        for step, i in enumerate(order):
+            if host and step == 3:
+                # a device-input step and a validation pass between host-input steps
+                ev = net.eval_losses(torch.tensor(xs[2], device=dev), torch.tensor(cs[2], device=dev))
+                losses.append(ev.clone())
+                out = net.train_step(torch.tensor(xs[i], device=dev), torch.tensor(cs[i], device=dev),
+                                     0.004)
+            else:
+                if step == 3:
+                    losses.append(net.eval_losses(xb[2], cb[2]).clone())
+                out = net.train_step(xb[i], cb[i], 0.004)
+            losses.append(out.clone())
+        torch.cuda.synchronize()
+        res.append((net.params.flat.clone(), torch.stack(losses)))
+    dl = (res[0][1] - res[1][1]).abs().max(dim=1).values.tolist()
+    dp = float((res[0][0] - res[1][0]).abs().max())
+    train_rows = [r for r in range(len(dl)) if r != 3]  # row 3 is the validation pass
+    assert all(dl[r] == 0.0 for r in train_rows), f"training losses differ (per row: {dl})"
+    # (the validation kernel adds the batch with float atomics: last-bit jitter between runs)
+    assert dl[3] <= 1e-5 * float(res[0][1][3].abs().max()), f"validation losses differ: {dl[3]}"
+    assert torch.equal(res[0][0], res[1][0]), f"parameters differ by {dp}"
