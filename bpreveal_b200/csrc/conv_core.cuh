@@ -257,7 +257,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
   // operand stages.
   // The SLAB-staged forward with resident weights (F = 64, d >= 128) does the same: 100.2 ->
   // 98.3 us over the nine forward launches of C1.  On the F = 64 data gradient it measured
-  // neutral with more spills (-DBPB_DIRECT_ALL), so that keeps its ring.
+  // neutral with more spills (-DBPB_DIRECT_ALL), so that keeps its ring; on the HALO-staged
+  // forward, whose residual is already in the box, it was slower (98.5 -> 112.6 us).
 #if defined(BPB_DIRECT_ALL)
   constexpr bool DIRECT_RESID = RESID && !(HALO && IS_FWD);
 #else
@@ -325,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvKParams p) {
       uint64_t* b1 = is_ring ? &empty[lane] : is_acc ? &acc_empty[lane - 16] : &rempty[lane - 24];
       // HALO forward: the box is released by the MMA commit AND by the 8 epilogue warps
       // (CG2: the leader's accumulator-empty barriers collect the epilogue warps of both CTAs)
-      const uint32_t c1 = is_ring ? ((HALO && IS_FWD && RESID) ? 9u : 1u)
+      const uint32_t c1 = is_ring ? ((HALO && IS_FWD && RESID && !DIRECT_RESID) ? 9u : 1u)
                                   : ((CG2 && is_acc) ? 16u : 8u);
       if (is_ring || is_acc || is_res) {
         mbar_init(b0, 1);
